@@ -1,0 +1,190 @@
+/*
+ * rcw_b200.h — C ABI of librcw_b200.so: the B200-native batched SingleRoom engine.
+ *
+ * This is the drop-in boundary for the hot path of RayCastWorlds.jl
+ *   act!(world)  ->  cast_rays!(world)  ->  update_camera_view!(env)
+ * (reference: src/single_room.jl:333-340, top view excluded).  The reference has no
+ * FFI of its own (it is pure Julia); the seam it offers is multiple dispatch on
+ * `AbstractGame` (src/RayCastWorlds.jl:5-14).  A Julia host keeps that API and calls
+ * these entry points with `ccall` (see INTEGRATION.md and
+ * raycastworlds.jl_b200/julia/BatchedRayCastWorlds.jl).  Each entry point below cites
+ * the reference function it replaces.
+ *
+ * Conventions
+ *   - every call returns RCW_OK (0) or a negative rcw_status; nothing throws or aborts;
+ *     the message of the last failure on the calling thread is rcw_last_error().
+ *   - all host pointers are caller-owned and only touched during the call.
+ *   - tile indices are 1-based (i in 1..height_tu, j in 1..width_tu), angles are
+ *     0..num_directions-1, exactly as in the reference (README.md:75-83).
+ *   - one handle = one device + one stream; calls on one handle must be serialised by
+ *     the caller; different handles may be driven from different host threads.
+ *   - rcw_step*, rcw_reset, rcw_render only enqueue work; rcw_sync / rcw_get_* /
+ *     rcw_copy_obs block until the handle's stream has drained.
+ *   - there is NO CPU fallback: without a CUDA device rcw_create fails with RCW_ECUDA.
+ */
+#ifndef RCW_B200_H
+#define RCW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCW_ABI_VERSION 1
+
+typedef enum rcw_status {
+    RCW_OK      = 0,
+    RCW_EINVAL  = -1, /* bad argument / bad config                                   */
+    RCW_EACTION = -2, /* action outside 1..4  (reference: @assert, single_room.jl:140) */
+    RCW_ECUDA   = -3, /* CUDA runtime error (or no device)                            */
+    RCW_ENOMEM  = -4, /* host or device allocation failed                             */
+    RCW_ESIZE   = -5  /* struct_size / range mismatch                                 */
+} rcw_status;
+
+/* Observation formats.  Both are "column-major" like the reference's
+ * camera_view::Array{UInt32}(height_px, num_rays) (single_room.jl:300): the pixel row is
+ * the fastest index after the channel, so one ray's column is contiguous. */
+typedef enum rcw_obs_format {
+    RCW_OBS_RGB8   = 0, /* uint8  [num_envs][num_rays][height_px][3]  (R,G,B bytes of the reference pixel) */
+    RCW_OBS_XRGB32 = 1  /* uint32 [num_envs][num_rays][height_px]     (bit-identical to the reference's UInt32 pixels) */
+} rcw_obs_format;
+
+/* Indices into rcw_config.palette (reference values: single_room.jl:291-296). */
+enum {
+    RCW_COLOR_CEILING = 0, /* 0x00FFFFFF */
+    RCW_COLOR_FLOOR   = 1, /* 0x00404040 */
+    RCW_COLOR_WALL_1  = 2, /* 0x00808080  wall hit across dimension 1 */
+    RCW_COLOR_WALL_2  = 3, /* 0x00c0c0c0 */
+    RCW_COLOR_GOAL_1  = 4, /* 0x00800000 */
+    RCW_COLOR_GOAL_2  = 5  /* 0x00c00000 */
+};
+
+/* Switches for the behaviour of RayCaster.cast_ray that the reference tree does not pin
+ * (RayCaster.jl 0.1 is not vendored; see DESIGN.md "Unpinned decisions" D1/D2). */
+enum {
+    RCW_DDA_TIE_LE    = 1u << 0, /* D1: advance along dimension 1 when side_x <= side_y (default: strict <) */
+    RCW_DDA_DIST_POST = 1u << 1  /* D2: distance = side - delta after the loop (default: side before the increment) */
+};
+
+/* Keyword arguments of SingleRoom(...) (single_room.jl:258-272) plus the batch fields. */
+typedef struct rcw_config {
+    uint32_t struct_size;            /* = sizeof(rcw_config); checked by rcw_create            */
+    int32_t  device;                 /* CUDA device ordinal                                    */
+    int64_t  num_envs;               /* environments owned by this handle                      */
+    int64_t  env_id_offset;          /* global id of env 0 (multi-GPU shards); keys the RNG    */
+    int32_t  height_tile_map_tu;     /* default 8                                              */
+    int32_t  width_tile_map_tu;      /* default 16                                             */
+    int32_t  num_directions;         /* default 128                                            */
+    int32_t  num_rays;               /* default 512                                            */
+    int32_t  height_camera_view_pu;  /* default 256                                            */
+    float    player_radius_wu;       /* default 1/8                                            */
+    float    position_increment_wu;  /* default 1/8                                            */
+    float    semi_field_of_view_wu;  /* default 2/3 (rounded to f32)                           */
+    float    camera_height_tile_wu;  /* default 1                                              */
+    float    goal_reward;            /* default 1                                              */
+    int32_t  obs_format;             /* rcw_obs_format, default RCW_OBS_RGB8                   */
+    int32_t  auto_reset;             /* 1: a terminated env is re-drawn inside the same step   */
+    uint64_t seed;                   /* Philox4x32-10 key                                      */
+    uint32_t palette[6];             /* 0x00RRGGBB, indices RCW_COLOR_*                        */
+    uint32_t dda_flags;              /* RCW_DDA_* (0 = default contract)                       */
+    uint32_t reserved[7];            /* must be zero                                           */
+} rcw_config;
+
+typedef struct rcw_batch rcw_batch; /* opaque */
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+int32_t rcw_version(void);
+
+/* Fill cfg with the reference's defaults (single_room.jl:43-52,258-272,288-296). */
+int32_t rcw_config_init(rcw_config* cfg);
+
+/* Replaces SingleRoom(...) / SingleRoomWorld(...) (single_room.jl:42-108,258-324) for a batch.
+ * directions_wu: [num_directions][2] float32 unit vectors; pass the Julia host's own table so
+ * the reference's cos/sin values are used (single_room.jl:65-69).  NULL => computed here as
+ * (float)cos(theta), (float)sin(theta), theta = i*2*pi/num_directions in double.
+ * The new batch is reset with on-device Philox draws and rendered once. */
+int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch** out);
+int32_t rcw_destroy(rcw_batch* b);
+
+/* Replace the wall layer (tile_map[WALL,:,:], single_room.jl:55-60) shared by every env of the
+ * batch.  wall: [width_tu][height_tu] bytes, Julia column-major (i fastest), nonzero = wall.
+ * Does not re-render; follow with rcw_reset or rcw_render. */
+int32_t rcw_set_wall_map(rcw_batch* b, const uint8_t* wall);
+
+/* ---- the reference's generic functions -------------------------------------------------- */
+
+/* reset!(env) (single_room.jl:110-137,326-331) for the envs whose mask byte is nonzero
+ * (mask NULL => all).  goal_ij/player_ij: [num_envs][2] int32 1-based tiles, dir_au:
+ * [num_envs] int32; the player is placed at the tile centre (i-0.5, j-0.5).  All three NULL =>
+ * the layout is drawn on the device (uniform interior goal, uniform empty player tile by
+ * rejection, uniform direction — same draw order as the reference).  Sets reward=0,
+ * done=false, then casts and renders. */
+int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij,
+                  const int32_t* dir_au, const uint8_t* mask);
+
+/* act!(env, action) (single_room.jl:139-191,333-340) for every env: actions[e] in 1..4
+ * (1 forward, 2 backward, 3 turn left, 4 turn right; single_room.jl:486).  `actions` may be a
+ * host pointer or a device pointer.  A host array holding a value outside 1..4 => RCW_EACTION
+ * and nothing is enqueued; for a device array the offending env is left untouched and the
+ * error is reported by the next blocking call. */
+int32_t rcw_step(rcw_batch* b, const uint8_t* actions);
+
+/* n_steps of rcw_step with a uniform random policy drawn on the device (Philox keyed by
+ * seed / global env id / step index); the benchmark path. */
+int32_t rcw_step_random(rcw_batch* b, int32_t n_steps);
+
+/* cast_rays!(world) + update_camera_view!(env) (single_room.jl:195-231,374-444) from the
+ * current state, without acting. */
+int32_t rcw_render(rcw_batch* b);
+
+/* ---- state access (parity injection, checkpoint/resume) -------------------------------- */
+
+/* Any pointer may be NULL (skipped).  pos_xy [num_envs][2] f32 world units, dir_au [num_envs],
+ * goal_ij [num_envs][2] 1-based, reward [num_envs] f32, done [num_envs] u8.
+ * rcw_set_state does not re-render; follow with rcw_render. */
+int32_t rcw_get_state(rcw_batch* b, float* pos_xy, int32_t* dir_au, int32_t* goal_ij,
+                      float* reward, uint8_t* done);
+int32_t rcw_set_state(rcw_batch* b, const float* pos_xy, const int32_t* dir_au,
+                      const int32_t* goal_ij, const float* reward, const uint8_t* done);
+
+/* world.ray_stop_position_tu / ray_hit_dimension / ray_distance_wu / ray_directions_wu
+ * (single_room.jl:29-31,39) for envs [env0, env0+n): hit_ij [n][num_rays][2] 1-based,
+ * hit_dim [n][num_rays], dist [n][num_rays], ray_dir [n][num_rays][2].  Debug / parity only:
+ * runs the ray-cast kernel in dump mode from the current state. */
+int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int32_t* hit_dim,
+                     float* dist, float* ray_dir);
+
+/* ---- observations (RLBase.state, single_room.jl:576) ------------------------------------ */
+
+/* Borrowed device pointer to the whole observation buffer (layout: rcw_obs_format), valid
+ * until the next rcw_step* / rcw_reset / rcw_render / rcw_destroy — the same aliasing rule as
+ * the reference, whose `state` returns the live camera_view array.
+ * env_stride_bytes: distance between consecutive envs (a multiple of 16). */
+int32_t rcw_obs_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_t* env_stride_bytes);
+
+/* Blocking copy of the observations of envs [env0, env0+n) to host memory, densely packed
+ * (n * num_rays * height_px * bytes_per_pixel). */
+int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host);
+
+/* ---- bookkeeping ------------------------------------------------------------------------ */
+
+/* Totals over finished episodes since creation (or the last call with reset_counters != 0). */
+int32_t rcw_episode_stats(rcw_batch* b, int64_t* episodes, double* sum_return,
+                          int64_t* sum_length, int32_t reset_counters);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
+int32_t rcw_launch_count(rcw_batch* b, int64_t* launches);
+
+/* The CUDA stream of the handle (a cudaStream_t) so a host can record events on it. */
+int32_t rcw_stream(rcw_batch* b, void** stream);
+
+int32_t rcw_sync(rcw_batch* b);
+const char* rcw_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCW_B200_H */

@@ -1,0 +1,746 @@
+// rcw_capi.cu — the C ABI of librcw_b200.so (include/rcw_b200.h): handle lifetime, HBM layout,
+// host<->device plumbing and kernel launches.  No CPU implementation of the hot path lives here:
+// without a CUDA device every entry point fails with RCW_ECUDA.
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rcw_internal.h"
+
+using namespace rcw;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+
+static thread_local std::string t_last_error;
+
+static int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    return code;
+}
+
+#define RCW_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            int32_t _c = (_e == cudaErrorMemoryAllocation) ? RCW_ENOMEM : RCW_ECUDA;           \
+            cudaGetLastError();                                                                \
+            return fail(_c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                        __LINE__);                                                             \
+        }                                                                                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// constant-memory slots for direction tables, per device
+static std::mutex g_slot_mutex;
+static bool g_slot_used[64][kDirSlots];
+
+static int acquire_dir_slot(int device) {
+    if (device < 0 || device >= 64) return -1;
+    std::lock_guard<std::mutex> lk(g_slot_mutex);
+    for (int s = 0; s < kDirSlots; ++s)
+        if (!g_slot_used[device][s]) {
+            g_slot_used[device][s] = true;
+            return s;
+        }
+    return -1;
+}
+
+static void release_dir_slot(int device, int slot) {
+    if (device < 0 || device >= 64 || slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_slot_mutex);
+    g_slot_used[device][slot] = false;
+}
+
+// ------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------
+
+constexpr int kActionRing = 4;
+
+struct rcw_batch {
+    rcw_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int bpp = 3;
+    int gpe = 0;
+    int wpr = 0;
+    int map_words = 0;
+    int dir_slot = -1;
+    int ctas_per_sm = 0;          // 0: one CTA per 8 items; >0: persistent grid of sm_count * this
+    // device memory
+    float2* d_dirs = nullptr;
+    float4* d_ray_table = nullptr;
+    uint32_t* d_wall_map = nullptr;
+    StateRef st[2]{};
+    int cur = 0;
+    float* d_reward = nullptr;
+    uint8_t* d_done = nullptr;
+    float* d_ep_return = nullptr;
+    uint32_t* d_ep_length = nullptr;
+    DeviceStats* d_stats = nullptr;
+    uint8_t* d_actions = nullptr;
+    uint8_t* d_obs = nullptr;
+    size_t obs_env_stride = 0;
+    size_t obs_bytes = 0;
+    // pinned staging for host-side action arrays
+    uint8_t* h_actions[kActionRing]{};
+    cudaEvent_t h_actions_free[kActionRing]{};
+    int ring = 0;
+    DeviceStats* h_stats = nullptr;  // pinned
+    // counters
+    uint64_t step_index = 0;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+};
+
+template <typename T>
+static cudaError_t dev_alloc(rcw_batch* b, T** out, size_t count, bool zero = true) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    b->allocs.push_back(p);
+    *out = static_cast<T*>(p);
+    if (zero) e = cudaMemsetAsync(p, 0, count * sizeof(T), b->stream);
+    return e;
+}
+
+static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
+    const rcw_config& c = b->cfg;
+    memset(&p, 0, sizeof(p));
+    p.H = c.height_tile_map_tu;
+    p.W = c.width_tile_map_tu;
+    p.wpr = b->wpr;
+    p.map_words = b->map_words;
+    p.N = c.num_directions;
+    p.R = c.num_rays;
+    p.P = c.height_camera_view_pu;
+    p.gpe = b->gpe;
+    p.col_bytes = c.height_camera_view_pu * b->bpp;
+    p.dda_flags = c.dda_flags;
+    p.radius = c.player_radius_wu;
+    p.incr = c.position_increment_wu;
+    p.goal_reward = c.goal_reward;
+    // single_room.jl:406 — camera_height_tile_wu * num_rays and 2 * semi_field_of_view_wu, each one
+    // binary32 rounding (volatile keeps the host compiler from widening or folding differently)
+    volatile float hl_num = c.camera_height_tile_wu * (float)c.num_rays;
+    volatile float two_s = 2.0f * c.semi_field_of_view_wu;
+    p.hl_num = hl_num;
+    p.two_s = two_s;
+    for (int i = 0; i < 6; ++i) p.palette[i] = c.palette[i] & 0x00FFFFFFu;
+    p.dir_slot = b->dir_slot;
+    p.dirs = b->d_dirs;
+    p.ray_table = b->d_ray_table;
+    p.wall_map = b->d_wall_map;
+    p.in = b->st[b->cur];
+    p.out = b->st[b->cur ^ 1];
+    p.actions = nullptr;
+    p.reward = b->d_reward;
+    p.done = b->d_done;
+    p.ep_return = b->d_ep_return;
+    p.ep_length = b->d_ep_length;
+    p.stats = b->d_stats;
+    p.obs = b->d_obs;
+    p.obs_env_stride = b->obs_env_stride;
+    p.num_envs = c.num_envs;
+    p.env_first = 0;
+    p.env_count = c.num_envs;
+    p.env_id_offset = (uint64_t)c.env_id_offset;
+    p.seed = c.seed;
+    p.step_index = b->step_index;
+    p.auto_reset = c.auto_reset;
+}
+
+static int grid_for(const rcw_batch* b, int64_t env_count) {
+    const int64_t items = env_count * b->gpe;
+    int64_t ctas = (items + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (b->ctas_per_sm > 0) {
+        const int64_t cap = (int64_t)b->sm_count * b->ctas_per_sm;
+        if (ctas > cap) ctas = cap;
+    }
+    return (int)(ctas < 1 ? 1 : ctas);
+}
+
+static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
+    FrameParams p;
+    fill_frame_params(b, p);
+    p.actions = d_actions;
+    RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, grid_for(b, p.env_count), b->stream));
+    b->launches += 1;
+    if (mode == kModeStep) {
+        b->cur ^= 1;
+        b->step_index += 1;
+    }
+    return RCW_OK;
+}
+
+static int32_t check_handle(const rcw_batch* b) {
+    if (!b) return fail(RCW_EINVAL, "null rcw_batch handle");
+    return RCW_OK;
+}
+
+// blocks, then reports (and clears) a device-side invalid-action flag
+static int32_t sync_and_check(rcw_batch* b) {
+    RCW_CUDA(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost,
+                             b->stream));
+    RCW_CUDA(cudaStreamSynchronize(b->stream));
+    if (b->h_stats->bad_action) {
+        RCW_CUDA(cudaMemsetAsync(&b->d_stats->bad_action, 0, sizeof(int), b->stream));
+        return fail(RCW_EACTION, "a device-side action array held a value outside 1..4; "
+                                 "the affected envs were not stepped");
+    }
+    return RCW_OK;
+}
+
+static void pack_border_walls(int H, int W, int wpr, std::vector<uint32_t>& words) {
+    // tile_map[WALL, :, 1] = tile_map[WALL, :, W] = tile_map[WALL, 1, :] = tile_map[WALL, H, :] = true
+    // (single_room.jl:57-60)
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j)
+            if (i == 0 || i == H - 1 || j == 0 || j == W - 1) words[(size_t)i * wpr + (j >> 5)] |= 1u << (j & 31);
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int32_t rcw_version(void) { return RCW_ABI_VERSION; }
+
+const char* rcw_last_error(void) { return t_last_error.c_str(); }
+
+int32_t rcw_config_init(rcw_config* cfg) {
+    if (!cfg) return fail(RCW_EINVAL, "cfg is null");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (uint32_t)sizeof(rcw_config);
+    cfg->device = 0;
+    cfg->num_envs = 1;
+    cfg->env_id_offset = 0;
+    cfg->height_tile_map_tu = 8;        // single_room.jl:44
+    cfg->width_tile_map_tu = 16;        // :45
+    cfg->num_directions = 128;          // :46
+    cfg->num_rays = 512;                // :52
+    cfg->height_camera_view_pu = 256;   // :271
+    cfg->player_radius_wu = (float)(1.0 / 8.0);       // :47
+    cfg->position_increment_wu = (float)(1.0 / 8.0);  // :48
+    cfg->semi_field_of_view_wu = (float)(2.0 / 3.0);  // :51
+    cfg->camera_height_tile_wu = 1.0f;  // :270
+    cfg->goal_reward = 1.0f;            // :82
+    cfg->obs_format = RCW_OBS_RGB8;
+    cfg->auto_reset = 1;
+    cfg->seed = 0;
+    cfg->palette[RCW_COLOR_CEILING] = 0x00FFFFFFu;  // :292
+    cfg->palette[RCW_COLOR_FLOOR] = 0x00404040u;    // :291
+    cfg->palette[RCW_COLOR_WALL_1] = 0x00808080u;   // :293
+    cfg->palette[RCW_COLOR_WALL_2] = 0x00c0c0c0u;   // :294
+    cfg->palette[RCW_COLOR_GOAL_1] = 0x00800000u;   // :295
+    cfg->palette[RCW_COLOR_GOAL_2] = 0x00c00000u;   // :296
+    cfg->dda_flags = 0;
+    return RCW_OK;
+}
+
+int32_t rcw_destroy(rcw_batch* b) {
+    if (!b) return RCW_OK;
+    DeviceGuard g(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void* p : b->allocs) cudaFree(p);
+    for (int i = 0; i < kActionRing; ++i) {
+        if (b->h_actions[i]) cudaFreeHost(b->h_actions[i]);
+        if (b->h_actions_free[i]) cudaEventDestroy(b->h_actions_free[i]);
+    }
+    if (b->h_stats) cudaFreeHost(b->h_stats);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    release_dir_slot(b->device, b->dir_slot);
+    cudaGetLastError();
+    delete b;
+    return RCW_OK;
+}
+
+static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
+    const rcw_config& c = b->cfg;
+    const int H = c.height_tile_map_tu, W = c.width_tile_map_tu, N = c.num_directions;
+    const int R = c.num_rays, P = c.height_camera_view_pu;
+    const int64_t E = c.num_envs;
+
+    cudaDeviceProp prop;
+    RCW_CUDA(cudaGetDeviceProperties(&prop, b->device));
+    b->sm_count = prop.multiProcessorCount;
+    RCW_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    if (const char* s = getenv("RCW_CTAS_PER_SM")) b->ctas_per_sm = atoi(s);
+
+    // ---- direction table (single_room.jl:65-69) -------------------------------------------
+    std::vector<float2> dirs((size_t)N);
+    if (directions_wu) {
+        for (int i = 0; i < N; ++i) dirs[i] = make_float2(directions_wu[2 * i], directions_wu[2 * i + 1]);
+    } else {
+        const double pi = 3.14159265358979323846;
+        for (int i = 1; i <= N; ++i) {
+            const double theta = (double)(i - 1) * 2 * pi / (double)N;
+            dirs[i - 1] = make_float2((float)cos(theta), (float)sin(theta));
+        }
+    }
+    RCW_CUDA(dev_alloc(b, &b->d_dirs, (size_t)N, false));
+    RCW_CUDA(cudaMemcpyAsync(b->d_dirs, dirs.data(), sizeof(float2) * (size_t)N,
+                             cudaMemcpyHostToDevice, b->stream));
+    if (N <= kDirSlotEntries) {
+        b->dir_slot = acquire_dir_slot(b->device);
+        if (b->dir_slot >= 0) RCW_CUDA(upload_dir_slot(b->dir_slot, dirs.data(), N, b->stream));
+    }
+    RCW_CUDA(cudaStreamSynchronize(b->stream));  // dirs is a host temporary
+
+    // ---- ray table ---------------------------------------------------------------------------
+    RCW_CUDA(dev_alloc(b, &b->d_ray_table, (size_t)N * (size_t)R, false));
+    RCW_CUDA(launch_build_ray_table(b->d_dirs, N, R, c.semi_field_of_view_wu, b->d_ray_table, b->stream));
+    b->launches += 1;
+
+    // ---- wall layer ---------------------------------------------------------------------------
+    b->wpr = (W + 31) / 32;
+    b->map_words = ((H * b->wpr + 3) / 4) * 4;
+    std::vector<uint32_t> words((size_t)b->map_words, 0u);
+    pack_border_walls(H, W, b->wpr, words);
+    RCW_CUDA(dev_alloc(b, &b->d_wall_map, (size_t)b->map_words, false));
+    RCW_CUDA(cudaMemcpyAsync(b->d_wall_map, words.data(), sizeof(uint32_t) * words.size(),
+                             cudaMemcpyHostToDevice, b->stream));
+    RCW_CUDA(cudaStreamSynchronize(b->stream));
+
+    // ---- state SoA -----------------------------------------------------------------------------
+    for (int k = 0; k < 2; ++k) {
+        RCW_CUDA(dev_alloc(b, &b->st[k].pos_x, (size_t)E));
+        RCW_CUDA(dev_alloc(b, &b->st[k].pos_y, (size_t)E));
+        RCW_CUDA(dev_alloc(b, &b->st[k].dir_au, (size_t)E));
+        RCW_CUDA(dev_alloc(b, &b->st[k].goal, (size_t)E));
+        RCW_CUDA(dev_alloc(b, &b->st[k].episode, (size_t)E));
+    }
+    RCW_CUDA(dev_alloc(b, &b->d_reward, (size_t)E));
+    RCW_CUDA(dev_alloc(b, &b->d_done, (size_t)E));
+    RCW_CUDA(dev_alloc(b, &b->d_ep_return, (size_t)E));
+    RCW_CUDA(dev_alloc(b, &b->d_ep_length, (size_t)E));
+    RCW_CUDA(dev_alloc(b, &b->d_stats, 1));
+    RCW_CUDA(dev_alloc(b, &b->d_actions, (size_t)E));
+    for (int i = 0; i < kActionRing; ++i) {
+        RCW_CUDA(cudaMallocHost((void**)&b->h_actions[i], (size_t)E));
+        RCW_CUDA(cudaEventCreateWithFlags(&b->h_actions_free[i], cudaEventDisableTiming));
+    }
+    RCW_CUDA(cudaMallocHost((void**)&b->h_stats, sizeof(DeviceStats)));
+
+    // ---- observations ---------------------------------------------------------------------------
+    b->obs_env_stride = (((size_t)R * P * b->bpp) + 15) & ~(size_t)15;
+    b->obs_bytes = b->obs_env_stride * (size_t)E;
+    RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, false));
+    return RCW_OK;
+}
+
+int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch** out) {
+    if (!cfg || !out) return fail(RCW_EINVAL, "cfg/out is null");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(rcw_config))
+        return fail(RCW_ESIZE, "rcw_config.struct_size is %u, this library expects %zu",
+                    cfg->struct_size, sizeof(rcw_config));
+    for (uint32_t r : cfg->reserved)
+        if (r) return fail(RCW_EINVAL, "rcw_config.reserved must be zero");
+    const int H = cfg->height_tile_map_tu, W = cfg->width_tile_map_tu;
+    if (H < 3 || W < 3 || H > 32767 || W > 32767)
+        return fail(RCW_EINVAL, "tile map must be between 3x3 and 32767x32767 (got %dx%d)", H, W);
+    if (cfg->num_directions < 1 || cfg->num_directions > (1 << 20))
+        return fail(RCW_EINVAL, "num_directions out of range: %d", cfg->num_directions);
+    if (cfg->num_rays < 1 || cfg->height_camera_view_pu < 1)
+        return fail(RCW_EINVAL, "num_rays and height_camera_view_pu must be positive");
+    if (cfg->height_camera_view_pu > 32767)
+        return fail(RCW_EINVAL, "height_camera_view_pu must be below 32768");
+    if (cfg->obs_format != RCW_OBS_RGB8 && cfg->obs_format != RCW_OBS_XRGB32)
+        return fail(RCW_EINVAL, "unknown obs_format %d", cfg->obs_format);
+    if (cfg->num_envs < 1) return fail(RCW_EINVAL, "num_envs must be positive");
+    if (!(cfg->player_radius_wu > 0.0f) || !(cfg->player_radius_wu < 0.5f))
+        return fail(RCW_EINVAL, "player_radius_wu must be in (0, 0.5) (single_room.jl:47)");
+    if (!(cfg->semi_field_of_view_wu > 0.0f)) return fail(RCW_EINVAL, "semi_field_of_view_wu must be positive");
+    if (cfg->dda_flags & ~(uint32_t)(RCW_DDA_TIE_LE | RCW_DDA_DIST_POST))
+        return fail(RCW_EINVAL, "unknown dda_flags 0x%x", cfg->dda_flags);
+    const int bpp = cfg->obs_format == RCW_OBS_RGB8 ? 3 : 4;
+    const int gpe = (cfg->num_rays + 31) / 32;
+    if ((int64_t)cfg->num_rays * cfg->height_camera_view_pu * bpp >= (1LL << 30))
+        return fail(RCW_ESIZE, "one observation must be smaller than 1 GiB");
+    if (cfg->num_envs * gpe >= (1LL << 31))
+        return fail(RCW_ESIZE, "num_envs * ceil(num_rays/32) must be below 2^31 per handle");
+    if ((int64_t)((H * ((W + 31) / 32) + 3) / 4) * 16 > 200 * 1024)
+        return fail(RCW_ESIZE, "bit-packed tile map does not fit in shared memory");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RCW_ECUDA, "no CUDA device available; librcw_b200 has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(RCW_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+
+    rcw_batch* b = new (std::nothrow) rcw_batch();
+    if (!b) return fail(RCW_ENOMEM, "out of host memory");
+    b->cfg = *cfg;
+    b->device = cfg->device;
+    b->bpp = bpp;
+    b->gpe = gpe;
+    DeviceGuard g(b->device);
+    if (!g.ok) {
+        delete b;
+        return fail(RCW_ECUDA, "cudaSetDevice(%d) failed", cfg->device);
+    }
+    int32_t rc = create_impl(b, directions_wu);
+    if (rc == RCW_OK) rc = rcw_reset(b, nullptr, nullptr, nullptr, nullptr);
+    if (rc == RCW_OK) rc = sync_and_check(b);
+    if (rc != RCW_OK) {
+        std::string keep = t_last_error;
+        rcw_destroy(b);
+        t_last_error = keep;
+        return rc;
+    }
+    *out = b;
+    return RCW_OK;
+}
+
+int32_t rcw_set_wall_map(rcw_batch* b, const uint8_t* wall) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!wall) return fail(RCW_EINVAL, "wall is null");
+    DeviceGuard g(b->device);
+    const int H = b->cfg.height_tile_map_tu, W = b->cfg.width_tile_map_tu;
+    std::vector<uint32_t> words((size_t)b->map_words, 0u);
+    for (int j = 0; j < W; ++j)
+        for (int i = 0; i < H; ++i)
+            if (wall[(size_t)j * H + i]) words[(size_t)i * b->wpr + (j >> 5)] |= 1u << (j & 31);
+    RCW_CUDA(cudaStreamSynchronize(b->stream));
+    RCW_CUDA(cudaMemcpy(b->d_wall_map, words.data(), sizeof(uint32_t) * words.size(),
+                        cudaMemcpyHostToDevice));
+    return RCW_OK;
+}
+
+int32_t rcw_render(rcw_batch* b) {
+    if (int32_t rc = check_handle(b)) return rc;
+    DeviceGuard g(b->device);
+    return enqueue_frame(b, kModeRender, nullptr);
+}
+
+int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij,
+                  const int32_t* dir_au, const uint8_t* mask) {
+    if (int32_t rc = check_handle(b)) return rc;
+    const bool any = goal_ij || player_ij || dir_au;
+    if (any && !(goal_ij && player_ij && dir_au))
+        return fail(RCW_EINVAL, "goal_ij, player_ij and dir_au must be all given or all null");
+    DeviceGuard g(b->device);
+    const rcw_config& c = b->cfg;
+    const int64_t E = c.num_envs;
+    int32_t *d_goal = nullptr, *d_player = nullptr, *d_dir = nullptr;
+    uint8_t* d_mask = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_goal);
+        cudaFree(d_player);
+        cudaFree(d_dir);
+        cudaFree(d_mask);
+    };
+    if (any) {
+        for (int64_t e = 0; e < E; ++e) {
+            if (mask && !mask[e]) continue;
+            const int gi = goal_ij[2 * e], gj = goal_ij[2 * e + 1];
+            const int pi = player_ij[2 * e], pj = player_ij[2 * e + 1];
+            if (gi < 1 || gi > c.height_tile_map_tu || gj < 1 || gj > c.width_tile_map_tu ||
+                pi < 1 || pi > c.height_tile_map_tu || pj < 1 || pj > c.width_tile_map_tu)
+                return fail(RCW_EINVAL, "env %lld: tile outside the map", (long long)e);
+            if (dir_au[e] < 0 || dir_au[e] >= c.num_directions)
+                return fail(RCW_EINVAL, "env %lld: direction %d outside 0..%d", (long long)e,
+                            dir_au[e], c.num_directions - 1);
+        }
+        cudaError_t e1 = cudaMalloc((void**)&d_goal, sizeof(int32_t) * 2 * (size_t)E);
+        cudaError_t e2 = cudaMalloc((void**)&d_player, sizeof(int32_t) * 2 * (size_t)E);
+        cudaError_t e3 = cudaMalloc((void**)&d_dir, sizeof(int32_t) * (size_t)E);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            cleanup();
+            cudaGetLastError();
+            return fail(RCW_ENOMEM, "device allocation for reset layouts failed");
+        }
+        cudaMemcpyAsync(d_goal, goal_ij, sizeof(int32_t) * 2 * (size_t)E, cudaMemcpyHostToDevice, b->stream);
+        cudaMemcpyAsync(d_player, player_ij, sizeof(int32_t) * 2 * (size_t)E, cudaMemcpyHostToDevice, b->stream);
+        cudaMemcpyAsync(d_dir, dir_au, sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, b->stream);
+    }
+    if (mask) {
+        if (cudaMalloc((void**)&d_mask, (size_t)E) != cudaSuccess) {
+            cleanup();
+            cudaGetLastError();
+            return fail(RCW_ENOMEM, "device allocation for the reset mask failed");
+        }
+        cudaMemcpyAsync(d_mask, mask, (size_t)E, cudaMemcpyHostToDevice, b->stream);
+    }
+    ResetParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.H = c.height_tile_map_tu;
+    rp.W = c.width_tile_map_tu;
+    rp.wpr = b->wpr;
+    rp.N = c.num_directions;
+    rp.wall_map = b->d_wall_map;
+    rp.st = b->st[b->cur];
+    rp.reward = b->d_reward;
+    rp.done = b->d_done;
+    rp.ep_return = b->d_ep_return;
+    rp.ep_length = b->d_ep_length;
+    rp.num_envs = E;
+    rp.env_id_offset = (uint64_t)c.env_id_offset;
+    rp.seed = c.seed;
+    rp.goal_ij = d_goal;
+    rp.player_ij = d_player;
+    rp.dir_au = d_dir;
+    rp.mask = d_mask;
+    cudaError_t le = launch_reset(rp, b->stream);
+    b->launches += 1;
+    if (any || mask) {
+        // the temporaries are host-visible only through this call: drain before freeing
+        cudaError_t se = cudaStreamSynchronize(b->stream);
+        cleanup();
+        if (le == cudaSuccess) le = se;
+    }
+    RCW_CUDA(le);
+    return enqueue_frame(b, kModeRender, nullptr);
+}
+
+int32_t rcw_step(rcw_batch* b, const uint8_t* actions) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!actions) return fail(RCW_EINVAL, "actions is null (use rcw_step_random for the random policy)");
+    DeviceGuard g(b->device);
+    const size_t E = (size_t)b->cfg.num_envs;
+    cudaPointerAttributes attr;
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, actions);
+    if (pe != cudaSuccess) cudaGetLastError();
+    const bool on_device = pe == cudaSuccess &&
+                           (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    if (on_device) return enqueue_frame(b, kModeStep, actions);
+
+    // host array: validate (the reference's @assert, single_room.jl:140) while staging into pinned memory
+    const int slot = b->ring;
+    RCW_CUDA(cudaEventSynchronize(b->h_actions_free[slot]));
+    uint8_t* stage = b->h_actions[slot];
+    uint32_t bad = 0;
+    for (size_t e = 0; e < E; ++e) {
+        const uint8_t a = actions[e];
+        bad |= (uint32_t)(a - 1u > 3u);
+        stage[e] = a;
+    }
+    if (bad) {
+        for (size_t e = 0; e < E; ++e)
+            if (actions[e] < 1 || actions[e] > 4)
+                return fail(RCW_EACTION, "Invalid action: %d (env %zu); actions must be in 1..4",
+                            (int)actions[e], e);
+    }
+    RCW_CUDA(cudaMemcpyAsync(b->d_actions, stage, E, cudaMemcpyHostToDevice, b->stream));
+    RCW_CUDA(cudaEventRecord(b->h_actions_free[slot], b->stream));
+    b->ring = (slot + 1) % kActionRing;
+    return enqueue_frame(b, kModeStep, b->d_actions);
+}
+
+int32_t rcw_step_random(rcw_batch* b, int32_t n_steps) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (n_steps < 0) return fail(RCW_EINVAL, "n_steps must be non-negative");
+    DeviceGuard g(b->device);
+    for (int32_t s = 0; s < n_steps; ++s)
+        if (int32_t rc = enqueue_frame(b, kModeStep, nullptr)) return rc;
+    return RCW_OK;
+}
+
+int32_t rcw_get_state(rcw_batch* b, float* pos_xy, int32_t* dir_au, int32_t* goal_ij, float* reward,
+                      uint8_t* done) {
+    if (int32_t rc = check_handle(b)) return rc;
+    DeviceGuard g(b->device);
+    const size_t E = (size_t)b->cfg.num_envs;
+    const StateRef& s = b->st[b->cur];
+    std::vector<float> px, py;
+    std::vector<uint32_t> goal;
+    if (pos_xy) {
+        px.resize(E);
+        py.resize(E);
+        RCW_CUDA(cudaMemcpyAsync(px.data(), s.pos_x, sizeof(float) * E, cudaMemcpyDeviceToHost, b->stream));
+        RCW_CUDA(cudaMemcpyAsync(py.data(), s.pos_y, sizeof(float) * E, cudaMemcpyDeviceToHost, b->stream));
+    }
+    if (dir_au) RCW_CUDA(cudaMemcpyAsync(dir_au, s.dir_au, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, b->stream));
+    if (goal_ij) {
+        goal.resize(E);
+        RCW_CUDA(cudaMemcpyAsync(goal.data(), s.goal, sizeof(uint32_t) * E, cudaMemcpyDeviceToHost, b->stream));
+    }
+    if (reward) RCW_CUDA(cudaMemcpyAsync(reward, b->d_reward, sizeof(float) * E, cudaMemcpyDeviceToHost, b->stream));
+    if (done) RCW_CUDA(cudaMemcpyAsync(done, b->d_done, E, cudaMemcpyDeviceToHost, b->stream));
+    if (int32_t rc = sync_and_check(b)) return rc;
+    if (pos_xy)
+        for (size_t e = 0; e < E; ++e) {
+            pos_xy[2 * e] = px[e];
+            pos_xy[2 * e + 1] = py[e];
+        }
+    if (goal_ij)
+        for (size_t e = 0; e < E; ++e) {
+            goal_ij[2 * e] = (int32_t)(goal[e] & 0xFFFFu);
+            goal_ij[2 * e + 1] = (int32_t)(goal[e] >> 16);
+        }
+    return RCW_OK;
+}
+
+int32_t rcw_set_state(rcw_batch* b, const float* pos_xy, const int32_t* dir_au,
+                      const int32_t* goal_ij, const float* reward, const uint8_t* done) {
+    if (int32_t rc = check_handle(b)) return rc;
+    DeviceGuard g(b->device);
+    const rcw_config& c = b->cfg;
+    const size_t E = (size_t)c.num_envs;
+    const StateRef& s = b->st[b->cur];
+    std::vector<float> px, py;
+    std::vector<uint32_t> goal;
+    if (dir_au)
+        for (size_t e = 0; e < E; ++e)
+            if (dir_au[e] < 0 || dir_au[e] >= c.num_directions)
+                return fail(RCW_EINVAL, "env %zu: direction %d outside 0..%d", e, dir_au[e], c.num_directions - 1);
+    if (goal_ij)
+        for (size_t e = 0; e < E; ++e)
+            if (goal_ij[2 * e] < 1 || goal_ij[2 * e] > c.height_tile_map_tu || goal_ij[2 * e + 1] < 1 ||
+                goal_ij[2 * e + 1] > c.width_tile_map_tu)
+                return fail(RCW_EINVAL, "env %zu: goal tile outside the map", e);
+    if (pos_xy) {
+        px.resize(E);
+        py.resize(E);
+        for (size_t e = 0; e < E; ++e) {
+            const float x = pos_xy[2 * e], y = pos_xy[2 * e + 1];
+            if (!(x >= 0.0f) || !(x < (float)c.height_tile_map_tu) || !(y >= 0.0f) || !(y < (float)c.width_tile_map_tu))
+                return fail(RCW_EINVAL, "env %zu: position (%g, %g) outside the map", e, (double)x, (double)y);
+            px[e] = x;
+            py[e] = y;
+        }
+        RCW_CUDA(cudaMemcpyAsync(s.pos_x, px.data(), sizeof(float) * E, cudaMemcpyHostToDevice, b->stream));
+        RCW_CUDA(cudaMemcpyAsync(s.pos_y, py.data(), sizeof(float) * E, cudaMemcpyHostToDevice, b->stream));
+    }
+    if (dir_au) RCW_CUDA(cudaMemcpyAsync(s.dir_au, dir_au, sizeof(int32_t) * E, cudaMemcpyHostToDevice, b->stream));
+    if (goal_ij) {
+        goal.resize(E);
+        for (size_t e = 0; e < E; ++e)
+            goal[e] = (uint32_t)goal_ij[2 * e] | ((uint32_t)goal_ij[2 * e + 1] << 16);
+        RCW_CUDA(cudaMemcpyAsync(s.goal, goal.data(), sizeof(uint32_t) * E, cudaMemcpyHostToDevice, b->stream));
+    }
+    if (reward) RCW_CUDA(cudaMemcpyAsync(b->d_reward, reward, sizeof(float) * E, cudaMemcpyHostToDevice, b->stream));
+    if (done) RCW_CUDA(cudaMemcpyAsync(b->d_done, done, E, cudaMemcpyHostToDevice, b->stream));
+    RCW_CUDA(cudaStreamSynchronize(b->stream));  // px/py/goal are host temporaries
+    return RCW_OK;
+}
+
+int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int32_t* hit_dim,
+                     float* dist, float* ray_dir) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (env0 < 0 || n < 1 || env0 + n > b->cfg.num_envs)
+        return fail(RCW_ESIZE, "env range [%lld, %lld) outside 0..%lld", (long long)env0,
+                    (long long)(env0 + n), (long long)b->cfg.num_envs);
+    DeviceGuard g(b->device);
+    const size_t cnt = (size_t)n * (size_t)b->cfg.num_rays;
+    int32_t *d_hit = nullptr, *d_dim = nullptr;
+    float *d_dist = nullptr, *d_dir = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_hit);
+        cudaFree(d_dim);
+        cudaFree(d_dist);
+        cudaFree(d_dir);
+    };
+    if (cudaMalloc((void**)&d_hit, cnt * 8) != cudaSuccess || cudaMalloc((void**)&d_dim, cnt * 4) != cudaSuccess ||
+        cudaMalloc((void**)&d_dist, cnt * 4) != cudaSuccess || cudaMalloc((void**)&d_dir, cnt * 8) != cudaSuccess) {
+        cleanup();
+        cudaGetLastError();
+        return fail(RCW_ENOMEM, "device allocation for the ray dump failed");
+    }
+    FrameParams p;
+    fill_frame_params(b, p);
+    p.env_first = env0;
+    p.env_count = n;
+    p.dump_hit = d_hit;
+    p.dump_dim = d_dim;
+    p.dump_dist = d_dist;
+    p.dump_dir = d_dir;
+    cudaError_t e = launch_frame(p, kModeRays, b->cfg.obs_format, grid_for(b, n), b->stream);
+    b->launches += 1;
+    if (e == cudaSuccess && hit_ij) e = cudaMemcpyAsync(hit_ij, d_hit, cnt * 8, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess && hit_dim) e = cudaMemcpyAsync(hit_dim, d_dim, cnt * 4, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess && dist) e = cudaMemcpyAsync(dist, d_dist, cnt * 4, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess && ray_dir) e = cudaMemcpyAsync(ray_dir, d_dir, cnt * 8, cudaMemcpyDeviceToHost, b->stream);
+    cudaError_t se = cudaStreamSynchronize(b->stream);
+    cleanup();
+    if (e == cudaSuccess) e = se;
+    RCW_CUDA(e);
+    return RCW_OK;
+}
+
+int32_t rcw_obs_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_t* env_stride_bytes) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (dptr) *dptr = b->d_obs;
+    if (total_bytes) *total_bytes = b->obs_bytes;
+    if (env_stride_bytes) *env_stride_bytes = b->obs_env_stride;
+    return RCW_OK;
+}
+
+int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!host) return fail(RCW_EINVAL, "host is null");
+    if (env0 < 0 || n < 1 || env0 + n > b->cfg.num_envs)
+        return fail(RCW_ESIZE, "env range [%lld, %lld) outside 0..%lld", (long long)env0,
+                    (long long)(env0 + n), (long long)b->cfg.num_envs);
+    DeviceGuard g(b->device);
+    const size_t dense = (size_t)b->cfg.num_rays * b->cfg.height_camera_view_pu * b->bpp;
+    const uint8_t* src = b->d_obs + (size_t)env0 * b->obs_env_stride;
+    if (dense == b->obs_env_stride)
+        RCW_CUDA(cudaMemcpyAsync(host, src, dense * (size_t)n, cudaMemcpyDeviceToHost, b->stream));
+    else
+        RCW_CUDA(cudaMemcpy2DAsync(host, dense, src, b->obs_env_stride, dense, (size_t)n,
+                                   cudaMemcpyDeviceToHost, b->stream));
+    return sync_and_check(b);
+}
+
+int32_t rcw_episode_stats(rcw_batch* b, int64_t* episodes, double* sum_return, int64_t* sum_length,
+                          int32_t reset_counters) {
+    if (int32_t rc = check_handle(b)) return rc;
+    DeviceGuard g(b->device);
+    if (int32_t rc = sync_and_check(b)) return rc;
+    if (episodes) *episodes = (int64_t)b->h_stats->episodes;
+    if (sum_return) *sum_return = b->h_stats->sum_return;
+    if (sum_length) *sum_length = (int64_t)b->h_stats->sum_length;
+    if (reset_counters) RCW_CUDA(cudaMemsetAsync(b->d_stats, 0, sizeof(DeviceStats), b->stream));
+    return RCW_OK;
+}
+
+int32_t rcw_launch_count(rcw_batch* b, int64_t* launches) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (launches) *launches = b->launches;
+    return RCW_OK;
+}
+
+int32_t rcw_stream(rcw_batch* b, void** stream) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (stream) *stream = (void*)b->stream;
+    return RCW_OK;
+}
+
+int32_t rcw_sync(rcw_batch* b) {
+    if (int32_t rc = check_handle(b)) return rc;
+    DeviceGuard g(b->device);
+    return sync_and_check(b);
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// rcw_internal.h — structures shared by the kernels and the C-ABI layer of librcw_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rcw_b200.h"
+
+namespace rcw {
+
+constexpr int kWarpsPerCta = 8;           // one warp = one (env, 32-ray group) work item at a time
+constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+constexpr int kDirSlots = 8;              // constant-memory slots for direction tables
+constexpr int kDirSlotEntries = 512;      // float2 entries per slot (4 KB)
+
+enum FrameMode : int {
+    kModeStep = 0,    // act! (+ auto-reset) -> cast_rays! -> update_camera_view!
+    kModeRender = 1,  // cast_rays! -> update_camera_view! from the current state
+    kModeRays = 2     // cast_rays! only, results dumped to global arrays (parity / debug)
+};
+
+// Totals over finished episodes + sticky error flags, one per handle, in device memory.
+struct DeviceStats {
+    unsigned long long episodes;
+    unsigned long long sum_length;
+    double sum_return;
+    int bad_action;   // set when a device-side action array held a value outside 1..4
+    int pad;
+};
+
+// Struct-of-arrays environment state in HBM.  The fields every warp of an env reads
+// (position, direction, goal, episode) are double-buffered: a step reads buffer `in`
+// and the env's group-0 warp writes buffer `out`, so the 16 warps that render one env
+// never race with the one that advances it.
+struct StateRef {
+    float* pos_x;
+    float* pos_y;
+    int32_t* dir_au;
+    uint32_t* goal;      // (i | j << 16), 1-based tile
+    uint32_t* episode;   // Philox episode counter of the env
+};
+
+struct FrameParams {
+    // geometry
+    int32_t H, W;            // tiles
+    int32_t wpr;             // 32-bit words per bit-packed map row (bit j-1 of row i-1)
+    int32_t map_words;       // H * wpr rounded up to a multiple of 4 (16-byte TMA granule)
+    int32_t N;               // num_directions
+    int32_t R;               // num_rays == observation width
+    int32_t P;               // height_camera_view_pu
+    int32_t gpe;             // 32-ray groups per env = ceil(R / 32)
+    int32_t col_bytes;       // P * bytes per pixel
+    uint32_t dda_flags;
+    // scalars of the reference constructor
+    float radius, incr, goal_reward;
+    float hl_num;            // camera_height_tile_wu * Float32(num_rays)   (single_room.jl:406)
+    float two_s;             // 2 * semi_field_of_view_wu
+    uint32_t palette[6];
+    // tables
+    int32_t dir_slot;        // >= 0: directions live in constant memory slot; < 0: use `dirs`
+    const float2* dirs;      // [N] unit vectors (global copy, also the source of the ray table)
+    const float4* ray_table; // [N][R] {ray_x, ray_y, |1/ray_x|, |1/ray_y|}
+    const uint32_t* wall_map;// [map_words] shared wall layer, bit-packed
+    // state
+    StateRef in, out;
+    const uint8_t* actions;  // device, 1..4 per env; nullptr => random policy
+    float* reward;
+    uint8_t* done;
+    float* ep_return;
+    uint32_t* ep_length;
+    DeviceStats* stats;
+    uint8_t* obs;
+    size_t obs_env_stride;   // bytes, multiple of 16
+    int64_t num_envs;
+    int64_t env_first;       // first env processed by this launch (kModeRays: dump window)
+    int64_t env_count;       // envs processed by this launch
+    uint64_t env_id_offset;
+    uint64_t seed;
+    uint64_t step_index;
+    int32_t auto_reset;
+    // kModeRays outputs, indexed relative to env_first
+    int32_t* dump_hit;       // [n][R][2]
+    int32_t* dump_dim;       // [n][R]
+    float* dump_dist;        // [n][R]
+    float* dump_dir;         // [n][R][2]
+};
+
+struct ResetParams {
+    int32_t H, W, wpr, N;
+    const uint32_t* wall_map;
+    StateRef st;
+    float* reward;
+    uint8_t* done;
+    float* ep_return;
+    uint32_t* ep_length;
+    int64_t num_envs;
+    uint64_t env_id_offset;
+    uint64_t seed;
+    const int32_t* goal_ij;   // device copies of the host layout, or nullptr => Philox
+    const int32_t* player_ij;
+    const int32_t* dir_au;
+    const uint8_t* mask;      // nullptr => all
+};
+
+// kernel launchers (rcw_kernels.cu)
+cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov, float4* table,
+                                   cudaStream_t s);
+cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, int ctas, cudaStream_t s);
+cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);
+cudaError_t upload_dir_slot(int slot, const float2* host_dirs, int n, cudaStream_t s);
+int frame_kernel_max_ctas_per_sm(int obs_format, int map_bytes);
+
+}  // namespace rcw

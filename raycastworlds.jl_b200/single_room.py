@@ -1,0 +1,397 @@
+"""Host-side mirror of the reference's game API for the SingleRoom hot path.
+
+The reference's host language is Julia (absent from this image), so the host side above the C ABI
+is written in Python and keeps the reference's names and meaning:
+
+    reference (src/RayCastWorlds.jl:5-14, src/single_room.jl)      here
+    ---------------------------------------------------------      -----------------------------
+    SingleRoom(; kw...)                      :258-324              SingleRoom(**kw)
+    RCW.reset!(env)                          :326-331              reset(env) / env.reset()
+    RCW.act!(env, action)                    :333-340              act(env, action) / env.act(a)
+    RCW.cast_rays!, RCW.update_camera_view!  :195-231, 374-444     env.render()  (both, fused)
+    RCW.get_action_names(env)                :486                  get_action_names(env)
+    env.world.reward / .done / ...           :21-40                env.world.reward / .done / ...
+    env.camera_view                          :300                  env.camera_view  (uint32 [P, R])
+    RLBaseEnv(env), RLBase.state/reward/...  rlbase.jl:1-7, :574-584   RLBaseEnv(env), state(...)...
+    (new) BatchedSingleRoom(; num_envs, ...)                       BatchedSingleRoom(num_envs, ...)
+
+Everything that computes runs in librcw_b200.so on the GPU; this file only moves pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+
+NUM_ACTIONS = 4  # single_room.jl:19
+ACTION_NAMES = ("MOVE_FORWARD", "MOVE_BACKWARD", "TURN_LEFT", "TURN_RIGHT")  # single_room.jl:486
+
+
+class AbstractGame:
+    """src/RayCastWorlds.jl:5"""
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class BatchedSingleRoom(AbstractGame):
+    """`num_envs` independent SingleRoom games advanced by one kernel launch per step.
+
+    Keyword arguments are those of the reference constructor (single_room.jl:258-272); the
+    additional ones are `num_envs`, `device`, `obs_format` ("rgb8" | "xrgb32"), `auto_reset`,
+    `seed`, `env_id_offset` (global id of env 0 when a batch is sharded over GPUs),
+    `directions_wu` (the host's own [N, 2] float32 direction table) and the two switches for the
+    unpinned RayCaster.cast_ray decisions (`dda_tie_le`, `dda_dist_post`).
+    """
+
+    def __init__(self, num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int = 8,
+                 width_tile_map_tu: int = 16, num_directions: int = 128,
+                 player_radius_wu: float = 1 / 8, position_increment_wu: float = 1 / 8,
+                 semi_field_of_view_wu: float = 2 / 3, num_rays: int = 512,
+                 camera_height_tile_wu: float = 1.0, height_camera_view_pu: int = 256,
+                 goal_reward: float = 1.0, obs_format: str = "rgb8", auto_reset: bool = True,
+                 seed: int = 0, env_id_offset: int = 0,
+                 directions_wu: Optional[np.ndarray] = None, palette: Optional[Sequence[int]] = None,
+                 dda_tie_le: bool = False, dda_dist_post: bool = False):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        cfg = _capi.default_config()
+        cfg.device = int(device)
+        cfg.num_envs = int(num_envs)
+        cfg.env_id_offset = int(env_id_offset)
+        cfg.height_tile_map_tu = int(height_tile_map_tu)
+        cfg.width_tile_map_tu = int(width_tile_map_tu)
+        cfg.num_directions = int(num_directions)
+        cfg.num_rays = int(num_rays)
+        cfg.height_camera_view_pu = int(height_camera_view_pu)
+        cfg.player_radius_wu = float(np.float32(player_radius_wu))
+        cfg.position_increment_wu = float(np.float32(position_increment_wu))
+        cfg.semi_field_of_view_wu = float(np.float32(semi_field_of_view_wu))
+        cfg.camera_height_tile_wu = float(np.float32(camera_height_tile_wu))
+        cfg.goal_reward = float(np.float32(goal_reward))
+        fmt = {"rgb8": _capi.RCW_OBS_RGB8, "xrgb32": _capi.RCW_OBS_XRGB32}
+        if obs_format not in fmt:
+            raise ValueError(f"obs_format must be one of {sorted(fmt)}")
+        cfg.obs_format = fmt[obs_format]
+        cfg.auto_reset = int(bool(auto_reset))
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        if palette is not None:
+            for i, c in enumerate(palette):
+                cfg.palette[i] = int(c)
+        cfg.dda_flags = (_capi.RCW_DDA_TIE_LE if dda_tie_le else 0) | (
+            _capi.RCW_DDA_DIST_POST if dda_dist_post else 0)
+        dirs = None
+        if directions_wu is not None:
+            dirs = np.ascontiguousarray(directions_wu, np.float32)
+            if dirs.shape != (cfg.num_directions, 2):
+                raise ValueError("directions_wu must have shape [num_directions, 2]")
+        _capi.check(self._lib.rcw_create(C.byref(cfg), _ptr(dirs), C.byref(self._h)))
+        self.cfg = cfg
+        self.num_envs = int(num_envs)
+        self.obs_format = obs_format
+        self.bytes_per_pixel = 3 if obs_format == "rgb8" else 4
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.rcw_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the reference's generic functions -----------------------------------------------------
+    def reset(self, goal_ij=None, player_ij=None, dir_au=None, mask=None):
+        """reset!(env): NULL layouts => drawn on the device."""
+        g = None if goal_ij is None else np.ascontiguousarray(goal_ij, np.int32).reshape(self.num_envs, 2)
+        p = None if player_ij is None else np.ascontiguousarray(player_ij, np.int32).reshape(self.num_envs, 2)
+        d = None if dir_au is None else np.ascontiguousarray(dir_au, np.int32).reshape(self.num_envs)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).reshape(self.num_envs)
+        _capi.check(self._lib.rcw_reset(self._h, _ptr(g), _ptr(p), _ptr(d), _ptr(m)))
+
+    def act(self, actions):
+        """act!(env, actions): one action in 1..4 per env.  Accepts a host array (numpy / list) or
+        a CUDA uint8 tensor (anything with __cuda_array_interface__)."""
+        cai = getattr(actions, "__cuda_array_interface__", None)
+        if cai is not None:
+            if cai["typestr"] not in ("|u1", "<u1") or int(np.prod(cai["shape"])) != self.num_envs:
+                raise ValueError("device actions must be uint8 [num_envs]")
+            _capi.check(self._lib.rcw_step(self._h, C.c_void_p(cai["data"][0])))
+            return
+        a = np.asarray(actions)
+        if a.shape != (self.num_envs,):
+            a = a.reshape(self.num_envs)
+        if a.dtype != np.uint8:
+            if ((a < 1) | (a > NUM_ACTIONS)).any():
+                bad = a[(a < 1) | (a > NUM_ACTIONS)][0]
+                raise _capi.InvalidActionError(_capi.RCW_EACTION, f"Invalid action: {bad}")
+            a = a.astype(np.uint8)
+        a = np.ascontiguousarray(a)
+        _capi.check(self._lib.rcw_step(self._h, _ptr(a)))
+
+    def step_random(self, n_steps: int = 1):
+        _capi.check(self._lib.rcw_step_random(self._h, int(n_steps)))
+
+    def render(self):
+        """cast_rays! + update_camera_view! from the current state."""
+        _capi.check(self._lib.rcw_render(self._h))
+
+    def get_action_names(self):
+        return ACTION_NAMES
+
+    # -- state ---------------------------------------------------------------------------------
+    def get_state(self):
+        n = self.num_envs
+        out = dict(pos=np.empty((n, 2), np.float32), dir_au=np.empty(n, np.int32),
+                   goal=np.empty((n, 2), np.int32), reward=np.empty(n, np.float32),
+                   done=np.empty(n, np.uint8))
+        _capi.check(self._lib.rcw_get_state(self._h, _ptr(out["pos"]), _ptr(out["dir_au"]),
+                                            _ptr(out["goal"]), _ptr(out["reward"]), _ptr(out["done"])))
+        return out
+
+    def reward_done(self, reward: Optional[np.ndarray] = None, done: Optional[np.ndarray] = None):
+        """reward / is_terminated of every env (blocking device->host read)."""
+        n = self.num_envs
+        r = np.empty(n, np.float32) if reward is None else reward
+        d = np.empty(n, np.uint8) if done is None else done
+        _capi.check(self._lib.rcw_get_state(self._h, None, None, None, _ptr(r), _ptr(d)))
+        return r, d
+
+    def set_state(self, pos=None, dir_au=None, goal=None, reward=None, done=None):
+        n = self.num_envs
+        p = None if pos is None else np.ascontiguousarray(pos, np.float32).reshape(n, 2)
+        a = None if dir_au is None else np.ascontiguousarray(dir_au, np.int32).reshape(n)
+        g = None if goal is None else np.ascontiguousarray(goal, np.int32).reshape(n, 2)
+        r = None if reward is None else np.ascontiguousarray(reward, np.float32).reshape(n)
+        d = None if done is None else np.ascontiguousarray(done, np.uint8).reshape(n)
+        _capi.check(self._lib.rcw_set_state(self._h, _ptr(p), _ptr(a), _ptr(g), _ptr(r), _ptr(d)))
+
+    def set_wall_map(self, wall_hw):
+        """wall_hw: bool [H, W] — replaces tile_map[WALL, :, :] for every env of the batch."""
+        w = np.asarray(wall_hw).astype(np.uint8)
+        if w.shape != (self.cfg.height_tile_map_tu, self.cfg.width_tile_map_tu):
+            raise ValueError("wall map must be [height_tile_map_tu, width_tile_map_tu]")
+        flat = np.ascontiguousarray(w.T.reshape(-1))  # [W][H], i fastest (Julia column-major)
+        _capi.check(self._lib.rcw_set_wall_map(self._h, _ptr(flat)))
+
+    def get_rays(self, env0: int = 0, n: Optional[int] = None):
+        n = self.num_envs - env0 if n is None else n
+        R = self.cfg.num_rays
+        out = dict(hit=np.empty((n, R, 2), np.int32), dim=np.empty((n, R), np.int32),
+                   dist=np.empty((n, R), np.float32), ray_dir=np.empty((n, R, 2), np.float32))
+        _capi.check(self._lib.rcw_get_rays(self._h, env0, n, _ptr(out["hit"]), _ptr(out["dim"]),
+                                           _ptr(out["dist"]), _ptr(out["ray_dir"])))
+        return out
+
+    # -- observations -----------------------------------------------------------------------------
+    @property
+    def obs_shape(self):
+        """[num_envs, width (= num_rays columns), height_camera_view_pu, (3)]; the pixel row is the
+        fastest index, as in the reference's Array{UInt32}(P, R)."""
+        R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
+        return (self.num_envs, R, P, 3) if self.obs_format == "rgb8" else (self.num_envs, R, P)
+
+    def obs_device_ptr(self):
+        ptr, total, stride = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        _capi.check(self._lib.rcw_obs_device_ptr(self._h, C.byref(ptr), C.byref(total), C.byref(stride)))
+        return ptr.value, total.value, stride.value
+
+    def obs_tensor(self):
+        """Zero-copy torch view of the device observation buffer (borrowed: valid until the next
+        act/reset/render, like the reference's aliased `state`, single_room.jl:576)."""
+        import torch
+
+        ptr, total, stride = self.obs_device_ptr()
+        R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
+        dense = R * P * self.bytes_per_pixel
+        holder = _CudaBuffer(ptr, total, self)
+        flat = torch.as_tensor(holder, device=torch.device("cuda", self.cfg.device))
+        if self.obs_format == "rgb8":
+            t = torch.as_strided(flat, (self.num_envs, R, P, 3), (stride, P * 3, 3, 1))
+        else:
+            t = torch.as_strided(flat, (self.num_envs, dense), (stride, 1)).view(torch.int32)
+            t = t.view(self.num_envs, R, P)
+        return t
+
+    def copy_obs(self, env0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None):
+        """Blocking device->host copy of the observations of envs [env0, env0+n)."""
+        n = self.num_envs - env0 if n is None else n
+        R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
+        shape = (n, R, P, 3) if self.obs_format == "rgb8" else (n, R, P)
+        dtype = np.uint8 if self.obs_format == "rgb8" else np.uint32
+        if out is None:
+            out = np.empty(shape, dtype)
+        _capi.check(self._lib.rcw_copy_obs(self._h, env0, n, _ptr(out)))
+        return out
+
+    # -- bookkeeping ------------------------------------------------------------------------------
+    def episode_stats(self, reset_counters: bool = False):
+        ep, sr, sl = C.c_int64(), C.c_double(), C.c_int64()
+        _capi.check(self._lib.rcw_episode_stats(self._h, C.byref(ep), C.byref(sr), C.byref(sl),
+                                                int(reset_counters)))
+        return ep.value, sr.value, sl.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _capi.check(self._lib.rcw_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def cuda_stream(self) -> int:
+        s = C.c_void_p()
+        _capi.check(self._lib.rcw_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def sync(self):
+        _capi.check(self._lib.rcw_sync(self._h))
+
+
+class _CudaBuffer:
+    """Minimal __cuda_array_interface__ holder for a borrowed device pointer."""
+
+    def __init__(self, ptr: int, nbytes: int, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+class _WorldView:
+    """Field access in the style of `env.world.<field>` (single_room.jl:21-40) for one env."""
+
+    def __init__(self, batch: BatchedSingleRoom, index: int = 0):
+        self._b, self._i = batch, index
+
+    def _s(self):
+        return self._b.get_state()
+
+    @property
+    def reward(self):
+        return np.float32(self._s()["reward"][self._i])
+
+    @property
+    def done(self):
+        return bool(self._s()["done"][self._i])
+
+    @property
+    def goal_reward(self):
+        return np.float32(self._b.cfg.goal_reward)
+
+    @property
+    def player_position_wu(self):
+        return self._s()["pos"][self._i].copy()
+
+    @property
+    def player_direction_au(self):
+        return int(self._s()["dir_au"][self._i])
+
+    @property
+    def goal_position(self):
+        g = self._s()["goal"][self._i]
+        return int(g[0]), int(g[1])
+
+    @property
+    def num_directions(self):
+        return self._b.cfg.num_directions
+
+    def _rays(self):
+        return self._b.get_rays(self._i, 1)
+
+    @property
+    def ray_stop_position_tu(self):
+        return self._rays()["hit"][0].T.copy()  # [2, R] like the reference
+
+    @property
+    def ray_hit_dimension(self):
+        return self._rays()["dim"][0]
+
+    @property
+    def ray_distance_wu(self):
+        return self._rays()["dist"][0]
+
+    @property
+    def ray_directions_wu(self):
+        return self._rays()["ray_dir"][0]
+
+
+class SingleRoom(BatchedSingleRoom):
+    """The reference's single game (single_room.jl:241-324): one env, no auto-reset, UInt32 pixels."""
+
+    def __init__(self, **kw):
+        kw.setdefault("auto_reset", False)
+        kw.setdefault("obs_format", "xrgb32")
+        super().__init__(1, **kw)
+        self.world = _WorldView(self, 0)
+
+    def act(self, action):  # act!(env::SingleRoom, action)
+        if isinstance(action, (int, np.integer)):
+            if not 1 <= int(action) <= NUM_ACTIONS:
+                raise _capi.InvalidActionError(_capi.RCW_EACTION, f"Invalid action: {action}")
+            action = np.array([action], np.uint8)
+        super().act(action)
+
+    @property
+    def camera_view(self):
+        """uint32 [height_camera_view_pu, num_rays], the reference's camera_view (single_room.jl:300)."""
+        if self.obs_format != "xrgb32":
+            raise ValueError("camera_view needs obs_format='xrgb32'")
+        return self.copy_obs(0, 1)[0].T
+
+
+class RLBaseEnv:
+    """rlbase.jl:1-3 — wraps a game; RLBase methods below follow single_room.jl:574-584."""
+
+    def __init__(self, env: BatchedSingleRoom):
+        self.env = env
+
+    def __call__(self, action):  # (env::RLBaseEnv)(action) = act!(env.env, action)   :581
+        self.env.act(action)
+
+
+# generic functions, named as in the reference without the `!`
+def reset(env):
+    (env.env if isinstance(env, RLBaseEnv) else env).reset()
+
+
+def act(env, action):
+    (env.env if isinstance(env, RLBaseEnv) else env).act(action)
+
+
+def get_action_names(env):
+    return (env.env if isinstance(env, RLBaseEnv) else env).get_action_names()
+
+
+def state(env: RLBaseEnv):
+    """RLBase.state(env) = env.env.camera_view (:576).  Batched: the device tensor of all envs."""
+    e = env.env
+    return e.camera_view if isinstance(e, SingleRoom) else e.obs_tensor()
+
+
+def state_space(env: RLBaseEnv):
+    return None  # :575
+
+
+def action_space(env: RLBaseEnv):
+    return range(1, NUM_ACTIONS + 1)  # Base.OneTo(NUM_ACTIONS)  :580
+
+
+def reward(env: RLBaseEnv):
+    r, _ = env.env.reward_done()
+    return np.float32(r[0]) if isinstance(env.env, SingleRoom) else r  # :583
+
+
+def is_terminated(env: RLBaseEnv):
+    _, d = env.env.reward_done()
+    return bool(d[0]) if isinstance(env.env, SingleRoom) else d.astype(bool)  # :584

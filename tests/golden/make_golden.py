@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Generate tests/golden/singleroom_golden.npz.
+
+The reference (/root/reference, pure Julia) cannot run in this image and its DDA lives in the
+un-vendored RayCaster.jl 0.1, so these fixtures are NOT outputs of the reference: PARITY IS
+UNPINNED versus Julia.  They are produced by a second, independent restatement of the reference
+source written in Python with numpy.float32 scalars (one IEEE rounding per operation), so that
+the C oracle (oracle/rcw_oracle.c) and the CUDA path are checked against something that was
+not derived from either.  Each function cites the reference lines it follows.
+
+Run:  python tests/golden/make_golden.py        (writes the .npz next to this file)
+"""
+from __future__ import annotations
+
+import math
+import os
+import zlib
+
+import numpy as np
+
+F = np.float32
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+PALETTE = dict(ceiling=0x00FFFFFF, floor=0x00404040, wall1=0x00808080, wall2=0x00C0C0C0,
+               goal1=0x00800000, goal2=0x00C00000)  # single_room.jl:291-296
+
+
+class PyWorld:
+    """SingleRoomWorld + camera view, src/single_room.jl:21-108,258-324."""
+
+    def __init__(self, H=8, W=16, N=128, R=512, P=256, radius=1 / 8, incr=1 / 8, sfov=2 / 3, cam_h=1.0,
+                 goal_reward=1.0, tie_le=False, dist_post=False):
+        self.H, self.W, self.N, self.R, self.P = H, W, N, R, P
+        self.radius, self.incr, self.sfov, self.cam_h = F(radius), F(incr), F(sfov), F(cam_h)
+        self.goal_reward = F(goal_reward)
+        self.tie_le, self.dist_post = tie_le, dist_post
+        self.wall = np.zeros((H + 1, W + 1), bool)  # 1-based
+        self.wall[1:, 1] = True   # :57
+        self.wall[1:, W] = True   # :58
+        self.wall[1, 1:] = True   # :59
+        self.wall[H, 1:] = True   # :60
+        # :65-69
+        self.dirs = []
+        for i in range(1, N + 1):
+            theta = (i - 1) * 2 * math.pi / N
+            self.dirs.append((F(math.cos(theta)), F(math.sin(theta))))
+        self.goal = (2, 2)
+        self.pos = (F(1.5), F(1.5))
+        self.au = 0
+        self.reward = F(0)
+        self.done = False
+
+    # ---- utils.jl:5
+    @staticmethod
+    def wu_to_tu(x):
+        return int(math.floor(float(x))) + 1
+
+    def layer(self, which, i, j):
+        if i < 1 or i > self.H or j < 1 or j > self.W:
+            return False  # new-engine rule for F6 (the reference throws)
+        if which == "wall":
+            return bool(self.wall[i, j])
+        return (i, j) == self.goal
+
+    # ---- collision_detection.jl:9-42
+    def is_player_colliding(self, which, x, y):
+        half = F(0.5)
+        ip, jp = self.wu_to_tu(x), self.wu_to_tu(y)
+        for j in range(jp - 1, jp + 2):
+            for i in range(ip - 1, ip + 2):
+                if not self.layer(which, i, j):
+                    continue
+                px = F(x - F(F(i) - half))
+                py = F(y - F(F(j) - half))
+                qx = min(max(px, -half), half)
+                qy = min(max(py, -half), half)
+                vx, vy = F(px - qx), F(py - qy)
+                if F(F(vx * vx) + F(vy * vy)) < F(self.radius * self.radius):
+                    return True
+        return False
+
+    # ---- single_room.jl:139-191
+    def act(self, a):
+        assert a in (1, 2, 3, 4)
+        if a <= 2:
+            dx, dy = self.dirs[self.au]
+            sx, sy = F(self.incr * dx), F(self.incr * dy)
+            if a == 1:
+                nx, ny = F(self.pos[0] + sx), F(self.pos[1] + sy)
+            else:
+                nx, ny = F(self.pos[0] - sx), F(self.pos[1] - sy)
+            hit_goal = self.is_player_colliding("goal", nx, ny)
+            hit_wall = self.is_player_colliding("wall", nx, ny)
+            if hit_goal:
+                self.reward, self.done = self.goal_reward, True
+            elif hit_wall:
+                self.reward, self.done = F(0), False
+            else:
+                self.pos = (nx, ny)
+                self.reward, self.done = F(0), False
+        else:
+            self.au = (self.au + 1) % self.N if a == 3 else (self.au - 1) % self.N
+            self.reward, self.done = F(0), False
+
+    # ---- [EXT] RayCaster.cast_ray, SURVEY.md §8(a) a10
+    def cast_ray(self, x, y, dx, dy):
+        one = F(1)
+        i, j = self.wu_to_tu(x), self.wu_to_tu(y)
+        with np.errstate(divide="ignore"):
+            ddx, ddy = F(abs(F(one / dx))), F(abs(F(one / dy)))
+        if dx < 0:
+            sx, tx = -1, F(F(x - F(i - 1)) * ddx)
+        else:
+            sx, tx = 1, F(F(F(i) - x) * ddx)
+        if dy < 0:
+            sy, ty = -1, F(F(y - F(j - 1)) * ddy)
+        else:
+            sy, ty = 1, F(F(F(j) - y) * ddy)
+        dim, d = 0, F(0)
+
+        def obstacle(i, j):
+            if i < 1 or i > self.H or j < 1 or j > self.W:
+                return True
+            return bool(self.wall[i, j]) or (i, j) == self.goal  # any(tile_map, dims=1) :209
+
+        while not obstacle(i, j):
+            take_x = (tx <= ty) if self.tie_le else (tx < ty)
+            if take_x:
+                d, tx, i, dim = tx, F(tx + ddx), i + sx, 1
+            else:
+                d, ty, j, dim = ty, F(ty + ddy), j + sy, 2
+        if self.dist_post and dim:
+            d = F(tx - ddx) if dim == 1 else F(ty - ddy)
+        return i, j, dim, d
+
+    # ---- single_room.jl:193-231
+    def cast_rays(self):
+        R, s = self.R, self.sfov
+        d0, d1 = self.dirs[self.au]
+        c0, c1 = d1, F(-d0)
+        f0, f1 = F(d0 + F(s * c0)), F(d1 + F(s * c1))
+        l0, l1 = F(d0 - F(s * c0)), F(d1 - F(s * c1))
+        lendiv = max(R - 1, 1)
+        self.ray_dir, self.hit, self.dim, self.dist = [], [], [], []
+        for i in range(1, R + 1):
+            t = (i - 1) / lendiv
+            u0 = F((1 - t) * float(f0) + t * float(l0))
+            u1 = F((1 - t) * float(f1) + t * float(l1))
+            n = F(np.sqrt(F(F(u0 * u0) + F(u1 * u1))))
+            q = F(F(1) / n)
+            r0, r1 = F(q * u0), F(q * u1)
+            ih, jh, dim, dist = self.cast_ray(self.pos[0], self.pos[1], r0, r1)
+            self.ray_dir.append((r0, r1))
+            self.hit.append((ih, jh))
+            self.dim.append(dim)
+            self.dist.append(dist)
+
+    # ---- single_room.jl:374-444
+    def height_line(self, i0):
+        d0, d1 = self.dirs[self.au]
+        r0, r1 = self.ray_dir[i0]
+        dot = F(F(d0 * r0) + F(d1 * r1))
+        proj = F(self.dist[i0] * dot)
+        num = F(self.cam_h * F(self.R))
+        den = F(F(F(2) * self.sfov) * proj)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            hl = F(num / den)
+        if not np.isfinite(hl):
+            return self.P
+        if hl >= self.P:
+            return self.P
+        return max(int(math.floor(float(hl))), 0)
+
+    def camera_view(self):
+        """uint32 [R columns][P rows]"""
+        R, P = self.R, self.P
+        img = np.zeros((R, P), np.uint32)
+        for i in range(1, R + 1):
+            h = self.height_line(i - 1)
+            ih, jh = self.hit[i - 1]
+            inside = 1 <= ih <= self.H and 1 <= jh <= self.W
+            is_wall = bool(self.wall[ih, jh]) if inside else True
+            if is_wall:
+                color = PALETTE["wall1"] if self.dim[i - 1] == 1 else PALETTE["wall2"]
+            else:
+                color = PALETTE["goal1"] if self.dim[i - 1] == 1 else PALETTE["goal2"]
+            k = R - i + 1
+            col = img[k - 1]
+            if h >= P - 1:
+                col[:] = color
+            else:
+                pad = (P - h) // 2
+                col[:pad] = PALETTE["ceiling"]
+                col[pad:P - pad] = color
+                col[P - pad:] = PALETTE["floor"]
+        return img
+
+
+def random_walk_states(w: PyWorld, rng, n_states, steps_between):
+    """Reachable states: start at a tile centre, take random actions (never entering the goal)."""
+    states = []
+    while len(states) < n_states:
+        gi, gj = int(rng.integers(2, w.H)), int(rng.integers(2, w.W))
+        while True:
+            pi, pj = int(rng.integers(2, w.H)), int(rng.integers(2, w.W))
+            if (pi, pj) != (gi, gj):
+                break
+        w.goal = (gi, gj)
+        w.pos = (F(pi - 0.5), F(pj - 0.5))
+        w.au = int(rng.integers(0, w.N))
+        for _ in range(int(rng.integers(0, steps_between))):
+            w.act(int(rng.integers(1, 5)))
+        states.append((w.pos[0], w.pos[1], w.au, gi, gj))
+    return states
+
+
+def cast_case(w: PyWorld, states, full_images=0):
+    out = dict(states=np.array([[s[0], s[1]] for s in states], np.float32),
+               au=np.array([s[2] for s in states], np.int32),
+               goal=np.array([[s[3], s[4]] for s in states], np.int32))
+    hits, dims, dists, rdirs, heights, crcs, imgs = [], [], [], [], [], [], []
+    for k, s in enumerate(states):
+        w.pos, w.au, w.goal = (F(s[0]), F(s[1])), int(s[2]), (int(s[3]), int(s[4]))
+        w.cast_rays()
+        img = w.camera_view()
+        hits.append(w.hit)
+        dims.append(w.dim)
+        dists.append(w.dist)
+        rdirs.append(w.ray_dir)
+        heights.append([w.height_line(i) for i in range(w.R)])
+        crcs.append(zlib.crc32(img.tobytes()))
+        if k < full_images:
+            imgs.append(img)
+    out.update(hit=np.array(hits, np.int32), dim=np.array(dims, np.int32),
+               dist=np.array(dists, np.float32), ray_dir=np.array(rdirs, np.float32),
+               height=np.array(heights, np.int32), crc=np.array(crcs, np.uint32))
+    if imgs:
+        out["image"] = np.array(imgs, np.uint32)
+    return out
+
+
+def act_case(w: PyWorld, rng, n_episodes, n_steps):
+    """Trajectories: (initial layout, action list) -> per-step pos/au/reward/done."""
+    init, actions, pos, au, rew, done = [], [], [], [], [], []
+    for _ in range(n_episodes):
+        gi, gj = int(rng.integers(2, w.H)), int(rng.integers(2, w.W))
+        while True:
+            pi, pj = int(rng.integers(2, w.H)), int(rng.integers(2, w.W))
+            if (pi, pj) != (gi, gj):
+                break
+        a0 = int(rng.integers(0, w.N))
+        w.goal, w.pos, w.au = (gi, gj), (F(pi - 0.5), F(pj - 0.5)), a0
+        init.append((gi, gj, pi, pj, a0))
+        # biased towards moving so walls and goals get hit
+        acts = rng.choice([1, 1, 1, 2, 3, 4], size=n_steps)
+        tp, ta, tr, td = [], [], [], []
+        for a in acts:
+            w.act(int(a))
+            tp.append((w.pos[0], w.pos[1]))
+            ta.append(w.au)
+            tr.append(w.reward)
+            td.append(w.done)
+        actions.append(acts)
+        pos.append(tp)
+        au.append(ta)
+        rew.append(tr)
+        done.append(td)
+    return dict(init=np.array(init, np.int32), actions=np.array(actions, np.uint8),
+                pos=np.array(pos, np.float32), au=np.array(au, np.int32),
+                reward=np.array(rew, np.float32), done=np.array(done, np.uint8))
+
+
+def main():
+    rng = np.random.default_rng(20261018)
+    out = {}
+
+    # A: reference default geometry (8x16, N=128, R=512, P=256)
+    w = PyWorld()
+    st = random_walk_states(w, rng, 24, 400)
+    # hand-picked: tile centre facing +x (au 0), facing the goal, hugging a corner
+    st += [(F(2.5), F(2.5), 0, 6, 14), (F(3.5), F(7.5), 32, 3, 9), (F(1.125), F(1.125), 80, 7, 15),
+           (F(6.875), F(14.875), 16, 2, 2), (F(4.5), F(8.5), 64, 4, 10), (F(4.5), F(8.5), 96, 4, 7)]
+    for k, v in cast_case(w, st, full_images=2).items():
+        out["A_" + k] = v
+    for k, v in act_case(w, rng, 12, 600).items():
+        out["A_act_" + k] = v
+
+    # B: config 5 geometry (64x64, N=256), fewer rays to keep the file small
+    w = PyWorld(H=64, W=64, N=256, R=128, P=96)
+    st = random_walk_states(w, rng, 12, 300)
+    for k, v in cast_case(w, st).items():
+        out["B_" + k] = v
+    for k, v in act_case(w, rng, 4, 400).items():
+        out["B_act_" + k] = v
+
+    # C: odd sizes (R not a multiple of 32, P odd, other radius / increment / fov)
+    w = PyWorld(H=5, W=7, N=36, R=45, P=51, radius=0.2, incr=0.3, sfov=0.5, cam_h=0.8)
+    st = random_walk_states(w, rng, 10, 100)
+    for k, v in cast_case(w, st, full_images=1).items():
+        out["C_" + k] = v
+    for k, v in act_case(w, rng, 4, 300).items():
+        out["C_act_" + k] = v
+
+    # D: the other DDA contract (D1 tie <=, D2 post-loop distance) on the default geometry
+    w = PyWorld(tie_le=True, dist_post=True)
+    st = random_walk_states(w, rng, 6, 400)
+    for k, v in cast_case(w, st).items():
+        out["D_" + k] = v
+
+    path = os.path.join(HERE, "singleroom_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

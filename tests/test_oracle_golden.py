@@ -1,0 +1,50 @@
+"""CPU oracle (C) versus the golden fixtures made by the independent Python restatement
+(tests/golden/make_golden.py).  Neither is the Julia reference: parity is unpinned."""
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CONFIGS
+
+
+@pytest.mark.parametrize("case", ["A", "B", "C", "D"])
+def test_cast_and_render_match_golden(oracle, golden, case):
+    cfg = oracle.default_config(**GOLDEN_CONFIGS[case])
+    w = oracle.World(cfg)
+    states, au, goal = golden[f"{case}_states"], golden[f"{case}_au"], golden[f"{case}_goal"]
+    for k in range(len(states)):
+        w.set_state(states[k, 0], states[k, 1], au[k], goal[k, 0], goal[k, 1])
+        w.cast_rays()
+        w.update_camera_view()
+        np.testing.assert_array_equal(w.ray_stop, golden[f"{case}_hit"][k])
+        np.testing.assert_array_equal(w.ray_dim, golden[f"{case}_dim"][k])
+        # bit-exact: same binary32 operation order
+        np.testing.assert_array_equal(w.ray_dist.view(np.uint32), golden[f"{case}_dist"][k].view(np.uint32))
+        np.testing.assert_array_equal(w.ray_dir.view(np.uint32), golden[f"{case}_ray_dir"][k].view(np.uint32))
+        np.testing.assert_array_equal(w.wall_heights(), golden[f"{case}_height"][k])
+        img = w.camera_view
+        assert zlib.crc32(img.tobytes()) == int(golden[f"{case}_crc"][k])
+        if f"{case}_image" in golden and k < len(golden[f"{case}_image"]):
+            np.testing.assert_array_equal(img, golden[f"{case}_image"][k])
+
+
+@pytest.mark.parametrize("case", ["A", "B", "C"])
+def test_act_trajectories_match_golden(oracle, golden, case):
+    cfg = oracle.default_config(**GOLDEN_CONFIGS[case])
+    w = oracle.World(cfg)
+    init, actions = golden[f"{case}_act_init"], golden[f"{case}_act_actions"]
+    n_done = 0
+    for ep in range(len(init)):
+        gi, gj, pi, pj, a0 = (int(v) for v in init[ep])
+        w.reset_to(gi, gj, pi, pj, a0)
+        for t, a in enumerate(actions[ep]):
+            assert w.act(int(a)) == 0
+            s = w.state()
+            assert s["pos"].view(np.uint32).tolist() == golden[f"{case}_act_pos"][ep, t].view(np.uint32).tolist()
+            assert s["au"] == golden[f"{case}_act_au"][ep, t]
+            assert s["reward"] == golden[f"{case}_act_reward"][ep, t]
+            assert s["done"] == bool(golden[f"{case}_act_done"][ep, t])
+            n_done += s["done"]
+    if case == "A":
+        assert n_done > 0, "fixture should contain goal hits"
