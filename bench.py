@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — rendered env-steps/s of the batched SingleRoom hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 200 --warmup 20
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 5 --warmup 1      # CPU arm (oracle port, all cores)
+
+A step = one random-policy env-step of every env of the batch: act! (+ same-step auto-reset), the
+512-ray DDA and the full 256x512 RGB8 observation written to HBM (BASELINE.json configs[1]:
+4096 envs per GPU, default camera).  One step is exactly one kernel launch.  Weak scaling: every
+rank owns `--envs-per-gpu` envs, global env ids key the RNG, no collective on the step path.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rendered env-steps/sec"
+UNIT = "env-steps/s"
+SEED = 0x5EED
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--envs-per-gpu", type=int, default=4096)
+    ap.add_argument("--obs-format", choices=["rgb8", "xrgb32"], default="rgb8")
+    ap.add_argument("--map", choices=["default", "large"], default="default",
+                    help="default: 8x16 tiles / 128 directions; large: 64x64 / 256 (BASELINE config 5)")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    kw = dict(height_tile_map_tu=8, width_tile_map_tu=16, num_directions=128)
+    if args.map == "large":
+        kw = dict(height_tile_map_tu=64, width_tile_map_tu=64, num_directions=256)
+    kw.update(num_rays=512, height_camera_view_pu=256)
+    return kw
+
+
+def mem_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, measured)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_rate(n_envs, kw, seconds, threads):
+    """Env-steps/s of the CPU oracle (C restatement of the reference, pthreads over envs) on a
+    bounded sample: the same batch, as many whole steps as fit in about `seconds`."""
+    from oracle import oracle as orc
+
+    cfg = orc.default_config(H=kw["height_tile_map_tu"], W=kw["width_tile_map_tu"],
+                             N=kw["num_directions"], R=kw["num_rays"], P=kw["height_camera_view_pu"])
+    b = orc.Batch(n_envs, cfg=cfg, seed=SEED)
+    t0 = time.perf_counter()
+    b.rollout(1, threads=threads)
+    t1 = time.perf_counter() - t0
+    steps = int(max(2, min(400, seconds / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    b.rollout(steps, threads=threads)
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, steps, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  Julia is absent from this image and the DDA
+    lives in un-vendored RayCaster.jl, so this times the oracle port (C restatement, pthreads over
+    envs = the analogue of Threads.@threads over envs) with every host core, on the same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    kw = workload(args)
+    n = args.envs_per_gpu
+    threads = os.cpu_count() or 1
+    cfg = orc.default_config(H=kw["height_tile_map_tu"], W=kw["width_tile_map_tu"],
+                             N=kw["num_directions"], R=kw["num_rays"], P=kw["height_camera_view_pu"])
+    b = orc.Batch(n, cfg=cfg, seed=SEED)
+    for _ in range(args.warmup):
+        b.rollout(1, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.rollout(1, threads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} envs x {args.steps} whole steps (full per-GPU batch of the b200 arm), UInt32 camera view"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"BatchedSingleRoom {n} envs, {kw['height_tile_map_tu']}x{kw['width_tile_map_tu']} tiles, "
+                               f"{kw['num_rays']} rays x {kw['height_camera_view_pu']} px, random policy + auto-reset",
+                   "note": "CPU oracle port of the reference (C, -O2, pthreads over envs); Julia is not in the image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import raycastworlds_jl_b200 as rcw
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    kw = workload(args)
+    n = args.envs_per_gpu
+    offset = rank * n
+    env = rcw.BatchedSingleRoom(n, device=local, seed=SEED, env_id_offset=offset,
+                                obs_format=args.obs_format, **kw)
+    stream = torch.cuda.ExternalStream(env.cuda_stream(), device=dev)
+    K, W = args.steps, args.warmup
+    bytes_per_step_env = kw["num_rays"] * kw["height_camera_view_pu"] * env.bytes_per_pixel
+
+    # ---- device-resident throughput: K launches back to back, CUDA events on the handle's stream
+    env.step_random(W)
+    env.sync()
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    launches0 = env.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    events[0].record(stream)
+    for k in range(K):
+        env.step_random(1)
+        events[k + 1].record(stream)
+    env.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = env.launch_count() - launches0
+    total_ms = events[0].elapsed_time(events[K])
+    per_launch_ms = [events[k].elapsed_time(events[k + 1]) for k in range(K)]
+    total_ms = rcw.max_over_ranks(total_ms, device=dev if world > 1 else None)
+    value = world * n * K / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: pinned host actions -> H2D -> step
+    #      -> D2H of reward + done, every step; observations stay in HBM for the learner
+    #      (rcw_obs_device_ptr, the reference's aliased `state`).  A second figure also pulls the
+    #      whole observation to the host each step (PCIe-bound).
+    e2e = None
+    e2e_obs = None
+    if not args.no_e2e:
+        rng = np.random.default_rng(SEED + rank)
+        pinned = torch.empty((K, n), dtype=torch.uint8).pin_memory()
+        actions = pinned.numpy()
+        actions[:] = rng.integers(1, 5, size=(K, n), dtype=np.uint8)
+        r_host = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
+        d_host = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+        for k in range(min(W, K)):
+            env.act(actions[k])
+            env.reward_done(r_host, d_host)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            env.act(actions[k])
+            env.reward_done(r_host, d_host)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        dt = rcw.max_over_ranks(dt, device=dev if world > 1 else None)
+        e2e = {"value": world * n * K / dt, "unit": UNIT, "h2d_bytes_per_step": n,
+               "d2h_bytes_per_step": n * 5 + 32, "ms_per_step": 1e3 * dt / K,
+               "note": "host actions in, host reward+done out, every step; observations stay in HBM"}
+        Ko = max(1, min(K, 5))
+        obs_host = torch.empty(env.obs_shape, dtype=torch.uint8 if args.obs_format == "rgb8" else torch.int32)
+        obs_host = obs_host.pin_memory().numpy()
+        if args.obs_format != "rgb8":
+            obs_host = obs_host.view(np.uint32)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ko):
+            env.act(actions[k])
+            env.reward_done(r_host, d_host)
+            env.copy_obs(out=obs_host)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        dt = rcw.max_over_ranks(dt, device=dev if world > 1 else None)
+        e2e_obs = {"value": world * n * Ko / dt, "unit": UNIT, "steps": Ko, "h2d_bytes_per_step": n,
+                   "d2h_bytes_per_step": n * 5 + 32 + n * bytes_per_step_env,
+                   "note": "as e2e plus the full observation copied to pinned host memory every step"}
+
+    stats = env.episode_stats()
+    stats = rcw.reduce_episode_stats(stats, device=dev if world > 1 else None)
+    env.close()
+
+    if rank == 0:
+        peak, peak_src = mem_peaks()
+        launch_ms = sum(per_launch_ms) / len(per_launch_ms)
+        achieved = n * bytes_per_step_env / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"BatchedSingleRoom {n} envs per GPU, {kw['height_tile_map_tu']}x{kw['width_tile_map_tu']} tiles, "
+                            f"{kw['num_directions']} directions, {kw['num_rays']} rays x {kw['height_camera_view_pu']} px "
+                            f"{args.obs_format}, random policy + auto-reset (BASELINE.json configs[1])",
+                "envs_per_gpu": n, "obs_bytes_per_env_step": bytes_per_step_env,
+                "l2": f"each step writes {n * bytes_per_step_env / 1e9:.2f} GB of observations, larger than the 126 MB L2; no flush needed",
+                "seed": SEED,
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "rcw::frame_kernel<kModeStep>",
+                "algorithmic_bytes_per_launch": n * bytes_per_step_env,
+                "launch_ms": launch_ms, "peak_source": peak_src,
+            },
+            "e2e": e2e, "e2e_obs_to_host": e2e_obs,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "episodes": {"finished": stats[0], "sum_return": stats[1], "sum_length": stats[2]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, steps, dt = cpu_port_rate(min(n, 1024), kw, args.cpu_baseline_seconds, threads)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{min(n, 1024)} envs x {steps} steps of the same workload in {dt:.1f} s "
+                          "(C restatement of the reference, pthreads over envs, UInt32 camera view)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
