@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "librcw_b200.so")
+# RCW_LIB: development knob to A/B a differently compiled build of the same library
+LIB_PATH = os.environ.get("RCW_LIB") or os.path.join(_PKG, "lib", "librcw_b200.so")
 
 RCW_OK, RCW_EINVAL, RCW_EACTION, RCW_ECUDA, RCW_ENOMEM, RCW_ESIZE = 0, -1, -2, -3, -4, -5
 RCW_OBS_RGB8, RCW_OBS_XRGB32 = 0, 1

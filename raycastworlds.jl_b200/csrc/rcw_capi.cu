@@ -93,6 +93,11 @@ struct rcw_batch {
     int map_words = 0;
     int dir_slot = -1;
     int ctas_per_sm = 0;          // 0: one CTA per 8 items; >0: persistent grid of sm_count * this
+    bool bulk = true;             // renderer: TMA bulk stores of whole bands (true) or per-lane vector stores
+    bool split = false;           // one env-step = front launch + paint launch (true) or one fused launch
+    uint32_t* d_col_info = nullptr;
+    int pat_stride = 0;
+    uint8_t* d_patterns = nullptr;
     // device memory
     float2* d_dirs = nullptr;
     float4* d_ray_table = nullptr;
@@ -157,6 +162,9 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.dirs = b->d_dirs;
     p.ray_table = b->d_ray_table;
     p.wall_map = b->d_wall_map;
+    p.patterns = b->d_patterns;
+    p.pat_stride = b->pat_stride;
+    p.col_info = b->d_col_info;
     p.in = b->st[b->cur];
     p.out = b->st[b->cur ^ 1];
     p.actions = nullptr;
@@ -190,8 +198,8 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
     FrameParams p;
     fill_frame_params(b, p);
     p.actions = d_actions;
-    RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, grid_for(b, p.env_count), b->stream));
-    b->launches += 1;
+    RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, b->bulk, b->split, grid_for(b, p.env_count), b->stream));
+    b->launches += b->split ? 2 : 1;
     if (mode == kModeStep) {
         b->cur ^= 1;
         b->step_index += 1;
@@ -328,6 +336,27 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     RCW_CUDA(cudaMemcpyAsync(b->d_wall_map, words.data(), sizeof(uint32_t) * words.size(),
                              cudaMemcpyHostToDevice, b->stream));
     RCW_CUDA(cudaStreamSynchronize(b->stream));
+
+    // ---- single-colour pattern buffers for the bulk renderer: palette entry k repeated as the
+    //      observation's byte stream (RGB8: R,G,B,R,...; XRGB32: little-endian 0x00RRGGBB words) ----
+    const int col_bytes = P * b->bpp;
+    b->pat_stride = ((col_bytes < 3072 ? col_bytes : 3072) + 32 + 15) & ~15;
+    b->bulk = col_bytes >= 256;   // shorter columns: the bands are too small for bulk copies to pay
+    if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "stg") != 0;
+    if (const char* s = getenv("RCW_SPLIT")) b->split = atoi(s) != 0;
+    RCW_CUDA(dev_alloc(b, &b->d_col_info, (size_t)E * (size_t)R));
+    {
+        std::vector<uint8_t> pat((size_t)6 * b->pat_stride);
+        for (int k = 0; k < 6; ++k)
+            for (int j = 0; j < b->pat_stride; ++j) {
+                const uint32_t col = c.palette[k] & 0x00FFFFFFu;
+                pat[(size_t)k * b->pat_stride + j] =
+                    b->bpp == 3 ? (uint8_t)(col >> (16 - 8 * (j % 3))) : (uint8_t)(col >> (8 * (j % 4)));
+            }
+        RCW_CUDA(dev_alloc(b, &b->d_patterns, pat.size(), false));
+        RCW_CUDA(cudaMemcpyAsync(b->d_patterns, pat.data(), pat.size(), cudaMemcpyHostToDevice, b->stream));
+        RCW_CUDA(cudaStreamSynchronize(b->stream));
+    }
 
     // ---- state SoA -----------------------------------------------------------------------------
     for (int k = 0; k < 2; ++k) {
@@ -675,7 +704,7 @@ int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int
     p.dump_dim = d_dim;
     p.dump_dist = d_dist;
     p.dump_dir = d_dir;
-    cudaError_t e = launch_frame(p, kModeRays, b->cfg.obs_format, grid_for(b, n), b->stream);
+    cudaError_t e = launch_frame(p, kModeRays, b->cfg.obs_format, false, false, grid_for(b, n), b->stream);
     b->launches += 1;
     if (e == cudaSuccess && hit_ij) e = cudaMemcpyAsync(hit_ij, d_hit, cnt * 8, cudaMemcpyDeviceToHost, b->stream);
     if (e == cudaSuccess && hit_dim) e = cudaMemcpyAsync(hit_dim, d_dim, cnt * 4, cudaMemcpyDeviceToHost, b->stream);

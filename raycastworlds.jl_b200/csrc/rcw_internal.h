@@ -8,8 +8,22 @@
 
 namespace rcw {
 
-constexpr int kWarpsPerCta = 8;           // one warp = one (env, 32-ray group) work item at a time
+#ifndef RCW_WARPS_PER_CTA
+#define RCW_WARPS_PER_CTA 8
+#endif
+#ifndef RCW_MIN_CTAS_PER_SM
+#define RCW_MIN_CTAS_PER_SM 1
+#endif
+#ifndef RCW_PAIR_UNROLL
+#define RCW_PAIR_UNROLL 2
+#endif
+#ifndef RCW_PASS1_UNROLL
+#define RCW_PASS1_UNROLL 4
+#endif
+constexpr int kWarpsPerCta = RCW_WARPS_PER_CTA;  // one warp = one (env, 32-ray group) work item at a time
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+constexpr int kPass1Unroll = RCW_PASS1_UNROLL;  // independent 16-byte stores kept in flight per warp
+constexpr int kPairUnroll = RCW_PAIR_UNROLL;    // mirror-pair renderer: two stores per unrolled iteration
 constexpr int kDirSlots = 8;              // constant-memory slots for direction tables
 constexpr int kDirSlotEntries = 512;      // float2 entries per slot (4 KB)
 
@@ -61,6 +75,9 @@ struct FrameParams {
     const float2* dirs;      // [N] unit vectors (global copy, also the source of the ray table)
     const float4* ray_table; // [N][R] {ray_x, ray_y, |1/ray_x|, |1/ray_y|}
     const uint32_t* wall_map;// [map_words] shared wall layer, bit-packed
+    const uint8_t* patterns; // [6][pat_stride] single-colour byte runs, one per palette entry (bulk renderer)
+    int32_t pat_stride;      // bytes, multiple of 16: min(col_bytes, 3072) + 32 rounded up
+    uint32_t* col_info;      // [num_envs][R] pad | palette index << 16, column order (split launches)
     // state
     StateRef in, out;
     const uint8_t* actions;  // device, 1..4 per env; nullptr => random policy
@@ -105,9 +122,9 @@ struct ResetParams {
 // kernel launchers (rcw_kernels.cu)
 cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov, float4* table,
                                    cudaStream_t s);
-cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, int ctas, cudaStream_t s);
+cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, bool bulk, bool split, int ctas,
+                         cudaStream_t s);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);
 cudaError_t upload_dir_slot(int slot, const float2* host_dirs, int n, cudaStream_t s);
-int frame_kernel_max_ctas_per_sm(int obs_format, int map_bytes);
 
 }  // namespace rcw

@@ -55,6 +55,20 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
         : "memory");
 }
 
+// TMA 1-D bulk copy shared -> global (SASS: UBLKCP), tracked by the thread's bulk async-group.
+__device__ __forceinline__ void bulk_copy_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk stores of this thread have finished READING shared memory (the CTA may exit)
+__device__ __forceinline__ void bulk_wait_group_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -156,6 +170,11 @@ struct PixelFormat<RCW_OBS_RGB8> {
         return (c >> (16 - 8 * k)) & 0xFFu;
     }
     // 16 bytes of a single-colour run that starts at byte `ob` of the column
+    // R == G == B: the byte stream of a run is the same byte repeated, whatever the phase
+    __device__ static __forceinline__ bool is_flat(uint32_t c) {
+        return ((c ^ (c >> 8)) & 0xFFFFu) == 0;
+    }
+    __device__ static __forceinline__ uint32_t flat_word(uint32_t c) { return (c & 0xFFu) * 0x01010101u; }
     __device__ static __forceinline__ uint4 run16(uint32_t c, int ob) {
         const int ph = ob % 3;
         const uint32_t p0 = __byte_perm(c, 0, 0x2012);  // R G B R
@@ -175,6 +194,8 @@ struct PixelFormat<RCW_OBS_XRGB32> {
     __device__ static __forceinline__ uint32_t byte_of(uint32_t c, int k) {
         return (c >> (8 * k)) & 0xFFu;  // little-endian UInt32 0x00RRGGBB
     }
+    __device__ static __forceinline__ bool is_flat(uint32_t) { return true; }   // one pixel = one word
+    __device__ static __forceinline__ uint32_t flat_word(uint32_t c) { return c; }
     __device__ static __forceinline__ uint4 run16(uint32_t c, int ob) {
         const uint32_t sh = 8u * (uint32_t)(ob & 3);
         const uint32_t w = __funnelshift_r(c, c, sh);
@@ -207,282 +228,575 @@ __device__ __forceinline__ uint32_t column_byte(const ColumnBands& cb, int ob) {
     return PixelFormat<FMT>::byte_of(cb.color_at(px * bpp), ob - px * bpp);
 }
 
+// Observation stores: written once, read later by another kernel (the learner), never re-read
+// here -> streaming (evict-first) by default.  RCW_STORE_POLICY / RCW_EXP are build-time A/B knobs.
+#ifndef RCW_EXP
+#define RCW_EXP 0   // development experiments: 1 = no act / DDA (store phase only), 2 = no stores
+#endif
+#ifndef RCW_STORE_POLICY
+#define RCW_STORE_POLICY 0
+#endif
 __device__ __forceinline__ void store_stream16(uint8_t* p, uint4 v) {
+#if RCW_EXP == 2
+    if (v.x == 0x12345u) __stcs(reinterpret_cast<uint4*>(p), v);   // experiment: compute only
+#elif RCW_STORE_POLICY == 0
     __stcs(reinterpret_cast<uint4*>(p), v);
+#elif RCW_STORE_POLICY == 1
+    *reinterpret_cast<uint4*>(p) = v;
+#elif RCW_STORE_POLICY == 2
+    __stwt(reinterpret_cast<uint4*>(p), v);
+#else
+    __stcg(reinterpret_cast<uint4*>(p), v);
+#endif
+}
+
+// mask of the bytes of a little-endian word whose index is below d (d <= 0: none, d >= 4: all)
+__device__ __forceinline__ uint32_t low_bytes_mask(int d) {
+    uint32_t r;
+    // shl.b32 clamps shift amounts above 31 to 32 (result 0), which a C shift does not promise
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(0xFFFFFFFFu), "r"(8u * (uint32_t)max(d, 0)));
+    return ~r;
+}
+
+// The 16 bytes at column offset ob when they straddle a band boundary: the three single-colour
+// runs merged under byte masks (ceiling below b1, wall colour below b2, floor above).
+template <int FMT>
+__device__ __forceinline__ uint4 compose16(const ColumnBands& cb, int ob) {
+    const uint4 c = PixelFormat<FMT>::run16(cb.ceiling, ob);
+    const uint4 w = PixelFormat<FMT>::run16(cb.wall, ob);
+    const uint4 f = PixelFormat<FMT>::run16(cb.floor, ob);
+    const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, ww[4] = {w.x, w.y, w.z, w.w}, fw[4] = {f.x, f.y, f.z, f.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t m1 = low_bytes_mask(cb.b1 - ob - 4 * k);
+        const uint32_t m2 = low_bytes_mask(cb.b2 - ob - 4 * k);
+        const uint32_t wf = (ww[k] & m2) | (fw[k] & ~m2);
+        o[k] = (cw[k] & m1) | (wf & ~m1);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// The parts of one column (env-relative bytes [S, S + CB)) that are not whole single-colour
+// 16-byte vectors: the (at most two) aligned vectors that straddle a band boundary, and — only
+// when col_bytes is not a multiple of 16 — the unaligned head / tail bytes.
+template <int FMT>
+__device__ __forceinline__ void column_edges(uint8_t* env_obs, int S, int CB, const ColumnBands& cb) {
+    const int E = S + CB;
+    if ((S | CB) & 15) {
+        const int head_end = min(E, (S + 15) & ~15);
+        const int tail_start = max(head_end, E & ~15);
+        for (int b = S; b < head_end; ++b) env_obs[b] = (uint8_t)column_byte<FMT>(cb, b - S);
+        for (int b = tail_start; b < E; ++b) env_obs[b] = (uint8_t)column_byte<FMT>(cb, b - S);
+    }
+    const int va = (S + cb.b1) & ~15, vb = (S + cb.b2) & ~15;
+    const int oa = va - S, ob = vb - S;
+    if (oa >= 0 && oa + 16 <= CB && cb.classify16(oa) == 3)
+        store_stream16(env_obs + va, compose16<FMT>(cb, oa));
+    if (vb != va && ob >= 0 && ob + 16 <= CB && cb.classify16(ob) == 3)
+        store_stream16(env_obs + vb, compose16<FMT>(cb, ob));
+}
+
+constexpr int kPatChunk = 3072;   // bytes per bulk store: a multiple of 16 (TMA) and of 3 and 4 (pixel phase)
+
+// One band [lo, hi) (env-relative bytes) of a column starting at S: the 16-byte aligned interior is
+// one TMA bulk store (chunked) out of the band colour's pattern buffer, read at the offset that
+// has the same pixel phase as the destination.
+template <int FMT>
+__device__ __forceinline__ void band_bulk(uint8_t* env_obs, int S, int lo, int hi, uint32_t s_pat_color) {
+    const int alo = (lo + 15) & ~15, ahi = hi & ~15;
+    if (ahi <= alo) return;
+    const int ob = alo - S;
+    // RGB8: 16 = 1 (mod 3), so source offset 16 * (ob mod 3) is 16-byte aligned and in phase;
+    // XRGB32: columns start on pixel boundaries, every 16-byte aligned offset is in phase
+    const uint32_t src = s_pat_color + (FMT == RCW_OBS_RGB8 ? 16u * (uint32_t)(ob % 3) : 0u);
+    for (int off = alo; off < ahi; off += kPatChunk)
+        bulk_copy_s2g(env_obs + off, src, (uint32_t)min(kPatChunk, ahi - off));
+}
+
+template <int FMT>
+__device__ __forceinline__ void column_bulk(uint8_t* env_obs, int S, int CB, const ColumnBands& cb, int cid,
+                                            uint32_t s_pat, int pat_stride) {
+    band_bulk<FMT>(env_obs, S, S, S + cb.b1, s_pat + (uint32_t)(RCW_COLOR_CEILING * pat_stride));
+    band_bulk<FMT>(env_obs, S, S + cb.b1, S + cb.b2, s_pat + (uint32_t)(cid * pat_stride));
+    band_bulk<FMT>(env_obs, S, S + cb.b2, S + CB, s_pat + (uint32_t)(RCW_COLOR_FLOOR * pat_stride));
+}
+
+// ------------------------------------------------------------------------------------------
+// act! for one env, executed by a whole warp (state identical in all lanes on entry and exit)
+// ------------------------------------------------------------------------------------------
+
+struct EnvPose {
+    float x, y;
+    int au;
+    uint32_t goal;   // (i | j << 16), 1-based
+};
+
+// single_room.jl:139-191 (+ same-step auto-reset and episode bookkeeping of the batched engine).
+// `writer` is true in the one warp of the whole grid that owns the env's persistent state.
+__device__ __forceinline__ EnvPose act_env(const FrameParams& p, const uint32_t* s_map, int64_t env,
+                                           bool writer, int lane) {
+    const int H = p.H, W = p.W, wpr = p.wpr;
+    float x = __ldg(p.in.pos_x + env);
+    float y = __ldg(p.in.pos_y + env);
+    int au = __ldg(p.in.dir_au + env);
+    const uint32_t goal = __ldg(p.in.goal + env);
+    uint32_t episode = __ldg(p.in.episode + env);
+    int gi = (int)(goal & 0xFFFFu), gj = (int)(goal >> 16);
+    const uint64_t env_id = p.env_id_offset + (uint64_t)env;
+    const int a = p.actions ? (int)__ldg(p.actions + env) : draw_action(p.seed, env_id, p.step_index);
+    const bool valid = (a >= 1) && (a <= 4);
+    float reward = 0.0f;
+    bool done = false;
+    if (valid) {
+        if (a <= 2) {
+            // move_forward / move_backward (utils.jl:16-17): pos +- incr * dir
+            const float2 d = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
+            const float sx = __fmul_rn(p.incr, d.x), sy = __fmul_rn(p.incr, d.y);
+            const float nx = (a == 1) ? __fadd_rn(x, sx) : __fsub_rn(x, sx);
+            const float ny = (a == 1) ? __fadd_rn(y, sy) : __fsub_rn(y, sy);
+            // is_player_colliding (collision_detection.jl:21-42): lanes 0..8 probe the 3x3 tiles
+            // around wu_to_tu(candidate); tiles outside the map are empty.
+            const int ti = __float2int_rd(nx) + (lane % 3);        // = ip - 1 + di, 1-based
+            const int tj = __float2int_rd(ny) + ((lane / 3) % 3);
+            bool hit_goal = false, hit_wall = false;
+            if (lane < 9 && ti >= 1 && ti <= H && tj >= 1 && tj <= W) {
+                const bool is_goal = (ti == gi) && (tj == gj);
+                const bool is_wall = wall_bit(s_map, wpr, ti - 1, tj - 1);
+                if (is_goal || is_wall) {
+                    const bool c = circle_hits_tile(nx, ny, ti, tj, p.radius);
+                    hit_goal = is_goal && c;
+                    hit_wall = is_wall && c;
+                }
+            }
+            const bool any_goal = __any_sync(0xFFFFFFFFu, hit_goal);
+            const bool any_wall = __any_sync(0xFFFFFFFFu, hit_wall);
+            if (any_goal) {           // single_room.jl:166-168 — reward, done, no move
+                reward = p.goal_reward;
+                done = true;
+            } else if (!any_wall) {   // :174-176
+                x = nx;
+                y = ny;
+            }
+        } else {
+            // turn_left / turn_right (utils.jl:13-14): floored mod
+            au = (a == 3) ? (au + 1 == p.N ? 0 : au + 1) : (au == 0 ? p.N - 1 : au - 1);
+        }
+    }
+    // bookkeeping of the finished step, then (auto-reset) the next episode's layout
+    float ep_return = 0.0f;
+    uint32_t ep_length = 0;
+    const bool w0 = writer && lane == 0;
+    if (w0 && valid) {
+        ep_return = __fadd_rn(p.ep_return[env], reward);
+        ep_length = p.ep_length[env] + 1u;
+    }
+    if (done) {
+        if (w0) {
+            atomicAdd(&p.stats->episodes, 1ULL);
+            atomicAdd(&p.stats->sum_length, (unsigned long long)ep_length);
+            atomicAdd(&p.stats->sum_return, (double)ep_return);
+            ep_return = 0.0f;
+            ep_length = 0u;
+        }
+        if (p.auto_reset) {
+            episode += 1u;
+            int pi, pj;
+            draw_layout(s_map, H, W, wpr, p.N, p.seed, env_id, episode, gi, gj, pi, pj, au);
+            x = __fsub_rn((float)pi, 0.5f);   // tile centre (single_room.jl:125)
+            y = __fsub_rn((float)pj, 0.5f);
+        }
+    }
+    EnvPose pose;
+    pose.x = x;
+    pose.y = y;
+    pose.au = au;
+    pose.goal = (uint32_t)gi | ((uint32_t)gj << 16);
+    if (w0) {
+        p.out.pos_x[env] = x;
+        p.out.pos_y[env] = y;
+        p.out.dir_au[env] = au;
+        p.out.goal[env] = pose.goal;
+        p.out.episode[env] = episode;
+        if (valid) {
+            p.reward[env] = reward;
+            p.done[env] = done ? 1 : 0;
+            p.ep_return[env] = ep_return;
+            p.ep_length[env] = ep_length;
+        } else {
+            atomicExch(&p.stats->bad_action, 1);
+        }
+    }
+    return pose;
 }
 
 // ------------------------------------------------------------------------------------------
 // the frame kernel
 // ------------------------------------------------------------------------------------------
 
-template <int MODE, int FMT>
-__global__ void __launch_bounds__(kThreadsPerCta)
-frame_kernel(const __grid_constant__ FrameParams p) {
-    extern __shared__ __align__(16) uint32_t s_map[];   // bit-packed wall layer
-    __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ uint2 s_col[kWarpsPerCta][32];            // per column of the warp: {pad, colour}
+// What one lane knows about its ray's column after cast_rays! + the height computation.
+struct ColumnShade {
+    int pad;         // rows of ceiling (= rows of floor); 0 = full-height column
+    int cid;         // palette index of the wall / goal colour
+};
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+// cast_rays! for the 32 rays [32 g, 32 g + 32) of an env (single_room.jl:195-231) and the height /
+// colour of every ray's column (:404-429).  lane <-> ray.  Optionally dumps the ray results.
+template <int MODE>
+__device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, const uint32_t* s_map,
+                                                      const EnvPose& pose, int g, int lane,
+                                                      uint32_t env_rel) {
+    const int H = p.H, W = p.W, wpr = p.wpr, R = p.R, P = p.P;
+    const float x = pose.x, y = pose.y;
+    const int au = pose.au;
+    const int gi0 = (int)(pose.goal & 0xFFFFu) - 1, gj0 = (int)(pose.goal >> 16) - 1;
+    const int ray = g * 32 + lane;
+    const float2 dir = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
+    // lanes past the last ray shadow the last ray (same walk, nothing stored)
+    const float4 rt = __ldg(p.ray_table + (size_t)au * (size_t)R + min(ray, R - 1));
 
-    // ---- stage the wall layer: one TMA bulk copy per CTA, completion on an mbarrier ----------
-    if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)p.map_words * 4u;
-        mbar_arrive_expect_tx(&s_mbar, bytes);
-        bulk_copy_g2s(s_map, p.wall_map, bytes, &s_mbar);
+    // RayCaster.cast_ray contract: tiles here are 0-based
+    int ti = __float2int_rd(x), tj = __float2int_rd(y);
+    const int si = rt.x < 0.0f ? -1 : 1, sj = rt.y < 0.0f ? -1 : 1;
+    float tx = rt.x < 0.0f ? __fmul_rn(__fsub_rn(x, (float)ti), rt.z)
+                           : __fmul_rn(__fsub_rn((float)(ti + 1), x), rt.z);
+    float ty = rt.y < 0.0f ? __fmul_rn(__fsub_rn(y, (float)tj), rt.w)
+                           : __fmul_rn(__fsub_rn((float)(tj + 1), y), rt.w);
+    int dim = 0;
+    float dist = 0.0f;
+    const bool tie_le = (p.dda_flags & RCW_DDA_TIE_LE) != 0;
+    bool is_wall;   // the tile the ray stands on is a wall (outside the map counts as wall)
+    // A lane that has hit stays on its obstacle tile, so "stopped" needs no extra state; the warp
+    // leaves the loop together once no lane is still walking (ballot early-exit).
+#if RCW_EXP == 1
+    is_wall = true; dist = 1.0f + 0.01f * (float)lane; dim = 1 + (lane & 1);
+#else
+#pragma unroll 1
+    for (;;) {
+        const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
+        const int ci = inside ? ti : 0, cj = inside ? tj : 0;
+        is_wall = !inside | wall_bit(s_map, wpr, ci, cj);
+        const bool stop = is_wall | ((ti == gi0) & (tj == gj0));
+        if (!__any_sync(0xFFFFFFFFu, !stop)) break;
+        if (!stop) {
+            const bool take_x = (tx < ty) | (tie_le & (tx == ty));
+            dist = take_x ? tx : ty;
+            const float ax = __fadd_rn(tx, rt.z), ay = __fadd_rn(ty, rt.w);
+            tx = take_x ? ax : tx;
+            ty = take_x ? ty : ay;
+            ti += take_x ? si : 0;
+            tj += take_x ? 0 : sj;
+            dim = take_x ? 1 : 2;
+        }
     }
-    mbar_wait(&s_mbar, 0);
+#endif
+    if ((p.dda_flags & RCW_DDA_DIST_POST) && dim != 0)
+        dist = (dim == 1) ? __fsub_rn(tx, rt.z) : __fsub_rn(ty, rt.w);
 
-    constexpr int bpp = PixelFormat<FMT>::kBpp;
-    const int H = p.H, W = p.W, wpr = p.wpr, R = p.R, P = p.P, CB = p.col_bytes;
-    const uint32_t n_items = (uint32_t)(p.env_count * p.gpe);
-    const uint32_t item_stride = gridDim.x * kWarpsPerCta;
-
-    for (uint32_t item = blockIdx.x * kWarpsPerCta + warp; item < n_items; item += item_stride) {
-        const uint32_t env_rel = item / (uint32_t)p.gpe;
-        const int g = (int)(item - env_rel * (uint32_t)p.gpe);
-        const int64_t env = p.env_first + env_rel;
-
-        // ---- state (identical in all lanes) --------------------------------------------------
-        float x = __ldg(p.in.pos_x + env);
-        float y = __ldg(p.in.pos_y + env);
-        int au = __ldg(p.in.dir_au + env);
-        uint32_t goal = __ldg(p.in.goal + env);
-        int gi = (int)(goal & 0xFFFFu), gj = (int)(goal >> 16);
-
-        if (MODE == kModeStep) {
-            uint32_t episode = __ldg(p.in.episode + env);
-            const uint64_t env_id = p.env_id_offset + (uint64_t)env;
-            const int a = p.actions ? (int)__ldg(p.actions + env)
-                                    : draw_action(p.seed, env_id, p.step_index);
-            const bool valid = (a >= 1) && (a <= 4);
-            float reward = 0.0f;
-            bool done = false;
-            if (valid) {
-                if (a <= 2) {
-                    // move_forward / move_backward (utils.jl:16-17): pos +- incr * dir
-                    const float2 d = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
-                    const float sx = __fmul_rn(p.incr, d.x), sy = __fmul_rn(p.incr, d.y);
-                    const float nx = (a == 1) ? __fadd_rn(x, sx) : __fsub_rn(x, sx);
-                    const float ny = (a == 1) ? __fadd_rn(y, sy) : __fsub_rn(y, sy);
-                    // is_player_colliding (collision_detection.jl:21-42): lanes 0..8 probe the
-                    // 3x3 tiles around wu_to_tu(candidate); tiles outside the map are empty.
-                    const int ti = __float2int_rd(nx) + (lane % 3);        // = ip - 1 + di, 1-based
-                    const int tj = __float2int_rd(ny) + ((lane / 3) % 3);
-                    bool hit_goal = false, hit_wall = false;
-                    if (lane < 9 && ti >= 1 && ti <= H && tj >= 1 && tj <= W) {
-                        const bool is_goal = (ti == gi) && (tj == gj);
-                        const bool is_wall = wall_bit(s_map, wpr, ti - 1, tj - 1);
-                        if (is_goal || is_wall) {
-                            const bool c = circle_hits_tile(nx, ny, ti, tj, p.radius);
-                            hit_goal = is_goal && c;
-                            hit_wall = is_wall && c;
-                        }
-                    }
-                    const bool any_goal = __any_sync(0xFFFFFFFFu, hit_goal);
-                    const bool any_wall = __any_sync(0xFFFFFFFFu, hit_wall);
-                    if (any_goal) {           // single_room.jl:166-168 — reward, done, no move
-                        reward = p.goal_reward;
-                        done = true;
-                    } else if (!any_wall) {   // :174-176
-                        x = nx;
-                        y = ny;
-                    }
-                } else {
-                    // turn_left / turn_right (utils.jl:13-14): floored mod
-                    au = (a == 3) ? (au + 1 == p.N ? 0 : au + 1) : (au == 0 ? p.N - 1 : au - 1);
-                }
-            }
-            // bookkeeping of the finished step, then (auto-reset) the next episode's layout
-            float ep_return = 0.0f;
-            uint32_t ep_length = 0;
-            const bool writer = (g == 0) && (lane == 0);
-            if (writer && valid) {
-                ep_return = __fadd_rn(p.ep_return[env], reward);
-                ep_length = p.ep_length[env] + 1u;
-            }
-            if (done) {
-                if (writer) {
-                    atomicAdd(&p.stats->episodes, 1ULL);
-                    atomicAdd(&p.stats->sum_length, (unsigned long long)ep_length);
-                    atomicAdd(&p.stats->sum_return, (double)ep_return);
-                    ep_return = 0.0f;
-                    ep_length = 0u;
-                }
-                if (p.auto_reset) {
-                    episode += 1u;
-                    int pi, pj;
-                    draw_layout(s_map, H, W, wpr, p.N, p.seed, env_id, episode, gi, gj, pi, pj, au);
-                    x = __fsub_rn((float)pi, 0.5f);   // tile centre (single_room.jl:125)
-                    y = __fsub_rn((float)pj, 0.5f);
-                }
-            }
-            if (writer) {
-                p.out.pos_x[env] = x;
-                p.out.pos_y[env] = y;
-                p.out.dir_au[env] = au;
-                p.out.goal[env] = (uint32_t)gi | ((uint32_t)gj << 16);
-                p.out.episode[env] = episode;
-                if (valid) {
-                    p.reward[env] = reward;
-                    p.done[env] = done ? 1 : 0;
-                    p.ep_return[env] = ep_return;
-                    p.ep_length[env] = ep_length;
-                } else {
-                    atomicExch(&p.stats->bad_action, 1);
-                }
-            }
+    if (MODE == kModeRays) {
+        if (ray < R) {
+            const size_t k = (size_t)env_rel * (size_t)R + (size_t)ray;
+            p.dump_hit[2 * k + 0] = ti + 1;
+            p.dump_hit[2 * k + 1] = tj + 1;
+            p.dump_dim[k] = dim;
+            p.dump_dist[k] = dist;
+            p.dump_dir[2 * k + 0] = rt.x;
+            p.dump_dir[2 * k + 1] = rt.y;
         }
+    }
+    // update_camera_view!: height of the wall line (:404-411), padding (:433-436), colour (:417-429)
+    const float dot = __fadd_rn(__fmul_rn(dir.x, rt.x), __fmul_rn(dir.y, rt.y));
+    const float proj = __fmul_rn(dist, dot);
+    const float hl = __fdiv_rn(p.hl_num, __fmul_rn(p.two_s, proj));
+    int h = P;                                   // non-finite => full height (:409-410)
+    if (isfinite(hl) && hl < (float)P) h = max(__float2int_rd(hl), 0);
+    ColumnShade cs;
+    cs.pad = (h >= P - 1) ? 0 : ((P - h) >> 1);
+    cs.cid = (is_wall ? RCW_COLOR_WALL_1 : RCW_COLOR_GOAL_1) + (dim == 1 ? 0 : 1);
+    return cs;
+}
 
-        // ---- cast_rays! (single_room.jl:195-231): lane <-> ray ----------------------------------
-        const int r0 = g * 32;
-        const int ncols = min(32, R - r0);
-        const int ray = r0 + lane;
-        const bool active = lane < ncols;
-        const float2 dir = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
-        float4 rt = make_float4(1.0f, 0.0f, 1.0f, 1.0f);
-        if (active) rt = __ldg(p.ray_table + (size_t)au * (size_t)R + ray);
+// 32 bytes = one L2 / DRAM sector, written by one lane with one 256-bit store (sm_100: STG.256).
+// The observation stream must be written in whole sectors: a 16-byte store that leaves the other
+// half of its sector for later makes L2 fetch the sector from DRAM to merge it, which cost 35 % of
+// the step time when the renderer skipped the vectors that straddle a band boundary (profiles/).
+__device__ __forceinline__ void store_stream32(uint8_t* p, uint4 lo, uint4 hi) {
+#if RCW_EXP == 2
+    if (lo.x != 0x12345u) return;   // experiment: compute only
+#endif
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y),
+                 "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
 
-        // RayCaster.cast_ray contract: tiles here are 0-based
-        int ti = __float2int_rd(x), tj = __float2int_rd(y);
-        const int si = rt.x < 0.0f ? -1 : 1, sj = rt.y < 0.0f ? -1 : 1;
-        float tx = rt.x < 0.0f ? __fmul_rn(__fsub_rn(x, (float)ti), rt.z)
-                               : __fmul_rn(__fsub_rn((float)(ti + 1), x), rt.z);
-        float ty = rt.y < 0.0f ? __fmul_rn(__fsub_rn(y, (float)tj), rt.w)
-                               : __fmul_rn(__fsub_rn((float)(tj + 1), y), rt.w);
-        int dim = 0;
-        float dist = 0.0f;
-        bool hit_wall_tile = true;   // outside the map is painted as wall
-        const bool tie_le = (p.dda_flags & RCW_DDA_TIE_LE) != 0;
-        bool walking = active;
-        // the warp leaves the loop together when the last lane has hit (ballot early-exit)
-        while (__any_sync(0xFFFFFFFFu, walking)) {
-            if (walking) {
-                const bool inside = ((unsigned)ti < (unsigned)H) && ((unsigned)tj < (unsigned)W);
-                const bool is_goal = (ti + 1 == gi) && (tj + 1 == gj);
-                const bool is_wall = inside ? wall_bit(s_map, wpr, ti, tj) : true;
-                if (is_wall || is_goal) {
-                    hit_wall_tile = is_wall;
-                    walking = false;
-                } else {
-                    const bool take_x = tie_le ? (tx <= ty) : (tx < ty);
-                    if (take_x) {
-                        dist = tx;
-                        tx = __fadd_rn(tx, rt.z);
-                        ti += si;
-                        dim = 1;
-                    } else {
-                        dist = ty;
-                        ty = __fadd_rn(ty, rt.w);
-                        tj += sj;
-                        dim = 2;
-                    }
+// update_camera_view! stores (single_room.jl:431-439) for the 32 columns of one (env, ray group).
+// On entry s_col[k] = {b1 | slow << 31, colour word} for column k of the span (k = 0 is the lowest
+// address; ray r paints column R-1-r).  `item_slow`: some column of the span has a colour whose
+// bytes differ (RGB8 only), so single-colour runs need the phase rotation of run16.
+template <int FMT>
+__device__ __forceinline__ void render_span(const FrameParams& p, const uint2* colinfo, uint8_t* env_obs,
+                                            int B0, int ncols, int lane, bool item_slow) {
+    const int CB = p.col_bytes;
+    const uint32_t ceil_c = p.palette[RCW_COLOR_CEILING], floor_c = p.palette[RCW_COLOR_FLOOR];
+    uint8_t* const span = env_obs + B0;
+    ColumnBands cb;
+    cb.ceiling = ceil_c;
+    cb.floor = floor_c;
+
+    if ((CB & 63) == 0) {
+        // ---- whole sectors, mirror pairs -------------------------------------------------------
+        // A column is symmetric: ceiling rows [0, pad) <-> floor rows [P-pad, P).  The sector at
+        // column offset ob and its mirror at CB-32-ob are classified by one comparison against b1
+        // (ceiling/floor, wall/wall, or both straddling a band boundary).  All 32 lanes sweep the
+        // sector pairs of the span; a lane writes two sectors per iteration.  The sectors that
+        // straddle a boundary (at most two per column) are composed afterwards, lane <-> column.
+        const int HS = CB >> 6;                      // sector pairs per column
+        const int n_sp = ncols * HS;
+        const int n_iter = lane < n_sp ? ((n_sp - lane + 31) >> 5) : 0;
+        int cl = lane / HS, hs = lane - cl * HS;
+        const int adv_cl = 32 / HS, adv_hs = 32 - adv_cl * HS;
+        if (!item_slow) {
+            const uint32_t ceil_w = PixelFormat<FMT>::flat_word(ceil_c), floor_w = PixelFormat<FMT>::flat_word(floor_c);
+#pragma unroll kPairUnroll
+            for (int it = 0; it < n_iter; ++it) {
+                const uint2 info = colinfo[cl];
+                const int b1 = (int)info.x, ob = hs << 5;
+                const bool in_ceil = ob + 32 <= b1;
+                uint8_t* const top = span + cl * CB + ob;
+                if (in_ceil | (ob >= b1)) {
+                    const uint32_t wt = in_ceil ? ceil_w : info.y, wb = in_ceil ? floor_w : info.y;
+                    const uint4 vt = make_uint4(wt, wt, wt, wt), vb = make_uint4(wb, wb, wb, wb);
+                    store_stream32(top, vt, vt);
+                    store_stream32(top + (CB - 32 - 2 * ob), vb, vb);
+                }
+                cl += adv_cl;
+                hs += adv_hs;
+                if (hs >= HS) {
+                    hs -= HS;
+                    ++cl;
                 }
             }
-        }
-        if ((p.dda_flags & RCW_DDA_DIST_POST) && dim != 0)
-            dist = (dim == 1) ? __fsub_rn(tx, rt.z) : __fsub_rn(ty, rt.w);
-
-        if (MODE == kModeRays) {
-            if (active) {
-                const size_t k = (size_t)env_rel * (size_t)R + (size_t)ray;
-                p.dump_hit[2 * k + 0] = ti + 1;
-                p.dump_hit[2 * k + 1] = tj + 1;
-                p.dump_dim[k] = dim;
-                p.dump_dist[k] = dist;
-                p.dump_dir[2 * k + 0] = rt.x;
-                p.dump_dir[2 * k + 1] = rt.y;
-            }
-            continue;
-        }
-
-        // ---- update_camera_view! (single_room.jl:374-444) ---------------------------------------
-        // height of the wall line of this lane's ray (:404-411)
-        {
-            const float dot = __fadd_rn(__fmul_rn(dir.x, rt.x), __fmul_rn(dir.y, rt.y));
-            const float proj = __fmul_rn(dist, dot);
-            const float hl = __fdiv_rn(p.hl_num, __fmul_rn(p.two_s, proj));
-            int h = P;                                   // non-finite => full height (:409-410)
-            if (isfinite(hl) && hl < (float)P) h = max(__float2int_rd(hl), 0);
-            const int pad = (h >= P - 1) ? 0 : ((P - h) >> 1);   // :433-436
-            const uint32_t color = hit_wall_tile ? (dim == 1 ? p.palette[RCW_COLOR_WALL_1] : p.palette[RCW_COLOR_WALL_2])
-                                                 : (dim == 1 ? p.palette[RCW_COLOR_GOAL_1] : p.palette[RCW_COLOR_GOAL_2]);
-            // ray r paints column R-1-r (0-based); within the warp's span that is ncols-1-lane
-            if (active) s_col[warp][ncols - 1 - lane] = make_uint2((uint32_t)pad, color);
-        }
-        __syncwarp();
-
-        uint8_t* const env_obs = p.obs + (size_t)env * p.obs_env_stride;
-        const int B0 = (R - r0 - ncols) * CB;          // byte span of the warp's columns in the env image
-        const int B1 = B0 + ncols * CB;
-        ColumnBands cb;
-        cb.ceiling = p.palette[RCW_COLOR_CEILING];
-        cb.floor = p.palette[RCW_COLOR_FLOOR];
-
-        // pass 1: every aligned 16-byte vector of the span that lies inside one band of one column
-        {
-            const int v_hi = B1 >> 4;
-            int v = ((B0 + 15) >> 4) + lane;
-            int cl = 0, ob = 0;
-            if (v < v_hi) {
-                const int rel = (v << 4) - B0;
-                cl = rel / CB;
-                ob = rel - cl * CB;
-            }
-            for (; v < v_hi; v += 32) {
-                if (ob + 16 <= CB) {
-                    const uint2 info = s_col[warp][cl];
-                    cb.b1 = (int)info.x * bpp;
-                    cb.b2 = CB - cb.b1;
-                    cb.wall = info.y;
-                    const int cls = cb.classify16(ob);
-                    if (cls != 3) {
-                        const uint32_t c = cls == 0 ? cb.ceiling : (cls == 1 ? cb.wall : cb.floor);
-                        store_stream16(env_obs + ((size_t)v << 4), PixelFormat<FMT>::run16(c, ob));
-                    }
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < n_iter; ++it) {
+                const uint2 info = colinfo[cl];
+                const int b1 = (int)(info.x & 0x7FFFFFFFu), ob = hs << 5, mb = CB - 32 - ob;
+                const bool in_ceil = ob + 32 <= b1;
+                uint8_t* const top = span + cl * CB + ob;
+                if (in_ceil | (ob >= b1)) {
+                    const uint32_t ct = in_ceil ? ceil_c : info.y, cbm = in_ceil ? floor_c : info.y;
+                    store_stream32(top, PixelFormat<FMT>::run16(ct, ob), PixelFormat<FMT>::run16(ct, ob + 16));
+                    store_stream32(span + cl * CB + mb, PixelFormat<FMT>::run16(cbm, mb),
+                                   PixelFormat<FMT>::run16(cbm, mb + 16));
                 }
-                ob += 512;
-                while (ob >= CB) {
-                    ob -= CB;
+                cl += adv_cl;
+                hs += adv_hs;
+                if (hs >= HS) {
+                    hs -= HS;
                     ++cl;
                 }
             }
         }
-        // pass 2: lane <-> column; the (at most two) vectors that straddle a band boundary, and the
-        // unaligned head / tail bytes of the column when col_bytes is not a multiple of 16
-        if (active) {
-            const uint2 info = s_col[warp][lane];
-            cb.b1 = (int)info.x * bpp;
+        // lane <-> column: the sectors that contain a band boundary
+        if (lane < ncols) {
+            const uint2 info = colinfo[lane];
+            cb.b1 = (int)(info.x & 0x7FFFFFFFu);
             cb.b2 = CB - cb.b1;
-            cb.wall = info.y;
-            const int S = B0 + lane * CB, E = S + CB;
-            const int head_end = min(E, (S + 15) & ~15);
-            const int tail_start = max(head_end, E & ~15);
-            for (int b = S; b < head_end; ++b) env_obs[b] = (uint8_t)column_byte<FMT>(cb, b - S);
-            for (int b = tail_start; b < E; ++b) env_obs[b] = (uint8_t)column_byte<FMT>(cb, b - S);
-            const int va = (S + cb.b1) & ~15, vb = (S + cb.b2) & ~15;
-#pragma unroll 1
-            for (int k = 0; k < 2; ++k) {
-                const int vo = k == 0 ? va : vb;
-                if (k == 1 && vb == va) break;
-                const int ob = vo - S;
-                if (ob < 0 || ob + 16 > CB || cb.classify16(ob) != 3) continue;
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        acc |= column_byte<FMT>(cb, ob + 4 * q + t) << (8 * t);
-                    w[q] = acc;
-                }
-                store_stream16(env_obs + vo, make_uint4(w[0], w[1], w[2], w[3]));
+            cb.wall = info.y & 0x00FFFFFFu;
+            uint8_t* const col = span + lane * CB;
+            if (cb.b1 & 31) {
+                const int sa = cb.b1 & ~31, sb = cb.b2 & ~31;
+                store_stream32(col + sa, compose16<FMT>(cb, sa), compose16<FMT>(cb, sa + 16));
+                store_stream32(col + sb, compose16<FMT>(cb, sb), compose16<FMT>(cb, sb + 16));
             }
         }
-        __syncwarp();   // s_col is rewritten by the next item
+        return;
     }
+
+    // ---- generic sizes --------------------------------------------------------------------------
+    // Every aligned 16-byte vector of the span that lies inside one column is written (a vector that
+    // straddles a band boundary provisionally, with one of its colours), then, after a warp barrier
+    // that orders the two generations of stores, the boundary vectors are rewritten exactly and the
+    // unaligned column edges are filled bytewise.  No vector is left for later, see store_stream32.
+    const int B1 = B0 + ncols * CB;
+    const int v_hi = B1 >> 4;
+    const int v0 = ((B0 + 15) >> 4) + lane;
+    const int n_iter = v0 < v_hi ? ((v_hi - v0 + 31) >> 5) : 0;
+    int cl = 0, ob = 0;
+    if (n_iter > 0) {
+        const int rel = (v0 << 4) - B0;
+        cl = rel / CB;
+        ob = rel - cl * CB;
+    }
+    const int adv_cl = 512 / CB, adv_ob = 512 - adv_cl * CB;   // one iteration = 512 bytes
+    uint8_t* ptr = env_obs + ((size_t)v0 << 4);
+#pragma unroll kPass1Unroll
+    for (int it = 0; it < n_iter; ++it) {
+        const uint2 info = colinfo[cl];
+        const int b1 = (int)(info.x & 0x7FFFFFFFu), b2 = CB - b1;
+        const uint32_t c = ob < b1 ? ceil_c : (ob >= b2 ? floor_c : (info.y & 0x00FFFFFFu));
+        const uint4 val = PixelFormat<FMT>::run16(c, ob);
+        if (ob + 16 <= CB) store_stream16(ptr, val);
+        ptr += 512;
+        cl += adv_cl;
+        ob += adv_ob;
+        if (ob >= CB) {
+            ob -= CB;
+            ++cl;
+        }
+    }
+    __syncwarp();
+    if (lane < ncols) {
+        const uint2 info = colinfo[lane];
+        cb.b1 = (int)(info.x & 0x7FFFFFFFu);
+        cb.b2 = CB - cb.b1;
+        cb.wall = info.y & 0x00FFFFFFu;
+        column_edges<FMT>(env_obs, B0 + lane * CB, CB, cb);
+    }
+}
+
+// s_col entry of a column from its shade: single-colour vectors need no phase rotation when
+// R == G == B (RGB8) or always (XRGB32); otherwise the column takes the slow (funnel-shift) path
+template <int FMT>
+__device__ __forceinline__ uint2 column_entry(const FrameParams& p, int pad, int cid, bool& slow) {
+    const uint32_t color = p.palette[cid];
+    slow = FMT == RCW_OBS_RGB8 &&
+           !(PixelFormat<FMT>::is_flat(color) && PixelFormat<FMT>::is_flat(p.palette[RCW_COLOR_CEILING]) &&
+             PixelFormat<FMT>::is_flat(p.palette[RCW_COLOR_FLOOR]));
+    return make_uint2((uint32_t)(pad * PixelFormat<FMT>::kBpp) | (slow ? 0x80000000u : 0u),
+                      slow ? color : PixelFormat<FMT>::flat_word(color));
+}
+
+// STAGE: what one launch does for every (env, group of 32 rays) item, one warp per item
+//   kStageFused : act! -> cast_rays! -> update_camera_view!           (one kernel per env-step)
+//   kStageFront : act! -> cast_rays! -> {pad, colour} of every column written to p.col_info
+//   kStagePaint : p.col_info -> update_camera_view! stores            (pure store stream)
+// Front + Paint is the same step split in two launches: the latency-bound part runs without a
+// saturated store queue in front of its loads, and the store stream runs without waiting on it.
+// BULK (fused / paint): bands written as TMA bulk stores out of single-colour pattern buffers in
+// shared memory; otherwise every 16-byte vector is written by the lanes with st.global.v4.
+enum : int { kStageFused = 0, kStageFront = 1, kStagePaint = 2 };
+
+template <int MODE, int FMT, bool BULK, int STAGE>
+__global__ void __launch_bounds__(kThreadsPerCta, RCW_MIN_CTAS_PER_SM)
+frame_kernel(const __grid_constant__ FrameParams p) {
+    extern __shared__ __align__(128) uint32_t s_dyn[];  // [pattern buffers (BULK)] [bit-packed wall layer]
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint2 s_col[kWarpsPerCta][32];            // per column of the warp: {b1 | slow << 31, colour word}
+    __shared__ EnvPose s_env[2][kWarpsPerCta];           // poses after act!, one slot per env of the round
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    constexpr bool kPaints = STAGE != kStageFront && MODE != kModeRays;
+    constexpr bool kCasts = STAGE != kStagePaint;
+
+    // ---- stage the wall layer (and the pattern buffers): TMA bulk copies, one mbarrier -------
+    const uint32_t pat_bytes = (BULK && kPaints) ? 6u * (uint32_t)p.pat_stride : 0u;
+    uint32_t* const s_map = s_dyn + pat_bytes / 4;
+    if (kCasts || pat_bytes) {
+        if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = kCasts ? (uint32_t)p.map_words * 4u : 0u;
+            mbar_arrive_expect_tx(&s_mbar, bytes + pat_bytes);
+            if (bytes) bulk_copy_g2s(s_map, p.wall_map, bytes, &s_mbar);
+            if (pat_bytes) bulk_copy_g2s(s_dyn, p.patterns, pat_bytes, &s_mbar);
+        }
+        mbar_wait(&s_mbar, 0);
+    }
+    const uint32_t s_pat = smem_u32(s_dyn);
+
+    const int R = p.R, CB = p.col_bytes;
+    const uint32_t gpe = (uint32_t)p.gpe;
+    const uint32_t n_items = (uint32_t)p.env_count * gpe;
+    const uint32_t round_stride = gridDim.x * kWarpsPerCta;
+
+    uint32_t parity = 0;
+    for (uint32_t base = blockIdx.x * kWarpsPerCta; base < n_items; base += round_stride, parity ^= 1u) {
+        const uint32_t item = base + warp;
+        const bool item_ok = item < n_items;
+        const uint32_t env_rel = (item_ok ? item : n_items - 1) / gpe;
+        const int g = (int)(item - env_rel * gpe);
+        const int64_t env = p.env_first + env_rel;
+        const int r0 = g * 32;
+        const int ncols = min(32, R - r0);
+        const int col0 = R - r0 - ncols;               // first column of the span (ray r paints column R-1-r)
+
+        ColumnShade cs;
+        cs.pad = 0;
+        cs.cid = RCW_COLOR_WALL_1;
+        if (kCasts) {
+            // ---- act!: once per env of the round, by the first warp of the CTA that works on it
+            EnvPose pose;
+            if (MODE == kModeStep) {
+#if RCW_EXP != 1
+                const uint32_t slot = env_rel - base / gpe;
+                if (item_ok && (warp == 0 || g == 0)) {
+                    pose = act_env(p, s_map, env, /*writer=*/g == 0, lane);
+                    if (lane == 0) s_env[parity][slot] = pose;
+                }
+                __syncthreads();
+                pose = s_env[parity][slot];
+#else
+                pose.x = 2.5f; pose.y = 2.5f; pose.au = 3; pose.goal = 0x00050005u;
+#endif
+            } else {
+                pose.x = __ldg(p.in.pos_x + env);
+                pose.y = __ldg(p.in.pos_y + env);
+                pose.au = __ldg(p.in.dir_au + env);
+                pose.goal = __ldg(p.in.goal + env);
+            }
+            if (!item_ok) continue;   // (no block barrier below this point)
+            cs = cast_and_shade<MODE>(p, s_map, pose, g, lane, env_rel);
+            if (MODE == kModeRays) continue;
+            if (STAGE == kStageFront) {
+                // column order, so the paint launch reads its 32 columns with one coalesced load
+                if (lane < ncols)
+                    p.col_info[(size_t)env * (size_t)R + (size_t)(col0 + ncols - 1 - lane)] =
+                        (uint32_t)cs.pad | ((uint32_t)cs.cid << 16);
+                continue;
+            }
+        } else {
+            if (!item_ok) continue;
+        }
+
+        uint8_t* const env_obs = p.obs + (size_t)env * p.obs_env_stride;
+        const int B0 = col0 * CB;                      // byte span of the warp's columns in the env image
+        int my_col = ncols - 1 - lane;                 // span column of this lane's ray
+        if (STAGE == kStagePaint) {
+            my_col = lane;                             // the info array is already in column order
+            if (lane < ncols) {
+                const uint32_t info = __ldg(p.col_info + (size_t)env * (size_t)R + (size_t)(col0 + lane));
+                cs.pad = (int)(info & 0xFFFFu);
+                cs.cid = (int)(info >> 16);
+            }
+        }
+
+        if (BULK) {
+            // lane <-> one column: three TMA bulk stores out of the single-colour pattern buffers
+            // + the boundary vectors
+            if (lane < ncols) {
+                ColumnBands cb;
+                cb.ceiling = p.palette[RCW_COLOR_CEILING];
+                cb.floor = p.palette[RCW_COLOR_FLOOR];
+                cb.b1 = cs.pad * PixelFormat<FMT>::kBpp;
+                cb.b2 = CB - cb.b1;
+                cb.wall = p.palette[cs.cid];
+                const int S = B0 + my_col * CB;
+                column_bulk<FMT>(env_obs, S, CB, cb, cs.cid, s_pat, p.pat_stride);
+                column_edges<FMT>(env_obs, S, CB, cb);
+            }
+            bulk_commit_group();
+            continue;
+        }
+        bool slow = false;
+        if (lane < ncols) s_col[warp][my_col] = column_entry<FMT>(p, cs.pad, cs.cid, slow);
+        __syncwarp();
+        const bool item_slow = __any_sync(0xFFFFFFFFu, slow);
+        render_span<FMT>(p, s_col[warp], env_obs, B0, ncols, lane, item_slow);
+        __syncwarp();   // s_col is rewritten in the next round
+    }
+    if (BULK && kPaints) bulk_wait_group_read0();   // shared memory must outlive the TMA reads
 }
 
 // ------------------------------------------------------------------------------------------
@@ -553,46 +867,41 @@ cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov,
     return cudaGetLastError();
 }
 
-template <int MODE, int FMT>
+template <int MODE, int FMT, bool BULK, int STAGE>
 static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s) {
-    const size_t smem = (size_t)p.map_words * 4;
+    const bool casts = STAGE != kStagePaint, paints = STAGE != kStageFront && MODE != kModeRays;
+    const size_t smem = (casts ? (size_t)p.map_words * 4 : 0) + ((BULK && paints) ? 6 * (size_t)p.pat_stride : 0);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(frame_kernel<MODE, FMT>,
+        cudaError_t e = cudaFuncSetAttribute(frame_kernel<MODE, FMT, BULK, STAGE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    frame_kernel<MODE, FMT><<<ctas, kThreadsPerCta, smem, s>>>(p);
+    frame_kernel<MODE, FMT, BULK, STAGE><<<ctas, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, int ctas, cudaStream_t s) {
-    const bool rgb = obs_format == RCW_OBS_RGB8;
-    switch (mode) {
-        case kModeStep:
-            return rgb ? launch_frame_t<kModeStep, RCW_OBS_RGB8>(p, ctas, s)
-                       : launch_frame_t<kModeStep, RCW_OBS_XRGB32>(p, ctas, s);
-        case kModeRender:
-            return rgb ? launch_frame_t<kModeRender, RCW_OBS_RGB8>(p, ctas, s)
-                       : launch_frame_t<kModeRender, RCW_OBS_XRGB32>(p, ctas, s);
-        case kModeRays:
-            return launch_frame_t<kModeRays, RCW_OBS_RGB8>(p, ctas, s);
-        default:
-            return cudaErrorInvalidValue;
-    }
+template <int MODE, int STAGE>
+static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, bool bulk, int ctas, cudaStream_t s) {
+    if (obs_format == RCW_OBS_RGB8)
+        return bulk ? launch_frame_t<MODE, RCW_OBS_RGB8, true, STAGE>(p, ctas, s)
+                    : launch_frame_t<MODE, RCW_OBS_RGB8, false, STAGE>(p, ctas, s);
+    return bulk ? launch_frame_t<MODE, RCW_OBS_XRGB32, true, STAGE>(p, ctas, s)
+                : launch_frame_t<MODE, RCW_OBS_XRGB32, false, STAGE>(p, ctas, s);
 }
 
-int frame_kernel_max_ctas_per_sm(int obs_format, int map_bytes) {
-    int n = 0;
-    cudaError_t e = obs_format == RCW_OBS_RGB8
-                        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                              &n, frame_kernel<kModeStep, RCW_OBS_RGB8>, kThreadsPerCta, (size_t)map_bytes)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                              &n, frame_kernel<kModeStep, RCW_OBS_XRGB32>, kThreadsPerCta, (size_t)map_bytes);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    return n;
+// split = false: one fused launch.  split = true: two launches (front, then paint) through p.col_info.
+cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, bool bulk, bool split, int ctas,
+                         cudaStream_t s) {
+    if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused>(p, ctas, s);
+    if (mode != kModeStep && mode != kModeRender) return cudaErrorInvalidValue;
+    if (!split)
+        return mode == kModeStep ? launch_frame_m<kModeStep, kStageFused>(p, obs_format, bulk, ctas, s)
+                                 : launch_frame_m<kModeRender, kStageFused>(p, obs_format, bulk, ctas, s);
+    cudaError_t e = mode == kModeStep
+                        ? launch_frame_t<kModeStep, RCW_OBS_RGB8, false, kStageFront>(p, ctas, s)
+                        : launch_frame_t<kModeRender, RCW_OBS_RGB8, false, kStageFront>(p, ctas, s);
+    if (e != cudaSuccess) return e;
+    return launch_frame_m<kModeRender, kStagePaint>(p, obs_format, bulk, ctas, s);
 }
 
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s) {
