@@ -34,7 +34,7 @@ SEED = 0x5EED
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
@@ -64,7 +64,7 @@ def mem_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -117,6 +117,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(n_envs, kw, fmt):
+    """DRAM bytes (read + write) of one launch of the step kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    key = f"{n_envs}x{kw['num_rays']}x{kw['height_camera_view_pu']}x{fmt}x{kw['height_tile_map_tu']}x{kw['width_tile_map_tu']}"
+    try:
+        with open(path) as f:
+            return json.load(f).get(key)
+    except OSError:
+        return None
+
+
 def cpu_port_rate(n_envs, kw, seconds, threads):
     """Env-steps/s of the CPU oracle (C restatement of the reference, pthreads over envs) on a
     bounded sample: the same batch, as many whole steps as fit in about `seconds`."""
@@ -149,15 +161,25 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     cfg = orc.default_config(H=kw["height_tile_map_tu"], W=kw["width_tile_map_tu"],
                              N=kw["num_directions"], R=kw["num_rays"], P=kw["height_camera_view_pu"])
-    b = orc.Batch(n, cfg=cfg, seed=SEED)
+    # bounded sample: a step is one random-policy step of `m` of the batch's n envs, m chosen so that
+    # warmup + steps stay within about two minutes on this host
+    probe = orc.Batch(min(n, 4 * threads), cfg=cfg, seed=SEED)
+    t0 = time.perf_counter()
+    probe.rollout(2, threads=threads)
+    per_env_step = (time.perf_counter() - t0) / (2 * probe.num_envs)
+    del probe
+    budget = 120.0
+    m = int(min(n, max(threads, budget / (per_env_step * max(1, args.steps + args.warmup)))))
+    b = orc.Batch(m, cfg=cfg, seed=SEED)
     for _ in range(args.warmup):
         b.rollout(1, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         b.rollout(1, threads=threads)
     dt = time.perf_counter() - t0
-    value = n * args.steps / dt
-    sample = f"{n} envs x {args.steps} whole steps (full per-GPU batch of the b200 arm), UInt32 camera view"
+    value = m * args.steps / dt
+    sample = (f"{m} of the {n} envs per step x {args.steps} steps in {dt:.1f} s, UInt32 camera view, "
+              f"{threads} pthreads over envs")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -293,7 +315,7 @@ def run_b200(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "rcw::frame_kernel<kModeStep>",
+                "traffic": measured_traffic(n, kw, args.obs_format), "kernel": "rcw::frame_kernel<kModeStep, fused>",
                 "algorithmic_bytes_per_launch": n * bytes_per_step_env,
                 "launch_ms": launch_ms, "peak_source": peak_src,
             },

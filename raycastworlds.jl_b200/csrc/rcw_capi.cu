@@ -93,7 +93,7 @@ struct rcw_batch {
     int map_words = 0;
     int dir_slot = -1;
     int ctas_per_sm = 0;          // 0: one CTA per 8 items; >0: persistent grid of sm_count * this
-    bool bulk = true;             // renderer: TMA bulk stores of whole bands (true) or per-lane vector stores
+    bool bulk = false;            // renderer: TMA bulk stores of whole bands (true) or per-lane vector stores
     bool split = false;           // one env-step = front launch + paint launch (true) or one fused launch
     uint32_t* d_col_info = nullptr;
     int pat_stride = 0;
@@ -341,8 +341,11 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     //      observation's byte stream (RGB8: R,G,B,R,...; XRGB32: little-endian 0x00RRGGBB words) ----
     const int col_bytes = P * b->bpp;
     b->pat_stride = ((col_bytes < 3072 ? col_bytes : 3072) + 32 + 15) & ~15;
-    b->bulk = col_bytes >= 256;   // shorter columns: the bands are too small for bulk copies to pay
-    if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "stg") != 0;
+    // Renderer: lane-written whole sectors (default) or TMA bulk stores of the bands.  The bulk path
+    // is kept as a measured alternative (profiles/): its per-lane UBLKCP issue serialises and its
+    // 16-byte band edges leave partial sectors, so it is slower than the sector writer.
+    b->bulk = false;
+    if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0;
     if (const char* s = getenv("RCW_SPLIT")) b->split = atoi(s) != 0;
     RCW_CUDA(dev_alloc(b, &b->d_col_info, (size_t)E * (size_t)R));
     {
