@@ -1,0 +1,100 @@
+"""CPU checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/rcw_b200.h declares (and nothing else under the rcw_ prefix), the ctypes mirror of
+rcw_config matches the C layout, argument validation answers without a GPU, and creation fails
+loudly (RCW_ECUDA) instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import raycastworlds_jl_b200 as rcw
+from raycastworlds_jl_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rcw_b200.h")
+
+
+def header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcw_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(_capi.LIB_PATH), "run `python __graft_entry__.py build`"
+    assert os.path.realpath(_capi.LIB_PATH).startswith(os.path.realpath(ROOT))
+
+
+def test_exports_match_header():
+    declared = header_functions()
+    assert declared == sorted(_capi.SYMBOLS)
+    out = subprocess.run(["nm", "-D", "--defined-only", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r" T (rcw_[a-z_0-9]+)$", out, flags=re.M)))
+    assert exported == declared
+    lib = _capi.load()
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_library_has_sm100a_code_and_no_oracle():
+    out = subprocess.run(["cuobjdump", "-lelf", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    needed = subprocess.run(["readelf", "-d", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in needed.lower()
+
+
+def test_config_struct_layout_and_defaults():
+    cfg = _capi.default_config()
+    assert cfg.struct_size == C.sizeof(_capi.RcwConfig) == 136
+    assert (cfg.height_tile_map_tu, cfg.width_tile_map_tu) == (8, 16)        # single_room.jl:44-45
+    assert (cfg.num_directions, cfg.num_rays, cfg.height_camera_view_pu) == (128, 512, 256)
+    assert cfg.player_radius_wu == 0.125 and cfg.position_increment_wu == 0.125
+    assert cfg.semi_field_of_view_wu == pytest.approx(2 / 3, rel=1e-7)
+    assert list(cfg.palette) == [0xFFFFFF, 0x404040, 0x808080, 0xC0C0C0, 0x800000, 0xC00000]
+    assert _capi.load().rcw_version() == _capi.ABI_VERSION
+
+
+def test_validation_errors_without_gpu():
+    lib = _capi.load()
+    h = C.c_void_p()
+    cfg = _capi.default_config()
+    cfg.struct_size = 8
+    assert lib.rcw_create(C.byref(cfg), None, C.byref(h)) == _capi.RCW_ESIZE
+    assert b"struct_size" in lib.rcw_last_error()
+    for field, value in [("num_envs", 0), ("height_tile_map_tu", 2), ("player_radius_wu", 0.6),
+                         ("obs_format", 7), ("num_rays", 0), ("dda_flags", 8)]:
+        cfg = _capi.default_config()
+        setattr(cfg, field, value)
+        assert lib.rcw_create(C.byref(cfg), None, C.byref(h)) == _capi.RCW_EINVAL, field
+        assert not h.value
+    assert lib.rcw_step(None, None) == _capi.RCW_EINVAL
+    assert lib.rcw_sync(None) == _capi.RCW_EINVAL
+    assert lib.rcw_destroy(None) == _capi.RCW_OK
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rcw.RcwError) as e:
+        rcw.BatchedSingleRoom(4)
+    assert e.value.code == _capi.RCW_ECUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "raycastworlds.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "rcw_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_action_validation_in_host_mirror():
+    assert rcw.NUM_ACTIONS == 4
+    assert rcw.ACTION_NAMES == ("MOVE_FORWARD", "MOVE_BACKWARD", "TURN_LEFT", "TURN_RIGHT")
+    assert issubclass(rcw.InvalidActionError, AssertionError)
