@@ -1,0 +1,205 @@
+# BatchedRayCastWorlds.jl — the reference-side binding of librcw_b200.so.
+#
+# UNTESTED IN THIS IMAGE (no julia binary here or on the GPU box).  It is the binding a
+# RayCastWorlds.jl maintainer adds next to src/single_room.jl: the host stays in Julia and keeps the
+# package's API (AbstractGame, reset!, act!, get_action_names, RLBaseEnv); the hot path
+#   act!(world) -> cast_rays!(world) -> update_camera_view!(env)      (src/single_room.jl:333-340)
+# runs in hand-written sm_100a kernels behind the C ABI of include/rcw_b200.h.
+#
+# Usage
+#   include("BatchedRayCastWorlds.jl"); import .BatchedRayCastWorlds as BRCW
+#   env = BRCW.BatchedSingleRoom(num_envs = 4096)            # same keywords as SingleRoom(...)
+#   RCW.reset!(env); RCW.act!(env, rand(UInt8(1):UInt8(4), 4096))
+#   obs_ptr, nbytes, stride = BRCW.obs_device_ptr(env)       # wrap with CUDA.unsafe_wrap if CUDA.jl is loaded
+#   r, d = BRCW.reward_done(env)
+
+module BatchedRayCastWorlds
+
+import RayCastWorlds as RCW
+import ReinforcementLearningBase as RLBase
+
+const LIB = get(ENV, "RCW_B200_LIB", joinpath(@__DIR__, "..", "lib", "librcw_b200.so"))
+
+const RCW_OK = Int32(0)
+const RCW_EACTION = Int32(-2)
+const RCW_OBS_RGB8 = Int32(0)
+const RCW_OBS_XRGB32 = Int32(1)
+
+# mirrors `struct rcw_config` (include/rcw_b200.h); isbits, same field order and C layout
+struct RcwConfig
+    struct_size::UInt32
+    device::Int32
+    num_envs::Int64
+    env_id_offset::Int64
+    height_tile_map_tu::Int32
+    width_tile_map_tu::Int32
+    num_directions::Int32
+    num_rays::Int32
+    height_camera_view_pu::Int32
+    player_radius_wu::Float32
+    position_increment_wu::Float32
+    semi_field_of_view_wu::Float32
+    camera_height_tile_wu::Float32
+    goal_reward::Float32
+    obs_format::Int32
+    auto_reset::Int32
+    seed::UInt64
+    palette::NTuple{6, UInt32}
+    dda_flags::UInt32
+    reserved::NTuple{7, UInt32}
+end
+
+last_error() = unsafe_string(ccall((:rcw_last_error, LIB), Cstring, ()))
+
+function check(rc::Int32)
+    rc == RCW_OK && return nothing
+    msg = last_error()
+    # RCW_EACTION is the reference's `@assert action in Base.OneTo(NUM_ACTIONS)` (single_room.jl:140)
+    rc == RCW_EACTION && throw(AssertionError(msg))
+    error("librcw_b200 error $(rc): $(msg)")
+end
+
+mutable struct BatchedSingleRoom <: RCW.AbstractGame
+    handle::Ptr{Cvoid}
+    num_envs::Int
+    num_rays::Int
+    height_camera_view_pu::Int
+    obs_format::Int32
+    goal_reward::Float32
+    reward::Vector{Float32}     # host mirrors filled by reward_done!
+    done::Vector{UInt8}
+end
+
+function BatchedSingleRoom(;
+        num_envs = 1,
+        device = 0,
+        T = Float32,
+        height_tile_map_tu = 8,
+        width_tile_map_tu = 16,
+        num_directions = 128,
+        player_radius_wu = convert(T, 1 / 8),
+        position_increment_wu = convert(T, 1 / 8),
+        semi_field_of_view_wu = convert(T, 2 / 3),
+        num_rays = 512,
+        camera_height_tile_wu = convert(T, 1),
+        height_camera_view_pu = 256,
+        goal_reward = one(Float32),
+        obs_format = RCW_OBS_RGB8,
+        auto_reset = true,
+        seed = 0,
+        env_id_offset = 0,
+    )
+    T === Float32 || error("librcw_b200 computes in Float32 (the reference default, single_room.jl:43)")
+
+    # the reference's own direction table (single_room.jl:65-69), so that cos/sin come from Julia
+    directions = Matrix{Float32}(undef, 2, num_directions)
+    for i in 1:num_directions
+        theta = (i - 1) * 2 * pi / num_directions
+        directions[1, i] = convert(Float32, cos(theta))
+        directions[2, i] = convert(Float32, sin(theta))
+    end
+
+    palette = (0x00FFFFFF, 0x00404040, 0x00808080, 0x00c0c0c0, 0x00800000, 0x00c00000)  # single_room.jl:291-296
+    cfg = Ref(RcwConfig(UInt32(sizeof(RcwConfig)), Int32(device), Int64(num_envs), Int64(env_id_offset),
+                        Int32(height_tile_map_tu), Int32(width_tile_map_tu), Int32(num_directions),
+                        Int32(num_rays), Int32(height_camera_view_pu), Float32(player_radius_wu),
+                        Float32(position_increment_wu), Float32(semi_field_of_view_wu),
+                        Float32(camera_height_tile_wu), Float32(goal_reward), Int32(obs_format),
+                        Int32(auto_reset), UInt64(seed), palette, UInt32(0), ntuple(_ -> UInt32(0), 7)))
+    handle = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve directions begin
+        check(ccall((:rcw_create, LIB), Int32, (Ref{RcwConfig}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
+                    cfg, directions, handle))
+    end
+    env = BatchedSingleRoom(handle[], num_envs, num_rays, height_camera_view_pu, Int32(obs_format),
+                            Float32(goal_reward), zeros(Float32, num_envs), zeros(UInt8, num_envs))
+    finalizer(e -> (e.handle != C_NULL && ccall((:rcw_destroy, LIB), Int32, (Ptr{Cvoid},), e.handle); e.handle = C_NULL), env)
+    return env
+end
+
+# reset!(env) — src/single_room.jl:326-331 (layouts drawn on the device)
+function RCW.reset!(env::BatchedSingleRoom)
+    check(ccall((:rcw_reset, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}),
+                env.handle, C_NULL, C_NULL, C_NULL, C_NULL))
+    return nothing
+end
+
+# reset!(env; goal, player, direction) with host-supplied layouts: 2 x num_envs Int32 matrices (1-based tiles)
+function reset_to!(env::BatchedSingleRoom, goal_ij::Matrix{Int32}, player_ij::Matrix{Int32}, dir_au::Vector{Int32})
+    GC.@preserve goal_ij player_ij dir_au begin
+        check(ccall((:rcw_reset, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}),
+                    env.handle, goal_ij, player_ij, dir_au, C_NULL))
+    end
+    return nothing
+end
+
+# act!(env, actions) — src/single_room.jl:333-340 for every env; actions[e] in 1:4
+function RCW.act!(env::BatchedSingleRoom, actions::Vector{UInt8})
+    length(actions) == env.num_envs || throw(DimensionMismatch("one action per env"))
+    GC.@preserve actions begin
+        check(ccall((:rcw_step, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), env.handle, actions))
+    end
+    return nothing
+end
+RCW.act!(env::BatchedSingleRoom, actions::AbstractVector{<:Integer}) = RCW.act!(env, convert(Vector{UInt8}, actions))
+
+# random policy on the device (benchmark path)
+step_random!(env::BatchedSingleRoom, n_steps = 1) =
+    check(ccall((:rcw_step_random, LIB), Int32, (Ptr{Cvoid}, Int32), env.handle, Int32(n_steps)))
+
+# cast_rays! + update_camera_view! — src/single_room.jl:195-231, 374-444
+function RCW.cast_rays!(env::BatchedSingleRoom)
+    check(ccall((:rcw_render, LIB), Int32, (Ptr{Cvoid},), env.handle))
+    return nothing
+end
+RCW.update_camera_view!(env::BatchedSingleRoom) = nothing   # fused into cast_rays! above
+
+RCW.get_action_names(env::BatchedSingleRoom) = (:MOVE_FORWARD, :MOVE_BACKWARD, :TURN_LEFT, :TURN_RIGHT)  # :486
+
+function reward_done!(env::BatchedSingleRoom)
+    r, d = env.reward, env.done
+    GC.@preserve r d begin
+        check(ccall((:rcw_get_state, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{UInt8}),
+                    env.handle, C_NULL, C_NULL, C_NULL, r, d))
+    end
+    return r, d
+end
+
+# borrowed device pointer of the observations (valid until the next act!/reset!), RLBase.state below
+function obs_device_ptr(env::BatchedSingleRoom)
+    ptr = Ref{Ptr{Cvoid}}(C_NULL); total = Ref{Csize_t}(0); stride = Ref{Csize_t}(0)
+    check(ccall((:rcw_obs_device_ptr, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Csize_t}, Ref{Csize_t}),
+                env.handle, ptr, total, stride))
+    return ptr[], Int(total[]), Int(stride[])
+end
+
+# host copy of the observations of envs e0:e0+n-1 (1-based): UInt8[3, P, R, n] or UInt32[P, R, n]
+function copy_obs(env::BatchedSingleRoom, e0 = 1, n = env.num_envs)
+    P, R = env.height_camera_view_pu, env.num_rays
+    out = env.obs_format == RCW_OBS_RGB8 ? Array{UInt8}(undef, 3, P, R, n) : Array{UInt32}(undef, P, R, n)
+    GC.@preserve out begin
+        check(ccall((:rcw_copy_obs, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
+                    env.handle, Int64(e0 - 1), Int64(n), out))
+    end
+    return out
+end
+
+function episode_stats(env::BatchedSingleRoom; reset_counters = false)
+    ep = Ref{Int64}(0); sr = Ref{Float64}(0); sl = Ref{Int64}(0)
+    check(ccall((:rcw_episode_stats, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Float64}, Ref{Int64}, Int32),
+                env.handle, ep, sr, sl, Int32(reset_counters)))
+    return ep[], sr[], sl[]
+end
+
+# RLBase API — same shape as src/single_room.jl:574-584, vector-valued for the batch
+RLBase.StateStyle(env::RCW.RLBaseEnv{E}) where {E <: BatchedSingleRoom} = RLBase.Observation{Any}()
+RLBase.state_space(env::RCW.RLBaseEnv{E}, ::RLBase.Observation) where {E <: BatchedSingleRoom} = nothing
+RLBase.state(env::RCW.RLBaseEnv{E}, ::RLBase.Observation) where {E <: BatchedSingleRoom} = obs_device_ptr(env.env)
+RLBase.reset!(env::RCW.RLBaseEnv{E}) where {E <: BatchedSingleRoom} = RCW.reset!(env.env)
+RLBase.action_space(env::RCW.RLBaseEnv{E}) where {E <: BatchedSingleRoom} = Base.OneTo(4)
+(env::RCW.RLBaseEnv{E})(actions) where {E <: BatchedSingleRoom} = RCW.act!(env.env, actions)
+RLBase.reward(env::RCW.RLBaseEnv{E}) where {E <: BatchedSingleRoom} = reward_done!(env.env)[1]
+RLBase.is_terminated(env::RCW.RLBaseEnv{E}) where {E <: BatchedSingleRoom} = reward_done!(env.env)[2] .!= 0
+
+end # module
