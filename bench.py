@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--obs-format", choices=["rgb8", "xrgb32"], default="rgb8")
     ap.add_argument("--map", choices=["default", "large"], default="default",
                     help="default: 8x16 tiles / 128 directions; large: 64x64 / 256 (BASELINE config 5)")
+    ap.add_argument("--rays", type=int, default=512, help="num_rays = observation width (default 512)")
+    ap.add_argument("--height", type=int, default=256, help="height_camera_view_pu (default 256)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -51,7 +53,7 @@ def workload(args):
     kw = dict(height_tile_map_tu=8, width_tile_map_tu=16, num_directions=128)
     if args.map == "large":
         kw = dict(height_tile_map_tu=64, width_tile_map_tu=64, num_directions=256)
-    kw.update(num_rays=512, height_camera_view_pu=256)
+    kw.update(num_rays=args.rays, height_camera_view_pu=args.height)
     return kw
 
 

@@ -47,8 +47,9 @@ typedef enum rcw_status {
  * camera_view::Array{UInt32}(height_px, num_rays) (single_room.jl:300): the pixel row is
  * the fastest index after the channel, so one ray's column is contiguous. */
 typedef enum rcw_obs_format {
-    RCW_OBS_RGB8   = 0, /* uint8  [num_envs][num_rays][height_px][3]  (R,G,B bytes of the reference pixel) */
-    RCW_OBS_XRGB32 = 1  /* uint32 [num_envs][num_rays][height_px]     (bit-identical to the reference's UInt32 pixels) */
+    RCW_OBS_RGB8   = 0, /* uint8  [num_envs][num_rays columns][height_px][3]  (R,G,B bytes of the reference pixel) */
+    RCW_OBS_XRGB32 = 1  /* uint32 [num_envs][num_rays columns][height_px]     (bit-identical to the reference's UInt32 pixels) */
+    /* dense on the host (rcw_copy_obs); on the device columns may be pitched, see rcw_obs_layout */
 } rcw_obs_format;
 
 /* Indices into rcw_config.palette (reference values: single_room.jl:291-296). */
@@ -162,8 +163,16 @@ int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int
 /* Borrowed device pointer to the whole observation buffer (layout: rcw_obs_format), valid
  * until the next rcw_step* / rcw_reset / rcw_render / rcw_destroy — the same aliasing rule as
  * the reference, whose `state` returns the live camera_view array.
- * env_stride_bytes: distance between consecutive envs (a multiple of 16). */
+ * env_stride_bytes: distance between consecutive envs (see rcw_obs_layout). */
 int32_t rcw_obs_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_t* env_stride_bytes);
+
+/* Device layout of the observation buffer.  One env = num_rays columns; one column = height_px
+ * pixels (column_bytes) followed by padding up to column_stride_bytes, a multiple of 32, so that
+ * every column starts on a 32-byte sector and the renderer only ever writes whole sectors
+ * (column_stride_bytes == column_bytes whenever column_bytes is a multiple of 32, e.g. the default
+ * 256 px).  env_stride_bytes is a multiple of 128.  rcw_copy_obs removes the padding. */
+int32_t rcw_obs_layout(rcw_batch* b, size_t* env_stride_bytes, size_t* column_stride_bytes,
+                       size_t* column_bytes, int32_t* bytes_per_pixel);
 
 /* Blocking copy of the observations of envs [env0, env0+n) to host memory, densely packed
  * (n * num_rays * height_px * bytes_per_pixel). */

@@ -22,7 +22,7 @@ ABI_VERSION = 1
 SYMBOLS = (
     "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_reset",
     "rcw_step", "rcw_step_random", "rcw_render", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
-    "rcw_obs_device_ptr", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
+    "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
     "rcw_sync", "rcw_last_error",
 )
 
@@ -91,6 +91,7 @@ def load() -> C.CDLL:
         "rcw_set_state": (i32, [vp, vp, vp, vp, vp, vp]),
         "rcw_get_rays": (i32, [vp, i64, i64, vp, vp, vp, vp]),
         "rcw_obs_device_ptr": (i32, [vp, P(vp), P(C.c_size_t), P(C.c_size_t)]),
+        "rcw_obs_layout": (i32, [vp, P(C.c_size_t), P(C.c_size_t), P(C.c_size_t), P(i32)]),
         "rcw_copy_obs": (i32, [vp, i64, i64, vp]),
         "rcw_episode_stats": (i32, [vp, P(i64), P(C.c_double), P(i64), i32]),
         "rcw_launch_count": (i32, [vp, P(i64)]),

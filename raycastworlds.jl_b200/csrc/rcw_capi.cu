@@ -112,6 +112,7 @@ struct rcw_batch {
     uint8_t* d_actions = nullptr;
     uint8_t* d_obs = nullptr;
     size_t obs_env_stride = 0;
+    int col_pitch = 0;            // bytes between consecutive columns of an observation (multiple of 32)
     size_t obs_bytes = 0;
     // pinned staging for host-side action arrays
     uint8_t* h_actions[kActionRing]{};
@@ -147,6 +148,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.P = c.height_camera_view_pu;
     p.gpe = b->gpe;
     p.col_bytes = c.height_camera_view_pu * b->bpp;
+    p.col_pitch = b->col_pitch;
     p.dda_flags = c.dda_flags;
     p.radius = c.player_radius_wu;
     p.incr = c.position_increment_wu;
@@ -382,7 +384,9 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     RCW_CUDA(cudaMallocHost((void**)&b->h_stats, sizeof(DeviceStats)));
 
     // ---- observations ---------------------------------------------------------------------------
-    b->obs_env_stride = (((size_t)R * P * b->bpp) + 15) & ~(size_t)15;
+    // every column starts on a 32-byte sector, every env on a 128-byte line (see rcw_obs_layout)
+    b->col_pitch = (P * b->bpp + 31) & ~31;
+    b->obs_env_stride = (((size_t)R * b->col_pitch) + 127) & ~(size_t)127;
     b->obs_bytes = b->obs_env_stride * (size_t)E;
     RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, false));
     return RCW_OK;
@@ -728,6 +732,16 @@ int32_t rcw_obs_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_
     return RCW_OK;
 }
 
+int32_t rcw_obs_layout(rcw_batch* b, size_t* env_stride_bytes, size_t* column_stride_bytes,
+                       size_t* column_bytes, int32_t* bytes_per_pixel) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (env_stride_bytes) *env_stride_bytes = b->obs_env_stride;
+    if (column_stride_bytes) *column_stride_bytes = (size_t)b->col_pitch;
+    if (column_bytes) *column_bytes = (size_t)b->cfg.height_camera_view_pu * b->bpp;
+    if (bytes_per_pixel) *bytes_per_pixel = b->bpp;
+    return RCW_OK;
+}
+
 int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
     if (int32_t rc = check_handle(b)) return rc;
     if (!host) return fail(RCW_EINVAL, "host is null");
@@ -735,13 +749,21 @@ int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
         return fail(RCW_ESIZE, "env range [%lld, %lld) outside 0..%lld", (long long)env0,
                     (long long)(env0 + n), (long long)b->cfg.num_envs);
     DeviceGuard g(b->device);
-    const size_t dense = (size_t)b->cfg.num_rays * b->cfg.height_camera_view_pu * b->bpp;
+    const size_t R = (size_t)b->cfg.num_rays, col_bytes = (size_t)b->cfg.height_camera_view_pu * b->bpp;
     const uint8_t* src = b->d_obs + (size_t)env0 * b->obs_env_stride;
-    if (dense == b->obs_env_stride)
-        RCW_CUDA(cudaMemcpyAsync(host, src, dense * (size_t)n, cudaMemcpyDeviceToHost, b->stream));
-    else
-        RCW_CUDA(cudaMemcpy2DAsync(host, dense, src, b->obs_env_stride, dense, (size_t)n,
+    uint8_t* dst = static_cast<uint8_t*>(host);
+    if (col_bytes == (size_t)b->col_pitch && R * col_bytes == b->obs_env_stride) {
+        RCW_CUDA(cudaMemcpyAsync(dst, src, R * col_bytes * (size_t)n, cudaMemcpyDeviceToHost, b->stream));
+    } else if (R * (size_t)b->col_pitch == b->obs_env_stride) {
+        // pitched columns, envs back to back: one 2-D copy over all columns
+        RCW_CUDA(cudaMemcpy2DAsync(dst, col_bytes, src, (size_t)b->col_pitch, col_bytes, R * (size_t)n,
                                    cudaMemcpyDeviceToHost, b->stream));
+    } else {
+        for (int64_t e = 0; e < n; ++e)
+            RCW_CUDA(cudaMemcpy2DAsync(dst + (size_t)e * R * col_bytes, col_bytes,
+                                       src + (size_t)e * b->obs_env_stride, (size_t)b->col_pitch, col_bytes, R,
+                                       cudaMemcpyDeviceToHost, b->stream));
+    }
     return sync_and_check(b);
 }
 

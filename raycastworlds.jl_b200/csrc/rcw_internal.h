@@ -12,7 +12,7 @@ namespace rcw {
 #define RCW_WARPS_PER_CTA 8
 #endif
 #ifndef RCW_MIN_CTAS_PER_SM
-#define RCW_MIN_CTAS_PER_SM 1
+#define RCW_MIN_CTAS_PER_SM 3   // 80 registers per thread: measured best (2 and 4 CTAs per SM are slower)
 #endif
 #ifndef RCW_PAIR_UNROLL
 #define RCW_PAIR_UNROLL 2
@@ -64,6 +64,7 @@ struct FrameParams {
     int32_t P;               // height_camera_view_pu
     int32_t gpe;             // 32-ray groups per env = ceil(R / 32)
     int32_t col_bytes;       // P * bytes per pixel
+    int32_t col_pitch;       // bytes between consecutive columns: col_bytes rounded up to a multiple of 32
     uint32_t dda_flags;
     // scalars of the reference constructor
     float radius, incr, goal_reward;

@@ -332,19 +332,36 @@ struct EnvPose {
     uint32_t goal;   // (i | j << 16), 1-based
 };
 
+// what act! needs from HBM; loaded early so the latency overlaps the CTA prologue
+struct EnvInputs {
+    float x, y;
+    int au;
+    uint32_t goal, episode;
+    int action;
+};
+
+__device__ __forceinline__ EnvInputs load_env_inputs(const FrameParams& p, int64_t env) {
+    EnvInputs in;
+    in.x = __ldg(p.in.pos_x + env);
+    in.y = __ldg(p.in.pos_y + env);
+    in.au = __ldg(p.in.dir_au + env);
+    in.goal = __ldg(p.in.goal + env);
+    in.episode = __ldg(p.in.episode + env);
+    in.action = p.actions ? (int)__ldg(p.actions + env) : 0;
+    return in;
+}
+
 // single_room.jl:139-191 (+ same-step auto-reset and episode bookkeeping of the batched engine).
 // `writer` is true in the one warp of the whole grid that owns the env's persistent state.
 __device__ __forceinline__ EnvPose act_env(const FrameParams& p, const uint32_t* s_map, int64_t env,
-                                           bool writer, int lane) {
+                                           const EnvInputs& in, bool writer, int lane) {
     const int H = p.H, W = p.W, wpr = p.wpr;
-    float x = __ldg(p.in.pos_x + env);
-    float y = __ldg(p.in.pos_y + env);
-    int au = __ldg(p.in.dir_au + env);
-    const uint32_t goal = __ldg(p.in.goal + env);
-    uint32_t episode = __ldg(p.in.episode + env);
-    int gi = (int)(goal & 0xFFFFu), gj = (int)(goal >> 16);
+    float x = in.x, y = in.y;
+    int au = in.au;
+    uint32_t episode = in.episode;
+    int gi = (int)(in.goal & 0xFFFFu), gj = (int)(in.goal >> 16);
     const uint64_t env_id = p.env_id_offset + (uint64_t)env;
-    const int a = p.actions ? (int)__ldg(p.actions + env) : draw_action(p.seed, env_id, p.step_index);
+    const int a = p.actions ? in.action : draw_action(p.seed, env_id, p.step_index);
     const bool valid = (a >= 1) && (a <= 4);
     float reward = 0.0f;
     bool done = false;
@@ -444,7 +461,7 @@ struct ColumnShade {
 // colour of every ray's column (:404-429).  lane <-> ray.  Optionally dumps the ray results.
 template <int MODE>
 __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, const uint32_t* s_map,
-                                                      const EnvPose& pose, int g, int lane,
+                                                      const EnvPose& pose, const float4 rt, int g, int lane,
                                                       uint32_t env_rel) {
     const int H = p.H, W = p.W, wpr = p.wpr, R = p.R, P = p.P;
     const float x = pose.x, y = pose.y;
@@ -452,8 +469,6 @@ __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, cons
     const int gi0 = (int)(pose.goal & 0xFFFFu) - 1, gj0 = (int)(pose.goal >> 16) - 1;
     const int ray = g * 32 + lane;
     const float2 dir = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
-    // lanes past the last ray shadow the last ray (same walk, nothing stored)
-    const float4 rt = __ldg(p.ray_table + (size_t)au * (size_t)R + min(ray, R - 1));
 
     // RayCaster.cast_ray contract: tiles here are 0-based
     int ti = __float2int_rd(x), tj = __float2int_rd(y);
@@ -563,7 +578,11 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
                 const int b1 = (int)info.x, ob = hs << 5;
                 const bool in_ceil = ob + 32 <= b1;
                 uint8_t* const top = span + cl * CB + ob;
+#if RCW_EXP == 6 || RCW_EXP == 7
+                {
+#else
                 if (in_ceil | (ob >= b1)) {
+#endif
                     const uint32_t wt = in_ceil ? ceil_w : info.y, wb = in_ceil ? floor_w : info.y;
                     const uint4 vt = make_uint4(wt, wt, wt, wt), vb = make_uint4(wb, wb, wb, wb);
                     store_stream32(top, vt, vt);
@@ -597,6 +616,10 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
                 }
             }
         }
+#if RCW_EXP == 6
+        __syncwarp();
+#endif
+#if RCW_EXP != 7
         // lane <-> column: the sectors that contain a band boundary
         if (lane < ncols) {
             const uint2 info = colinfo[lane];
@@ -610,48 +633,54 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
                 store_stream32(col + sb, compose16<FMT>(cb, sb), compose16<FMT>(cb, sb + 16));
             }
         }
+#endif
         return;
     }
 
-    // ---- generic sizes --------------------------------------------------------------------------
-    // Every aligned 16-byte vector of the span that lies inside one column is written (a vector that
-    // straddles a band boundary provisionally, with one of its colours), then, after a warp barrier
-    // that orders the two generations of stores, the boundary vectors are rewritten exactly and the
-    // unaligned column edges are filled bytewise.  No vector is left for later, see store_stream32.
-    const int B1 = B0 + ncols * CB;
-    const int v_hi = B1 >> 4;
-    const int v0 = ((B0 + 15) >> 4) + lane;
-    const int n_iter = v0 < v_hi ? ((v_hi - v0 + 31) >> 5) : 0;
-    int cl = 0, ob = 0;
-    if (n_iter > 0) {
-        const int rel = (v0 << 4) - B0;
-        cl = rel / CB;
-        ob = rel - cl * CB;
-    }
-    const int adv_cl = 512 / CB, adv_ob = 512 - adv_cl * CB;   // one iteration = 512 bytes
-    uint8_t* ptr = env_obs + ((size_t)v0 << 4);
-#pragma unroll kPass1Unroll
+    // ---- any column size: whole sectors of a pitched column ---------------------------------------
+    // Columns whose byte length is not a multiple of 32 are laid out with a pitch rounded up to 32
+    // bytes (rcw_obs_layout), so that every column starts on a sector boundary and the renderer never
+    // writes part of a sector.  A sector is ceiling, wall colour or floor (the padding behind the last
+    // row counts as floor), or it contains a band boundary and is composed, lane <-> column, below.
+    const int CP = p.col_pitch;
+    const int NS = CP >> 5;                          // sectors per column
+    const int n_sec = ncols * NS;
+    const int n_iter = lane < n_sec ? ((n_sec - lane + 31) >> 5) : 0;
+    int cl = lane / NS, sc = lane - cl * NS;
+    const int adv_cl = 32 / NS, adv_sc = 32 - adv_cl * NS;
+#pragma unroll 2
     for (int it = 0; it < n_iter; ++it) {
         const uint2 info = colinfo[cl];
-        const int b1 = (int)(info.x & 0x7FFFFFFFu), b2 = CB - b1;
-        const uint32_t c = ob < b1 ? ceil_c : (ob >= b2 ? floor_c : (info.y & 0x00FFFFFFu));
-        const uint4 val = PixelFormat<FMT>::run16(c, ob);
-        if (ob + 16 <= CB) store_stream16(ptr, val);
-        ptr += 512;
+        const int b1 = (int)(info.x & 0x7FFFFFFFu), b2 = CB - b1, ob = sc << 5;
+        const bool in_ceil = ob + 32 <= b1, in_floor = ob >= b2, in_wall = (ob >= b1) & (ob + 32 <= b2);
+        if (in_ceil | in_floor | in_wall) {
+            const uint32_t c = in_ceil ? ceil_c : (in_floor ? floor_c : (info.y & 0x00FFFFFFu));
+            uint8_t* const dst = span + cl * CP + ob;
+            if (!item_slow) {
+                const uint32_t w = PixelFormat<FMT>::flat_word(c);
+                const uint4 v = make_uint4(w, w, w, w);
+                store_stream32(dst, v, v);
+            } else {
+                store_stream32(dst, PixelFormat<FMT>::run16(c, ob), PixelFormat<FMT>::run16(c, ob + 16));
+            }
+        }
         cl += adv_cl;
-        ob += adv_ob;
-        if (ob >= CB) {
-            ob -= CB;
+        sc += adv_sc;
+        if (sc >= NS) {
+            sc -= NS;
             ++cl;
         }
     }
-    __syncwarp();
     if (lane < ncols) {
         const uint2 info = colinfo[lane];
         cb.b1 = (int)(info.x & 0x7FFFFFFFu);
         cb.b2 = CB - cb.b1;
         cb.wall = info.y & 0x00FFFFFFu;
-        column_edges<FMT>(env_obs, B0 + lane * CB, CB, cb);
+        uint8_t* const col = span + lane * CP;
+        const int sa = cb.b1 & ~31, sb = cb.b2 & ~31;
+        if (cb.b1 & 31) store_stream32(col + sa, compose16<FMT>(cb, sa), compose16<FMT>(cb, sa + 16));
+        if ((cb.b2 & 31) && (sb != sa || !(cb.b1 & 31)))
+            store_stream32(col + sb, compose16<FMT>(cb, sb), compose16<FMT>(cb, sb + 16));
     }
 }
 
@@ -702,8 +731,8 @@ frame_kernel(const __grid_constant__ FrameParams p) {
             if (bytes) bulk_copy_g2s(s_map, p.wall_map, bytes, &s_mbar);
             if (pat_bytes) bulk_copy_g2s(s_dyn, p.patterns, pat_bytes, &s_mbar);
         }
-        mbar_wait(&s_mbar, 0);
     }
+    bool staged = !(kCasts || pat_bytes);   // the wait is deferred until shared memory is first needed
     const uint32_t s_pat = smem_u32(s_dyn);
 
     const int R = p.R, CB = p.col_bytes;
@@ -726,28 +755,56 @@ frame_kernel(const __grid_constant__ FrameParams p) {
         cs.pad = 0;
         cs.cid = RCW_COLOR_WALL_1;
         if (kCasts) {
-            // ---- act!: once per env of the round, by the first warp of the CTA that works on it
             EnvPose pose;
+            float4 rt;
+            // lanes past the last ray shadow the last ray (same walk, nothing stored)
+            const float4* const rt_lane = p.ray_table + min(r0 + lane, R - 1);
             if (MODE == kModeStep) {
 #if RCW_EXP != 1
+                // ---- act!: once per env of the round, by the first warp of the CTA that works on it.
+                // Loads are issued before the prologue wait; every warp meanwhile fetches the ray-table
+                // rows of the three directions the env can face after this step (turn right / keep /
+                // turn left), so the DDA does not start with a dependent L2 round trip.
                 const uint32_t slot = env_rel - base / gpe;
-                if (item_ok && (warp == 0 || g == 0)) {
-                    pose = act_env(p, s_map, env, /*writer=*/g == 0, lane);
+                const bool leader = item_ok && (warp == 0 || g == 0);
+                EnvInputs in;
+                if (leader) in = load_env_inputs(p, env);
+                const int au_in = __ldg(p.in.dir_au + env);
+                const int au_m = au_in == 0 ? p.N - 1 : au_in - 1, au_p = au_in + 1 == p.N ? 0 : au_in + 1;
+                const float4 rt_m = __ldg(rt_lane + (size_t)au_m * (size_t)R);
+                const float4 rt_0 = __ldg(rt_lane + (size_t)au_in * (size_t)R);
+                const float4 rt_p = __ldg(rt_lane + (size_t)au_p * (size_t)R);
+                if (!staged) {
+                    mbar_wait(&s_mbar, 0);
+                    staged = true;
+                }
+                if (leader) {
+                    pose = act_env(p, s_map, env, in, /*writer=*/g == 0, lane);
                     if (lane == 0) s_env[parity][slot] = pose;
                 }
                 __syncthreads();
                 pose = s_env[parity][slot];
+                if (pose.au == au_in) rt = rt_0;
+                else if (pose.au == au_m) rt = rt_m;
+                else if (pose.au == au_p) rt = rt_p;
+                else rt = __ldg(rt_lane + (size_t)pose.au * (size_t)R);   // auto-reset drew a new direction
 #else
                 pose.x = 2.5f; pose.y = 2.5f; pose.au = 3; pose.goal = 0x00050005u;
+                rt = __ldg(rt_lane + (size_t)pose.au * (size_t)R);
 #endif
             } else {
                 pose.x = __ldg(p.in.pos_x + env);
                 pose.y = __ldg(p.in.pos_y + env);
                 pose.au = __ldg(p.in.dir_au + env);
                 pose.goal = __ldg(p.in.goal + env);
+                rt = __ldg(rt_lane + (size_t)pose.au * (size_t)R);
+                if (!staged) {
+                    mbar_wait(&s_mbar, 0);
+                    staged = true;
+                }
             }
             if (!item_ok) continue;   // (no block barrier below this point)
-            cs = cast_and_shade<MODE>(p, s_map, pose, g, lane, env_rel);
+            cs = cast_and_shade<MODE>(p, s_map, pose, rt, g, lane, env_rel);
             if (MODE == kModeRays) continue;
             if (STAGE == kStageFront) {
                 // column order, so the paint launch reads its 32 columns with one coalesced load
@@ -758,10 +815,14 @@ frame_kernel(const __grid_constant__ FrameParams p) {
             }
         } else {
             if (!item_ok) continue;
+            if (!staged) {
+                mbar_wait(&s_mbar, 0);
+                staged = true;
+            }
         }
 
         uint8_t* const env_obs = p.obs + (size_t)env * p.obs_env_stride;
-        const int B0 = col0 * CB;                      // byte span of the warp's columns in the env image
+        const int B0 = col0 * p.col_pitch;             // byte span of the warp's columns in the env image
         int my_col = ncols - 1 - lane;                 // span column of this lane's ray
         if (STAGE == kStagePaint) {
             my_col = lane;                             // the info array is already in column order
@@ -782,7 +843,7 @@ frame_kernel(const __grid_constant__ FrameParams p) {
                 cb.b1 = cs.pad * PixelFormat<FMT>::kBpp;
                 cb.b2 = CB - cb.b1;
                 cb.wall = p.palette[cs.cid];
-                const int S = B0 + my_col * CB;
+                const int S = B0 + my_col * p.col_pitch;
                 column_bulk<FMT>(env_obs, S, CB, cb, cs.cid, s_pat, p.pat_stride);
                 column_edges<FMT>(env_obs, S, CB, cb);
             }

@@ -209,22 +209,28 @@ class BatchedSingleRoom(AbstractGame):
         _capi.check(self._lib.rcw_obs_device_ptr(self._h, C.byref(ptr), C.byref(total), C.byref(stride)))
         return ptr.value, total.value, stride.value
 
+    def obs_layout(self):
+        """(env_stride_bytes, column_stride_bytes, column_bytes, bytes_per_pixel) of the device buffer."""
+        es, cs, cbytes, bpp = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int32()
+        _capi.check(self._lib.rcw_obs_layout(self._h, C.byref(es), C.byref(cs), C.byref(cbytes), C.byref(bpp)))
+        return es.value, cs.value, cbytes.value, bpp.value
+
     def obs_tensor(self):
-        """Zero-copy torch view of the device observation buffer (borrowed: valid until the next
-        act/reset/render, like the reference's aliased `state`, single_room.jl:576)."""
+        """Zero-copy torch view of the device observation buffer, shape obs_shape (borrowed: valid
+        until the next act/reset/render, like the reference's aliased `state`, single_room.jl:576).
+        Columns whose byte length is not a multiple of 32 are pitched (rcw_obs_layout): the view is
+        then strided; `.contiguous()` or copy_obs() give a dense copy."""
         import torch
 
-        ptr, total, stride = self.obs_device_ptr()
+        ptr, total, _ = self.obs_device_ptr()
+        env_stride, col_stride, _, _ = self.obs_layout()
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
-        dense = R * P * self.bytes_per_pixel
         holder = _CudaBuffer(ptr, total, self)
         flat = torch.as_tensor(holder, device=torch.device("cuda", self.cfg.device))
         if self.obs_format == "rgb8":
-            t = torch.as_strided(flat, (self.num_envs, R, P, 3), (stride, P * 3, 3, 1))
-        else:
-            t = torch.as_strided(flat, (self.num_envs, dense), (stride, 1)).view(torch.int32)
-            t = t.view(self.num_envs, R, P)
-        return t
+            return torch.as_strided(flat, (self.num_envs, R, P, 3), (env_stride, col_stride, 3, 1))
+        words = flat.view(torch.int32)
+        return torch.as_strided(words, (self.num_envs, R, P), (env_stride // 4, col_stride // 4, 1))
 
     def copy_obs(self, env0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None):
         """Blocking device->host copy of the observations of envs [env0, env0+n)."""
