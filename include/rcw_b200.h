@@ -115,6 +115,11 @@ int32_t rcw_destroy(rcw_batch* b);
  * Does not re-render; follow with rcw_reset or rcw_render. */
 int32_t rcw_set_wall_map(rcw_batch* b, const uint8_t* wall);
 
+/* One wall layer per env: walls is [num_envs][width_tu][height_tu] bytes (each env as above).
+ * Each env's layer is staged into shared memory by its own TMA bulk copy.  rcw_set_wall_map
+ * switches back to a layer shared by the batch.  Does not re-render. */
+int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls);
+
 /* ---- the reference's generic functions -------------------------------------------------- */
 
 /* reset!(env) (single_room.jl:110-137,326-331) for the envs whose mask byte is nonzero

@@ -20,7 +20,7 @@ ABI_VERSION = 1
 
 # every symbol include/rcw_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
-    "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_reset",
+    "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_set_wall_maps", "rcw_reset",
     "rcw_step", "rcw_step_random", "rcw_render", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
     "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
     "rcw_sync", "rcw_last_error",
@@ -83,6 +83,7 @@ def load() -> C.CDLL:
         "rcw_create": (i32, [P(RcwConfig), vp, P(vp)]),
         "rcw_destroy": (i32, [vp]),
         "rcw_set_wall_map": (i32, [vp, vp]),
+        "rcw_set_wall_maps": (i32, [vp, vp]),
         "rcw_reset": (i32, [vp, vp, vp, vp, vp]),
         "rcw_step": (i32, [vp, vp]),
         "rcw_step_random": (i32, [vp, i32]),

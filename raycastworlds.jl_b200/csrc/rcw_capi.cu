@@ -101,7 +101,9 @@ struct rcw_batch {
     // device memory
     float2* d_dirs = nullptr;
     float4* d_ray_table = nullptr;
-    uint32_t* d_wall_map = nullptr;
+    uint32_t* d_wall_map = nullptr;      // wall layer shared by the batch
+    uint32_t* d_wall_maps_env = nullptr; // [num_envs][map_words], allocated by rcw_set_wall_maps
+    bool per_env_maps = false;
     StateRef st[2]{};
     int cur = 0;
     float* d_reward = nullptr;
@@ -163,7 +165,8 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.dir_slot = b->dir_slot;
     p.dirs = b->d_dirs;
     p.ray_table = b->d_ray_table;
-    p.wall_map = b->d_wall_map;
+    p.wall_map = b->per_env_maps ? b->d_wall_maps_env : b->d_wall_map;
+    p.map_env_stride = b->per_env_maps ? (uint32_t)b->map_words : 0u;
     p.patterns = b->d_patterns;
     p.pat_stride = b->pat_stride;
     p.col_info = b->d_col_info;
@@ -189,7 +192,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
 static int grid_for(const rcw_batch* b, int64_t env_count) {
     const int64_t items = env_count * b->gpe;
     int64_t ctas = (items + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (b->ctas_per_sm > 0) {
+    if (b->ctas_per_sm > 0 && !b->per_env_maps) {   // per-env wall layers: one round per CTA
         const int64_t cap = (int64_t)b->sm_count * b->ctas_per_sm;
         if (ctas > cap) ctas = cap;
     }
@@ -470,6 +473,36 @@ int32_t rcw_set_wall_map(rcw_batch* b, const uint8_t* wall) {
     RCW_CUDA(cudaStreamSynchronize(b->stream));
     RCW_CUDA(cudaMemcpy(b->d_wall_map, words.data(), sizeof(uint32_t) * words.size(),
                         cudaMemcpyHostToDevice));
+    b->per_env_maps = false;
+    return RCW_OK;
+}
+
+int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!walls) return fail(RCW_EINVAL, "walls is null");
+    DeviceGuard g(b->device);
+    const int H = b->cfg.height_tile_map_tu, W = b->cfg.width_tile_map_tu;
+    const size_t E = (size_t)b->cfg.num_envs, mw = (size_t)b->map_words, tiles = (size_t)H * W;
+    if ((size_t)kWarpsPerCta * mw * 4 > 200 * 1024)
+        return fail(RCW_ESIZE, "per-env tile maps of %dx%d do not fit in shared memory", H, W);
+    std::vector<uint32_t> words;
+    try {
+        words.assign(E * mw, 0u);
+    } catch (const std::bad_alloc&) {
+        return fail(RCW_ENOMEM, "out of host memory packing %zu wall layers", E);
+    }
+    for (size_t e = 0; e < E; ++e) {
+        const uint8_t* w = walls + e * tiles;
+        uint32_t* out = words.data() + e * mw;
+        for (int j = 0; j < W; ++j)
+            for (int i = 0; i < H; ++i)
+                if (w[(size_t)j * H + i]) out[(size_t)i * b->wpr + (j >> 5)] |= 1u << (j & 31);
+    }
+    RCW_CUDA(cudaStreamSynchronize(b->stream));
+    if (!b->d_wall_maps_env) RCW_CUDA(dev_alloc(b, &b->d_wall_maps_env, E * mw, false));
+    RCW_CUDA(cudaMemcpy(b->d_wall_maps_env, words.data(), sizeof(uint32_t) * words.size(),
+                        cudaMemcpyHostToDevice));
+    b->per_env_maps = true;
     return RCW_OK;
 }
 
@@ -534,7 +567,8 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
     rp.W = c.width_tile_map_tu;
     rp.wpr = b->wpr;
     rp.N = c.num_directions;
-    rp.wall_map = b->d_wall_map;
+    rp.wall_map = b->per_env_maps ? b->d_wall_maps_env : b->d_wall_map;
+    rp.map_env_stride = b->per_env_maps ? (uint32_t)b->map_words : 0u;
     rp.st = b->st[b->cur];
     rp.reward = b->d_reward;
     rp.done = b->d_done;

@@ -75,7 +75,8 @@ struct FrameParams {
     int32_t dir_slot;        // >= 0: directions live in constant memory slot; < 0: use `dirs`
     const float2* dirs;      // [N] unit vectors (global copy, also the source of the ray table)
     const float4* ray_table; // [N][R] {ray_x, ray_y, |1/ray_x|, |1/ray_y|}
-    const uint32_t* wall_map;// [map_words] shared wall layer, bit-packed
+    const uint32_t* wall_map;// [map_words] shared wall layer, bit-packed, or [num_envs][map_words] per env
+    uint32_t map_env_stride; // words between the wall layers of consecutive envs; 0 = one layer shared by all
     const uint8_t* patterns; // [6][pat_stride] single-colour byte runs, one per palette entry (bulk renderer)
     int32_t pat_stride;      // bytes, multiple of 16: min(col_bytes, 3072) + 32 rounded up
     uint32_t* col_info;      // [num_envs][R] pad | palette index << 16, column order (split launches)
@@ -106,6 +107,7 @@ struct FrameParams {
 struct ResetParams {
     int32_t H, W, wpr, N;
     const uint32_t* wall_map;
+    uint32_t map_env_stride;   // 0 = shared wall layer
     StateRef st;
     float* reward;
     uint8_t* done;

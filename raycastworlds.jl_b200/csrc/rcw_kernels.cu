@@ -231,7 +231,7 @@ __device__ __forceinline__ uint32_t column_byte(const ColumnBands& cb, int ob) {
 // Observation stores: written once, read later by another kernel (the learner), never re-read
 // here -> streaming (evict-first) by default.  RCW_STORE_POLICY / RCW_EXP are build-time A/B knobs.
 #ifndef RCW_EXP
-#define RCW_EXP 0   // development experiments: 1 = no act / DDA (store phase only), 2 = no stores
+#define RCW_EXP 0   // development experiments (profiles/README.md): 1 = no act / DDA (store phase only), 2 = no stores
 #endif
 #ifndef RCW_STORE_POLICY
 #define RCW_STORE_POLICY 0
@@ -578,11 +578,7 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
                 const int b1 = (int)info.x, ob = hs << 5;
                 const bool in_ceil = ob + 32 <= b1;
                 uint8_t* const top = span + cl * CB + ob;
-#if RCW_EXP == 6 || RCW_EXP == 7
-                {
-#else
                 if (in_ceil | (ob >= b1)) {
-#endif
                     const uint32_t wt = in_ceil ? ceil_w : info.y, wb = in_ceil ? floor_w : info.y;
                     const uint4 vt = make_uint4(wt, wt, wt, wt), vb = make_uint4(wb, wb, wb, wb);
                     store_stream32(top, vt, vt);
@@ -616,10 +612,6 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
                 }
             }
         }
-#if RCW_EXP == 6
-        __syncwarp();
-#endif
-#if RCW_EXP != 7
         // lane <-> column: the sectors that contain a band boundary
         if (lane < ncols) {
             const uint2 info = colinfo[lane];
@@ -633,7 +625,6 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
                 store_stream32(col + sb, compose16<FMT>(cb, sb), compose16<FMT>(cb, sb + 16));
             }
         }
-#endif
         return;
     }
 
@@ -711,6 +702,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, RCW_MIN_CTAS_PER_SM)
 frame_kernel(const __grid_constant__ FrameParams p) {
     extern __shared__ __align__(128) uint32_t s_dyn[];  // [pattern buffers (BULK)] [bit-packed wall layer]
     __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ __align__(8) uint64_t s_mbar_env[kWarpsPerCta];   // per-env wall layers: one per env slot
     __shared__ uint2 s_col[kWarpsPerCta][32];            // per column of the warp: {b1 | slow << 31, colour word}
     __shared__ EnvPose s_env[2][kWarpsPerCta];           // poses after act!, one slot per env of the round
 
@@ -719,20 +711,28 @@ frame_kernel(const __grid_constant__ FrameParams p) {
     constexpr bool kPaints = STAGE != kStageFront && MODE != kModeRays;
     constexpr bool kCasts = STAGE != kStagePaint;
 
-    // ---- stage the wall layer (and the pattern buffers): TMA bulk copies, one mbarrier -------
+    // ---- stage the wall layer (and the pattern buffers): TMA bulk copies, completion on mbarriers.
+    // A wall layer shared by the batch is copied once per CTA here; per-env wall layers
+    // (map_env_stride != 0) are copied per env of the round by that env's first warp, below.
     const uint32_t pat_bytes = (BULK && kPaints) ? 6u * (uint32_t)p.pat_stride : 0u;
     uint32_t* const s_map = s_dyn + pat_bytes / 4;
+    const bool per_env_maps = kCasts && p.map_env_stride != 0;
+    const uint32_t map_bytes = (uint32_t)p.map_words * 4u;
+    const uint32_t shared_bytes = (kCasts && !per_env_maps) ? map_bytes : 0u;
     if (kCasts || pat_bytes) {
-        if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
-        __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t bytes = kCasts ? (uint32_t)p.map_words * 4u : 0u;
-            mbar_arrive_expect_tx(&s_mbar, bytes + pat_bytes);
-            if (bytes) bulk_copy_g2s(s_map, p.wall_map, bytes, &s_mbar);
+            mbar_init(&s_mbar, 1);
+            if (per_env_maps)
+                for (int k = 0; k < kWarpsPerCta; ++k) mbar_init(&s_mbar_env[k], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && shared_bytes + pat_bytes) {
+            mbar_arrive_expect_tx(&s_mbar, shared_bytes + pat_bytes);
+            if (shared_bytes) bulk_copy_g2s(s_map, p.wall_map, shared_bytes, &s_mbar);
             if (pat_bytes) bulk_copy_g2s(s_dyn, p.patterns, pat_bytes, &s_mbar);
         }
     }
-    bool staged = !(kCasts || pat_bytes);   // the wait is deferred until shared memory is first needed
+    bool staged = (shared_bytes + pat_bytes) == 0;   // the wait is deferred until shared memory is first needed
     const uint32_t s_pat = smem_u32(s_dyn);
 
     const int R = p.R, CB = p.col_bytes;
@@ -759,14 +759,24 @@ frame_kernel(const __grid_constant__ FrameParams p) {
             float4 rt;
             // lanes past the last ray shadow the last ray (same walk, nothing stored)
             const float4* const rt_lane = p.ray_table + min(r0 + lane, R - 1);
+            const uint32_t slot = env_rel - base / gpe;          // envs of this round, in order
+            const bool leader = item_ok && (warp == 0 || g == 0);
+            const uint32_t* my_map = s_map;
+            if (per_env_maps) {
+                // this env's wall layer -> its slot (one round per CTA in this mode, see grid_for)
+                my_map = s_map + slot * (uint32_t)p.map_words;
+                if (leader && lane == 0) {
+                    mbar_arrive_expect_tx(&s_mbar_env[slot], map_bytes);
+                    bulk_copy_g2s(const_cast<uint32_t*>(my_map), p.wall_map + (size_t)env * p.map_env_stride,
+                                  map_bytes, &s_mbar_env[slot]);
+                }
+            }
             if (MODE == kModeStep) {
 #if RCW_EXP != 1
                 // ---- act!: once per env of the round, by the first warp of the CTA that works on it.
                 // Loads are issued before the prologue wait; every warp meanwhile fetches the ray-table
                 // rows of the three directions the env can face after this step (turn right / keep /
                 // turn left), so the DDA does not start with a dependent L2 round trip.
-                const uint32_t slot = env_rel - base / gpe;
-                const bool leader = item_ok && (warp == 0 || g == 0);
                 EnvInputs in;
                 if (leader) in = load_env_inputs(p, env);
                 const int au_in = __ldg(p.in.dir_au + env);
@@ -778,8 +788,9 @@ frame_kernel(const __grid_constant__ FrameParams p) {
                     mbar_wait(&s_mbar, 0);
                     staged = true;
                 }
+                if (per_env_maps) mbar_wait(&s_mbar_env[slot], 0);
                 if (leader) {
-                    pose = act_env(p, s_map, env, in, /*writer=*/g == 0, lane);
+                    pose = act_env(p, my_map, env, in, /*writer=*/g == 0, lane);
                     if (lane == 0) s_env[parity][slot] = pose;
                 }
                 __syncthreads();
@@ -802,9 +813,10 @@ frame_kernel(const __grid_constant__ FrameParams p) {
                     mbar_wait(&s_mbar, 0);
                     staged = true;
                 }
+                if (per_env_maps) mbar_wait(&s_mbar_env[slot], 0);
             }
             if (!item_ok) continue;   // (no block barrier below this point)
-            cs = cast_and_shade<MODE>(p, s_map, pose, rt, g, lane, env_rel);
+            cs = cast_and_shade<MODE>(p, my_map, pose, rt, g, lane, env_rel);
             if (MODE == kModeRays) continue;
             if (STAGE == kStageFront) {
                 // column order, so the paint launch reads its 32 columns with one coalesced load
@@ -878,7 +890,8 @@ __global__ void reset_kernel(const ResetParams p) {
         au = p.dir_au[env];
     } else {
         episode += 1u;
-        draw_layout(p.wall_map, p.H, p.W, p.wpr, p.N, p.seed, p.env_id_offset + (uint64_t)env,
+        draw_layout(p.wall_map + (size_t)env * p.map_env_stride, p.H, p.W, p.wpr, p.N, p.seed,
+                    p.env_id_offset + (uint64_t)env,
                     episode, gi, gj, pi, pj, au);
     }
     p.st.pos_x[env] = __fsub_rn((float)pi, 0.5f);
@@ -931,7 +944,8 @@ cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov,
 template <int MODE, int FMT, bool BULK, int STAGE>
 static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s) {
     const bool casts = STAGE != kStagePaint, paints = STAGE != kStageFront && MODE != kModeRays;
-    const size_t smem = (casts ? (size_t)p.map_words * 4 : 0) + ((BULK && paints) ? 6 * (size_t)p.pat_stride : 0);
+    const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;   // per-env wall layers: one slot per env of a round
+    const size_t smem = (casts ? map_slots * (size_t)p.map_words * 4 : 0) + ((BULK && paints) ? 6 * (size_t)p.pat_stride : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(frame_kernel<MODE, FMT, BULK, STAGE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -187,6 +187,14 @@ class BatchedSingleRoom(AbstractGame):
         flat = np.ascontiguousarray(w.T.reshape(-1))  # [W][H], i fastest (Julia column-major)
         _capi.check(self._lib.rcw_set_wall_map(self._h, _ptr(flat)))
 
+    def set_wall_maps(self, walls_ehw):
+        """walls_ehw: bool [num_envs, H, W] — one wall layer per env (tile_map[WALL, :, :] of env e)."""
+        w = np.asarray(walls_ehw).astype(np.uint8)
+        if w.shape != (self.num_envs, self.cfg.height_tile_map_tu, self.cfg.width_tile_map_tu):
+            raise ValueError("wall maps must be [num_envs, height_tile_map_tu, width_tile_map_tu]")
+        flat = np.ascontiguousarray(w.transpose(0, 2, 1).reshape(-1))  # [E][W][H], i fastest
+        _capi.check(self._lib.rcw_set_wall_maps(self._h, _ptr(flat)))
+
     def get_rays(self, env0: int = 0, n: Optional[int] = None):
         n = self.num_envs - env0 if n is None else n
         R = self.cfg.num_rays

@@ -289,6 +289,47 @@ def test_custom_wall_map_matches_oracle(rcw, oracle):
     env.close()
 
 
+@pytest.mark.parametrize("R", [32, 96, 512])
+def test_per_env_wall_maps_match_oracle(rcw, oracle, R):
+    """Every env has its own wall layer (random pillars), staged per env by TMA; R = 32 puts eight
+    envs in one CTA, R = 512 spreads one env over two CTAs."""
+    H, W, n, seed = 16, 24, 40, 5
+    rng = np.random.default_rng(R)
+    walls = np.zeros((n, H, W), bool)
+    walls[:, 0, :] = walls[:, -1, :] = walls[:, :, 0] = walls[:, :, -1] = True
+    walls[:, 2:-2, 2:-2] |= rng.random((n, H - 4, W - 4)) < 0.12
+    env = rcw.BatchedSingleRoom(n, seed=seed, height_tile_map_tu=H, width_tile_map_tu=W, num_rays=R,
+                                height_camera_view_pu=64)
+    env.set_wall_maps(walls)
+    env.reset()
+    ref = oracle.Batch(n, cfg=oracle.default_config(H=H, W=W, R=R, P=64), seed=seed)
+    for e in range(n):
+        ref.world(e).set_wall_map(walls[e])
+    ref.reset()
+    for _ in range(3):
+        env.step_random(100)
+        ref.rollout(100, threads=4)
+        st = env.get_state()
+        pos, au, goal = ref.states()
+        np.testing.assert_array_equal(bits(st["pos"]), bits(pos))
+        np.testing.assert_array_equal(st["dir_au"], au)
+        np.testing.assert_array_equal(st["goal"], goal)
+        np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    rays = env.get_rays()
+    for e in range(n):
+        np.testing.assert_array_equal(rays["hit"][e], ref.world(e).ray_stop)
+    # back to one shared layer
+    env.set_wall_map(walls[0])
+    env.reset()
+    for e in range(n):
+        ref.world(e).set_wall_map(walls[0])
+    ref.reset()
+    env.step_random(50)
+    ref.rollout(50, threads=4)
+    np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    env.close()
+
+
 @pytest.mark.parametrize("R,P", [(1, 1), (2, 3), (31, 7), (33, 16), (64, 84), (100, 17)])
 @pytest.mark.parametrize("fmt", ["rgb8", "xrgb32"])
 def test_ragged_observation_sizes(rcw, oracle, R, P, fmt):
