@@ -310,7 +310,7 @@ def run_b200(args):
             "config": {
                 "workload": f"BatchedSingleRoom {n} envs per GPU, {kw['height_tile_map_tu']}x{kw['width_tile_map_tu']} tiles, "
                             f"{kw['num_directions']} directions, {kw['num_rays']} rays x {kw['height_camera_view_pu']} px "
-                            f"{args.obs_format}, random policy + auto-reset (BASELINE.json configs[1])",
+                            f"{args.obs_format}, random policy + auto-reset" + (" (BASELINE.json configs[1])" if (n, args.map, args.rays, args.height) == (4096, "default", 512, 256) else ""),
                 "envs_per_gpu": n, "obs_bytes_per_env_step": bytes_per_step_env,
                 "l2": f"each step writes {n * bytes_per_step_env / 1e9:.2f} GB of observations, larger than the 126 MB L2; no flush needed",
                 "seed": SEED,

@@ -14,6 +14,9 @@ namespace rcw {
 #ifndef RCW_MIN_CTAS_PER_SM
 #define RCW_MIN_CTAS_PER_SM 3   // 80 registers per thread: measured best (2 and 4 CTAs per SM are slower)
 #endif
+#ifndef RCW_DDA_STEPS_PER_VOTE
+#define RCW_DDA_STEPS_PER_VOTE 2
+#endif
 #ifndef RCW_PAIR_UNROLL
 #define RCW_PAIR_UNROLL 2
 #endif
@@ -23,6 +26,7 @@ namespace rcw {
 constexpr int kWarpsPerCta = RCW_WARPS_PER_CTA;  // one warp = one (env, 32-ray group) work item at a time
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kPass1Unroll = RCW_PASS1_UNROLL;  // independent 16-byte stores kept in flight per warp
+constexpr int kDdaStepsPerVote = RCW_DDA_STEPS_PER_VOTE;
 constexpr int kPairUnroll = RCW_PAIR_UNROLL;    // mirror-pair renderer: two stores per unrolled iteration
 constexpr int kDirSlots = 8;              // constant-memory slots for direction tables
 constexpr int kDirSlotEntries = 512;      // float2 entries per slot (4 KB)

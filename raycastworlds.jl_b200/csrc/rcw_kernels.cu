@@ -486,22 +486,30 @@ __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, cons
 #if RCW_EXP == 1
     is_wall = true; dist = 1.0f + 0.01f * (float)lane; dim = 1 + (lane & 1);
 #else
-#pragma unroll 1
-    for (;;) {
+    // probe the tile the ray stands on: wall (outside the map counts as wall) or this env's goal
+    auto probe = [&]() {
         const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
         const int ci = inside ? ti : 0, cj = inside ? tj : 0;
         is_wall = !inside | wall_bit(s_map, wpr, ci, cj);
-        const bool stop = is_wall | ((ti == gi0) & (tj == gj0));
-        if (!__any_sync(0xFFFFFFFFu, !stop)) break;
-        if (!stop) {
-            const bool take_x = (tx < ty) | (tie_le & (tx == ty));
-            dist = take_x ? tx : ty;
-            const float ax = __fadd_rn(tx, rt.z), ay = __fadd_rn(ty, rt.w);
-            tx = take_x ? ax : tx;
-            ty = take_x ? ty : ay;
-            ti += take_x ? si : 0;
-            tj += take_x ? 0 : sj;
-            dim = take_x ? 1 : 2;
+        return is_wall | ((ti == gi0) & (tj == gj0));
+    };
+    bool stop = probe();
+#pragma unroll 1
+    while (__any_sync(0xFFFFFFFFu, !stop)) {
+        // kDdaStepsPerVote DDA steps per warp vote: a stopped lane just probes its own tile again
+#pragma unroll
+        for (int u = 0; u < kDdaStepsPerVote; ++u) {
+            if (!stop) {
+                const bool take_x = (tx < ty) | (tie_le & (tx == ty));
+                dist = take_x ? tx : ty;
+                const float ax = __fadd_rn(tx, rt.z), ay = __fadd_rn(ty, rt.w);
+                tx = take_x ? ax : tx;
+                ty = take_x ? ty : ay;
+                ti += take_x ? si : 0;
+                tj += take_x ? 0 : sj;
+                dim = take_x ? 1 : 2;
+            }
+            stop = probe();
         }
     }
 #endif

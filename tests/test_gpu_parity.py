@@ -343,6 +343,57 @@ def test_ragged_observation_sizes(rcw, oracle, R, P, fmt):
     env.close()
 
 
+@pytest.mark.parametrize("R,P", [(64, 64), (40, 50), (96, 256)])
+@pytest.mark.parametrize("fmt", ["rgb8", "xrgb32"])
+def test_custom_palette_takes_the_phase_rotated_path(rcw, oracle, R, P, fmt):
+    """A palette whose colours have three different bytes: single-colour runs are no longer one byte
+    repeated, so every sector goes through the funnel-shift path (mirror-pair and pitched renderers)."""
+    pal = [0x00102030, 0x00A0B0C0, 0x00112233, 0x00445566, 0x00778899, 0x00AABBCC]
+    n, seed = 6, 31
+    env = rcw.BatchedSingleRoom(n, seed=seed, num_rays=R, height_camera_view_pu=P, obs_format=fmt, palette=pal)
+    ref = oracle.Batch(n, cfg=oracle.default_config(R=R, P=P, palette=pal), seed=seed)
+    env.step_random(40)
+    ref.rollout(40)
+    np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8() if fmt == "rgb8" else ref.obs_u32())
+    env.close()
+
+
+def test_device_tensor_view_matches_host_copy(rcw):
+    """obs_tensor() is a zero-copy (possibly pitched) view of the same bytes copy_obs() returns."""
+    import torch
+
+    for kw in (dict(), dict(num_rays=45, height_camera_view_pu=51), dict(num_rays=64, height_camera_view_pu=84)):
+        for fmt in ("rgb8", "xrgb32"):
+            env = rcw.BatchedSingleRoom(5, seed=2, obs_format=fmt, **kw)
+            env.step_random(7)
+            env.sync()
+            t = env.obs_tensor()
+            assert tuple(t.shape) == env.obs_shape
+            host = env.copy_obs()
+            dev = t.contiguous().cpu().numpy()
+            if fmt == "xrgb32":
+                dev = dev.view(np.uint32)
+            np.testing.assert_array_equal(dev, host)
+            es, cs, cbytes, bpp = env.obs_layout()
+            assert cs % 32 == 0 and es % 128 == 0 and cs >= cbytes and bpp == env.bytes_per_pixel
+            env.close()
+
+
+def test_range_errors(rcw):
+    env = rcw.BatchedSingleRoom(4, seed=1)
+    with pytest.raises(rcw.RcwError):
+        env.get_rays(3, 2)
+    with pytest.raises(rcw.RcwError):
+        env.copy_obs(-1, 1)
+    with pytest.raises(rcw.RcwError):
+        env.set_state(pos=np.full((4, 2), 99.0, np.float32))
+    with pytest.raises(rcw.RcwError):
+        env.set_state(dir_au=np.full(4, 128, np.int32))
+    with pytest.raises(rcw.RcwError):
+        env.reset(goal_ij=np.full((4, 2), 3))          # the three layout arrays go together
+    env.close()
+
+
 def test_create_errors(rcw):
     with pytest.raises(rcw.RcwError):
         rcw.BatchedSingleRoom(0)
