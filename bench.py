@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
-    ap.add_argument("--obs-format", choices=["rgb8", "xrgb32"], default="rgb8")
+    ap.add_argument("--obs-format", choices=["rgb8", "xrgb32", "gray8"], default="rgb8")
     ap.add_argument("--map", choices=["default", "large"], default="default",
                     help="default: 8x16 tiles / 128 directions; large: 64x64 / 256 (BASELINE config 5)")
     ap.add_argument("--rays", type=int, default=512, help="num_rays = observation width (default 512)")
@@ -278,9 +278,9 @@ def run_b200(args):
                "d2h_bytes_per_step": n * 5 + 32, "ms_per_step": 1e3 * dt / K,
                "note": "host actions in, host reward+done out, every step; observations stay in HBM"}
         Ko = max(1, min(K, 5))
-        obs_host = torch.empty(env.obs_shape, dtype=torch.uint8 if args.obs_format == "rgb8" else torch.int32)
+        obs_host = torch.empty(env.obs_shape, dtype=torch.int32 if args.obs_format == "xrgb32" else torch.uint8)
         obs_host = obs_host.pin_memory().numpy()
-        if args.obs_format != "rgb8":
+        if args.obs_format == "xrgb32":
             obs_host = obs_host.view(np.uint32)
         barrier()
         t0 = time.perf_counter()

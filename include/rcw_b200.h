@@ -48,7 +48,9 @@ typedef enum rcw_status {
  * the fastest index after the channel, so one ray's column is contiguous. */
 typedef enum rcw_obs_format {
     RCW_OBS_RGB8   = 0, /* uint8  [num_envs][num_rays columns][height_px][3]  (R,G,B bytes of the reference pixel) */
-    RCW_OBS_XRGB32 = 1  /* uint32 [num_envs][num_rays columns][height_px]     (bit-identical to the reference's UInt32 pixels) */
+    RCW_OBS_XRGB32 = 1, /* uint32 [num_envs][num_rays columns][height_px]     (bit-identical to the reference's UInt32 pixels) */
+    RCW_OBS_GRAY8  = 2  /* uint8  [num_envs][num_rays columns][height_px]     learner-facing: BT.601 luma of the reference
+                           pixel, (77 R + 150 G + 29 B + 128) >> 8; a third of the RGB8 write */
     /* dense on the host (rcw_copy_obs); on the device columns may be pitched, see rcw_obs_layout */
 } rcw_obs_format;
 

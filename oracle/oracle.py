@@ -299,6 +299,12 @@ class Batch:
             out[e] = self.world(e).obs_rgb8()
         return out
 
+    def obs_gray8(self):
+        """BT.601 luma of the reference pixels (the engine's learner-facing format, no reference counterpart)."""
+        c = self.obs_u32()
+        r, g, b = (c >> 16) & 255, (c >> 8) & 255, c & 255
+        return ((77 * r + 150 * g + 29 * b + 128) >> 8).astype(np.uint8)
+
     def obs_u32(self):
         out = np.empty((self.num_envs, self.cfg.R, self.cfg.P), np.uint32)
         for e in range(self.num_envs):

@@ -161,7 +161,16 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     volatile float two_s = 2.0f * c.semi_field_of_view_wu;
     p.hl_num = hl_num;
     p.two_s = two_s;
-    for (int i = 0; i < 6; ++i) p.palette[i] = c.palette[i] & 0x00FFFFFFu;
+    for (int i = 0; i < 6; ++i) {
+        const uint32_t col = c.palette[i] & 0x00FFFFFFu;
+        if (c.obs_format == RCW_OBS_GRAY8) {
+            // BT.601 luma of the reference pixel, replicated so the colour is "flat" for the renderer
+            const uint32_t y = (77u * ((col >> 16) & 255u) + 150u * ((col >> 8) & 255u) + 29u * (col & 255u) + 128u) >> 8;
+            p.palette[i] = y * 0x00010101u;
+        } else {
+            p.palette[i] = col;
+        }
+    }
     p.dir_slot = b->dir_slot;
     p.dirs = b->d_dirs;
     p.ray_table = b->d_ray_table;
@@ -350,7 +359,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // is kept as a measured alternative (profiles/): its per-lane UBLKCP issue serialises and its
     // 16-byte band edges leave partial sectors, so it is slower than the sector writer.
     b->bulk = false;
-    if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0;
+    if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0 && c.obs_format != RCW_OBS_GRAY8;
     if (const char* s = getenv("RCW_SPLIT")) b->split = atoi(s) != 0;
     RCW_CUDA(dev_alloc(b, &b->d_col_info, (size_t)E * (size_t)R));
     {
@@ -412,7 +421,7 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
         return fail(RCW_EINVAL, "num_rays and height_camera_view_pu must be positive");
     if (cfg->height_camera_view_pu > 32767)
         return fail(RCW_EINVAL, "height_camera_view_pu must be below 32768");
-    if (cfg->obs_format != RCW_OBS_RGB8 && cfg->obs_format != RCW_OBS_XRGB32)
+    if (cfg->obs_format != RCW_OBS_RGB8 && cfg->obs_format != RCW_OBS_XRGB32 && cfg->obs_format != RCW_OBS_GRAY8)
         return fail(RCW_EINVAL, "unknown obs_format %d", cfg->obs_format);
     if (cfg->num_envs < 1) return fail(RCW_EINVAL, "num_envs must be positive");
     if (!(cfg->player_radius_wu > 0.0f) || !(cfg->player_radius_wu < 0.5f))
@@ -420,7 +429,7 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
     if (!(cfg->semi_field_of_view_wu > 0.0f)) return fail(RCW_EINVAL, "semi_field_of_view_wu must be positive");
     if (cfg->dda_flags & ~(uint32_t)(RCW_DDA_TIE_LE | RCW_DDA_DIST_POST))
         return fail(RCW_EINVAL, "unknown dda_flags 0x%x", cfg->dda_flags);
-    const int bpp = cfg->obs_format == RCW_OBS_RGB8 ? 3 : 4;
+    const int bpp = cfg->obs_format == RCW_OBS_RGB8 ? 3 : (cfg->obs_format == RCW_OBS_XRGB32 ? 4 : 1);
     const int gpe = (cfg->num_rays + 31) / 32;
     if ((int64_t)cfg->num_rays * cfg->height_camera_view_pu * bpp >= (1LL << 30))
         return fail(RCW_ESIZE, "one observation must be smaller than 1 GiB");

@@ -203,6 +203,19 @@ struct PixelFormat<RCW_OBS_XRGB32> {
     }
 };
 
+// one byte per pixel; the palette handed to the kernel already holds the luma in all three bytes
+template <>
+struct PixelFormat<RCW_OBS_GRAY8> {
+    static constexpr int kBpp = 1;
+    __device__ static __forceinline__ uint32_t byte_of(uint32_t c, int) { return c & 0xFFu; }
+    __device__ static __forceinline__ bool is_flat(uint32_t) { return true; }
+    __device__ static __forceinline__ uint32_t flat_word(uint32_t c) { return (c & 0xFFu) * 0x01010101u; }
+    __device__ static __forceinline__ uint4 run16(uint32_t c, int) {
+        const uint32_t w = (c & 0xFFu) * 0x01010101u;
+        return make_uint4(w, w, w, w);
+    }
+};
+
 // One observation column: rows [0, pad) ceiling, [pad, P - pad) wall colour, [P - pad, P) floor
 // (single_room.jl:433-439; a full-height column is pad = 0).  In bytes: b1 = bpp * pad,
 // b2 = col_bytes - b1.
@@ -965,6 +978,7 @@ static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s
 
 template <int MODE, int STAGE>
 static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, bool bulk, int ctas, cudaStream_t s) {
+    if (obs_format == RCW_OBS_GRAY8) return launch_frame_t<MODE, RCW_OBS_GRAY8, false, STAGE>(p, ctas, s);
     if (obs_format == RCW_OBS_RGB8)
         return bulk ? launch_frame_t<MODE, RCW_OBS_RGB8, true, STAGE>(p, ctas, s)
                     : launch_frame_t<MODE, RCW_OBS_RGB8, false, STAGE>(p, ctas, s);

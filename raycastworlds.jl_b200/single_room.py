@@ -42,7 +42,7 @@ class BatchedSingleRoom(AbstractGame):
     """`num_envs` independent SingleRoom games advanced by one kernel launch per step.
 
     Keyword arguments are those of the reference constructor (single_room.jl:258-272); the
-    additional ones are `num_envs`, `device`, `obs_format` ("rgb8" | "xrgb32"), `auto_reset`,
+    additional ones are `num_envs`, `device`, `obs_format` ("rgb8" | "xrgb32" | "gray8"), `auto_reset`,
     `seed`, `env_id_offset` (global id of env 0 when a batch is sharded over GPUs),
     `directions_wu` (the host's own [N, 2] float32 direction table) and the two switches for the
     unpinned RayCaster.cast_ray decisions (`dda_tie_le`, `dda_dist_post`).
@@ -73,7 +73,7 @@ class BatchedSingleRoom(AbstractGame):
         cfg.semi_field_of_view_wu = float(np.float32(semi_field_of_view_wu))
         cfg.camera_height_tile_wu = float(np.float32(camera_height_tile_wu))
         cfg.goal_reward = float(np.float32(goal_reward))
-        fmt = {"rgb8": _capi.RCW_OBS_RGB8, "xrgb32": _capi.RCW_OBS_XRGB32}
+        fmt = {"rgb8": _capi.RCW_OBS_RGB8, "xrgb32": _capi.RCW_OBS_XRGB32, "gray8": _capi.RCW_OBS_GRAY8}
         if obs_format not in fmt:
             raise ValueError(f"obs_format must be one of {sorted(fmt)}")
         cfg.obs_format = fmt[obs_format]
@@ -93,7 +93,7 @@ class BatchedSingleRoom(AbstractGame):
         self.cfg = cfg
         self.num_envs = int(num_envs)
         self.obs_format = obs_format
-        self.bytes_per_pixel = 3 if obs_format == "rgb8" else 4
+        self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1}[obs_format]
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -237,6 +237,8 @@ class BatchedSingleRoom(AbstractGame):
         flat = torch.as_tensor(holder, device=torch.device("cuda", self.cfg.device))
         if self.obs_format == "rgb8":
             return torch.as_strided(flat, (self.num_envs, R, P, 3), (env_stride, col_stride, 3, 1))
+        if self.obs_format == "gray8":
+            return torch.as_strided(flat, (self.num_envs, R, P), (env_stride, col_stride, 1))
         words = flat.view(torch.int32)
         return torch.as_strided(words, (self.num_envs, R, P), (env_stride // 4, col_stride // 4, 1))
 
@@ -245,7 +247,7 @@ class BatchedSingleRoom(AbstractGame):
         n = self.num_envs - env0 if n is None else n
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
         shape = (n, R, P, 3) if self.obs_format == "rgb8" else (n, R, P)
-        dtype = np.uint8 if self.obs_format == "rgb8" else np.uint32
+        dtype = np.uint32 if self.obs_format == "xrgb32" else np.uint8
         if out is None:
             out = np.empty(shape, dtype)
         _capi.check(self._lib.rcw_copy_obs(self._h, env0, n, _ptr(out)))

@@ -358,12 +358,27 @@ def test_custom_palette_takes_the_phase_rotated_path(rcw, oracle, R, P, fmt):
     env.close()
 
 
+@pytest.mark.parametrize("R,P", [(512, 256), (84, 84), (33, 50)])
+def test_gray8_format_matches_oracle(rcw, oracle, R, P):
+    """Learner-facing one-byte format: luma of the reference pixel."""
+    n, seed = 12, 77
+    env = rcw.BatchedSingleRoom(n, seed=seed, num_rays=R, height_camera_view_pu=P, obs_format="gray8")
+    ref = oracle.Batch(n, cfg=oracle.default_config(R=R, P=P), seed=seed)
+    env.step_random(60)
+    ref.rollout(60, threads=4)
+    obs = env.copy_obs()
+    assert obs.shape == (n, R, P) and obs.dtype == np.uint8
+    np.testing.assert_array_equal(obs, ref.obs_gray8())
+    assert set(np.unique(obs).tolist()) <= {255, 64, 128, 192, 39, 58}
+    env.close()
+
+
 def test_device_tensor_view_matches_host_copy(rcw):
     """obs_tensor() is a zero-copy (possibly pitched) view of the same bytes copy_obs() returns."""
     import torch
 
     for kw in (dict(), dict(num_rays=45, height_camera_view_pu=51), dict(num_rays=64, height_camera_view_pu=84)):
-        for fmt in ("rgb8", "xrgb32"):
+        for fmt in ("rgb8", "xrgb32", "gray8"):
             env = rcw.BatchedSingleRoom(5, seed=2, obs_format=fmt, **kw)
             env.step_random(7)
             env.sync()
