@@ -565,6 +565,18 @@ __device__ __forceinline__ void store_stream32(uint8_t* p, uint4 lo, uint4 hi) {
                  : "memory");
 }
 
+// A sector with one band boundary n bytes in, when both bands are "flat" words (one byte repeated,
+// or whole 4-byte pixels with n a multiple of 4): bytes [0, n) from word a, [n, 32) from word b.
+__device__ __forceinline__ void store_split32(uint8_t* dst, uint32_t a, uint32_t b, int n) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t m = low_bytes_mask(n - 4 * k);
+        w[k] = (a & m) | (b & ~m);
+    }
+    store_stream32(dst, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+}
+
 // update_camera_view! stores (single_room.jl:431-439) for the 32 columns of one (env, ray group).
 // On entry s_col[k] = {b1 | slow << 31, colour word} for column k of the span (k = 0 is the lowest
 // address; ray r paints column R-1-r).  `item_slow`: some column of the span has a colour whose
@@ -642,8 +654,13 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
             uint8_t* const col = span + lane * CB;
             if (cb.b1 & 31) {
                 const int sa = cb.b1 & ~31, sb = cb.b2 & ~31;
-                store_stream32(col + sa, compose16<FMT>(cb, sa), compose16<FMT>(cb, sa + 16));
-                store_stream32(col + sb, compose16<FMT>(cb, sb), compose16<FMT>(cb, sb + 16));
+                if (!item_slow) {
+                    store_split32(col + sa, PixelFormat<FMT>::flat_word(ceil_c), info.y, cb.b1 - sa);
+                    store_split32(col + sb, info.y, PixelFormat<FMT>::flat_word(floor_c), cb.b2 - sb);
+                } else {
+                    store_stream32(col + sa, compose16<FMT>(cb, sa), compose16<FMT>(cb, sa + 16));
+                    store_stream32(col + sb, compose16<FMT>(cb, sb), compose16<FMT>(cb, sb + 16));
+                }
             }
         }
         return;
@@ -690,9 +707,14 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
         cb.wall = info.y & 0x00FFFFFFu;
         uint8_t* const col = span + lane * CP;
         const int sa = cb.b1 & ~31, sb = cb.b2 & ~31;
-        if (cb.b1 & 31) store_stream32(col + sa, compose16<FMT>(cb, sa), compose16<FMT>(cb, sa + 16));
-        if ((cb.b2 & 31) && (sb != sa || !(cb.b1 & 31)))
-            store_stream32(col + sb, compose16<FMT>(cb, sb), compose16<FMT>(cb, sb + 16));
+        if (!item_slow && sa != sb) {
+            if (cb.b1 & 31) store_split32(col + sa, PixelFormat<FMT>::flat_word(ceil_c), info.y, cb.b1 - sa);
+            if (cb.b2 & 31) store_split32(col + sb, info.y, PixelFormat<FMT>::flat_word(floor_c), cb.b2 - sb);
+        } else {
+            if (cb.b1 & 31) store_stream32(col + sa, compose16<FMT>(cb, sa), compose16<FMT>(cb, sa + 16));
+            if ((cb.b2 & 31) && (sb != sa || !(cb.b1 & 31)))
+                store_stream32(col + sb, compose16<FMT>(cb, sb), compose16<FMT>(cb, sb + 16));
+        }
     }
 }
 
