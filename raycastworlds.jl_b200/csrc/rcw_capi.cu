@@ -315,6 +315,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     b->sm_count = prop.multiProcessorCount;
     RCW_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     if (const char* s = getenv("RCW_CTAS_PER_SM")) b->ctas_per_sm = atoi(s);
+    else b->ctas_per_sm = -1;   // decided below, once the observation geometry is known
 
     // ---- direction table (single_room.jl:65-69) -------------------------------------------
     std::vector<float2> dirs((size_t)N);
@@ -399,6 +400,10 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // every column starts on a 32-byte sector, every env on a 128-byte line (see rcw_obs_layout)
     b->col_pitch = (P * b->bpp + 31) & ~31;
     b->obs_env_stride = (((size_t)R * b->col_pitch) + 127) & ~(size_t)127;
+    // Grid shape.  Large items (a warp's 32 columns >= 12 KB): one CTA per 8 items, the hardware
+    // scheduler balances the tail (measured best, profiles/README.md).  Small items: a grid capped at
+    // 12 CTAs per SM that loops, which amortises the per-CTA prologue (+8 % at 64x64 px).
+    if (b->ctas_per_sm < 0) b->ctas_per_sm = (32 * b->col_pitch <= 12288) ? 12 : 0;
     b->obs_bytes = b->obs_env_stride * (size_t)E;
     RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, false));
     return RCW_OK;

@@ -394,6 +394,27 @@ def test_device_tensor_view_matches_host_copy(rcw):
             env.close()
 
 
+def test_looping_grid_matches_oracle(rcw, oracle, monkeypatch):
+    """Small items run on a capped grid whose CTAs loop over several rounds of eight items (shared
+    act! pose double-buffered across rounds).  Force one CTA per SM so that 700 envs x 3 groups need
+    two rounds, with env boundaries inside CTAs and a ragged last group."""
+    monkeypatch.setenv("RCW_CTAS_PER_SM", "1")
+    n, seed, R, P = 700, 13, 80, 40
+    env = rcw.BatchedSingleRoom(n, seed=seed, num_rays=R, height_camera_view_pu=P)
+    ref = oracle.Batch(n, cfg=oracle.default_config(R=R, P=P), seed=seed)
+    for _ in range(2):
+        env.step_random(60)
+        ref.rollout(60, threads=4)
+        st = env.get_state()
+        pos, au, goal = ref.states()
+        np.testing.assert_array_equal(bits(st["pos"]), bits(pos))
+        np.testing.assert_array_equal(st["dir_au"], au)
+        np.testing.assert_array_equal(st["goal"], goal)
+        np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    assert env.episode_stats() == ref.episode_stats()
+    env.close()
+
+
 def test_range_errors(rcw):
     env = rcw.BatchedSingleRoom(4, seed=1)
     with pytest.raises(rcw.RcwError):
