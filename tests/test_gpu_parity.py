@@ -482,3 +482,64 @@ def test_full_size_properties(rcw, oracle):
     np.testing.assert_array_equal(sub.copy_obs(), ref.obs_rgb8())
     sub.close()
     env.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs at their full sizes
+# ------------------------------------------------------------------------------------------------
+
+def test_config1_single_env_10k_random_steps(rcw, oracle):
+    """configs[0]: one default SingleRoom, reset + 10,000 uniformly random act! steps with the camera
+    view rendered every step.  Reward and termination are compared at every step, the UInt32 camera
+    view (the reference's own pixel format) every 250 steps; no auto-reset, like the reference."""
+    env = rcw.SingleRoom(seed=4)
+    ref = oracle.Batch(1, seed=4, auto_reset=False)
+    rng = np.random.default_rng(10)
+    actions = rng.integers(1, 5, 10_000)
+    n_done = 0
+    for t, a in enumerate(actions):
+        env.act(int(a))
+        assert ref.step(np.array([a], np.uint8)) == 0
+        r, d = env.reward_done()
+        rr, rd = ref.reward_done()
+        assert r[0] == rr[0] and d[0] == rd[0]
+        n_done += int(d[0])
+        if t % 250 == 249:
+            np.testing.assert_array_equal(env.camera_view, ref.world(0).camera_view.T)
+            st = env.get_state()
+            assert bits(st["pos"]).tolist() == bits(ref.states()[0]).tolist()
+    env.close()
+
+
+def _sampled_shards_match_oracle(rcw, oracle, env, kw_oracle, n_total, seed, steps, starts, width=8):
+    for s0 in starts:
+        ref = oracle.Batch(width, cfg=oracle.default_config(**kw_oracle), seed=seed, env_id_offset=s0)
+        ref.rollout(steps, threads=4)
+        np.testing.assert_array_equal(env.copy_obs(s0, width), ref.obs_rgb8())
+        pos, au, goal = ref.states()
+        st = env.get_state()
+        np.testing.assert_array_equal(bits(st["pos"][s0:s0 + width]), bits(pos))
+        np.testing.assert_array_equal(st["goal"][s0:s0 + width], goal)
+
+
+def test_config4_65536_envs_sampled_against_oracle(rcw, oracle):
+    """configs[3]: 65,536 envs at 512 rays x 256 px (25.8 GB of observations per step).  Windows of
+    eight envs spread over the batch, including both ends, are replayed by the oracle."""
+    n, seed, steps = 65536, 0x5EED, 12
+    env = rcw.BatchedSingleRoom(n, seed=seed)
+    env.step_random(steps)
+    _sampled_shards_match_oracle(rcw, oracle, env, {}, n, seed, steps, [0, 4093, 32768, 50001, n - 8])
+    ep, sr, sl = env.episode_stats()
+    assert sr == float(ep) and sl >= ep          # every finished episode returned goal_reward = 1
+    env.close()
+
+
+def test_config5_262144_envs_large_map_sampled_against_oracle(rcw, oracle):
+    """configs[4]: 262,144 envs on 64x64 tile maps with 256 directions (103 GB of observations)."""
+    n, seed, steps = 262144, 5, 6
+    kw = dict(height_tile_map_tu=64, width_tile_map_tu=64, num_directions=256)
+    env = rcw.BatchedSingleRoom(n, seed=seed, **kw)
+    env.step_random(steps)
+    _sampled_shards_match_oracle(rcw, oracle, env, dict(H=64, W=64, N=256), n, seed, steps,
+                                 [0, 131071, n - 8])
+    env.close()
