@@ -415,6 +415,44 @@ def test_looping_grid_matches_oracle(rcw, oracle, monkeypatch):
     env.close()
 
 
+def test_direction_table_fallbacks_match_oracle(rcw, oracle):
+    """The direction table normally sits in one of 8 constant-memory slots of 512 entries; more
+    handles than slots, or more directions than a slot holds, read it from global memory instead."""
+    seed = 41
+    handles = [rcw.BatchedSingleRoom(3, seed=seed + k, num_rays=64, height_camera_view_pu=32) for k in range(11)]
+    for k, env in enumerate(handles):
+        env.step_random(25)
+        ref = oracle.Batch(3, cfg=oracle.default_config(R=64, P=32), seed=seed + k)
+        ref.rollout(25)
+        np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    for env in handles:
+        env.close()
+    env = rcw.BatchedSingleRoom(4, seed=seed, num_directions=600, num_rays=64, height_camera_view_pu=32)
+    ref = oracle.Batch(4, cfg=oracle.default_config(N=600, R=64, P=32), seed=seed)
+    env.step_random(80)
+    ref.rollout(80)
+    np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    np.testing.assert_array_equal(env.get_state()["dir_au"], ref.states()[1])
+    env.close()
+
+
+def test_wide_map_and_large_env_ids_match_oracle(rcw, oracle):
+    """A 40 x 100 tile map (four 32-bit words per bit-packed row) and global env ids above 2^32
+    (the high counter word of the Philox streams)."""
+    n, seed, off = 10, 3, (1 << 33) + 5
+    kw = dict(height_tile_map_tu=40, width_tile_map_tu=100, num_rays=96, height_camera_view_pu=64)
+    env = rcw.BatchedSingleRoom(n, seed=seed, env_id_offset=off, **kw)
+    ref = oracle.Batch(n, cfg=oracle.default_config(H=40, W=100, R=96, P=64), seed=seed, env_id_offset=off)
+    env.step_random(150)
+    ref.rollout(150, threads=4)
+    st = env.get_state()
+    pos, au, goal = ref.states()
+    np.testing.assert_array_equal(bits(st["pos"]), bits(pos))
+    np.testing.assert_array_equal(st["goal"], goal)
+    np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    env.close()
+
+
 def test_range_errors(rcw):
     env = rcw.BatchedSingleRoom(4, seed=1)
     with pytest.raises(rcw.RcwError):
