@@ -5,15 +5,17 @@
 // (reference: src/single_room.jl:139-191, 195-231, 374-444; collision_detection.jl:9-42).
 //
 // Mapping.  A work item is (env, group of 32 consecutive rays) and belongs to one warp:
-// lane <-> ray for the DDA, then all 32 lanes stream the group's 32 observation columns,
-// which are contiguous in memory (ray i paints column R-i+1, single_room.jl:431), with
-// 16-byte stores.  The eight warps of a CTA take eight consecutive items, so a CTA writes one
-// contiguous span of the observation buffer.  The path is bound by HBM writes (393 KB per
-// env-step at the default resolution versus a few hundred bytes of state), so everything else
-// is arranged to keep the store stream dense: the shared wall layer is staged once per CTA into
-// shared memory with a TMA bulk copy, the per-(direction, ray) table {ray, |1/ray|} is read with
-// one coalesced 16-byte load per lane from an L2-resident table, and act!/auto-reset are
-// recomputed by every warp of an env from double-buffered state instead of synchronising.
+// lane <-> ray for the DDA, then all 32 lanes stream the group's 32 observation columns, which
+// are contiguous in memory (ray i paints column R-i+1, single_room.jl:431), in whole 32-byte
+// sectors with 256-bit stores.  The eight warps of a CTA take eight consecutive items, so a CTA
+// writes one contiguous span of the observation buffer.  The path is bound by HBM writes (393 KB
+// per env-step at the default resolution versus a few hundred bytes of state), so everything else
+// is arranged to keep the store stream dense and complete: the wall layer is staged into shared
+// memory with TMA bulk copies (once per CTA when the batch shares it, once per env otherwise),
+// the per-(direction, ray) table {ray, |1/ray|} is read with one coalesced 16-byte load per lane
+// from an L2-resident table (prefetched for the three directions the env can face next), act! /
+// auto-reset run once per env of a CTA and reach the other warps through shared memory, and the
+// state they read is double-buffered so that the warps of an env in other CTAs never race.
 //
 // Arithmetic.  Every binary32 operation that the reference performs is written with an explicit
 // round-to-nearest intrinsic (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn), which the compiler
@@ -737,7 +739,7 @@ __device__ __forceinline__ uint2 column_entry(const FrameParams& p, int pad, int
 // Front + Paint is the same step split in two launches: the latency-bound part runs without a
 // saturated store queue in front of its loads, and the store stream runs without waiting on it.
 // BULK (fused / paint): bands written as TMA bulk stores out of single-colour pattern buffers in
-// shared memory; otherwise every 16-byte vector is written by the lanes with st.global.v4.
+// shared memory (measured alternative, slower); otherwise the lanes write whole 32-byte sectors.
 enum : int { kStageFused = 0, kStageFront = 1, kStagePaint = 2 };
 
 template <int MODE, int FMT, bool BULK, int STAGE>
