@@ -453,6 +453,43 @@ def test_wide_map_and_large_env_ids_match_oracle(rcw, oracle):
     env.close()
 
 
+def test_two_host_threads_drive_two_handles(rcw, oracle):
+    """Threading contract of the ABI: distinct handles may be driven concurrently from different host
+    threads (each has its own stream); results are those of the sequential oracle."""
+    import threading
+
+    results, errors = {}, []
+
+    def worker(k):
+        try:
+            env = rcw.BatchedSingleRoom(48, seed=100 + k, num_rays=128, height_camera_view_pu=64)
+            rng = np.random.default_rng(k)
+            acts = rng.integers(1, 5, size=(120, 48)).astype(np.uint8)
+            for t in range(120):
+                env.act(acts[t])
+                if t % 7 == 0:
+                    env.reward_done()
+            results[k] = (acts, env.copy_obs(), env.get_state(), env.episode_stats())
+            env.close()
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(2):
+        acts, obs, st, stats = results[k]
+        ref = oracle.Batch(48, cfg=oracle.default_config(R=128, P=64), seed=100 + k)
+        for t in range(120):
+            assert ref.step(acts[t]) == 0
+        np.testing.assert_array_equal(obs, ref.obs_rgb8())
+        np.testing.assert_array_equal(bits(st["pos"]), bits(ref.states()[0]))
+        assert stats == ref.episode_stats()
+
+
 def test_range_errors(rcw):
     env = rcw.BatchedSingleRoom(4, seed=1)
     with pytest.raises(rcw.RcwError):
