@@ -121,6 +121,8 @@ struct rcw_batch {
     cudaEvent_t h_actions_free[kActionRing]{};
     int ring = 0;
     DeviceStats* h_stats = nullptr;  // pinned
+    uint8_t* h_reward_done = nullptr; // pinned staging: reward f32[E] followed by done u8[E]
+    bool device_actions_pending = false;  // a device-side action array was used since the last check
     // counters
     uint64_t step_index = 0;
     int64_t launches = 0;
@@ -227,15 +229,21 @@ static int32_t check_handle(const rcw_batch* b) {
 }
 
 // blocks, then reports (and clears) a device-side invalid-action flag
-static int32_t sync_and_check(rcw_batch* b) {
-    RCW_CUDA(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost,
-                             b->stream));
+static int32_t sync_and_check(rcw_batch* b, bool need_stats = false) {
+    // the stats block is only fetched when somebody needs it: the caller, or a device-side action
+    // array whose values could not be validated on the host
+    const bool fetch = need_stats || b->device_actions_pending;
+    if (fetch)
+        RCW_CUDA(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost,
+                                 b->stream));
     RCW_CUDA(cudaStreamSynchronize(b->stream));
-    if (b->h_stats->bad_action) {
+    if (fetch && b->h_stats->bad_action) {
         RCW_CUDA(cudaMemsetAsync(&b->d_stats->bad_action, 0, sizeof(int), b->stream));
+        b->device_actions_pending = false;
         return fail(RCW_EACTION, "a device-side action array held a value outside 1..4; "
                                  "the affected envs were not stepped");
     }
+    if (fetch) b->device_actions_pending = false;
     return RCW_OK;
 }
 
@@ -297,6 +305,7 @@ int32_t rcw_destroy(rcw_batch* b) {
         if (b->h_actions_free[i]) cudaEventDestroy(b->h_actions_free[i]);
     }
     if (b->h_stats) cudaFreeHost(b->h_stats);
+    if (b->h_reward_done) cudaFreeHost(b->h_reward_done);
     if (b->stream) cudaStreamDestroy(b->stream);
     release_dir_slot(b->device, b->dir_slot);
     cudaGetLastError();
@@ -384,8 +393,12 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
         RCW_CUDA(dev_alloc(b, &b->st[k].goal, (size_t)E));
         RCW_CUDA(dev_alloc(b, &b->st[k].episode, (size_t)E));
     }
-    RCW_CUDA(dev_alloc(b, &b->d_reward, (size_t)E));
-    RCW_CUDA(dev_alloc(b, &b->d_done, (size_t)E));
+    {   // reward f32[E] and done u8[E] share one allocation so that both reach the host in one copy
+        uint8_t* rd = nullptr;
+        RCW_CUDA(dev_alloc(b, &rd, (size_t)E * 5));
+        b->d_reward = reinterpret_cast<float*>(rd);
+        b->d_done = rd + (size_t)E * 4;
+    }
     RCW_CUDA(dev_alloc(b, &b->d_ep_return, (size_t)E));
     RCW_CUDA(dev_alloc(b, &b->d_ep_length, (size_t)E));
     RCW_CUDA(dev_alloc(b, &b->d_stats, 1));
@@ -395,6 +408,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
         RCW_CUDA(cudaEventCreateWithFlags(&b->h_actions_free[i], cudaEventDisableTiming));
     }
     RCW_CUDA(cudaMallocHost((void**)&b->h_stats, sizeof(DeviceStats)));
+    RCW_CUDA(cudaMallocHost((void**)&b->h_reward_done, (size_t)E * 5));
 
     // ---- observations ---------------------------------------------------------------------------
     // every column starts on a 32-byte sector, every env on a 128-byte line (see rcw_obs_layout)
@@ -617,7 +631,10 @@ int32_t rcw_step(rcw_batch* b, const uint8_t* actions) {
     if (pe != cudaSuccess) cudaGetLastError();
     const bool on_device = pe == cudaSuccess &&
                            (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
-    if (on_device) return enqueue_frame(b, kModeStep, actions);
+    if (on_device) {
+        b->device_actions_pending = true;
+        return enqueue_frame(b, kModeStep, actions);
+    }
 
     // host array: validate (the reference's @assert, single_room.jl:140) while staging into pinned memory
     const int slot = b->ring;
@@ -669,9 +686,11 @@ int32_t rcw_get_state(rcw_batch* b, float* pos_xy, int32_t* dir_au, int32_t* goa
         goal.resize(E);
         RCW_CUDA(cudaMemcpyAsync(goal.data(), s.goal, sizeof(uint32_t) * E, cudaMemcpyDeviceToHost, b->stream));
     }
-    if (reward) RCW_CUDA(cudaMemcpyAsync(reward, b->d_reward, sizeof(float) * E, cudaMemcpyDeviceToHost, b->stream));
-    if (done) RCW_CUDA(cudaMemcpyAsync(done, b->d_done, E, cudaMemcpyDeviceToHost, b->stream));
+    if (reward || done)
+        RCW_CUDA(cudaMemcpyAsync(b->h_reward_done, b->d_reward, E * 5, cudaMemcpyDeviceToHost, b->stream));
     if (int32_t rc = sync_and_check(b)) return rc;
+    if (reward) memcpy(reward, b->h_reward_done, sizeof(float) * E);
+    if (done) memcpy(done, b->h_reward_done + E * 4, E);
     if (pos_xy)
         for (size_t e = 0; e < E; ++e) {
             pos_xy[2 * e] = px[e];
@@ -819,7 +838,7 @@ int32_t rcw_episode_stats(rcw_batch* b, int64_t* episodes, double* sum_return, i
                           int32_t reset_counters) {
     if (int32_t rc = check_handle(b)) return rc;
     DeviceGuard g(b->device);
-    if (int32_t rc = sync_and_check(b)) return rc;
+    if (int32_t rc = sync_and_check(b, /*need_stats=*/true)) return rc;
     if (episodes) *episodes = (int64_t)b->h_stats->episodes;
     if (sum_return) *sum_return = b->h_stats->sum_return;
     if (sum_length) *sum_length = (int64_t)b->h_stats->sum_length;
