@@ -242,6 +242,13 @@ class BatchedSingleRoom(AbstractGame):
         words = flat.view(torch.int32)
         return torch.as_strided(words, (self.num_envs, R, P), (env_stride // 4, col_stride // 4, 1))
 
+    def obs_tensor_nchw(self):
+        """The same buffer as a [N, C, num_rays, height_px] torch view for convolutional learners: the
+        image is presented transposed (camera columns along torch's "height"), which is exactly torch's
+        channels_last memory format whenever the columns are not pitched — no copy, no permute kernel."""
+        t = self.obs_tensor()
+        return t.permute(0, 3, 1, 2) if self.obs_format == "rgb8" else t.unsqueeze(1)
+
     def copy_obs(self, env0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None):
         """Blocking device->host copy of the observations of envs [env0, env0+n)."""
         n = self.num_envs - env0 if n is None else n

@@ -490,6 +490,28 @@ def test_two_host_threads_drive_two_handles(rcw, oracle):
         assert stats == ref.episode_stats()
 
 
+def test_learner_view_is_channels_last_and_feeds_a_conv(rcw):
+    """obs_tensor_nchw(): zero-copy NCHW view in channels_last format, consumable by torch convs."""
+    import torch
+
+    env = rcw.BatchedSingleRoom(6, seed=8)
+    env.step_random(5)
+    env.sync()
+    x = env.obs_tensor_nchw()
+    assert tuple(x.shape) == (6, 3, 512, 256)
+    assert x.is_contiguous(memory_format=torch.channels_last)
+    assert x.data_ptr() == env.obs_device_ptr()[0]
+    host = env.copy_obs()                                    # [N, R, P, 3]
+    np.testing.assert_array_equal(x.cpu().numpy(), host.transpose(0, 3, 1, 2))
+    conv = torch.nn.Conv2d(3, 4, 3, padding=1).cuda().to(memory_format=torch.channels_last)
+    y = conv(x.float() / 255)
+    assert tuple(y.shape) == (6, 4, 512, 256) and torch.isfinite(y).all()
+    g = rcw.BatchedSingleRoom(2, seed=8, obs_format="gray8")
+    assert tuple(g.obs_tensor_nchw().shape) == (2, 1, 512, 256) and g.obs_tensor_nchw().is_contiguous()
+    g.close()
+    env.close()
+
+
 def test_range_errors(rcw):
     env = rcw.BatchedSingleRoom(4, seed=1)
     with pytest.raises(rcw.RcwError):
