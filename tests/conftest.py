@@ -14,6 +14,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run under gpurun")
 
 
+def pytest_sessionstart(session):
+    """The CUDA library is a build artefact (git-ignored): compile it with nvcc if it is missing, so
+    that a fresh checkout can run the suite.  No GPU is needed to build."""
+    lib = os.path.join(ROOT, "raycastworlds.jl_b200", "lib", "librcw_b200.so")
+    if not os.path.exists(lib):
+        import importlib.util as u
+
+        spec = u.spec_from_file_location("_rcw_build", os.path.join(ROOT, "raycastworlds.jl_b200", "build.py"))
+        mod = u.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build(force=True)
+
+
 @pytest.fixture(scope="session")
 def golden():
     path = os.path.join(ROOT, "tests", "golden", "singleroom_golden.npz")
