@@ -95,6 +95,7 @@ struct rcw_batch {
     int ctas_per_sm = 0;          // 0: one CTA per 8 items; >0: persistent grid of sm_count * this
     bool bulk = false;            // renderer: TMA bulk stores of whole bands (true) or per-lane vector stores
     bool split = false;           // one env-step = front launch + paint launch (true) or one fused launch
+    bool occ4 = false;            // fused kernel variant compiled for 4 CTAs per SM (front-bound steps)
     uint32_t* d_col_info = nullptr;
     int pat_stride = 0;
     uint8_t* d_patterns = nullptr;
@@ -214,7 +215,8 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
     FrameParams p;
     fill_frame_params(b, p);
     p.actions = d_actions;
-    RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, b->bulk, b->split, grid_for(b, p.env_count), b->stream));
+    const LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, p.env_count)};
+    RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream));
     b->launches += b->split ? 2 : 1;
     if (mode == kModeStep) {
         b->cur ^= 1;
@@ -414,10 +416,15 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // every column starts on a 32-byte sector, every env on a 128-byte line (see rcw_obs_layout)
     b->col_pitch = (P * b->bpp + 31) & ~31;
     b->obs_env_stride = (((size_t)R * b->col_pitch) + 127) & ~(size_t)127;
-    // Grid shape.  Large items (a warp's 32 columns >= 12 KB): one CTA per 8 items, the hardware
-    // scheduler balances the tail (measured best, profiles/README.md).  Small items: a grid capped at
-    // 12 CTAs per SM that loops, which amortises the per-CTA prologue (+8 % at 64x64 px).
-    if (b->ctas_per_sm < 0) b->ctas_per_sm = (32 * b->col_pitch <= 12288) ? 12 : 0;
+    // Grid shape: one CTA per 8 items and the hardware scheduler balances the tail (measured best once
+    // the register budget below is chosen per geometry; RCW_CTAS_PER_SM > 0 caps the grid and loops).
+    if (b->ctas_per_sm < 0) b->ctas_per_sm = 0;
+    // Register budget.  When a warp's item is small (< 20 KB: small or medium frames, one-byte pixels) or
+    // the map is large (long DDA walks), act! + DDA bound the step and 4 CTAs per SM hide their latency
+    // better (+6..14 %); when the store stream bounds it (default camera), 3 CTAs per SM with more
+    // registers are 2 % faster (profiles/README.md).
+    b->occ4 = (32 * b->col_pitch < 20000) || ((int64_t)H * W >= 1024);
+    if (const char* s = getenv("RCW_OCC")) b->occ4 = atoi(s) == 4;
     b->obs_bytes = b->obs_env_stride * (size_t)E;
     RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, false));
     return RCW_OK;
@@ -778,7 +785,8 @@ int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int
     p.dump_dim = d_dim;
     p.dump_dist = d_dist;
     p.dump_dir = d_dir;
-    cudaError_t e = launch_frame(p, kModeRays, b->cfg.obs_format, false, false, grid_for(b, n), b->stream);
+    const LaunchShape sh{false, false, false, grid_for(b, n)};
+    cudaError_t e = launch_frame(p, kModeRays, b->cfg.obs_format, sh, b->stream);
     b->launches += 1;
     if (e == cudaSuccess && hit_ij) e = cudaMemcpyAsync(hit_ij, d_hit, cnt * 8, cudaMemcpyDeviceToHost, b->stream);
     if (e == cudaSuccess && hit_dim) e = cudaMemcpyAsync(hit_dim, d_dim, cnt * 4, cudaMemcpyDeviceToHost, b->stream);

@@ -12,7 +12,7 @@ namespace rcw {
 #define RCW_WARPS_PER_CTA 8
 #endif
 #ifndef RCW_MIN_CTAS_PER_SM
-#define RCW_MIN_CTAS_PER_SM 3   // 80 registers per thread: measured best (2 and 4 CTAs per SM are slower)
+#define RCW_MIN_CTAS_PER_SM 3   // 80 registers per thread: best for store-bound steps (LaunchShape::occ4 otherwise)
 #endif
 #ifndef RCW_DDA_STEPS_PER_VOTE
 #define RCW_DDA_STEPS_PER_VOTE 2
@@ -129,8 +129,14 @@ struct ResetParams {
 // kernel launchers (rcw_kernels.cu)
 cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov, float4* table,
                                    cudaStream_t s);
-cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, bool bulk, bool split, int ctas,
-                         cudaStream_t s);
+// how a frame launch is shaped (decided per handle in rcw_capi.cu)
+struct LaunchShape {
+    bool bulk;    // renderer variant: per-lane TMA bulk stores (measured alternative)
+    bool split;   // two launches (front, paint) instead of the fused kernel (measured alternative)
+    bool occ4;    // fused kernel compiled for 4 CTAs per SM (steps bound by act! / DDA rather than by stores)
+    int ctas;     // grid size
+};
+cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);
 cudaError_t upload_dir_slot(int slot, const float2* host_dirs, int n, cudaStream_t s);
 

@@ -742,8 +742,11 @@ __device__ __forceinline__ uint2 column_entry(const FrameParams& p, int pad, int
 // shared memory (measured alternative, slower); otherwise the lanes write whole 32-byte sectors.
 enum : int { kStageFused = 0, kStageFront = 1, kStagePaint = 2 };
 
-template <int MODE, int FMT, bool BULK, int STAGE>
-__global__ void __launch_bounds__(kThreadsPerCta, RCW_MIN_CTAS_PER_SM)
+// OCC = CTAs per SM the register allocation aims for.  3 (80 registers) is best when the step is bound by
+// the store stream (default camera, RGB8 / XRGB32); 4 (60 registers) is 6-9 % faster when act! and the
+// DDA bound it (small frames, one-byte pixels, large maps) — profiles/README.md.
+template <int MODE, int FMT, bool BULK, int STAGE, int OCC>
+__global__ void __launch_bounds__(kThreadsPerCta, OCC)
 frame_kernel(const __grid_constant__ FrameParams p) {
     extern __shared__ __align__(128) uint32_t s_dyn[];  // [pattern buffers (BULK)] [bit-packed wall layer]
     __shared__ __align__(8) uint64_t s_mbar;
@@ -986,43 +989,56 @@ cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov,
     return cudaGetLastError();
 }
 
-template <int MODE, int FMT, bool BULK, int STAGE>
+template <int MODE, int FMT, bool BULK, int STAGE, int OCC>
 static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s) {
     const bool casts = STAGE != kStagePaint, paints = STAGE != kStageFront && MODE != kModeRays;
     const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;   // per-env wall layers: one slot per env of a round
     const size_t smem = (casts ? map_slots * (size_t)p.map_words * 4 : 0) + ((BULK && paints) ? 6 * (size_t)p.pat_stride : 0);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(frame_kernel<MODE, FMT, BULK, STAGE>,
+        cudaError_t e = cudaFuncSetAttribute(frame_kernel<MODE, FMT, BULK, STAGE, OCC>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    frame_kernel<MODE, FMT, BULK, STAGE><<<ctas, kThreadsPerCta, smem, s>>>(p);
+    frame_kernel<MODE, FMT, BULK, STAGE, OCC><<<ctas, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
 
+constexpr int kOcc = RCW_MIN_CTAS_PER_SM;
+
+// the shipped path (fused stage, lane-written sectors) exists for both register budgets
+template <int MODE, int FMT>
+static cudaError_t launch_fused(const FrameParams& p, const LaunchShape& sh, cudaStream_t s) {
+    return sh.occ4 ? launch_frame_t<MODE, FMT, false, kStageFused, 4>(p, sh.ctas, s)
+                   : launch_frame_t<MODE, FMT, false, kStageFused, kOcc>(p, sh.ctas, s);
+}
+
 template <int MODE, int STAGE>
-static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, bool bulk, int ctas, cudaStream_t s) {
-    if (obs_format == RCW_OBS_GRAY8) return launch_frame_t<MODE, RCW_OBS_GRAY8, false, STAGE>(p, ctas, s);
+static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, const LaunchShape& sh, cudaStream_t s) {
+    if (STAGE == kStageFused && !sh.bulk) {
+        if (obs_format == RCW_OBS_GRAY8) return launch_fused<MODE, RCW_OBS_GRAY8>(p, sh, s);
+        if (obs_format == RCW_OBS_RGB8) return launch_fused<MODE, RCW_OBS_RGB8>(p, sh, s);
+        return launch_fused<MODE, RCW_OBS_XRGB32>(p, sh, s);
+    }
+    if (obs_format == RCW_OBS_GRAY8) return launch_frame_t<MODE, RCW_OBS_GRAY8, false, STAGE, kOcc>(p, sh.ctas, s);
     if (obs_format == RCW_OBS_RGB8)
-        return bulk ? launch_frame_t<MODE, RCW_OBS_RGB8, true, STAGE>(p, ctas, s)
-                    : launch_frame_t<MODE, RCW_OBS_RGB8, false, STAGE>(p, ctas, s);
-    return bulk ? launch_frame_t<MODE, RCW_OBS_XRGB32, true, STAGE>(p, ctas, s)
-                : launch_frame_t<MODE, RCW_OBS_XRGB32, false, STAGE>(p, ctas, s);
+        return sh.bulk ? launch_frame_t<MODE, RCW_OBS_RGB8, true, STAGE, kOcc>(p, sh.ctas, s)
+                       : launch_frame_t<MODE, RCW_OBS_RGB8, false, STAGE, kOcc>(p, sh.ctas, s);
+    return sh.bulk ? launch_frame_t<MODE, RCW_OBS_XRGB32, true, STAGE, kOcc>(p, sh.ctas, s)
+                   : launch_frame_t<MODE, RCW_OBS_XRGB32, false, STAGE, kOcc>(p, sh.ctas, s);
 }
 
 // split = false: one fused launch.  split = true: two launches (front, then paint) through p.col_info.
-cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, bool bulk, bool split, int ctas,
-                         cudaStream_t s) {
-    if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused>(p, ctas, s);
+cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s) {
+    if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc>(p, sh.ctas, s);
     if (mode != kModeStep && mode != kModeRender) return cudaErrorInvalidValue;
-    if (!split)
-        return mode == kModeStep ? launch_frame_m<kModeStep, kStageFused>(p, obs_format, bulk, ctas, s)
-                                 : launch_frame_m<kModeRender, kStageFused>(p, obs_format, bulk, ctas, s);
+    if (!sh.split)
+        return mode == kModeStep ? launch_frame_m<kModeStep, kStageFused>(p, obs_format, sh, s)
+                                 : launch_frame_m<kModeRender, kStageFused>(p, obs_format, sh, s);
     cudaError_t e = mode == kModeStep
-                        ? launch_frame_t<kModeStep, RCW_OBS_RGB8, false, kStageFront>(p, ctas, s)
-                        : launch_frame_t<kModeRender, RCW_OBS_RGB8, false, kStageFront>(p, ctas, s);
+                        ? launch_frame_t<kModeStep, RCW_OBS_RGB8, false, kStageFront, kOcc>(p, sh.ctas, s)
+                        : launch_frame_t<kModeRender, RCW_OBS_RGB8, false, kStageFront, kOcc>(p, sh.ctas, s);
     if (e != cudaSuccess) return e;
-    return launch_frame_m<kModeRender, kStagePaint>(p, obs_format, bulk, ctas, s);
+    return launch_frame_m<kModeRender, kStagePaint>(p, obs_format, sh, s);
 }
 
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s) {
