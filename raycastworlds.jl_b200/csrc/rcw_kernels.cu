@@ -1012,6 +1012,7 @@ static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s
     }
     frame_kernel<MODE, FMT, BULK, STAGE, OCC><<<ctas, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
+
 }
 
 constexpr int kOcc = RCW_MIN_CTAS_PER_SM;
