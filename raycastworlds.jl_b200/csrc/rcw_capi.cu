@@ -95,7 +95,7 @@ struct rcw_batch {
     int ctas_per_sm = 0;          // 0: one CTA per 8 items; >0: persistent grid of sm_count * this
     bool bulk = false;            // renderer: TMA bulk stores of whole bands (true) or per-lane vector stores
     bool split = false;           // one env-step = front launch + paint launch (true) or one fused launch
-    bool occ4 = false;            // fused kernel variant compiled for 4 CTAs per SM (front-bound steps)
+    bool occ4 = false;            // fused kernel variant compiled for 32 instead of 24 warps per SM (front-bound steps)
     uint32_t* d_col_info = nullptr;
     int pat_stride = 0;
     uint8_t* d_patterns = nullptr;

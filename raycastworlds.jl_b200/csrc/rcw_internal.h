@@ -9,10 +9,13 @@
 namespace rcw {
 
 #ifndef RCW_WARPS_PER_CTA
-#define RCW_WARPS_PER_CTA 8
+#define RCW_WARPS_PER_CTA 4
 #endif
-#ifndef RCW_MIN_CTAS_PER_SM
-#define RCW_MIN_CTAS_PER_SM 3   // 80 registers per thread: best for store-bound steps (LaunchShape::occ4 otherwise)
+#ifndef RCW_WARPS_PER_SM_LO
+#define RCW_WARPS_PER_SM_LO 24   // register budget of the store-bound variant: 24 warps/SM, <= 85 registers
+#endif
+#ifndef RCW_WARPS_PER_SM_HI
+#define RCW_WARPS_PER_SM_HI 32   // register budget of the front-bound variant (LaunchShape::occ4): <= 64 registers
 #endif
 #ifndef RCW_DDA_STEPS_PER_VOTE
 #define RCW_DDA_STEPS_PER_VOTE 2
@@ -23,8 +26,11 @@ namespace rcw {
 #ifndef RCW_PASS1_UNROLL
 #define RCW_PASS1_UNROLL 4
 #endif
-constexpr int kWarpsPerCta = RCW_WARPS_PER_CTA;  // one warp = one (env, 32-ray group) work item at a time
+constexpr int kWarpsPerCta = RCW_WARPS_PER_CTA;  // one warp = one (env, 32-ray group) work item at a time;
+                                                 // 4 measured best (8: -1.2 %, 16: -18 %, 2 and 1: same as 4)
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+constexpr int kCtasPerSmLo = RCW_WARPS_PER_SM_LO / RCW_WARPS_PER_CTA;   // __launch_bounds__ minimum, store-bound variant
+constexpr int kCtasPerSmHi = RCW_WARPS_PER_SM_HI / RCW_WARPS_PER_CTA;   // front-bound variant
 constexpr int kPass1Unroll = RCW_PASS1_UNROLL;  // independent 16-byte stores kept in flight per warp
 constexpr int kDdaStepsPerVote = RCW_DDA_STEPS_PER_VOTE;
 constexpr int kPairUnroll = RCW_PAIR_UNROLL;    // mirror-pair renderer: two stores per unrolled iteration

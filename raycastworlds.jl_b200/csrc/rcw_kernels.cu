@@ -753,9 +753,9 @@ __device__ __forceinline__ uint2 column_entry(const FrameParams& p, int pad, int
 // shared memory (measured alternative, slower); otherwise the lanes write whole 32-byte sectors.
 enum : int { kStageFused = 0, kStageFront = 1, kStagePaint = 2 };
 
-// OCC = CTAs per SM the register allocation aims for.  3 (80 registers) is best when the step is bound by
-// the store stream (default camera, RGB8 / XRGB32); 4 (60 registers) is 6-9 % faster when act! and the
-// DDA bound it (small frames, one-byte pixels, large maps) — profiles/README.md.
+// OCC = CTAs per SM the register allocation aims for.  24 warps per SM (80 registers) is best when the step
+// is bound by the store stream (default camera, RGB8 / XRGB32); 32 warps per SM (<= 64 registers) is 6-14 %
+// faster when act! and the DDA bound it (small frames, one-byte pixels, large maps) — profiles/README.md.
 template <int MODE, int FMT, bool BULK, int STAGE, int OCC>
 __global__ void __launch_bounds__(kThreadsPerCta, OCC)
 frame_kernel(const __grid_constant__ FrameParams p) {
@@ -1015,12 +1015,12 @@ static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s
 
 }
 
-constexpr int kOcc = RCW_MIN_CTAS_PER_SM;
+constexpr int kOcc = kCtasPerSmLo;
 
 // the shipped path (fused stage, lane-written sectors) exists for both register budgets
 template <int MODE, int FMT>
 static cudaError_t launch_fused(const FrameParams& p, const LaunchShape& sh, cudaStream_t s) {
-    return sh.occ4 ? launch_frame_t<MODE, FMT, false, kStageFused, 4>(p, sh.ctas, s)
+    return sh.occ4 ? launch_frame_t<MODE, FMT, false, kStageFused, kCtasPerSmHi>(p, sh.ctas, s)
                    : launch_frame_t<MODE, FMT, false, kStageFused, kOcc>(p, sh.ctas, s);
 }
 
