@@ -753,7 +753,7 @@ __device__ __forceinline__ uint2 column_entry(const FrameParams& p, int pad, int
 // shared memory (measured alternative, slower); otherwise the lanes write whole 32-byte sectors.
 enum : int { kStageFused = 0, kStageFront = 1, kStagePaint = 2 };
 
-// OCC = CTAs per SM the register allocation aims for.  24 warps per SM (80 registers) is best when the step
+// OCC = CTAs per SM the register allocation aims for.  20 warps per SM (91 registers) is best when the step
 // is bound by the store stream (default camera, RGB8 / XRGB32); 32 warps per SM (<= 64 registers) is 6-14 %
 // faster when act! and the DDA bound it (small frames, one-byte pixels, large maps) — profiles/README.md.
 template <int MODE, int FMT, bool BULK, int STAGE, int OCC>
