@@ -619,6 +619,29 @@ def _sampled_shards_match_oracle(rcw, oracle, env, kw_oracle, n_total, seed, ste
         np.testing.assert_array_equal(st["goal"][s0:s0 + width], goal)
 
 
+def test_long_horizon_20k_steps_sampled_against_oracle(rcw, oracle):
+    """configs[1] for 20,000 steps (about one auto-reset per env on average under the random policy): a
+    window of eight envs is replayed by the oracle and compared bit for bit; the episode counters obey
+    return == episodes (goal_reward 1)."""
+    n, seed, steps, s0 = 4096, 0x5EED, 20_000, 2040
+    env = rcw.BatchedSingleRoom(n, seed=seed)
+    env.step_random(steps)
+    ref = oracle.Batch(8, seed=seed, env_id_offset=s0)
+    ref.rollout(steps, threads=4, render=False)
+    for e in range(8):
+        ref.world(e).update_camera_view()
+    st = env.get_state()
+    pos, au, goal = ref.states()
+    np.testing.assert_array_equal(bits(st["pos"][s0:s0 + 8]), bits(pos))
+    np.testing.assert_array_equal(st["dir_au"][s0:s0 + 8], au)
+    np.testing.assert_array_equal(st["goal"][s0:s0 + 8], goal)
+    np.testing.assert_array_equal(env.copy_obs(s0, 8), ref.obs_rgb8())
+    assert ref.episode_stats()[0] >= 4, "the window should have gone through several episodes"
+    ep, sr, sl = env.episode_stats()
+    assert ep > n // 2 and sr == float(ep) and ep <= sl <= n * steps
+    env.close()
+
+
 def test_config4_65536_envs_sampled_against_oracle(rcw, oracle):
     """configs[3]: 65,536 envs at 512 rays x 256 px (25.8 GB of observations per step).  Windows of
     eight envs spread over the batch, including both ends, are replayed by the oracle."""
