@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RCW_ABI_VERSION 1
+#define RCW_ABI_VERSION 2
 
 typedef enum rcw_status {
     RCW_OK      = 0,
@@ -92,7 +92,13 @@ typedef struct rcw_config {
     uint64_t seed;                   /* Philox4x32-10 key                                      */
     uint32_t palette[6];             /* 0x00RRGGBB, indices RCW_COLOR_*                        */
     uint32_t dda_flags;              /* RCW_DDA_* (0 = default contract)                       */
-    uint32_t reserved[7];            /* must be zero                                           */
+    int32_t  obs_window_envs;        /* 0: the observation buffer holds every env (default).  K > 0: it holds K
+                                        env slots and env e is rendered into slot e mod K, so a batch whose
+                                        observations exceed HBM (2^20 default-camera envs = 412 GB) can still be
+                                        stepped: rcw_step* renders the batch window by window (every frame is
+                                        still written to HBM), rcw_step_range steps one window for a learner
+                                        that consumes it before the next one is rendered.                  */
+    uint32_t reserved[6];            /* must be zero                                           */
 } rcw_config;
 
 typedef struct rcw_batch rcw_batch; /* opaque */
@@ -140,6 +146,13 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
  * error is reported by the next blocking call. */
 int32_t rcw_step(rcw_batch* b, const uint8_t* actions);
 
+/* rcw_step for the envs [env0, env0 + n) only; the other envs keep their state, reward and done.
+ * actions: [n] (actions[k] belongs to env env0 + k), host or device pointer, 1..4 as in rcw_step.
+ * With an observation window (rcw_config.obs_window_envs = K) n must not exceed K; the range's
+ * observations are then in slots (env0 + k) mod K — this is how a learner walks a batch whose
+ * observations do not fit in HBM: step a window, consume it, step the next one. */
+int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64_t n);
+
 /* n_steps of rcw_step with a uniform random policy drawn on the device (Philox keyed by
  * seed / global env id / step index); the benchmark path. */
 int32_t rcw_step_random(rcw_batch* b, int32_t n_steps);
@@ -170,7 +183,8 @@ int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int
 /* Borrowed device pointer to the whole observation buffer (layout: rcw_obs_format), valid
  * until the next rcw_step* / rcw_reset / rcw_render / rcw_destroy — the same aliasing rule as
  * the reference, whose `state` returns the live camera_view array.
- * env_stride_bytes: distance between consecutive envs (see rcw_obs_layout). */
+ * env_stride_bytes: distance between consecutive envs (see rcw_obs_layout).
+ * total_bytes covers obs_window_envs env slots when a window is configured, num_envs otherwise. */
 int32_t rcw_obs_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_t* env_stride_bytes);
 
 /* Device layout of the observation buffer.  One env = num_rays columns; one column = height_px
@@ -182,7 +196,8 @@ int32_t rcw_obs_layout(rcw_batch* b, size_t* env_stride_bytes, size_t* column_st
                        size_t* column_bytes, int32_t* bytes_per_pixel);
 
 /* Blocking copy of the observations of envs [env0, env0+n) to host memory, densely packed
- * (n * num_rays * height_px * bytes_per_pixel). */
+ * (n * num_rays * height_px * bytes_per_pixel).  With an observation window n must not exceed it and
+ * the copy returns what the slots (env0 + k) mod K hold — the caller knows which envs it rendered last. */
 int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host);
 
 /* ---- bookkeeping ------------------------------------------------------------------------ */

@@ -16,12 +16,12 @@ LIB_PATH = os.environ.get("RCW_LIB") or os.path.join(_PKG, "lib", "librcw_b200.s
 RCW_OK, RCW_EINVAL, RCW_EACTION, RCW_ECUDA, RCW_ENOMEM, RCW_ESIZE = 0, -1, -2, -3, -4, -5
 RCW_OBS_RGB8, RCW_OBS_XRGB32, RCW_OBS_GRAY8 = 0, 1, 2
 RCW_DDA_TIE_LE, RCW_DDA_DIST_POST = 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/rcw_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_set_wall_maps", "rcw_reset",
-    "rcw_step", "rcw_step_random", "rcw_render", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
+    "rcw_step", "rcw_step_range", "rcw_step_random", "rcw_render", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
     "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
     "rcw_sync", "rcw_last_error",
 )
@@ -48,7 +48,8 @@ class RcwConfig(C.Structure):
         ("seed", C.c_uint64),
         ("palette", C.c_uint32 * 6),
         ("dda_flags", C.c_uint32),
-        ("reserved", C.c_uint32 * 7),
+        ("obs_window_envs", C.c_int32),
+        ("reserved", C.c_uint32 * 6),
     ]
 
 
@@ -86,6 +87,7 @@ def load() -> C.CDLL:
         "rcw_set_wall_maps": (i32, [vp, vp]),
         "rcw_reset": (i32, [vp, vp, vp, vp, vp]),
         "rcw_step": (i32, [vp, vp]),
+        "rcw_step_range": (i32, [vp, vp, i64, i64]),
         "rcw_step_random": (i32, [vp, i32]),
         "rcw_render": (i32, [vp]),
         "rcw_get_state": (i32, [vp, vp, vp, vp, vp, vp]),

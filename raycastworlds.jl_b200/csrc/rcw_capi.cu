@@ -115,6 +115,7 @@ struct rcw_batch {
     uint8_t* d_actions = nullptr;
     uint8_t* d_obs = nullptr;
     size_t obs_env_stride = 0;
+    int64_t obs_window = 0;       // env slots of the observation buffer (num_envs unless cfg.obs_window_envs)
     int col_pitch = 0;            // bytes between consecutive columns of an observation (multiple of 32)
     size_t obs_bytes = 0;
     // pinned staging for host-side action arrays
@@ -192,6 +193,8 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.stats = b->d_stats;
     p.obs = b->d_obs;
     p.obs_env_stride = b->obs_env_stride;
+    p.obs_window = (uint32_t)b->obs_window;
+    p.obs_slot0 = 0;
     p.num_envs = c.num_envs;
     p.env_first = 0;
     p.env_count = c.num_envs;
@@ -211,17 +214,41 @@ static int grid_for(const rcw_batch* b, int64_t env_count) {
     return (int)(ctas < 1 ? 1 : ctas);
 }
 
+// One frame of the whole batch.  With an observation window the batch is rendered window by window
+// (one launch each, every frame still written to HBM); all launches read state `cur` and write `cur ^ 1`.
 static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
     FrameParams p;
     fill_frame_params(b, p);
     p.actions = d_actions;
-    const LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, p.env_count)};
-    RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream));
-    b->launches += b->split ? 2 : 1;
+    const int64_t E = b->cfg.num_envs;
+    for (int64_t e0 = 0; e0 < E; e0 += b->obs_window) {
+        p.env_first = e0;
+        p.env_count = E - e0 < b->obs_window ? E - e0 : b->obs_window;
+        p.obs_slot0 = 0;
+        const LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, p.env_count)};
+        RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream));
+        b->launches += b->split ? 2 : 1;
+    }
     if (mode == kModeStep) {
         b->cur ^= 1;
         b->step_index += 1;
     }
+    return RCW_OK;
+}
+
+// act! for the envs [env0, env0 + n) only: the launch reads state `cur` and writes `cur ^ 1` like a
+// full step, then the range is copied back so that `cur` stays the handle's one current buffer.
+static int32_t enqueue_range_step(rcw_batch* b, const uint8_t* d_actions_env0, int64_t env0, int64_t n) {
+    FrameParams p;
+    fill_frame_params(b, p);
+    p.actions = d_actions_env0 - env0;   // the kernel indexes actions by env
+    p.env_first = env0;
+    p.env_count = n;
+    p.obs_slot0 = (uint32_t)(env0 % b->obs_window);
+    const LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, n)};
+    RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, sh, b->stream));
+    RCW_CUDA(launch_commit_range(b->st[b->cur ^ 1], b->st[b->cur], env0, n, b->stream));
+    b->launches += (b->split ? 2 : 1) + 1;
     return RCW_OK;
 }
 
@@ -373,7 +400,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     b->bulk = false;
     if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0 && c.obs_format != RCW_OBS_GRAY8;
     if (const char* s = getenv("RCW_SPLIT")) b->split = atoi(s) != 0;
-    RCW_CUDA(dev_alloc(b, &b->d_col_info, (size_t)E * (size_t)R));
+    if (b->split) RCW_CUDA(dev_alloc(b, &b->d_col_info, (size_t)E * (size_t)R));   // 4 B per column, two-launch path only
     {
         std::vector<uint8_t> pat((size_t)6 * b->pat_stride);
         for (int k = 0; k < 6; ++k)
@@ -425,7 +452,8 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // registers are 2 % faster (profiles/README.md).
     b->occ4 = (32 * b->col_pitch < 20000) || ((int64_t)H * W >= 1024);
     if (const char* s = getenv("RCW_OCC")) b->occ4 = atoi(s) == 4;
-    b->obs_bytes = b->obs_env_stride * (size_t)E;
+    b->obs_window = (c.obs_window_envs > 0 && c.obs_window_envs < E) ? c.obs_window_envs : E;
+    b->obs_bytes = b->obs_env_stride * (size_t)b->obs_window;
     RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, false));
     return RCW_OK;
 }
@@ -455,6 +483,7 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
     if (!(cfg->semi_field_of_view_wu > 0.0f)) return fail(RCW_EINVAL, "semi_field_of_view_wu must be positive");
     if (cfg->dda_flags & ~(uint32_t)(RCW_DDA_TIE_LE | RCW_DDA_DIST_POST))
         return fail(RCW_EINVAL, "unknown dda_flags 0x%x", cfg->dda_flags);
+    if (cfg->obs_window_envs < 0) return fail(RCW_EINVAL, "obs_window_envs must be >= 0");
     const int bpp = cfg->obs_format == RCW_OBS_RGB8 ? 3 : (cfg->obs_format == RCW_OBS_XRGB32 ? 4 : 1);
     const int gpe = (cfg->num_rays + 31) / 32;
     if ((int64_t)cfg->num_rays * cfg->height_camera_view_pu * bpp >= (1LL << 30))
@@ -628,41 +657,62 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
     return enqueue_frame(b, kModeRender, nullptr);
 }
 
+// The actions of envs [env0, env0 + n) as a device pointer to the first of them.  A device array is used
+// in place (its values are checked by the kernel); a host array is validated (the reference's @assert,
+// single_room.jl:140) while it is staged into pinned memory, then copied to the handle's action buffer.
+static int32_t stage_actions(rcw_batch* b, const uint8_t* actions, int64_t env0, int64_t n, const uint8_t** d_out) {
+    cudaPointerAttributes attr;
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, actions);
+    if (pe != cudaSuccess) cudaGetLastError();
+    if (pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+        b->device_actions_pending = true;
+        *d_out = actions;
+        return RCW_OK;
+    }
+    const int slot = b->ring;
+    RCW_CUDA(cudaEventSynchronize(b->h_actions_free[slot]));
+    uint8_t* stage = b->h_actions[slot] + env0;
+    uint32_t bad = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        const uint8_t a = actions[k];
+        bad |= (uint32_t)(a - 1u > 3u);
+        stage[k] = a;
+    }
+    if (bad) {
+        for (int64_t k = 0; k < n; ++k)
+            if (actions[k] < 1 || actions[k] > 4)
+                return fail(RCW_EACTION, "Invalid action: %d (env %lld); actions must be in 1..4",
+                            (int)actions[k], (long long)(env0 + k));
+    }
+    RCW_CUDA(cudaMemcpyAsync(b->d_actions + env0, stage, (size_t)n, cudaMemcpyHostToDevice, b->stream));
+    RCW_CUDA(cudaEventRecord(b->h_actions_free[slot], b->stream));
+    b->ring = (slot + 1) % kActionRing;
+    *d_out = b->d_actions + env0;
+    return RCW_OK;
+}
+
 int32_t rcw_step(rcw_batch* b, const uint8_t* actions) {
     if (int32_t rc = check_handle(b)) return rc;
     if (!actions) return fail(RCW_EINVAL, "actions is null (use rcw_step_random for the random policy)");
     DeviceGuard g(b->device);
-    const size_t E = (size_t)b->cfg.num_envs;
-    cudaPointerAttributes attr;
-    const cudaError_t pe = cudaPointerGetAttributes(&attr, actions);
-    if (pe != cudaSuccess) cudaGetLastError();
-    const bool on_device = pe == cudaSuccess &&
-                           (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
-    if (on_device) {
-        b->device_actions_pending = true;
-        return enqueue_frame(b, kModeStep, actions);
-    }
+    const uint8_t* d_actions = nullptr;
+    if (int32_t rc = stage_actions(b, actions, 0, b->cfg.num_envs, &d_actions)) return rc;
+    return enqueue_frame(b, kModeStep, d_actions);
+}
 
-    // host array: validate (the reference's @assert, single_room.jl:140) while staging into pinned memory
-    const int slot = b->ring;
-    RCW_CUDA(cudaEventSynchronize(b->h_actions_free[slot]));
-    uint8_t* stage = b->h_actions[slot];
-    uint32_t bad = 0;
-    for (size_t e = 0; e < E; ++e) {
-        const uint8_t a = actions[e];
-        bad |= (uint32_t)(a - 1u > 3u);
-        stage[e] = a;
-    }
-    if (bad) {
-        for (size_t e = 0; e < E; ++e)
-            if (actions[e] < 1 || actions[e] > 4)
-                return fail(RCW_EACTION, "Invalid action: %d (env %zu); actions must be in 1..4",
-                            (int)actions[e], e);
-    }
-    RCW_CUDA(cudaMemcpyAsync(b->d_actions, stage, E, cudaMemcpyHostToDevice, b->stream));
-    RCW_CUDA(cudaEventRecord(b->h_actions_free[slot], b->stream));
-    b->ring = (slot + 1) % kActionRing;
-    return enqueue_frame(b, kModeStep, b->d_actions);
+int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64_t n) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!actions) return fail(RCW_EINVAL, "actions is null");
+    if (env0 < 0 || n < 1 || env0 + n > b->cfg.num_envs)
+        return fail(RCW_ESIZE, "env range [%lld, %lld) outside 0..%lld", (long long)env0,
+                    (long long)(env0 + n), (long long)b->cfg.num_envs);
+    if (n > b->obs_window)
+        return fail(RCW_ESIZE, "a range of %lld envs does not fit the observation window of %lld",
+                    (long long)n, (long long)b->obs_window);
+    DeviceGuard g(b->device);
+    const uint8_t* d_actions = nullptr;
+    if (int32_t rc = stage_actions(b, actions, env0, n, &d_actions)) return rc;
+    return enqueue_range_step(b, d_actions, env0, n);
 }
 
 int32_t rcw_step_random(rcw_batch* b, int32_t n_steps) {
@@ -823,9 +873,18 @@ int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
     if (env0 < 0 || n < 1 || env0 + n > b->cfg.num_envs)
         return fail(RCW_ESIZE, "env range [%lld, %lld) outside 0..%lld", (long long)env0,
                     (long long)(env0 + n), (long long)b->cfg.num_envs);
+    if (n > b->obs_window)
+        return fail(RCW_ESIZE, "%lld envs requested, the observation window holds %lld", (long long)n,
+                    (long long)b->obs_window);
     DeviceGuard g(b->device);
     const size_t R = (size_t)b->cfg.num_rays, col_bytes = (size_t)b->cfg.height_camera_view_pu * b->bpp;
-    const uint8_t* src = b->d_obs + (size_t)env0 * b->obs_env_stride;
+    const int64_t slot0 = env0 % b->obs_window;
+    if (slot0 + n > b->obs_window) {   // the range wraps around the window: two pieces
+        const int64_t n1 = b->obs_window - slot0;
+        if (int32_t rc = rcw_copy_obs(b, env0, n1, host)) return rc;
+        return rcw_copy_obs(b, env0 + n1, n - n1, static_cast<uint8_t*>(host) + (size_t)n1 * R * col_bytes);
+    }
+    const uint8_t* src = b->d_obs + (size_t)slot0 * b->obs_env_stride;
     uint8_t* dst = static_cast<uint8_t*>(host);
     if (col_bytes == (size_t)b->col_pitch && R * col_bytes == b->obs_env_stride) {
         RCW_CUDA(cudaMemcpyAsync(dst, src, R * col_bytes * (size_t)n, cudaMemcpyDeviceToHost, b->stream));

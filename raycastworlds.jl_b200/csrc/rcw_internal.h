@@ -100,6 +100,8 @@ struct FrameParams {
     DeviceStats* stats;
     uint8_t* obs;
     size_t obs_env_stride;   // bytes, multiple of 16
+    uint32_t obs_window;     // env slots in the observation buffer (== num_envs unless rcw_config.obs_window_envs)
+    uint32_t obs_slot0;      // slot of env_first; env_first + k lives in slot (obs_slot0 + k) mod obs_window
     int64_t num_envs;
     int64_t env_first;       // first env processed by this launch (kModeRays: dump window)
     int64_t env_count;       // envs processed by this launch
@@ -144,6 +146,8 @@ struct LaunchShape {
 };
 cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);
+// state `from` -> state `to` for envs [env0, env0 + n): makes a range step visible in the buffer it read
+cudaError_t launch_commit_range(const StateRef& from, const StateRef& to, int64_t env0, int64_t n, cudaStream_t s);
 cudaError_t upload_dir_slot(int slot, const float2* host_dirs, int n, cudaStream_t s);
 
 }  // namespace rcw

@@ -892,7 +892,10 @@ frame_kernel(const __grid_constant__ FrameParams p) {
             }
         }
 
-        uint8_t* const env_obs = p.obs + (size_t)env * p.obs_env_stride;
+        // the env's slot in the observation buffer (a window of obs_window envs; the whole batch by default)
+        uint32_t obs_slot = p.obs_slot0 + env_rel;
+        if (obs_slot >= p.obs_window) obs_slot -= p.obs_window;
+        uint8_t* const env_obs = p.obs + (size_t)obs_slot * p.obs_env_stride;
         const int B0 = col0 * p.col_pitch;             // byte span of the warp's columns in the env image
         int my_col = ncols - 1 - lane;                 // span column of this lane's ray
         if (STAGE == kStagePaint) {
@@ -962,6 +965,19 @@ __global__ void reset_kernel(const ResetParams p) {
     p.done[env] = 0;
     p.ep_return[env] = 0.0f;
     p.ep_length[env] = 0u;
+}
+
+// After a step of the env range [env0, env0 + n) only (rcw_step_range): copy the range's new state
+// back into the buffer the step read, so that the handle's current state stays in one buffer.
+__global__ void commit_range_kernel(const StateRef from, const StateRef to, int64_t env0, int64_t n) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t env = env0 + k;
+    to.pos_x[env] = from.pos_x[env];
+    to.pos_y[env] = from.pos_y[env];
+    to.dir_au[env] = from.dir_au[env];
+    to.goal[env] = from.goal[env];
+    to.episode[env] = from.episode[env];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1056,6 +1072,11 @@ cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const L
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s) {
     const int64_t blocks = (p.num_envs + 255) / 256;
     reset_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_commit_range(const StateRef& from, const StateRef& to, int64_t env0, int64_t n, cudaStream_t s) {
+    commit_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(from, to, env0, n);
     return cudaGetLastError();
 }
 

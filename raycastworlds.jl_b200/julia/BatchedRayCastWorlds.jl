@@ -46,7 +46,8 @@ struct RcwConfig
     seed::UInt64
     palette::NTuple{6, UInt32}
     dda_flags::UInt32
-    reserved::NTuple{7, UInt32}
+    obs_window_envs::Int32
+    reserved::NTuple{6, UInt32}
 end
 
 last_error() = unsafe_string(ccall((:rcw_last_error, LIB), Cstring, ()))
@@ -88,6 +89,7 @@ function BatchedSingleRoom(;
         auto_reset = true,
         seed = 0,
         env_id_offset = 0,
+        obs_window_envs = 0,
     )
     T === Float32 || error("librcw_b200 computes in Float32 (the reference default, single_room.jl:43)")
 
@@ -105,7 +107,8 @@ function BatchedSingleRoom(;
                         Int32(num_rays), Int32(height_camera_view_pu), Float32(player_radius_wu),
                         Float32(position_increment_wu), Float32(semi_field_of_view_wu),
                         Float32(camera_height_tile_wu), Float32(goal_reward), Int32(obs_format),
-                        Int32(auto_reset), UInt64(seed), palette, UInt32(0), ntuple(_ -> UInt32(0), 7)))
+                        Int32(auto_reset), UInt64(seed), palette, UInt32(0), Int32(obs_window_envs),
+                        ntuple(_ -> UInt32(0), 6)))
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve directions begin
         check(ccall((:rcw_create, LIB), Int32, (Ref{RcwConfig}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
@@ -142,6 +145,16 @@ function RCW.act!(env::BatchedSingleRoom, actions::Vector{UInt8})
     return nothing
 end
 RCW.act!(env::BatchedSingleRoom, actions::AbstractVector{<:Integer}) = RCW.act!(env, convert(Vector{UInt8}, actions))
+
+# act! for the envs env0+1 : env0+length(actions) only (0-based env0); with an observation window
+# (`obs_window_envs`) this is how a learner walks a batch whose observations do not fit in HBM
+function act_range!(env::BatchedSingleRoom, actions::Vector{UInt8}, env0::Integer)
+    GC.@preserve actions begin
+        check(ccall((:rcw_step_range, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64),
+                    env.handle, actions, Int64(env0), Int64(length(actions))))
+    end
+    return nothing
+end
 
 # random policy on the device (benchmark path)
 step_random!(env::BatchedSingleRoom, n_steps = 1) =

@@ -44,8 +44,10 @@ class BatchedSingleRoom(AbstractGame):
     Keyword arguments are those of the reference constructor (single_room.jl:258-272); the
     additional ones are `num_envs`, `device`, `obs_format` ("rgb8" | "xrgb32" | "gray8"), `auto_reset`,
     `seed`, `env_id_offset` (global id of env 0 when a batch is sharded over GPUs),
-    `directions_wu` (the host's own [N, 2] float32 direction table) and the two switches for the
-    unpinned RayCaster.cast_ray decisions (`dda_tie_le`, `dda_dist_post`).
+    `directions_wu` (the host's own [N, 2] float32 direction table), the two switches for the
+    unpinned RayCaster.cast_ray decisions (`dda_tie_le`, `dda_dist_post`) and `obs_window_envs`
+    (the observation buffer holds only that many env slots, env e in slot e mod K — for batches whose
+    observations exceed HBM; see `act_range`).
     """
 
     def __init__(self, num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int = 8,
@@ -56,7 +58,7 @@ class BatchedSingleRoom(AbstractGame):
                  goal_reward: float = 1.0, obs_format: str = "rgb8", auto_reset: bool = True,
                  seed: int = 0, env_id_offset: int = 0,
                  directions_wu: Optional[np.ndarray] = None, palette: Optional[Sequence[int]] = None,
-                 dda_tie_le: bool = False, dda_dist_post: bool = False):
+                 dda_tie_le: bool = False, dda_dist_post: bool = False, obs_window_envs: int = 0):
         self._lib = _capi.load()
         self._h = C.c_void_p()
         cfg = _capi.default_config()
@@ -84,6 +86,7 @@ class BatchedSingleRoom(AbstractGame):
                 cfg.palette[i] = int(c)
         cfg.dda_flags = (_capi.RCW_DDA_TIE_LE if dda_tie_le else 0) | (
             _capi.RCW_DDA_DIST_POST if dda_dist_post else 0)
+        cfg.obs_window_envs = int(obs_window_envs)
         dirs = None
         if directions_wu is not None:
             dirs = np.ascontiguousarray(directions_wu, np.float32)
@@ -92,6 +95,7 @@ class BatchedSingleRoom(AbstractGame):
         _capi.check(self._lib.rcw_create(C.byref(cfg), _ptr(dirs), C.byref(self._h)))
         self.cfg = cfg
         self.num_envs = int(num_envs)
+        self.obs_window = int(obs_window_envs) if 0 < int(obs_window_envs) < int(num_envs) else int(num_envs)
         self.obs_format = obs_format
         self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1}[obs_format]
 
@@ -141,6 +145,29 @@ class BatchedSingleRoom(AbstractGame):
             a = a.astype(np.uint8)
         a = np.ascontiguousarray(a)
         _capi.check(self._lib.rcw_step(self._h, _ptr(a)))
+
+    def act_range(self, actions, env0: int, n: Optional[int] = None):
+        """act! for the envs [env0, env0 + n) only (rcw_step_range): `actions` holds n values in 1..4,
+        host array or CUDA uint8 tensor.  With an observation window the range's observations are in
+        slots (env0 + k) mod obs_window afterwards."""
+        cai = getattr(actions, "__cuda_array_interface__", None)
+        if cai is not None:
+            n = int(np.prod(cai["shape"])) if n is None else int(n)
+            if cai["typestr"] not in ("|u1", "<u1") or int(np.prod(cai["shape"])) != n:
+                raise ValueError("device actions must be uint8 [n]")
+            _capi.check(self._lib.rcw_step_range(self._h, C.c_void_p(cai["data"][0]), int(env0), n))
+            return
+        a = np.asarray(actions).reshape(-1)
+        n = a.shape[0] if n is None else int(n)
+        if a.shape[0] != n:
+            raise ValueError("actions must hold one value per env of the range")
+        if a.dtype != np.uint8:
+            if ((a < 1) | (a > NUM_ACTIONS)).any():
+                bad = a[(a < 1) | (a > NUM_ACTIONS)][0]
+                raise _capi.InvalidActionError(_capi.RCW_EACTION, f"Invalid action: {bad}")
+            a = a.astype(np.uint8)
+        a = np.ascontiguousarray(a)
+        _capi.check(self._lib.rcw_step_range(self._h, _ptr(a), int(env0), n))
 
     def step_random(self, n_steps: int = 1):
         _capi.check(self._lib.rcw_step_random(self._h, int(n_steps)))
@@ -207,10 +234,11 @@ class BatchedSingleRoom(AbstractGame):
     # -- observations -----------------------------------------------------------------------------
     @property
     def obs_shape(self):
-        """[num_envs, width (= num_rays columns), height_camera_view_pu, (3)]; the pixel row is the
-        fastest index, as in the reference's Array{UInt32}(P, R)."""
+        """[env slots, width (= num_rays columns), height_camera_view_pu, (3)]; the pixel row is the
+        fastest index, as in the reference's Array{UInt32}(P, R).  env slots = num_envs unless an
+        observation window was configured."""
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
-        return (self.num_envs, R, P, 3) if self.obs_format == "rgb8" else (self.num_envs, R, P)
+        return (self.obs_window, R, P, 3) if self.obs_format == "rgb8" else (self.obs_window, R, P)
 
     def obs_device_ptr(self):
         ptr, total, stride = C.c_void_p(), C.c_size_t(), C.c_size_t()
@@ -235,12 +263,13 @@ class BatchedSingleRoom(AbstractGame):
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
         holder = _CudaBuffer(ptr, total, self)
         flat = torch.as_tensor(holder, device=torch.device("cuda", self.cfg.device))
+        slots = self.obs_window
         if self.obs_format == "rgb8":
-            return torch.as_strided(flat, (self.num_envs, R, P, 3), (env_stride, col_stride, 3, 1))
+            return torch.as_strided(flat, (slots, R, P, 3), (env_stride, col_stride, 3, 1))
         if self.obs_format == "gray8":
-            return torch.as_strided(flat, (self.num_envs, R, P), (env_stride, col_stride, 1))
+            return torch.as_strided(flat, (slots, R, P), (env_stride, col_stride, 1))
         words = flat.view(torch.int32)
-        return torch.as_strided(words, (self.num_envs, R, P), (env_stride // 4, col_stride // 4, 1))
+        return torch.as_strided(words, (slots, R, P), (env_stride // 4, col_stride // 4, 1))
 
     def obs_tensor_nchw(self):
         """The same buffer as a [N, C, num_rays, height_px] torch view for convolutional learners: the
@@ -251,7 +280,7 @@ class BatchedSingleRoom(AbstractGame):
 
     def copy_obs(self, env0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None):
         """Blocking device->host copy of the observations of envs [env0, env0+n)."""
-        n = self.num_envs - env0 if n is None else n
+        n = min(self.num_envs - env0, self.obs_window) if n is None else n
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
         shape = (n, R, P, 3) if self.obs_format == "rgb8" else (n, R, P)
         dtype = np.uint32 if self.obs_format == "xrgb32" else np.uint8
