@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--obs-window-envs", type=int, default=0,
                     help="observation buffer of this many env slots (0 = every env); for batches whose "
                          "observations exceed HBM, e.g. BASELINE config 3 at 2 GPUs: 524288 envs per GPU")
+    ap.add_argument("--top-view", action="store_true",
+                    help="also redraw the top view inside every step (the reference's act!(env), single_room.jl:337); "
+                         "not part of the north-star path, a second kernel launch and 512 KB more per env-step")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -226,11 +229,14 @@ def run_b200(args):
     n = args.envs_per_gpu
     offset = rank * n
     env = rcw.BatchedSingleRoom(n, device=local, seed=SEED, env_id_offset=offset,
-                                obs_format=args.obs_format, obs_window_envs=args.obs_window_envs, **kw)
+                                obs_format=args.obs_format, obs_window_envs=args.obs_window_envs,
+                                top_view=args.top_view, **kw)
     windowed = env.obs_window < n
     stream = torch.cuda.ExternalStream(env.cuda_stream(), device=dev)
     K, W = args.steps, args.warmup
     bytes_per_step_env = kw["num_rays"] * kw["height_camera_view_pu"] * env.bytes_per_pixel
+    if args.top_view:
+        bytes_per_step_env += 4 * int(np.prod(env.top_view_shape[1:]))
 
     # ---- device-resident throughput: K launches back to back, CUDA events on the handle's stream
     env.step_random(W)
@@ -329,13 +335,15 @@ def run_b200(args):
                             f"{kw['num_directions']} directions, {kw['num_rays']} rays x {kw['height_camera_view_pu']} px "
                             f"{args.obs_format}, random policy + auto-reset" + (" (BASELINE.json configs[1])" if (n, args.map, args.rays, args.height) == (4096, "default", 512, 256) else ""),
                 "envs_per_gpu": n, "obs_bytes_per_env_step": bytes_per_step_env,
-                "obs_window_envs": env_window, "launches_per_step": -(-n // env_window),
+                "obs_window_envs": env_window, "launches_per_step": -(-n // env_window) * (2 if args.top_view else 1),
+                "top_view": bool(args.top_view),
                 "l2": f"each step writes {n * bytes_per_step_env / 1e9:.2f} GB of observations, larger than the 126 MB L2; no flush needed",
                 "seed": SEED,
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": measured_traffic(n, kw, args.obs_format), "kernel": "rcw::frame_kernel<kModeStep, fused>",
+                "traffic": None if args.top_view else measured_traffic(n, kw, args.obs_format),
+                "kernel": "rcw::frame_kernel<kModeStep, fused>" + (" + rcw::top_view_kernel" if args.top_view else ""),
                 "algorithmic_bytes_per_launch": min(n, env_window) * bytes_per_step_env,
                 "launch_ms": launch_ms / (-(-n // env_window)), "peak_source": peak_src,
             },

@@ -64,6 +64,16 @@ enum {
     RCW_COLOR_GOAL_2  = 5  /* 0x00c00000 */
 };
 
+/* Indices into rcw_config.top_palette: the colours of the top view (single_room.jl:288-290, 364-367). */
+enum {
+    RCW_TOP_COLOR_WALL   = 0, /* 0x00FFFFFF  tile_map_colors[WALL]            */
+    RCW_TOP_COLOR_GOAL   = 1, /* 0x00FF0000  tile_map_colors[GOAL]            */
+    RCW_TOP_COLOR_EMPTY  = 2, /* 0x00000000  tile_map_colors[end]: no object  */
+    RCW_TOP_COLOR_BORDER = 3, /* 0x00cccccc  one-pixel border of every tile   */
+    RCW_TOP_COLOR_RAY    = 4, /* 0x00808080  ray_color                        */
+    RCW_TOP_COLOR_PLAYER = 5  /* 0x00c0c0c0  player_color                     */
+};
+
 /* Switches for the behaviour of RayCaster.cast_ray that the reference tree does not pin
  * (RayCaster.jl 0.1 is not vendored; see DESIGN.md "Unpinned decisions" D1/D2). */
 enum {
@@ -98,7 +108,13 @@ typedef struct rcw_config {
                                         stepped: rcw_step* renders the batch window by window (every frame is
                                         still written to HBM), rcw_step_range steps one window for a learner
                                         that consumes it before the next one is rendered.                  */
-    uint32_t reserved[6];            /* must be zero                                           */
+    int32_t  top_view;               /* 1: update_top_view! runs inside every rcw_step* / rcw_reset / rcw_render, the
+                                        reference's act!(env) sequence (single_room.jl:333-340); 0 (default for a
+                                        batch): only on rcw_render_top_view — the top view is a debug picture and
+                                        doubles the HBM writes of a step                                       */
+    int32_t  pu_per_tu;              /* pixels per tile of the top view, default 32 (single_room.jl:269)       */
+    uint32_t top_palette[6];         /* 0x00RRGGBB, indices RCW_TOP_COLOR_*                                    */
+    uint32_t reserved[4];            /* must be zero                                           */
 } rcw_config;
 
 typedef struct rcw_batch rcw_batch; /* opaque */
@@ -199,6 +215,23 @@ int32_t rcw_obs_layout(rcw_batch* b, size_t* env_stride_bytes, size_t* column_st
  * (n * num_rays * height_px * bytes_per_pixel).  With an observation window n must not exceed it and
  * the copy returns what the slots (env0 + k) mod K hold — the caller knows which envs it rendered last. */
 int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host);
+
+/* ---- top view (single_room.jl:342-372, 446-483) ------------------------ */
+
+/* update_top_view!(env) from the current state of every env: tile grid with borders, the num_rays ray
+ * segments, the player's circle, as the reference's top_view::Array{UInt32}(height_tu * pu_per_tu,
+ * width_tu * pu_per_tu) (single_room.jl:302).  Runs automatically after every step / reset / render
+ * when rcw_config.top_view = 1.  The shapes are SimpleDraw.jl 0.3's (not vendored): Bresenham line,
+ * midpoint circle, clipped to the image — unpinned against Julia like the DDA. */
+int32_t rcw_render_top_view(rcw_batch* b);
+
+/* Borrowed device pointer to the top views: uint32 [env slots][width_tu * pu columns][height_tu * pu rows],
+ * the pixel row fastest like the reference's column-major array; env_stride_bytes between envs (a multiple
+ * of 128).  NULL until the first top view was drawn.  Same aliasing rule and window as the observations. */
+int32_t rcw_top_view_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_t* env_stride_bytes);
+
+/* Blocking copy of the top views of envs [env0, env0+n) to host memory, densely packed uint32. */
+int32_t rcw_copy_top_view(rcw_batch* b, int64_t env0, int64_t n, void* host);
 
 /* ---- bookkeeping ------------------------------------------------------------------------ */
 

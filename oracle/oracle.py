@@ -23,6 +23,7 @@ class OrcConfig(C.Structure):
         ("goal_reward", C.c_float),
         ("palette", C.c_uint32 * 6),
         ("tie_le", C.c_int32), ("dist_post", C.c_int32),
+        ("pu_per_tu", C.c_int32), ("top_palette", C.c_uint32 * 6),
     ]
 
 
@@ -62,6 +63,8 @@ def lib() -> C.CDLL:
         "orc_cast_rays": (None, [vp]),
         "orc_update_camera_view": (None, [vp]),
         "orc_step": (i32, [vp, i32]),
+        "orc_update_top_view": (None, [vp]),
+        "orc_top_view": (vp, [vp]),
         "orc_cast_ray": (None, [vp, f32, f32, f32, f32, vp, vp, vp, vp]),
         "orc_ray_stop": (vp, [vp]),
         "orc_ray_dim": (vp, [vp]),
@@ -95,9 +98,9 @@ def default_config(**kw) -> OrcConfig:
     cfg = OrcConfig()
     lib().orc_config_default(C.byref(cfg))
     for k, v in kw.items():
-        if k == "palette":
+        if k in ("palette", "top_palette"):
             for i, c in enumerate(v):
-                cfg.palette[i] = int(c)
+                getattr(cfg, k)[i] = int(c)
         else:
             setattr(cfg, k, v)
     return cfg
@@ -216,6 +219,15 @@ class World:
     def camera_view(self):
         """uint32 [R columns, P rows] (the Julia Array{UInt32}(P, R), transposed view)."""
         return _view(self.L.orc_camera_view(self.p), (self.cfg.R, self.cfg.P), np.uint32).copy()
+
+    def update_top_view(self):
+        self.L.orc_update_top_view(self.p)
+
+    @property
+    def top_view(self):
+        """uint32 [W*pu columns, H*pu rows] (the Julia Array{UInt32}(H*pu, W*pu), transposed view)."""
+        pu = self.cfg.pu_per_tu
+        return _view(self.L.orc_top_view(self.p), (self.cfg.W * pu, self.cfg.H * pu), np.uint32).copy()
 
     def wall_heights(self):
         out = np.empty(self.cfg.R, np.int32)

@@ -29,6 +29,7 @@ struct orc_world {
     float* ray_dist;     /* ray_distance_wu */
     float* ray_dir;      /* ray_directions_wu [R][2] */
     uint32_t* camera;    /* camera_view [R columns][P rows], row fastest (Array{UInt32}(P,R)) */
+    uint32_t* top;       /* top_view [W*pu columns][H*pu rows], row fastest (Array{UInt32}(H*pu, W*pu), :302) */
 };
 
 /* ------------------------------------------------------------------------------------- */
@@ -54,6 +55,13 @@ void orc_config_default(orc_config* c) {
     c->palette[3] = 0x00c0c0c0u; /* wall_dim_2     :294 */
     c->palette[4] = 0x00800000u; /* goal_dim_1     :295 */
     c->palette[5] = 0x00c00000u; /* goal_dim_2     :296 */
+    c->pu_per_tu = 32;               /* :269 */
+    c->top_palette[0] = 0x00FFFFFFu; /* tile_map_colors[WALL]  :288 */
+    c->top_palette[1] = 0x00FF0000u; /* tile_map_colors[GOAL]  :288 */
+    c->top_palette[2] = 0x00000000u; /* tile_map_colors[end] (no object) :288 */
+    c->top_palette[3] = 0x00ccccccu; /* tile border            :365-368 */
+    c->top_palette[4] = 0x00808080u; /* ray_color              :289 */
+    c->top_palette[5] = 0x00c0c0c0u; /* player_color           :290 */
 }
 
 /* single_room.jl:65-69 — theta in Float64, cos/sin in Float64, convert to T */
@@ -109,6 +117,7 @@ void orc_destroy(orc_world* w) {
     free(w->ray_dist);
     free(w->ray_dir);
     free(w->camera);
+    free(w->top);
     free(w);
 }
 
@@ -374,6 +383,102 @@ void orc_update_camera_view(orc_world* w) {
         }
     }
 }
+
+/* ---- top view (single_room.jl:342-372, 446-483) ------------------------------------------------
+ * The shapes are drawn by SimpleDraw.jl 0.3 [EXT, not vendored, no Manifest]: FilledRectangle(position,
+ * height, width), Line(point1, point2), Circle(position, diameter).  Restated here from the algorithms
+ * that package documents — Bresenham's line over all octants and the midpoint circle — with every pixel
+ * write bounds-checked.  UNPINNED: the exact error-term conventions of SimpleDraw are not checkable here. */
+
+static int wu_to_pu(float x_wu, int pu_per_wu) { return (int)floorf(x_wu * (float)pu_per_wu) + 1; } /* utils.jl:6 */
+
+static void put_pixel(orc_world* w, int i, int j, uint32_t color) { /* 1-based, clipped */
+    const int Hp = w->cfg.H * w->cfg.pu_per_tu, Wp = w->cfg.W * w->cfg.pu_per_tu;
+    if (i >= 1 && i <= Hp && j >= 1 && j <= Wp) w->top[(size_t)(i - 1) + (size_t)Hp * (j - 1)] = color;
+}
+
+/* [EXT SimpleDraw] Line: Bresenham, all octants, both end points drawn */
+static void draw_line(orc_world* w, int i1, int j1, int i2, int j2, uint32_t color) {
+    const int di = abs(i2 - i1), dj = -abs(j2 - j1);
+    const int si = i1 < i2 ? 1 : -1, sj = j1 < j2 ? 1 : -1;
+    int err = di + dj, i = i1, j = j1;
+    for (;;) {
+        put_pixel(w, i, j, color);
+        if (i == i2 && j == j2) break;
+        const int e2 = 2 * err;
+        if (e2 >= dj) {
+            err += dj;
+            i += si;
+        }
+        if (e2 <= di) {
+            err += di;
+            j += sj;
+        }
+    }
+}
+
+/* [EXT SimpleDraw] Circle(position = top-left of the bounding box, odd diameter 2r + 1): midpoint circle of
+ * radius r about the centre pixel, eight-way symmetric */
+static void draw_circle(orc_world* w, int ic, int jc, int r, uint32_t color) {
+    int a = 0, b = r, d = 1 - r;
+    while (a <= b) {
+        put_pixel(w, ic + a, jc + b, color);
+        put_pixel(w, ic - a, jc + b, color);
+        put_pixel(w, ic + a, jc - b, color);
+        put_pixel(w, ic - a, jc - b, color);
+        put_pixel(w, ic + b, jc + a, color);
+        put_pixel(w, ic - b, jc + a, color);
+        put_pixel(w, ic + b, jc - a, color);
+        put_pixel(w, ic - b, jc - a, color);
+        if (d < 0) {
+            d += 2 * a + 3;
+        } else {
+            d += 2 * (a - b) + 5;
+            b -= 1;
+        }
+        a += 1;
+    }
+}
+
+/* draw_tile_map! single_room.jl:342-372 */
+static void draw_tile_map(orc_world* w) {
+    const int H = w->cfg.H, W = w->cfg.W, pu = w->cfg.pu_per_tu;
+    const uint32_t border = w->cfg.top_palette[3];
+    for (int j = 1; j <= W; ++j)
+        for (int i = 1; i <= H; ++i) {
+            const int it = (i - 1) * pu + 1, jt = (j - 1) * pu + 1; /* :350-351 */
+            /* findfirst over the layers WALL = 1, GOAL = 2 (:355-360) */
+            uint32_t color = w->cfg.top_palette[2];
+            if (w->wall[(i - 1) + H * (j - 1)]) color = w->cfg.top_palette[0];
+            else if (i == w->goal[0] && j == w->goal[1]) color = w->cfg.top_palette[1];
+            for (int b = 0; b < pu; ++b)
+                for (int a = 0; a < pu; ++a) put_pixel(w, it + a, jt + b, color); /* :353,362 */
+            for (int b = 0; b < pu; ++b) {
+                put_pixel(w, it, jt + b, border);          /* :364 */
+                put_pixel(w, it + pu - 1, jt + b, border); /* :365 */
+                put_pixel(w, it + b, jt, border);          /* :366 */
+                put_pixel(w, it + b, jt + pu - 1, border); /* :367 */
+            }
+        }
+}
+
+/* update_top_view! single_room.jl:446-483 */
+void orc_update_top_view(orc_world* w) {
+    const int pu = w->cfg.pu_per_tu, R = w->cfg.R;
+    if (!w->top) w->top = (uint32_t*)calloc((size_t)w->cfg.H * pu * w->cfg.W * pu, sizeof(uint32_t));
+    const int ip = wu_to_pu(w->pos[0], pu), jp = wu_to_pu(w->pos[1], pu); /* :469 */
+    const int rp = wu_to_pu(w->cfg.radius, pu);                           /* :470 */
+    draw_tile_map(w);                                                     /* :472 */
+    for (int i = 0; i < R; ++i) {                                         /* :474-478 */
+        const float sx = w->pos[0] + w->ray_dist[i] * w->ray_dir[2 * i + 0];
+        const float sy = w->pos[1] + w->ray_dist[i] * w->ray_dir[2 * i + 1];
+        draw_line(w, ip, jp, wu_to_pu(sx, pu), wu_to_pu(sy, pu), w->cfg.top_palette[4]);
+    }
+    /* Circle(Point(i - r, j - r), 2r + 1) (:480): centre (ip, jp), radius rp */
+    draw_circle(w, ip, jp, rp, w->cfg.top_palette[5]);
+}
+
+const uint32_t* orc_top_view(const orc_world* w) { return w->top; }
 
 /* act!(env) without the top view: single_room.jl:333-340 */
 int32_t orc_step(orc_world* w, int32_t action) {

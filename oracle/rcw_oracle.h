@@ -34,6 +34,9 @@ typedef struct orc_config {
     uint32_t palette[6];   /* ceiling, floor, wall1, wall2, goal1, goal2 (single_room.jl:291-296) */
     int32_t tie_le;        /* D1: 1 => tx <= ty advances dimension 1 */
     int32_t dist_post;     /* D2: 1 => distance = side - delta after the loop */
+    int32_t pu_per_tu;     /* pu_per_tu of the top view                (single_room.jl:269)  */
+    uint32_t top_palette[6]; /* tile_map_colors (wall, goal, empty :288), tile border (:364-367), ray_color (:289),
+                                player_color (:290) */
 } orc_config;
 
 typedef struct orc_world orc_world;
@@ -60,6 +63,11 @@ int32_t orc_act(orc_world* w, int32_t action);   /* returns 0, or -2 for an inva
 void orc_cast_rays(orc_world* w);
 void orc_update_camera_view(orc_world* w);
 int32_t orc_step(orc_world* w, int32_t action);  /* act -> cast_rays -> update_camera_view */
+/* update_top_view!(env) (single_room.jl:446-483) from the rays of the last orc_cast_rays.  The drawing
+ * primitives come from the un-vendored package SimpleDraw.jl 0.3 (Project.toml) and are restated from their
+ * published algorithms: UNPINNED like the DDA (see rcw_oracle.c). */
+void orc_update_top_view(orc_world* w);
+const uint32_t* orc_top_view(const orc_world* w); /* [W*pu columns][H*pu rows], row fastest (Array{UInt32}(H*pu, W*pu)) */
 
 /* one ray, exposed for unit tests: returns hit tile (1-based), dim, dist */
 void orc_cast_ray(const orc_world* w, float x, float y, float dx, float dy, int32_t* i_hit,

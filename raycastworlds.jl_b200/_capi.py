@@ -21,7 +21,8 @@ ABI_VERSION = 2
 # every symbol include/rcw_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_set_wall_maps", "rcw_reset",
-    "rcw_step", "rcw_step_range", "rcw_step_random", "rcw_render", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
+    "rcw_step", "rcw_step_range", "rcw_step_random", "rcw_render",
+    "rcw_render_top_view", "rcw_top_view_device_ptr", "rcw_copy_top_view", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
     "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
     "rcw_sync", "rcw_last_error",
 )
@@ -49,7 +50,10 @@ class RcwConfig(C.Structure):
         ("palette", C.c_uint32 * 6),
         ("dda_flags", C.c_uint32),
         ("obs_window_envs", C.c_int32),
-        ("reserved", C.c_uint32 * 6),
+        ("top_view", C.c_int32),
+        ("pu_per_tu", C.c_int32),
+        ("top_palette", C.c_uint32 * 6),
+        ("reserved", C.c_uint32 * 4),
     ]
 
 
@@ -90,6 +94,9 @@ def load() -> C.CDLL:
         "rcw_step_range": (i32, [vp, vp, i64, i64]),
         "rcw_step_random": (i32, [vp, i32]),
         "rcw_render": (i32, [vp]),
+        "rcw_render_top_view": (i32, [vp]),
+        "rcw_top_view_device_ptr": (i32, [vp, P(vp), P(C.c_size_t), P(C.c_size_t)]),
+        "rcw_copy_top_view": (i32, [vp, i64, i64, vp]),
         "rcw_get_state": (i32, [vp, vp, vp, vp, vp, vp]),
         "rcw_set_state": (i32, [vp, vp, vp, vp, vp, vp]),
         "rcw_get_rays": (i32, [vp, i64, i64, vp, vp, vp, vp]),

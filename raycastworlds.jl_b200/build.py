@@ -7,7 +7,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB = os.path.join(_PKG, "lib", "librcw_b200.so")
-SOURCES = ("rcw_kernels.cu", "rcw_capi.cu", "rcw_internal.h", "Makefile")
+SOURCES = ("rcw_kernels.cu", "rcw_capi.cu", "rcw_internal.h", "rcw_topview.cuh", "Makefile")
 
 
 def is_stale() -> bool:

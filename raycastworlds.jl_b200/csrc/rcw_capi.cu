@@ -118,6 +118,9 @@ struct rcw_batch {
     int64_t obs_window = 0;       // env slots of the observation buffer (num_envs unless cfg.obs_window_envs)
     int col_pitch = 0;            // bytes between consecutive columns of an observation (multiple of 32)
     size_t obs_bytes = 0;
+    // top view (update_top_view!): allocated when first drawn
+    uint8_t* d_top = nullptr;
+    size_t top_env_stride = 0;
     // pinned staging for host-side action arrays
     uint8_t* h_actions[kActionRing]{};
     cudaEvent_t h_actions_free[kActionRing]{};
@@ -214,6 +217,45 @@ static int grid_for(const rcw_batch* b, int64_t env_count) {
     return (int)(ctas < 1 ? 1 : ctas);
 }
 
+// update_top_view! for envs [env0, env0 + n) from state `st`, into the slots that start at slot0.
+static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, int64_t n, uint32_t slot0) {
+    const rcw_config& c = b->cfg;
+    if (!b->d_top) {
+        const size_t px = (size_t)c.height_tile_map_tu * c.pu_per_tu * (size_t)c.width_tile_map_tu * c.pu_per_tu;
+        b->top_env_stride = (px * 4 + 127) & ~(size_t)127;
+        RCW_CUDA(dev_alloc(b, &b->d_top, b->top_env_stride * (size_t)b->obs_window, false));
+    }
+    TopViewParams t;
+    memset(&t, 0, sizeof(t));
+    t.H = c.height_tile_map_tu;
+    t.W = c.width_tile_map_tu;
+    t.wpr = b->wpr;
+    t.map_words = b->map_words;
+    t.N = c.num_directions;
+    t.R = c.num_rays;
+    t.pu = c.pu_per_tu;
+    t.Hp = t.H * t.pu;
+    t.Wp = t.W * t.pu;
+    t.dda_flags = c.dda_flags;
+    t.radius = c.player_radius_wu;
+    for (int i = 0; i < 6; ++i) t.palette[i] = c.top_palette[i] & 0x00FFFFFFu;
+    t.dir_slot = b->dir_slot;
+    t.dirs = b->d_dirs;
+    t.ray_table = b->d_ray_table;
+    t.wall_map = b->per_env_maps ? b->d_wall_maps_env : b->d_wall_map;
+    t.map_env_stride = b->per_env_maps ? (uint32_t)b->map_words : 0u;
+    t.st = st;
+    t.top = b->d_top;
+    t.env_stride = b->top_env_stride;
+    t.window = (uint32_t)b->obs_window;
+    t.slot0 = slot0;
+    t.env_first = env0;
+    t.env_count = n;
+    RCW_CUDA(launch_top_view(t, b->stream));
+    b->launches += 1;
+    return RCW_OK;
+}
+
 // One frame of the whole batch.  With an observation window the batch is rendered window by window
 // (one launch each, every frame still written to HBM); all launches read state `cur` and write `cur ^ 1`.
 static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
@@ -228,6 +270,9 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
         const LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, p.env_count)};
         RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream));
         b->launches += b->split ? 2 : 1;
+        // the reference's act!(env) / reset!(env) also redraw the top view (single_room.jl:329,337)
+        if (b->cfg.top_view)
+            if (int32_t rc = enqueue_top_view(b, mode == kModeStep ? p.out : p.in, e0, p.env_count, 0)) return rc;
     }
     if (mode == kModeStep) {
         b->cur ^= 1;
@@ -249,6 +294,7 @@ static int32_t enqueue_range_step(rcw_batch* b, const uint8_t* d_actions_env0, i
     RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, sh, b->stream));
     RCW_CUDA(launch_commit_range(b->st[b->cur ^ 1], b->st[b->cur], env0, n, b->stream));
     b->launches += (b->split ? 2 : 1) + 1;
+    if (b->cfg.top_view) return enqueue_top_view(b, b->st[b->cur], env0, n, p.obs_slot0);
     return RCW_OK;
 }
 
@@ -282,6 +328,17 @@ static void pack_border_walls(int H, int W, int wpr, std::vector<uint32_t>& word
     for (int i = 0; i < H; ++i)
         for (int j = 0; j < W; ++j)
             if (i == 0 || i == H - 1 || j == 0 || j == W - 1) words[(size_t)i * wpr + (j >> 5)] |= 1u << (j & 31);
+}
+
+// the top view of one env is composed in shared memory (two bit planes + tile tables): bounded by the SM
+static int32_t check_top_view_fits(const rcw_config& c) {
+    const int64_t Hp = (int64_t)c.height_tile_map_tu * c.pu_per_tu, Wp = (int64_t)c.width_tile_map_tu * c.pu_per_tu;
+    const int map_words = ((c.height_tile_map_tu * ((c.width_tile_map_tu + 31) / 32) + 3) / 4) * 4;
+    if (Hp > 32767 || Wp > 32767 || Hp * Wp >= (1LL << 28) ||
+        top_view_smem_bytes(c.height_tile_map_tu, c.width_tile_map_tu, c.pu_per_tu, map_words) > 200 * 1024)
+        return fail(RCW_ESIZE, "a top view of %lldx%lld pixels does not fit the renderer's shared memory; "
+                    "lower pu_per_tu", (long long)Hp, (long long)Wp);
+    return RCW_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -321,6 +378,15 @@ int32_t rcw_config_init(rcw_config* cfg) {
     cfg->palette[RCW_COLOR_GOAL_1] = 0x00800000u;   // :295
     cfg->palette[RCW_COLOR_GOAL_2] = 0x00c00000u;   // :296
     cfg->dda_flags = 0;
+    cfg->obs_window_envs = 0;
+    cfg->top_view = 0;
+    cfg->pu_per_tu = 32;                                   // :269
+    cfg->top_palette[RCW_TOP_COLOR_WALL] = 0x00FFFFFFu;    // tile_map_colors :288
+    cfg->top_palette[RCW_TOP_COLOR_GOAL] = 0x00FF0000u;
+    cfg->top_palette[RCW_TOP_COLOR_EMPTY] = 0x00000000u;
+    cfg->top_palette[RCW_TOP_COLOR_BORDER] = 0x00ccccccu;  // :364-367
+    cfg->top_palette[RCW_TOP_COLOR_RAY] = 0x00808080u;     // ray_color :289
+    cfg->top_palette[RCW_TOP_COLOR_PLAYER] = 0x00c0c0c0u;  // player_color :290
     return RCW_OK;
 }
 
@@ -484,6 +550,8 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
     if (cfg->dda_flags & ~(uint32_t)(RCW_DDA_TIE_LE | RCW_DDA_DIST_POST))
         return fail(RCW_EINVAL, "unknown dda_flags 0x%x", cfg->dda_flags);
     if (cfg->obs_window_envs < 0) return fail(RCW_EINVAL, "obs_window_envs must be >= 0");
+    if (cfg->pu_per_tu < 1 || cfg->pu_per_tu > 1024) return fail(RCW_EINVAL, "pu_per_tu must be in 1..1024");
+    if (cfg->top_view != 0 && cfg->top_view != 1) return fail(RCW_EINVAL, "top_view must be 0 or 1");
     const int bpp = cfg->obs_format == RCW_OBS_RGB8 ? 3 : (cfg->obs_format == RCW_OBS_XRGB32 ? 4 : 1);
     const int gpe = (cfg->num_rays + 31) / 32;
     if ((int64_t)cfg->num_rays * cfg->height_camera_view_pu * bpp >= (1LL << 30))
@@ -500,6 +568,9 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
     }
     if (cfg->device < 0 || cfg->device >= ndev)
         return fail(RCW_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+
+    if (cfg->top_view)
+        if (int32_t rc = check_top_view_fits(*cfg)) return rc;
 
     rcw_batch* b = new (std::nothrow) rcw_batch();
     if (!b) return fail(RCW_ENOMEM, "out of host memory");
@@ -568,6 +639,48 @@ int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls) {
                         cudaMemcpyHostToDevice));
     b->per_env_maps = true;
     return RCW_OK;
+}
+
+int32_t rcw_render_top_view(rcw_batch* b) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (int32_t rc = check_top_view_fits(b->cfg)) return rc;
+    DeviceGuard g(b->device);
+    const int64_t E = b->cfg.num_envs;
+    for (int64_t e0 = 0; e0 < E; e0 += b->obs_window)
+        if (int32_t rc = enqueue_top_view(b, b->st[b->cur], e0, E - e0 < b->obs_window ? E - e0 : b->obs_window, 0))
+            return rc;
+    return RCW_OK;
+}
+
+int32_t rcw_top_view_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_t* env_stride_bytes) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (dptr) *dptr = b->d_top;
+    if (total_bytes) *total_bytes = b->d_top ? b->top_env_stride * (size_t)b->obs_window : 0;
+    if (env_stride_bytes) *env_stride_bytes = b->top_env_stride;
+    return RCW_OK;
+}
+
+int32_t rcw_copy_top_view(rcw_batch* b, int64_t env0, int64_t n, void* host) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!host) return fail(RCW_EINVAL, "host is null");
+    if (!b->d_top) return fail(RCW_EINVAL, "no top view has been drawn yet (rcw_render_top_view or rcw_config.top_view)");
+    if (env0 < 0 || n < 1 || env0 + n > b->cfg.num_envs)
+        return fail(RCW_ESIZE, "env range [%lld, %lld) outside 0..%lld", (long long)env0,
+                    (long long)(env0 + n), (long long)b->cfg.num_envs);
+    if (n > b->obs_window)
+        return fail(RCW_ESIZE, "%lld envs requested, the window holds %lld", (long long)n, (long long)b->obs_window);
+    DeviceGuard g(b->device);
+    const rcw_config& c = b->cfg;
+    const size_t bytes = (size_t)c.height_tile_map_tu * c.pu_per_tu * (size_t)c.width_tile_map_tu * c.pu_per_tu * 4;
+    const int64_t slot0 = env0 % b->obs_window;
+    if (slot0 + n > b->obs_window) {
+        const int64_t n1 = b->obs_window - slot0;
+        if (int32_t rc = rcw_copy_top_view(b, env0, n1, host)) return rc;
+        return rcw_copy_top_view(b, env0 + n1, n - n1, static_cast<uint8_t*>(host) + (size_t)n1 * bytes);
+    }
+    RCW_CUDA(cudaMemcpy2DAsync(host, bytes, b->d_top + (size_t)slot0 * b->top_env_stride, b->top_env_stride, bytes,
+                               (size_t)n, cudaMemcpyDeviceToHost, b->stream));
+    return sync_and_check(b);
 }
 
 int32_t rcw_render(rcw_batch* b) {

@@ -134,6 +134,27 @@ struct ResetParams {
     const uint8_t* mask;      // nullptr => all
 };
 
+// update_top_view! for envs [env_first, env_first + env_count) (rcw_topview.cuh)
+struct TopViewParams {
+    int32_t H, W, wpr, map_words;
+    int32_t N, R;
+    int32_t pu;              // pu_per_tu
+    int32_t Hp, Wp;          // H * pu, W * pu
+    uint32_t dda_flags;
+    float radius;            // player_radius_wu
+    uint32_t palette[6];     // RCW_TOP_COLOR_*
+    int32_t dir_slot;
+    const float2* dirs;
+    const float4* ray_table;
+    const uint32_t* wall_map;
+    uint32_t map_env_stride;
+    StateRef st;             // the state to draw
+    uint8_t* top;            // [window][env_stride] bytes; one env = uint32 [Wp][Hp], row fastest
+    size_t env_stride;       // bytes, multiple of 128
+    uint32_t window, slot0;  // env_first + k lives in slot (slot0 + k) mod window
+    int64_t env_first, env_count;
+};
+
 // kernel launchers (rcw_kernels.cu)
 cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov, float4* table,
                                    cudaStream_t s);
@@ -148,6 +169,8 @@ cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const L
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);
 // state `from` -> state `to` for envs [env0, env0 + n): makes a range step visible in the buffer it read
 cudaError_t launch_commit_range(const StateRef& from, const StateRef& to, int64_t env0, int64_t n, cudaStream_t s);
+size_t top_view_smem_bytes(int H, int W, int pu, int map_words);
+cudaError_t launch_top_view(const TopViewParams& p, cudaStream_t s);
 cudaError_t upload_dir_slot(int slot, const float2* host_dirs, int n, cudaStream_t s);
 
 }  // namespace rcw

@@ -472,20 +472,20 @@ struct ColumnShade {
     int cid;         // palette index of the wall / goal colour
 };
 
-// cast_rays! for the 32 rays [32 g, 32 g + 32) of an env (single_room.jl:195-231) and the height /
-// colour of every ray's column (:404-429).  lane <-> ray.  Optionally dumps the ray results.
-template <int MODE>
-__device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, const uint32_t* s_map,
-                                                      const EnvPose& pose, const float4 rt, int g, int lane,
-                                                      uint32_t env_rel) {
-    const int H = p.H, W = p.W, wpr = p.wpr, R = p.R, P = p.P;
-    const float x = pose.x, y = pose.y;
-    const int au = pose.au;
-    const int gi0 = (int)(pose.goal & 0xFFFFu) - 1, gj0 = (int)(pose.goal >> 16) - 1;
-    const int ray = g * 32 + lane;
-    const float2 dir = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
+// What RayCaster.cast_ray returns for one ray (tiles 0-based here), plus which layer stopped it.
+struct RayHit {
+    int ti, tj;      // hit tile
+    int dim;         // 1: crossed along dimension 1 (i), 2: along dimension 2 (j), 0: started inside an obstacle
+    float dist;      // Euclidean distance along the unit ray
+    bool is_wall;    // the hit tile is a wall (outside the map counts as wall); otherwise it is the goal
+};
 
-    // RayCaster.cast_ray contract: tiles here are 0-based
+// RayCaster.cast_ray contract for the ray rt = {ray_x, ray_y, |1/ray_x|, |1/ray_y|} from (x, y).
+// Must be called by all 32 lanes of a warp (lane <-> ray): a lane that has hit stays on its obstacle
+// tile, so "stopped" needs no extra state, and the warp leaves the loop together once no lane is still
+// walking (ballot early-exit).
+__device__ __forceinline__ RayHit dda_cast(const uint32_t* s_map, int H, int W, int wpr, uint32_t dda_flags,
+                                           float x, float y, int gi0, int gj0, const float4 rt, int lane) {
     int ti = __float2int_rd(x), tj = __float2int_rd(y);
     const int si = rt.x < 0.0f ? -1 : 1, sj = rt.y < 0.0f ? -1 : 1;
     float tx = rt.x < 0.0f ? __fmul_rn(__fsub_rn(x, (float)ti), rt.z)
@@ -494,13 +494,12 @@ __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, cons
                            : __fmul_rn(__fsub_rn((float)(tj + 1), y), rt.w);
     int dim = 0;
     float dist = 0.0f;
-    const bool tie_le = (p.dda_flags & RCW_DDA_TIE_LE) != 0;
+    const bool tie_le = (dda_flags & RCW_DDA_TIE_LE) != 0;
     bool is_wall;   // the tile the ray stands on is a wall (outside the map counts as wall)
-    // A lane that has hit stays on its obstacle tile, so "stopped" needs no extra state; the warp
-    // leaves the loop together once no lane is still walking (ballot early-exit).
 #if RCW_EXP == 1
     is_wall = true; dist = 1.0f + 0.01f * (float)lane; dim = 1 + (lane & 1);
 #else
+    (void)lane;
     // probe the tile the ray stands on: wall (outside the map counts as wall) or this env's goal
     auto probe = [&]() {
         const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
@@ -528,8 +527,32 @@ __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, cons
         }
     }
 #endif
-    if ((p.dda_flags & RCW_DDA_DIST_POST) && dim != 0)
+    if ((dda_flags & RCW_DDA_DIST_POST) && dim != 0)
         dist = (dim == 1) ? __fsub_rn(tx, rt.z) : __fsub_rn(ty, rt.w);
+    RayHit h;
+    h.ti = ti;
+    h.tj = tj;
+    h.dim = dim;
+    h.dist = dist;
+    h.is_wall = is_wall;
+    return h;
+}
+
+// cast_rays! for the 32 rays [32 g, 32 g + 32) of an env (single_room.jl:195-231) and the height /
+// colour of every ray's column (:404-429).  lane <-> ray.  Optionally dumps the ray results.
+template <int MODE>
+__device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, const uint32_t* s_map,
+                                                      const EnvPose& pose, const float4 rt, int g, int lane,
+                                                      uint32_t env_rel) {
+    const int R = p.R, P = p.P;
+    const int au = pose.au;
+    const int gi0 = (int)(pose.goal & 0xFFFFu) - 1, gj0 = (int)(pose.goal >> 16) - 1;
+    const int ray = g * 32 + lane;
+    const float2 dir = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
+    const RayHit hit = dda_cast(s_map, p.H, p.W, p.wpr, p.dda_flags, pose.x, pose.y, gi0, gj0, rt, lane);
+    const int ti = hit.ti, tj = hit.tj, dim = hit.dim;
+    const float dist = hit.dist;
+    const bool is_wall = hit.is_wall;
 
     if (MODE == kModeRays) {
         if (ray < R) {
@@ -1079,6 +1102,8 @@ cudaError_t launch_commit_range(const StateRef& from, const StateRef& to, int64_
     commit_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(from, to, env0, n);
     return cudaGetLastError();
 }
+
+#include "rcw_topview.cuh"
 
 cudaError_t upload_dir_slot(int slot, const float2* host_dirs, int n, cudaStream_t s) {
     return cudaMemcpyToSymbolAsync(c_dirs, host_dirs, sizeof(float2) * (size_t)n,

@@ -1,0 +1,179 @@
+// rcw_topview.cuh — update_top_view!(env) for a batch (reference: src/single_room.jl:342-372, 446-483).
+// Included by rcw_kernels.cu inside namespace rcw (it shares dda_cast, the TMA helpers and c_dirs).
+//
+// The reference redraws, per env and per step, the tile grid (filled 32x32 squares with a one-pixel
+// border), the 512 ray segments from the player to where each ray stopped, and the player's circle, into
+// top_view::Array{UInt32}(H * pu, W * pu) (:302).  The drawing primitives belong to SimpleDraw.jl 0.3, which
+// is not vendored: they are restated from the algorithms that package documents (Bresenham line over all
+// octants, midpoint circle), every pixel bounds-checked — UNPINNED like the DDA.
+//
+// One CTA draws one env.  The image is never read back from HBM: rays and circle are rasterised into two
+// bit planes in shared memory (one bit per pixel each, atomicOr), then the CTA streams the whole image out
+// once, in whole 32-byte sectors, composing every pixel as circle > ray > tile border > tile colour — the
+// draw order of the reference (:472, :474-478, :480).  512 KB per env at the defaults: HBM-write bound.
+
+constexpr int kTopThreads = 256;
+
+// utils.jl:6 — wu_to_pu(x_wu, pu_per_wu) = floor(Int, x_wu * pu_per_wu) + 1 (Float32 product)
+__device__ __forceinline__ int wu_to_pu(float x_wu, float pu) { return __float2int_rd(__fmul_rn(x_wu, pu)) + 1; }
+
+__device__ __forceinline__ void plane_set(uint32_t* plane, int i, int j, int Hp, int Wp) {   // 1-based, clipped
+    if (i >= 1 && i <= Hp && j >= 1 && j <= Wp) {
+        const uint32_t idx = (uint32_t)(i - 1) + (uint32_t)Hp * (uint32_t)(j - 1);
+        atomicOr(plane + (idx >> 5), 1u << (idx & 31u));
+    }
+}
+
+__global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_constant__ TopViewParams p) {
+    extern __shared__ __align__(128) uint32_t s_top[];   // [wall layer][ray plane][player plane][row info u16][col info u16][tile code u8]
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.H, W = p.W, Hp = p.Hp, Wp = p.Wp, pu = p.pu, R = p.R;
+    const uint32_t L = (uint32_t)Hp * (uint32_t)Wp;          // pixels
+    const uint32_t plane_words = (L + 31u) >> 5;
+    uint32_t* const s_map = s_top;
+    uint32_t* const s_ray = s_map + p.map_words;
+    uint32_t* const s_player = s_ray + plane_words;
+    uint16_t* const s_row = reinterpret_cast<uint16_t*>(s_player + plane_words);   // [Hp] tile row | border << 15
+    uint16_t* const s_colinfo = s_row + ((Hp + 1) & ~1);                           // [Wp] tile column | border << 15
+    uint8_t* const s_tile = reinterpret_cast<uint8_t*>(s_colinfo + ((Wp + 1) & ~1)); // [W][H] colour code of the tile
+
+    const uint32_t env_rel = blockIdx.x;
+    const int64_t env = p.env_first + env_rel;
+
+    // ---- this env's wall layer: one TMA bulk copy; the planes are cleared meanwhile
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)p.map_words * 4u);
+        bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.map_words * 4u, &s_bar);
+    }
+    for (uint32_t k = tid; k < 2u * plane_words; k += kTopThreads) s_ray[k] = 0u;
+    const float x = __ldg(p.st.pos_x + env), y = __ldg(p.st.pos_y + env);
+    const int au = __ldg(p.st.dir_au + env);
+    const uint32_t goal = __ldg(p.st.goal + env);
+    const int gi0 = (int)(goal & 0xFFFFu) - 1, gj0 = (int)(goal >> 16) - 1;
+    for (int i = tid; i < Hp; i += kTopThreads) {
+        const int t = i / pu, r = i - t * pu;
+        s_row[i] = (uint16_t)(t | ((r == 0 || r == pu - 1) ? 0x8000 : 0));
+    }
+    for (int j = tid; j < Wp; j += kTopThreads) {
+        const int t = j / pu, r = j - t * pu;
+        s_colinfo[j] = (uint16_t)(t | ((r == 0 || r == pu - 1) ? 0x8000 : 0));
+    }
+    __syncthreads();          // mbarrier initialised, planes cleared
+    mbar_wait(&s_bar, 0);
+
+    // ---- draw_tile_map! colour of every tile: findfirst over the layers WALL, GOAL (:355-360)
+    for (int t = tid; t < H * W; t += kTopThreads) {
+        const int j0 = t / H, i0 = t - j0 * H;
+        s_tile[t] = wall_bit(s_map, p.wpr, i0, j0) ? RCW_TOP_COLOR_WALL
+                                                   : ((i0 == gi0 && j0 == gj0) ? RCW_TOP_COLOR_GOAL : RCW_TOP_COLOR_EMPTY);
+    }
+
+    // ---- the ray segments (:474-478): lane <-> ray, Bresenham into the ray plane
+    const float fpu = (float)pu;
+    const int ip = wu_to_pu(x, fpu), jp = wu_to_pu(y, fpu);           // :469
+    const int groups = (R + 31) >> 5;
+    for (int g = warp; g < groups; g += kTopThreads / 32) {
+        const int ray = g * 32 + lane;
+        const float4 rt = __ldg(p.ray_table + (size_t)au * (size_t)R + (size_t)min(ray, R - 1));
+        const RayHit hit = dda_cast(s_map, H, W, p.wpr, p.dda_flags, x, y, gi0, gj0, rt, lane);
+        if (ray < R) {
+            // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
+            const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
+            const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
+            // [EXT SimpleDraw] Line(point1, point2): Bresenham, all octants, both end points drawn
+            const int di = abs(i2 - ip), dj = -abs(j2 - jp);
+            const int si = ip < i2 ? 1 : -1, sj = jp < j2 ? 1 : -1;
+            int err = di + dj, i = ip, j = jp;
+            for (;;) {
+                plane_set(s_ray, i, j, Hp, Wp);
+                if (i == i2 && j == j2) break;
+                const int e2 = 2 * err;
+                if (e2 >= dj) {
+                    err += dj;
+                    i += si;
+                }
+                if (e2 <= di) {
+                    err += di;
+                    j += sj;
+                }
+            }
+        }
+    }
+
+    // ---- the player (:480): [EXT SimpleDraw] Circle(Point(i - r, j - r), 2r + 1) = midpoint circle of radius r
+    if (tid == 0) {
+        const int rp = wu_to_pu(p.radius, fpu);                        // :470
+        int a = 0, b = rp, d = 1 - rp;
+        while (a <= b) {
+            plane_set(s_player, ip + a, jp + b, Hp, Wp);
+            plane_set(s_player, ip - a, jp + b, Hp, Wp);
+            plane_set(s_player, ip + a, jp - b, Hp, Wp);
+            plane_set(s_player, ip - a, jp - b, Hp, Wp);
+            plane_set(s_player, ip + b, jp + a, Hp, Wp);
+            plane_set(s_player, ip - b, jp + a, Hp, Wp);
+            plane_set(s_player, ip + b, jp - a, Hp, Wp);
+            plane_set(s_player, ip - b, jp - a, Hp, Wp);
+            if (d < 0) {
+                d += 2 * a + 3;
+            } else {
+                d += 2 * (a - b) + 5;
+                b -= 1;
+            }
+            a += 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- stream the image out: one 32-byte sector (8 pixels along a column) per lane and iteration
+    uint32_t slot = p.slot0 + env_rel;
+    if (slot >= p.window) slot -= p.window;
+    uint8_t* const img = p.top + (size_t)slot * p.env_stride;
+    const uint8_t* const ray_bytes = reinterpret_cast<const uint8_t*>(s_ray);
+    const uint8_t* const player_bytes = reinterpret_cast<const uint8_t*>(s_player);
+    const uint32_t border_c = p.palette[RCW_TOP_COLOR_BORDER], ray_c = p.palette[RCW_TOP_COLOR_RAY],
+                   player_c = p.palette[RCW_TOP_COLOR_PLAYER];
+    const uint32_t n_sec = (L + 7u) >> 3;
+#pragma unroll 2
+    for (uint32_t s = tid; s < n_sec; s += kTopThreads) {
+        const uint32_t idx0 = s << 3;
+        uint32_t j0 = idx0 / (uint32_t)Hp, i0 = idx0 - j0 * (uint32_t)Hp;
+        const uint32_t rb = ray_bytes[s], pb = player_bytes[s];
+        uint32_t cinfo = s_colinfo[min(j0, (uint32_t)Wp - 1u)];
+        uint32_t px[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t rinfo = s_row[i0];
+            const uint32_t code = s_tile[(rinfo & 0x7FFFu) + (uint32_t)H * (cinfo & 0x7FFFu)];
+            uint32_t c = ((rinfo | cinfo) & 0x8000u) ? border_c : p.palette[code];
+            c = ((rb >> k) & 1u) ? ray_c : c;
+            c = ((pb >> k) & 1u) ? player_c : c;
+            px[k] = (idx0 + (uint32_t)k < L) ? c : 0u;    // bytes behind the last pixel are padding
+            if (++i0 == (uint32_t)Hp) {                    // next column of the image
+                i0 = 0;
+                ++j0;
+                cinfo = s_colinfo[min(j0, (uint32_t)Wp - 1u)];
+            }
+        }
+        store_stream32(img + ((size_t)s << 5), make_uint4(px[0], px[1], px[2], px[3]),
+                       make_uint4(px[4], px[5], px[6], px[7]));
+    }
+}
+
+size_t top_view_smem_bytes(int H, int W, int pu, int map_words) {
+    const size_t Hp = (size_t)H * pu, Wp = (size_t)W * pu, L = Hp * Wp;
+    const size_t plane_words = (L + 31) / 32;
+    return (size_t)map_words * 4 + 2 * plane_words * 4 + 2 * ((Hp + 1) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1) +
+           (((size_t)H * W + 15) & ~(size_t)15);
+}
+
+cudaError_t launch_top_view(const TopViewParams& p, cudaStream_t s) {
+    const size_t smem = top_view_smem_bytes(p.H, p.W, p.pu, p.map_words);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(top_view_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    top_view_kernel<<<(unsigned)p.env_count, kTopThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}

@@ -47,7 +47,10 @@ struct RcwConfig
     palette::NTuple{6, UInt32}
     dda_flags::UInt32
     obs_window_envs::Int32
-    reserved::NTuple{6, UInt32}
+    top_view::Int32
+    pu_per_tu::Int32
+    top_palette::NTuple{6, UInt32}
+    reserved::NTuple{4, UInt32}
 end
 
 last_error() = unsafe_string(ccall((:rcw_last_error, LIB), Cstring, ()))
@@ -90,6 +93,8 @@ function BatchedSingleRoom(;
         seed = 0,
         env_id_offset = 0,
         obs_window_envs = 0,
+        top_view = false,
+        pu_per_tu = 32,
     )
     T === Float32 || error("librcw_b200 computes in Float32 (the reference default, single_room.jl:43)")
 
@@ -102,13 +107,15 @@ function BatchedSingleRoom(;
     end
 
     palette = (0x00FFFFFF, 0x00404040, 0x00808080, 0x00c0c0c0, 0x00800000, 0x00c00000)  # single_room.jl:291-296
+    # tile_map_colors, tile border, ray_color, player_color  (single_room.jl:288-290, 364-367)
+    top_palette = (0x00FFFFFF, 0x00FF0000, 0x00000000, 0x00cccccc, 0x00808080, 0x00c0c0c0)
     cfg = Ref(RcwConfig(UInt32(sizeof(RcwConfig)), Int32(device), Int64(num_envs), Int64(env_id_offset),
                         Int32(height_tile_map_tu), Int32(width_tile_map_tu), Int32(num_directions),
                         Int32(num_rays), Int32(height_camera_view_pu), Float32(player_radius_wu),
                         Float32(position_increment_wu), Float32(semi_field_of_view_wu),
                         Float32(camera_height_tile_wu), Float32(goal_reward), Int32(obs_format),
                         Int32(auto_reset), UInt64(seed), palette, UInt32(0), Int32(obs_window_envs),
-                        ntuple(_ -> UInt32(0), 6)))
+                        Int32(top_view), Int32(pu_per_tu), top_palette, ntuple(_ -> UInt32(0), 4)))
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve directions begin
         check(ccall((:rcw_create, LIB), Int32, (Ref{RcwConfig}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
@@ -166,6 +173,12 @@ function RCW.cast_rays!(env::BatchedSingleRoom)
     return nothing
 end
 RCW.update_camera_view!(env::BatchedSingleRoom) = nothing   # fused into cast_rays! above
+
+# update_top_view! — src/single_room.jl:446-483, for every env (UInt32 images on the device)
+function RCW.update_top_view!(env::BatchedSingleRoom)
+    check(ccall((:rcw_render_top_view, LIB), Int32, (Ptr{Cvoid},), env.handle))
+    return nothing
+end
 
 RCW.get_action_names(env::BatchedSingleRoom) = (:MOVE_FORWARD, :MOVE_BACKWARD, :TURN_LEFT, :TURN_RIGHT)  # :486
 

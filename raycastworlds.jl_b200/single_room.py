@@ -47,7 +47,9 @@ class BatchedSingleRoom(AbstractGame):
     `directions_wu` (the host's own [N, 2] float32 direction table), the two switches for the
     unpinned RayCaster.cast_ray decisions (`dda_tie_le`, `dda_dist_post`) and `obs_window_envs`
     (the observation buffer holds only that many env slots, env e in slot e mod K — for batches whose
-    observations exceed HBM; see `act_range`).
+    observations exceed HBM; see `act_range`), `top_view` (redraw the top view inside every step /
+    reset / render like the reference's act!(env), single_room.jl:333-340; off by default for a batch),
+    `pu_per_tu` (:269) and `top_palette`.
     """
 
     def __init__(self, num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int = 8,
@@ -58,7 +60,8 @@ class BatchedSingleRoom(AbstractGame):
                  goal_reward: float = 1.0, obs_format: str = "rgb8", auto_reset: bool = True,
                  seed: int = 0, env_id_offset: int = 0,
                  directions_wu: Optional[np.ndarray] = None, palette: Optional[Sequence[int]] = None,
-                 dda_tie_le: bool = False, dda_dist_post: bool = False, obs_window_envs: int = 0):
+                 dda_tie_le: bool = False, dda_dist_post: bool = False, obs_window_envs: int = 0,
+                 top_view: bool = False, pu_per_tu: int = 32, top_palette: Optional[Sequence[int]] = None):
         self._lib = _capi.load()
         self._h = C.c_void_p()
         cfg = _capi.default_config()
@@ -87,6 +90,11 @@ class BatchedSingleRoom(AbstractGame):
         cfg.dda_flags = (_capi.RCW_DDA_TIE_LE if dda_tie_le else 0) | (
             _capi.RCW_DDA_DIST_POST if dda_dist_post else 0)
         cfg.obs_window_envs = int(obs_window_envs)
+        cfg.top_view = int(bool(top_view))
+        cfg.pu_per_tu = int(pu_per_tu)
+        if top_palette is not None:
+            for i, c in enumerate(top_palette):
+                cfg.top_palette[i] = int(c)
         dirs = None
         if directions_wu is not None:
             dirs = np.ascontiguousarray(directions_wu, np.float32)
@@ -289,6 +297,36 @@ class BatchedSingleRoom(AbstractGame):
         _capi.check(self._lib.rcw_copy_obs(self._h, env0, n, _ptr(out)))
         return out
 
+    # -- top view (single_room.jl:342-372, 446-483) -----------------------------------------------------
+    @property
+    def top_view_shape(self):
+        """[env slots, width_tu * pu (columns), height_tu * pu (rows)] uint32; row fastest, as in the
+        reference's Array{UInt32}(H * pu, W * pu) (:302)."""
+        pu = self.cfg.pu_per_tu
+        return (self.obs_window, self.cfg.width_tile_map_tu * pu, self.cfg.height_tile_map_tu * pu)
+
+    def render_top_view(self):
+        """update_top_view!(env) from the current state of every env."""
+        _capi.check(self._lib.rcw_render_top_view(self._h))
+
+    def copy_top_view(self, env0: int = 0, n: Optional[int] = None):
+        n = min(self.num_envs - env0, self.obs_window) if n is None else n
+        out = np.empty((n,) + self.top_view_shape[1:], np.uint32)
+        _capi.check(self._lib.rcw_copy_top_view(self._h, env0, n, _ptr(out)))
+        return out
+
+    def top_view_tensor(self):
+        """Zero-copy torch view (int32) of the device top views, shape top_view_shape; borrowed like obs_tensor()."""
+        import torch
+
+        ptr, total, stride = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        _capi.check(self._lib.rcw_top_view_device_ptr(self._h, C.byref(ptr), C.byref(total), C.byref(stride)))
+        if not ptr.value:
+            raise RuntimeError("no top view has been drawn yet")
+        flat = torch.as_tensor(_CudaBuffer(ptr.value, total.value, self), device=torch.device("cuda", self.cfg.device))
+        slots, wp, hp = self.top_view_shape
+        return torch.as_strided(flat.view(torch.int32), (slots, wp, hp), (stride.value // 4, hp, 1))
+
     # -- bookkeeping ------------------------------------------------------------------------------
     def episode_stats(self, reset_counters: bool = False):
         ep, sr, sl = C.c_int64(), C.c_double(), C.c_int64()
@@ -379,11 +417,13 @@ class _WorldView:
 
 
 class SingleRoom(BatchedSingleRoom):
-    """The reference's single game (single_room.jl:241-324): one env, no auto-reset, UInt32 pixels."""
+    """The reference's single game (single_room.jl:241-324): one env, no auto-reset, UInt32 pixels, the
+    top view redrawn by every act! / reset! (:329,337)."""
 
     def __init__(self, **kw):
         kw.setdefault("auto_reset", False)
         kw.setdefault("obs_format", "xrgb32")
+        kw.setdefault("top_view", True)
         super().__init__(1, **kw)
         self.world = _WorldView(self, 0)
 
@@ -400,6 +440,13 @@ class SingleRoom(BatchedSingleRoom):
         if self.obs_format != "xrgb32":
             raise ValueError("camera_view needs obs_format='xrgb32'")
         return self.copy_obs(0, 1)[0].T
+
+    @property
+    def top_view(self):
+        """uint32 [height_tu * pu, width_tu * pu], the reference's top_view (single_room.jl:302)."""
+        if not self.cfg.top_view:
+            self.render_top_view()
+        return self.copy_top_view(0, 1)[0].T
 
 
 class RLBaseEnv:

@@ -43,8 +43,8 @@ def oracle():
 
 GOLDEN_CONFIGS = {
     "A": dict(),
-    "B": dict(H=64, W=64, N=256, R=128, P=96),
+    "B": dict(H=64, W=64, N=256, R=128, P=96, pu_per_tu=4),
     "C": dict(H=5, W=7, N=36, R=45, P=51, radius=np.float32(0.2), incr=np.float32(0.3),
-              sfov=np.float32(0.5), cam_h=np.float32(0.8)),
+              sfov=np.float32(0.5), cam_h=np.float32(0.8), pu_per_tu=7),
     "D": dict(tie_le=1, dist_post=1),
 }

@@ -196,6 +196,70 @@ class PyWorld:
         return img
 
 
+    # ---- single_room.jl:342-372, 446-483 (shapes: [EXT] SimpleDraw.jl 0.3 — Bresenham line, midpoint circle, clipped)
+    def top_view(self, pu):
+        """uint32 [W*pu columns][H*pu rows] after cast_rays()."""
+        H, W = self.H, self.W
+        img = np.zeros((H * pu + 2, W * pu + 2), np.uint32)   # 1-based [i, j], one spare row / column
+
+        def put(i, j, c):
+            if 1 <= i <= H * pu and 1 <= j <= W * pu:
+                img[i, j] = c
+
+        for j in range(1, W + 1):
+            for i in range(1, H + 1):
+                it, jt = (i - 1) * pu + 1, (j - 1) * pu + 1                      # :350-351
+                if self.wall[i, j]:                                              # findfirst, :355-360
+                    color = 0x00FFFFFF
+                elif (i, j) == self.goal:
+                    color = 0x00FF0000
+                else:
+                    color = 0x00000000
+                img[it:it + pu, jt:jt + pu] = color                              # :353,362
+                img[it, jt:jt + pu] = 0x00CCCCCC                                 # :364
+                img[it + pu - 1, jt:jt + pu] = 0x00CCCCCC                        # :365
+                img[it:it + pu, jt] = 0x00CCCCCC                                 # :366
+                img[it:it + pu, jt + pu - 1] = 0x00CCCCCC                        # :367
+
+        def wu_to_pu(x):                                                         # utils.jl:6
+            return int(math.floor(float(F(F(x) * F(pu))))) + 1
+
+        ip, jp = wu_to_pu(self.pos[0]), wu_to_pu(self.pos[1])                    # :469
+        rp = wu_to_pu(self.radius)                                               # :470
+        for k in range(self.R):                                                  # :474-478
+            r0, r1 = self.ray_dir[k]
+            i2 = wu_to_pu(F(self.pos[0] + F(self.dist[k] * r0)))
+            j2 = wu_to_pu(F(self.pos[1] + F(self.dist[k] * r1)))
+            i, j = ip, jp
+            di, dj = abs(i2 - i), -abs(j2 - j)
+            si, sj = (1 if i < i2 else -1), (1 if j < j2 else -1)
+            err = di + dj
+            while True:
+                put(i, j, 0x00808080)
+                if (i, j) == (i2, j2):
+                    break
+                e2 = 2 * err
+                if e2 >= dj:
+                    err += dj
+                    i += si
+                if e2 <= di:
+                    err += di
+                    j += sj
+        a, b, d = 0, rp, 1 - rp                                                  # :480
+        while a <= b:
+            for (u, v) in ((a, b), (b, a)):
+                for su in (1, -1):
+                    for sv in (1, -1):
+                        put(ip + su * u, jp + sv * v, 0x00C0C0C0)
+            if d < 0:
+                d += 2 * a + 3
+            else:
+                d += 2 * (a - b) + 5
+                b -= 1
+            a += 1
+        return np.ascontiguousarray(img[1:H * pu + 1, 1:W * pu + 1].T)
+
+
 def random_walk_states(w: PyWorld, rng, n_states, steps_between):
     """Reachable states: start at a tile centre, take random actions (never entering the goal)."""
     states = []
@@ -214,11 +278,11 @@ def random_walk_states(w: PyWorld, rng, n_states, steps_between):
     return states
 
 
-def cast_case(w: PyWorld, states, full_images=0):
+def cast_case(w: PyWorld, states, full_images=0, pu=32):
     out = dict(states=np.array([[s[0], s[1]] for s in states], np.float32),
                au=np.array([s[2] for s in states], np.int32),
                goal=np.array([[s[3], s[4]] for s in states], np.int32))
-    hits, dims, dists, rdirs, heights, crcs, imgs = [], [], [], [], [], [], []
+    hits, dims, dists, rdirs, heights, crcs, imgs, top_crcs, tops = [], [], [], [], [], [], [], [], []
     for k, s in enumerate(states):
         w.pos, w.au, w.goal = (F(s[0]), F(s[1])), int(s[2]), (int(s[3]), int(s[4]))
         w.cast_rays()
@@ -229,13 +293,20 @@ def cast_case(w: PyWorld, states, full_images=0):
         rdirs.append(w.ray_dir)
         heights.append([w.height_line(i) for i in range(w.R)])
         crcs.append(zlib.crc32(img.tobytes()))
+        top = w.top_view(pu)
+        top_crcs.append(zlib.crc32(top.tobytes()))
         if k < full_images:
             imgs.append(img)
+            if top.size <= 1 << 16:
+                tops.append(top)
     out.update(hit=np.array(hits, np.int32), dim=np.array(dims, np.int32),
                dist=np.array(dists, np.float32), ray_dir=np.array(rdirs, np.float32),
                height=np.array(heights, np.int32), crc=np.array(crcs, np.uint32))
+    out["top_crc"] = np.array(top_crcs, np.uint32)
     if imgs:
         out["image"] = np.array(imgs, np.uint32)
+    if tops:
+        out["top_image"] = np.array(tops, np.uint32)
     return out
 
 
@@ -288,7 +359,7 @@ def main():
     # B: config 5 geometry (64x64, N=256), fewer rays to keep the file small
     w = PyWorld(H=64, W=64, N=256, R=128, P=96)
     st = random_walk_states(w, rng, 12, 300)
-    for k, v in cast_case(w, st).items():
+    for k, v in cast_case(w, st, pu=4).items():
         out["B_" + k] = v
     for k, v in act_case(w, rng, 4, 400).items():
         out["B_act_" + k] = v
@@ -296,7 +367,7 @@ def main():
     # C: odd sizes (R not a multiple of 32, P odd, other radius / increment / fov)
     w = PyWorld(H=5, W=7, N=36, R=45, P=51, radius=0.2, incr=0.3, sfov=0.5, cam_h=0.8)
     st = random_walk_states(w, rng, 10, 100)
-    for k, v in cast_case(w, st, full_images=1).items():
+    for k, v in cast_case(w, st, full_images=1, pu=7).items():
         out["C_" + k] = v
     for k, v in act_case(w, rng, 4, 300).items():
         out["C_act_" + k] = v

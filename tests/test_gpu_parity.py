@@ -17,11 +17,11 @@ pytestmark = pytest.mark.gpu
 RCW_KW = {
     "A": dict(),
     "B": dict(height_tile_map_tu=64, width_tile_map_tu=64, num_directions=256, num_rays=128,
-              height_camera_view_pu=96),
+              height_camera_view_pu=96, pu_per_tu=4),
     "C": dict(height_tile_map_tu=5, width_tile_map_tu=7, num_directions=36, num_rays=45,
               height_camera_view_pu=51, player_radius_wu=np.float32(0.2),
               position_increment_wu=np.float32(0.3), semi_field_of_view_wu=np.float32(0.5),
-              camera_height_tile_wu=np.float32(0.8)),
+              camera_height_tile_wu=np.float32(0.8), pu_per_tu=7),
     "D": dict(dda_tie_le=True, dda_dist_post=True),
 }
 

@@ -27,6 +27,12 @@ def test_cast_and_render_match_golden(oracle, golden, case):
         assert zlib.crc32(img.tobytes()) == int(golden[f"{case}_crc"][k])
         if f"{case}_image" in golden and k < len(golden[f"{case}_image"]):
             np.testing.assert_array_equal(img, golden[f"{case}_image"][k])
+        # update_top_view! (single_room.jl:446-483)
+        w.update_top_view()
+        top = w.top_view
+        assert zlib.crc32(top.tobytes()) == int(golden[f"{case}_top_crc"][k])
+        if f"{case}_top_image" in golden and k < len(golden[f"{case}_top_image"]):
+            np.testing.assert_array_equal(top, golden[f"{case}_top_image"][k])
 
 
 @pytest.mark.parametrize("case", ["A", "B", "C"])

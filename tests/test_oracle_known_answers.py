@@ -140,3 +140,29 @@ def test_batch_is_independent_of_threads_and_shards(oracle):
     pc, ac, gc = c.states()
     assert np.array_equal(pa[6:], pc) and np.array_equal(aa[6:], ac)
     assert np.array_equal(a.obs_rgb8()[6:], c.obs_rgb8())
+
+
+def test_top_view_hand_derived(oracle):
+    """update_top_view! (single_room.jl:342-372, 446-483) from (2.5, 2.5) facing +i (au 0) on the default map:
+    player pixel = floor(2.5 * 32) + 1 = 81 (utils.jl:6), radius floor(0.125 * 32) + 1 = 5 pixels."""
+    w = oracle.World()
+    w.set_state(2.5, 2.5, 0, 6, 14)
+    w.cast_rays()
+    w.update_top_view()
+    top = w.top_view.T                       # [i, j], 0-based here
+    WALL, GOAL, EMPTY, BORDER, RAY, PLAYER = 0xFFFFFF, 0xFF0000, 0x000000, 0xCCCCCC, 0x808080, 0xC0C0C0
+    assert top.shape == (256, 512)
+    assert top[0, 0] == BORDER and top[31, 31] == BORDER and top[1, 1] == WALL          # wall tile (1, 1)
+    assert top[5 * 32 + 1, 13 * 32 + 1] == GOAL and top[5 * 32, 13 * 32 + 5] == BORDER  # goal tile (6, 14)
+    assert top[3 * 32 + 1, 7 * 32 + 1] == EMPTY
+    # the centre ray runs along +i from the player pixel (81, 81) to the wall at x = 7: pixel floor(7 * 32) + 1 = 225
+    for i in range(81 + 6, 225 + 1):
+        assert top[i - 1, 81 - 1] == RAY, i
+    assert top[226 - 1, 81 - 1] in (BORDER, WALL) and top[226 - 1, 81 - 1] != RAY
+    # the circle of radius 5 about (81, 81): its four axis points, and the centre is not part of the outline
+    for (i, j) in ((86, 81), (76, 81), (81, 86), (81, 76)):
+        assert top[i - 1, j - 1] == PLAYER
+    assert top[81 - 1, 81 - 1] == RAY          # every ray starts at the player pixel
+    # nothing is drawn behind the player: the field of view is +-atan(2/3) about +i
+    assert top[60 - 1, 81 - 1] == EMPTY
+    assert int((top == PLAYER).sum()) in range(20, 41)
