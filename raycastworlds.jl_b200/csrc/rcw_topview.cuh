@@ -17,41 +17,65 @@ constexpr int kTopThreads = 256;
 // utils.jl:6 — wu_to_pu(x_wu, pu_per_wu) = floor(Int, x_wu * pu_per_wu) + 1 (Float32 product)
 __device__ __forceinline__ int wu_to_pu(float x_wu, float pu) { return __float2int_rd(__fmul_rn(x_wu, pu)) + 1; }
 
-__device__ __forceinline__ void plane_set(uint32_t* plane, int i, int j, int Hp, int Wp) {   // 1-based, clipped
+// Bit planes: pixel (i0, j0) (0-based) is bit j0 * SB + i0, SB = Hp rounded up to a multiple of 32, plus 32:
+// every image column starts on a word of its own and consecutive columns start in consecutive banks, so a
+// warp whose 32 rays sit in 32 different columns at the same row does not collide on one bank.
+__host__ __device__ __forceinline__ uint32_t plane_col_bits(int Hp) { return (((uint32_t)Hp + 31u) & ~31u) + 32u; }
+
+// Set pixel (i, j) (1-based, clipped) in a plane; called by the lanes of a warp that are still drawing.
+// lane <-> ray, and adjacent rays share most of their pixels (they leave the same pixel with slopes that
+// differ by 1/400): a lane whose pixel equals its lower neighbour's leaves the atomic to that neighbour.
+__device__ __forceinline__ void plane_set_warp(uint32_t* plane, int i, int j, int Hp, int Wp, uint32_t SB, int lane) {
+    const bool inside = (i >= 1) & (i <= Hp) & (j >= 1) & (j <= Wp);
+    const uint32_t idx = (uint32_t)(j - 1) * SB + (uint32_t)(i - 1);
+    const unsigned act = __activemask();
+    const uint32_t below = __shfl_up_sync(act, idx, 1);
+    const bool dup = (lane > 0) && ((act >> (lane - 1)) & 1u) && below == idx;
+    if (inside && !dup) atomicOr(plane + (idx >> 5), 1u << (idx & 31u));
+}
+
+__device__ __forceinline__ void plane_set(uint32_t* plane, int i, int j, int Hp, int Wp, uint32_t SB) {
     if (i >= 1 && i <= Hp && j >= 1 && j <= Wp) {
-        const uint32_t idx = (uint32_t)(i - 1) + (uint32_t)Hp * (uint32_t)(j - 1);
+        const uint32_t idx = (uint32_t)(j - 1) * SB + (uint32_t)(i - 1);
         atomicOr(plane + (idx >> 5), 1u << (idx & 31u));
     }
 }
 
 __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_constant__ TopViewParams p) {
-    extern __shared__ __align__(128) uint32_t s_top[];   // [wall layer][ray plane][player plane][row info u16][col info u16][tile code u8]
+    // [wall layer][ray plane][player plane][palette 8 x u32][row info u16][column info u16][row-sector info u16][tile code u8]
+    extern __shared__ __align__(128) uint32_t s_top[];
     __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, Hp = p.Hp, Wp = p.Wp, pu = p.pu, R = p.R;
-    const uint32_t L = (uint32_t)Hp * (uint32_t)Wp;          // pixels
-    const uint32_t plane_words = (L + 31u) >> 5;
+    const uint32_t SB = plane_col_bits(Hp);                    // bits per plane column
+    const uint32_t plane_words = ((uint32_t)Wp * (SB >> 5) + 1u) & ~1u;   // even: the two planes are cleared as uint4
     uint32_t* const s_map = s_top;
     uint32_t* const s_ray = s_map + p.map_words;
     uint32_t* const s_player = s_ray + plane_words;
-    uint16_t* const s_row = reinterpret_cast<uint16_t*>(s_player + plane_words);   // [Hp] tile row | border << 15
+    uint32_t* const s_pal = s_player + plane_words;
+    uint16_t* const s_row = reinterpret_cast<uint16_t*>(s_pal + 8);                // [Hp] tile row | border << 15
     uint16_t* const s_colinfo = s_row + ((Hp + 1) & ~1);                           // [Wp] tile column | border << 15
-    uint8_t* const s_tile = reinterpret_cast<uint8_t*>(s_colinfo + ((Wp + 1) & ~1)); // [W][H] colour code of the tile
+    uint16_t* const s_rowsec = s_colinfo + ((Wp + 1) & ~1);                        // [Hp / 8] tile row | first px border << 14 | last << 15
+    uint8_t* const s_tile = reinterpret_cast<uint8_t*>(s_rowsec + (((Hp >> 3) + 2) & ~1)); // [W][H] colour code of the tile
 
     const uint32_t env_rel = blockIdx.x;
     const int64_t env = p.env_first + env_rel;
 
-    // ---- this env's wall layer: one TMA bulk copy; the planes are cleared meanwhile
+    // ---- this env's wall layer: one TMA bulk copy; planes cleared and tables built meanwhile
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         mbar_arrive_expect_tx(&s_bar, (uint32_t)p.map_words * 4u);
         bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.map_words * 4u, &s_bar);
     }
-    for (uint32_t k = tid; k < 2u * plane_words; k += kTopThreads) s_ray[k] = 0u;
+    {
+        uint4* const z = reinterpret_cast<uint4*>(s_ray);       // both planes, contiguous, 16-byte aligned
+        for (uint32_t k = tid; k < plane_words >> 1; k += kTopThreads) z[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
     const float x = __ldg(p.st.pos_x + env), y = __ldg(p.st.pos_y + env);
     const int au = __ldg(p.st.dir_au + env);
     const uint32_t goal = __ldg(p.st.goal + env);
     const int gi0 = (int)(goal & 0xFFFFu) - 1, gj0 = (int)(goal >> 16) - 1;
+    if (tid < 6) s_pal[tid] = p.palette[tid];
     for (int i = tid; i < Hp; i += kTopThreads) {
         const int t = i / pu, r = i - t * pu;
         s_row[i] = (uint16_t)(t | ((r == 0 || r == pu - 1) ? 0x8000 : 0));
@@ -59,6 +83,10 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     for (int j = tid; j < Wp; j += kTopThreads) {
         const int t = j / pu, r = j - t * pu;
         s_colinfo[j] = (uint16_t)(t | ((r == 0 || r == pu - 1) ? 0x8000 : 0));
+    }
+    for (int q = tid; q < (Hp >> 3); q += kTopThreads) {        // used when pu % 8 == 0: a sector lies in one tile
+        const int i = q << 3, t = i / pu, r = i - t * pu;
+        s_rowsec[q] = (uint16_t)(t | (r == 0 ? 0x4000 : 0) | (r + 7 == pu - 1 ? 0x8000 : 0));
     }
     __syncthreads();          // mbarrier initialised, planes cleared
     mbar_wait(&s_bar, 0);
@@ -82,13 +110,14 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
             // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
             const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
             const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
-            // [EXT SimpleDraw] Line(point1, point2): Bresenham, all octants, both end points drawn
+            // [EXT SimpleDraw] Line(point1, point2): Bresenham, all octants, both end points drawn; the walk
+            // reaches (i2, j2) after exactly max(|di|, |dj|) steps
             const int di = abs(i2 - ip), dj = -abs(j2 - jp);
             const int si = ip < i2 ? 1 : -1, sj = jp < j2 ? 1 : -1;
             int err = di + dj, i = ip, j = jp;
-            for (;;) {
-                plane_set(s_ray, i, j, Hp, Wp);
-                if (i == i2 && j == j2) break;
+            for (int n = max(di, -dj);; --n) {
+                plane_set_warp(s_ray, i, j, Hp, Wp, SB, lane);
+                if (n == 0) break;
                 const int e2 = 2 * err;
                 if (e2 >= dj) {
                     err += dj;
@@ -107,14 +136,14 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         const int rp = wu_to_pu(p.radius, fpu);                        // :470
         int a = 0, b = rp, d = 1 - rp;
         while (a <= b) {
-            plane_set(s_player, ip + a, jp + b, Hp, Wp);
-            plane_set(s_player, ip - a, jp + b, Hp, Wp);
-            plane_set(s_player, ip + a, jp - b, Hp, Wp);
-            plane_set(s_player, ip - a, jp - b, Hp, Wp);
-            plane_set(s_player, ip + b, jp + a, Hp, Wp);
-            plane_set(s_player, ip - b, jp + a, Hp, Wp);
-            plane_set(s_player, ip + b, jp - a, Hp, Wp);
-            plane_set(s_player, ip - b, jp - a, Hp, Wp);
+            plane_set(s_player, ip + a, jp + b, Hp, Wp, SB);
+            plane_set(s_player, ip - a, jp + b, Hp, Wp, SB);
+            plane_set(s_player, ip + a, jp - b, Hp, Wp, SB);
+            plane_set(s_player, ip - a, jp - b, Hp, Wp, SB);
+            plane_set(s_player, ip + b, jp + a, Hp, Wp, SB);
+            plane_set(s_player, ip - b, jp + a, Hp, Wp, SB);
+            plane_set(s_player, ip + b, jp - a, Hp, Wp, SB);
+            plane_set(s_player, ip - b, jp - a, Hp, Wp, SB);
             if (d < 0) {
                 d += 2 * a + 3;
             } else {
@@ -126,34 +155,62 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     }
     __syncthreads();
 
-    // ---- stream the image out: one 32-byte sector (8 pixels along a column) per lane and iteration
+    // ---- stream the image out: one 32-byte sector (8 consecutive pixels of the column-major image) per
+    //      lane and iteration, every pixel composed as circle > ray > tile border > tile colour
     uint32_t slot = p.slot0 + env_rel;
     if (slot >= p.window) slot -= p.window;
     uint8_t* const img = p.top + (size_t)slot * p.env_stride;
     const uint8_t* const ray_bytes = reinterpret_cast<const uint8_t*>(s_ray);
     const uint8_t* const player_bytes = reinterpret_cast<const uint8_t*>(s_player);
-    const uint32_t border_c = p.palette[RCW_TOP_COLOR_BORDER], ray_c = p.palette[RCW_TOP_COLOR_RAY],
-                   player_c = p.palette[RCW_TOP_COLOR_PLAYER];
+    const uint32_t border_c = s_pal[RCW_TOP_COLOR_BORDER], ray_c = s_pal[RCW_TOP_COLOR_RAY],
+                   player_c = s_pal[RCW_TOP_COLOR_PLAYER];
+    const uint32_t L = (uint32_t)Hp * (uint32_t)Wp;          // pixels
     const uint32_t n_sec = (L + 7u) >> 3;
+    if (((Hp | pu) & 7) == 0) {
+        // a sector lies inside one tile of one image column: one colour, borders only at its two ends
+        const uint32_t SPC = (uint32_t)Hp >> 3, SBy = SB >> 3;   // sectors / plane bytes per column
 #pragma unroll 2
+        for (uint32_t s = tid; s < n_sec; s += kTopThreads) {
+            const uint32_t j0 = s / SPC, q = s - j0 * SPC;
+            const uint32_t rs = s_rowsec[q], cinfo = s_colinfo[j0];
+            const uint32_t tile_c = s_pal[s_tile[(rs & 0x3FFFu) + (uint32_t)H * (cinfo & 0x7FFFu)]];
+            const uint32_t base = (cinfo & 0x8000u) ? border_c : tile_c;
+            const uint32_t rb = ray_bytes[j0 * SBy + q], pb = player_bytes[j0 * SBy + q];
+            uint32_t px[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) px[k] = base;
+            if (rs & 0x4000u) px[0] = border_c;
+            if (rs & 0x8000u) px[7] = border_c;
+            if (rb | pb) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    px[k] = ((rb >> k) & 1u) ? ray_c : px[k];
+                    px[k] = ((pb >> k) & 1u) ? player_c : px[k];
+                }
+            }
+            store_stream32(img + ((size_t)s << 5), make_uint4(px[0], px[1], px[2], px[3]),
+                           make_uint4(px[4], px[5], px[6], px[7]));
+        }
+        return;
+    }
+    // any size: pixel by pixel through the row / column tables
     for (uint32_t s = tid; s < n_sec; s += kTopThreads) {
         const uint32_t idx0 = s << 3;
         uint32_t j0 = idx0 / (uint32_t)Hp, i0 = idx0 - j0 * (uint32_t)Hp;
-        const uint32_t rb = ray_bytes[s], pb = player_bytes[s];
-        uint32_t cinfo = s_colinfo[min(j0, (uint32_t)Wp - 1u)];
         uint32_t px[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint32_t rinfo = s_row[i0];
+            const uint32_t jc = min(j0, (uint32_t)Wp - 1u);
+            const uint32_t rinfo = s_row[i0], cinfo = s_colinfo[jc];
             const uint32_t code = s_tile[(rinfo & 0x7FFFu) + (uint32_t)H * (cinfo & 0x7FFFu)];
-            uint32_t c = ((rinfo | cinfo) & 0x8000u) ? border_c : p.palette[code];
-            c = ((rb >> k) & 1u) ? ray_c : c;
-            c = ((pb >> k) & 1u) ? player_c : c;
+            uint32_t c = ((rinfo | cinfo) & 0x8000u) ? border_c : s_pal[code];
+            const uint32_t bit = jc * SB + i0;
+            c = ((s_ray[bit >> 5] >> (bit & 31u)) & 1u) ? ray_c : c;
+            c = ((s_player[bit >> 5] >> (bit & 31u)) & 1u) ? player_c : c;
             px[k] = (idx0 + (uint32_t)k < L) ? c : 0u;    // bytes behind the last pixel are padding
             if (++i0 == (uint32_t)Hp) {                    // next column of the image
                 i0 = 0;
                 ++j0;
-                cinfo = s_colinfo[min(j0, (uint32_t)Wp - 1u)];
             }
         }
         store_stream32(img + ((size_t)s << 5), make_uint4(px[0], px[1], px[2], px[3]),
@@ -162,10 +219,10 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
 }
 
 size_t top_view_smem_bytes(int H, int W, int pu, int map_words) {
-    const size_t Hp = (size_t)H * pu, Wp = (size_t)W * pu, L = Hp * Wp;
-    const size_t plane_words = (L + 31) / 32;
-    return (size_t)map_words * 4 + 2 * plane_words * 4 + 2 * ((Hp + 1) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1) +
-           (((size_t)H * W + 15) & ~(size_t)15);
+    const size_t Hp = (size_t)H * pu, Wp = (size_t)W * pu;
+    const size_t plane_words = (Wp * (plane_col_bits((int)Hp) >> 5) + 1) & ~(size_t)1;
+    return (size_t)map_words * 4 + 2 * plane_words * 4 + 8 * 4 + 2 * ((Hp + 1) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1) +
+           2 * (((Hp >> 3) + 2) & ~(size_t)1) + (((size_t)H * W + 15) & ~(size_t)15);
 }
 
 cudaError_t launch_top_view(const TopViewParams& p, cudaStream_t s) {
