@@ -22,18 +22,6 @@ __device__ __forceinline__ int wu_to_pu(float x_wu, float pu) { return __float2i
 // warp whose 32 rays sit in 32 different columns at the same row does not collide on one bank.
 __host__ __device__ __forceinline__ uint32_t plane_col_bits(int Hp) { return (((uint32_t)Hp + 31u) & ~31u) + 32u; }
 
-// Set pixel (i, j) (1-based, clipped) in a plane; called by the lanes of a warp that are still drawing.
-// lane <-> ray, and adjacent rays share most of their pixels (they leave the same pixel with slopes that
-// differ by 1/400): a lane whose pixel equals its lower neighbour's leaves the atomic to that neighbour.
-__device__ __forceinline__ void plane_set_warp(uint32_t* plane, int i, int j, int Hp, int Wp, uint32_t SB, int lane) {
-    const bool inside = (i >= 1) & (i <= Hp) & (j >= 1) & (j <= Wp);
-    const uint32_t idx = (uint32_t)(j - 1) * SB + (uint32_t)(i - 1);
-    const unsigned act = __activemask();
-    const uint32_t below = __shfl_up_sync(act, idx, 1);
-    const bool dup = (lane > 0) && ((act >> (lane - 1)) & 1u) && below == idx;
-    if (inside && !dup) atomicOr(plane + (idx >> 5), 1u << (idx & 31u));
-}
-
 __device__ __forceinline__ void plane_set(uint32_t* plane, int i, int j, int Hp, int Wp, uint32_t SB) {
     if (i >= 1 && i <= Hp && j >= 1 && j <= Wp) {
         const uint32_t idx = (uint32_t)(j - 1) * SB + (uint32_t)(i - 1);
@@ -106,18 +94,40 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         const int ray = g * 32 + lane;
         const float4 rt = __ldg(p.ray_table + (size_t)au * (size_t)R + (size_t)min(ray, R - 1));
         const RayHit hit = dda_cast(s_map, H, W, p.wpr, p.dda_flags, x, y, gi0, gj0, rt, lane);
-        if (ray < R) {
-            // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
-            const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
-            const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
-            // [EXT SimpleDraw] Line(point1, point2): Bresenham, all octants, both end points drawn; the walk
-            // reaches (i2, j2) after exactly max(|di|, |dj|) steps
-            const int di = abs(i2 - ip), dj = -abs(j2 - jp);
-            const int si = ip < i2 ? 1 : -1, sj = jp < j2 ? 1 : -1;
-            int err = di + dj, i = ip, j = jp;
-            for (int n = max(di, -dj);; --n) {
-                plane_set_warp(s_ray, i, j, Hp, Wp, SB, lane);
-                if (n == 0) break;
+        // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
+        const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
+        const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
+        // [EXT SimpleDraw] Line(point1, point2): Bresenham, all octants, both end points drawn; the walk
+        // reaches (i2, j2) after exactly max(|di|, |dj|) steps.  The warp walks its 32 lines in lock step up
+        // to the longest one.  lane <-> ray, and adjacent rays share most of their pixels (they leave the same
+        // pixel with slopes that differ by 1/400): a lane whose pixel equals its lower neighbour's leaves the
+        // shared-memory atomic to that neighbour.
+        const int di = abs(i2 - ip), dj = -abs(j2 - jp);
+        const int si = ip < i2 ? 1 : -1, sj = jp < j2 ? 1 : -1;
+        const int n = ray < R ? max(di, -dj) : -1;                // steps of this lane's line; -1: no line
+        const int n_max = __reduce_max_sync(0xFFFFFFFFu, n);
+        const int n_below = __shfl_up_sync(0xFFFFFFFFu, n, 1);
+        // both end points inside the image => every pixel of the line is (it stays in their bounding box)
+        const bool clip = (ip < 1) | (ip > Hp) | (jp < 1) | (jp > Wp) | (i2 < 1) | (i2 > Hp) | (j2 < 1) | (j2 > Wp);
+        int err = di + dj;
+        if (!__any_sync(0xFFFFFFFFu, clip && n >= 0)) {
+            uint32_t idx = (uint32_t)(jp - 1) * SB + (uint32_t)(ip - 1);
+            const int idx_si = si, idx_sj = sj * (int)SB;
+#pragma unroll 2
+            for (int k = 0; k <= n_max; ++k) {
+                const uint32_t below = __shfl_up_sync(0xFFFFFFFFu, idx, 1);
+                const bool dup = (lane > 0) & (k <= n_below) & (below == idx);
+                if ((k <= n) & !dup) atomicOr(s_ray + (idx >> 5), 1u << (idx & 31u));
+                const int e2 = 2 * err;
+                const bool step_i = e2 >= dj, step_j = e2 <= di;
+                err += (step_i ? dj : 0) + (step_j ? di : 0);
+                idx += (uint32_t)((step_i ? idx_si : 0) + (step_j ? idx_sj : 0));
+            }
+        } else if (n >= 0) {
+            int i = ip, j = jp;
+            for (int k = n;; --k) {
+                plane_set(s_ray, i, j, Hp, Wp, SB);
+                if (k == 0) break;
                 const int e2 = 2 * err;
                 if (e2 >= dj) {
                     err += dj;
@@ -169,9 +179,10 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     if (((Hp | pu) & 7) == 0) {
         // a sector lies inside one tile of one image column: one colour, borders only at its two ends
         const uint32_t SPC = (uint32_t)Hp >> 3, SBy = SB >> 3;   // sectors / plane bytes per column
+        uint32_t j0 = (uint32_t)tid / SPC, q = (uint32_t)tid - j0 * SPC;
+        const uint32_t adv_j = kTopThreads / SPC, adv_q = kTopThreads - adv_j * SPC;
 #pragma unroll 2
         for (uint32_t s = tid; s < n_sec; s += kTopThreads) {
-            const uint32_t j0 = s / SPC, q = s - j0 * SPC;
             const uint32_t rs = s_rowsec[q], cinfo = s_colinfo[j0];
             const uint32_t tile_c = s_pal[s_tile[(rs & 0x3FFFu) + (uint32_t)H * (cinfo & 0x7FFFu)]];
             const uint32_t base = (cinfo & 0x8000u) ? border_c : tile_c;
@@ -190,6 +201,12 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
             }
             store_stream32(img + ((size_t)s << 5), make_uint4(px[0], px[1], px[2], px[3]),
                            make_uint4(px[4], px[5], px[6], px[7]));
+            j0 += adv_j;
+            q += adv_q;
+            if (q >= SPC) {
+                q -= SPC;
+                ++j0;
+            }
         }
         return;
     }
