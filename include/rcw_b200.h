@@ -187,6 +187,18 @@ int32_t rcw_get_state(rcw_batch* b, float* pos_xy, int32_t* dir_au, int32_t* goa
 int32_t rcw_set_state(rcw_batch* b, const float* pos_xy, const int32_t* dir_au,
                       const int32_t* goal_ij, const float* reward, const uint8_t* done);
 
+/* Exact snapshot of the dynamic state of a batch (checkpoint / resume): positions, directions, goals,
+ * rewards, terminations, the per-env Philox episode counters, the running episode returns / lengths, the
+ * episode totals and the step index that keys the random policy.  A handle created with the same rcw_config
+ * that loads the snapshot continues bit-identically to the run that saved it (tested); the Philox key
+ * (seed) and env_id_offset of the saved run are restored with it.  Wall layers and the rest of the
+ * configuration are not part of the snapshot: the caller supplies them as it did originally.
+ * rcw_checkpoint_size: bytes needed; rcw_save_checkpoint blocks and fills `host`; rcw_load_checkpoint
+ * validates the header against the handle (RCW_ESIZE on a mismatch), restores the state and re-renders. */
+int32_t rcw_checkpoint_size(rcw_batch* b, size_t* bytes);
+int32_t rcw_save_checkpoint(rcw_batch* b, void* host, size_t bytes);
+int32_t rcw_load_checkpoint(rcw_batch* b, const void* host, size_t bytes);
+
 /* world.ray_stop_position_tu / ray_hit_dimension / ray_distance_wu / ray_directions_wu
  * (single_room.jl:29-31,39) for envs [env0, env0+n): hit_ij [n][num_rays][2] 1-based,
  * hit_dim [n][num_rays], dist [n][num_rays], ray_dir [n][num_rays][2].  Debug / parity only:

@@ -23,6 +23,7 @@ SYMBOLS = (
     "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_set_wall_maps", "rcw_reset",
     "rcw_step", "rcw_step_range", "rcw_step_random", "rcw_render",
     "rcw_render_top_view", "rcw_top_view_device_ptr", "rcw_copy_top_view", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
+    "rcw_checkpoint_size", "rcw_save_checkpoint", "rcw_load_checkpoint",
     "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
     "rcw_sync", "rcw_last_error",
 )
@@ -99,6 +100,9 @@ def load() -> C.CDLL:
         "rcw_copy_top_view": (i32, [vp, i64, i64, vp]),
         "rcw_get_state": (i32, [vp, vp, vp, vp, vp, vp]),
         "rcw_set_state": (i32, [vp, vp, vp, vp, vp, vp]),
+        "rcw_checkpoint_size": (i32, [vp, P(C.c_size_t)]),
+        "rcw_save_checkpoint": (i32, [vp, vp, C.c_size_t]),
+        "rcw_load_checkpoint": (i32, [vp, vp, C.c_size_t]),
         "rcw_get_rays": (i32, [vp, i64, i64, vp, vp, vp, vp]),
         "rcw_obs_device_ptr": (i32, [vp, P(vp), P(C.c_size_t), P(C.c_size_t)]),
         "rcw_obs_layout": (i32, [vp, P(C.c_size_t), P(C.c_size_t), P(C.c_size_t), P(i32)]),

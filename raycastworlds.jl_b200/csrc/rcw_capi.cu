@@ -12,9 +12,17 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost a pointer test unless a profiler is attached
+
 #include "rcw_internal.h"
 
 using namespace rcw;
+
+// NVTX range around the enqueue work of an entry point (tracing)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -642,6 +650,7 @@ int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls) {
 }
 
 int32_t rcw_render_top_view(rcw_batch* b) {
+    NvtxRange nvtx("rcw_render_top_view");
     if (int32_t rc = check_handle(b)) return rc;
     if (int32_t rc = check_top_view_fits(b->cfg)) return rc;
     DeviceGuard g(b->device);
@@ -684,6 +693,7 @@ int32_t rcw_copy_top_view(rcw_batch* b, int64_t env0, int64_t n, void* host) {
 }
 
 int32_t rcw_render(rcw_batch* b) {
+    NvtxRange nvtx("rcw_render");
     if (int32_t rc = check_handle(b)) return rc;
     DeviceGuard g(b->device);
     return enqueue_frame(b, kModeRender, nullptr);
@@ -691,6 +701,7 @@ int32_t rcw_render(rcw_batch* b) {
 
 int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij,
                   const int32_t* dir_au, const uint8_t* mask) {
+    NvtxRange nvtx("rcw_reset");
     if (int32_t rc = check_handle(b)) return rc;
     const bool any = goal_ij || player_ij || dir_au;
     if (any && !(goal_ij && player_ij && dir_au))
@@ -805,6 +816,7 @@ static int32_t stage_actions(rcw_batch* b, const uint8_t* actions, int64_t env0,
 }
 
 int32_t rcw_step(rcw_batch* b, const uint8_t* actions) {
+    NvtxRange nvtx("rcw_step");
     if (int32_t rc = check_handle(b)) return rc;
     if (!actions) return fail(RCW_EINVAL, "actions is null (use rcw_step_random for the random policy)");
     DeviceGuard g(b->device);
@@ -814,6 +826,7 @@ int32_t rcw_step(rcw_batch* b, const uint8_t* actions) {
 }
 
 int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64_t n) {
+    NvtxRange nvtx("rcw_step_range");
     if (int32_t rc = check_handle(b)) return rc;
     if (!actions) return fail(RCW_EINVAL, "actions is null");
     if (env0 < 0 || n < 1 || env0 + n > b->cfg.num_envs)
@@ -829,6 +842,7 @@ int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64
 }
 
 int32_t rcw_step_random(rcw_batch* b, int32_t n_steps) {
+    NvtxRange nvtx("rcw_step_random");
     if (int32_t rc = check_handle(b)) return rc;
     if (n_steps < 0) return fail(RCW_EINVAL, "n_steps must be non-negative");
     DeviceGuard g(b->device);
@@ -918,6 +932,118 @@ int32_t rcw_set_state(rcw_batch* b, const float* pos_xy, const int32_t* dir_au,
     return RCW_OK;
 }
 
+// ---- checkpoint / resume ---------------------------------------------------------------------
+struct CheckpointHeader {
+    uint32_t magic;      // 'RCWC'
+    uint32_t version;
+    int64_t num_envs;
+    int64_t env_id_offset;
+    uint64_t seed;
+    uint64_t step_index;
+    int32_t H, W, N, pad;
+    unsigned long long episodes, sum_length;
+    double sum_return;
+};
+constexpr uint32_t kCheckpointMagic = 0x43574352u, kCheckpointVersion = 1u;
+// per env: pos_x, pos_y, dir_au, goal, episode, reward, ep_return, ep_length (4 bytes each) + done (1 byte)
+constexpr size_t kCheckpointWordsPerEnv = 8;
+
+static size_t checkpoint_bytes(const rcw_batch* b) {
+    return sizeof(CheckpointHeader) + (size_t)b->cfg.num_envs * (kCheckpointWordsPerEnv * 4 + 1);
+}
+
+int32_t rcw_checkpoint_size(rcw_batch* b, size_t* bytes) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (bytes) *bytes = checkpoint_bytes(b);
+    return RCW_OK;
+}
+
+int32_t rcw_save_checkpoint(rcw_batch* b, void* host, size_t bytes) {
+    NvtxRange nvtx("rcw_save_checkpoint");
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!host) return fail(RCW_EINVAL, "host is null");
+    if (bytes < checkpoint_bytes(b))
+        return fail(RCW_ESIZE, "checkpoint buffer of %zu bytes, %zu needed", bytes, checkpoint_bytes(b));
+    DeviceGuard g(b->device);
+    const size_t E = (size_t)b->cfg.num_envs;
+    const StateRef& s = b->st[b->cur];
+    uint8_t* out = static_cast<uint8_t*>(host) + sizeof(CheckpointHeader);
+    const void* words[kCheckpointWordsPerEnv] = {s.pos_x, s.pos_y, s.dir_au, s.goal, s.episode,
+                                                 b->d_reward, b->d_ep_return, b->d_ep_length};
+    for (size_t k = 0; k < kCheckpointWordsPerEnv; ++k)
+        RCW_CUDA(cudaMemcpyAsync(out + k * E * 4, words[k], E * 4, cudaMemcpyDeviceToHost, b->stream));
+    RCW_CUDA(cudaMemcpyAsync(out + kCheckpointWordsPerEnv * E * 4, b->d_done, E, cudaMemcpyDeviceToHost, b->stream));
+    if (int32_t rc = sync_and_check(b, /*need_stats=*/true)) return rc;
+    CheckpointHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = kCheckpointMagic;
+    h.version = kCheckpointVersion;
+    h.num_envs = b->cfg.num_envs;
+    h.env_id_offset = b->cfg.env_id_offset;
+    h.seed = b->cfg.seed;
+    h.step_index = b->step_index;
+    h.H = b->cfg.height_tile_map_tu;
+    h.W = b->cfg.width_tile_map_tu;
+    h.N = b->cfg.num_directions;
+    h.episodes = b->h_stats->episodes;
+    h.sum_length = b->h_stats->sum_length;
+    h.sum_return = b->h_stats->sum_return;
+    memcpy(host, &h, sizeof(h));
+    return RCW_OK;
+}
+
+int32_t rcw_load_checkpoint(rcw_batch* b, const void* host, size_t bytes) {
+    NvtxRange nvtx("rcw_load_checkpoint");
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!host) return fail(RCW_EINVAL, "host is null");
+    if (bytes < sizeof(CheckpointHeader)) return fail(RCW_ESIZE, "checkpoint of %zu bytes has no header", bytes);
+    CheckpointHeader h;
+    memcpy(&h, host, sizeof(h));
+    if (h.magic != kCheckpointMagic || h.version != kCheckpointVersion)
+        return fail(RCW_EINVAL, "not a librcw_b200 checkpoint (magic 0x%x, version %u)", h.magic, h.version);
+    const rcw_config& c = b->cfg;
+    if (h.num_envs != c.num_envs || h.H != c.height_tile_map_tu || h.W != c.width_tile_map_tu ||
+        h.N != c.num_directions)
+        return fail(RCW_ESIZE, "checkpoint of %lld envs on %dx%d tiles / %d directions does not match this batch "
+                    "(%lld envs, %dx%d / %d)", (long long)h.num_envs, h.H, h.W, h.N, (long long)c.num_envs,
+                    c.height_tile_map_tu, c.width_tile_map_tu, c.num_directions);
+    if (bytes < checkpoint_bytes(b))
+        return fail(RCW_ESIZE, "checkpoint truncated: %zu bytes, %zu needed", bytes, checkpoint_bytes(b));
+    DeviceGuard g(b->device);
+    const size_t E = (size_t)c.num_envs;
+    const StateRef& s = b->st[b->cur];
+    const uint8_t* in = static_cast<const uint8_t*>(host) + sizeof(CheckpointHeader);
+    {   // the same validation as rcw_set_state: a corrupt snapshot must not index outside the tables
+        const float* px = reinterpret_cast<const float*>(in);
+        const float* py = px + E;
+        const int32_t* au = reinterpret_cast<const int32_t*>(in + 2 * E * 4);
+        const uint32_t* goal = reinterpret_cast<const uint32_t*>(in + 3 * E * 4);
+        for (size_t e = 0; e < E; ++e) {
+            const int gi = (int)(goal[e] & 0xFFFFu), gj = (int)(goal[e] >> 16);
+            if (!(px[e] >= 0.0f) || !(px[e] < (float)c.height_tile_map_tu) || !(py[e] >= 0.0f) ||
+                !(py[e] < (float)c.width_tile_map_tu) || au[e] < 0 || au[e] >= c.num_directions || gi < 1 ||
+                gi > c.height_tile_map_tu || gj < 1 || gj > c.width_tile_map_tu)
+                return fail(RCW_EINVAL, "checkpoint holds an invalid state for env %zu", e);
+        }
+    }
+    void* words[kCheckpointWordsPerEnv] = {s.pos_x, s.pos_y, s.dir_au, s.goal, s.episode,
+                                           b->d_reward, b->d_ep_return, b->d_ep_length};
+    for (size_t k = 0; k < kCheckpointWordsPerEnv; ++k)
+        RCW_CUDA(cudaMemcpyAsync(words[k], in + k * E * 4, E * 4, cudaMemcpyHostToDevice, b->stream));
+    RCW_CUDA(cudaMemcpyAsync(b->d_done, in + kCheckpointWordsPerEnv * E * 4, E, cudaMemcpyHostToDevice, b->stream));
+    DeviceStats st;
+    memset(&st, 0, sizeof(st));
+    st.episodes = h.episodes;
+    st.sum_length = h.sum_length;
+    st.sum_return = h.sum_return;
+    RCW_CUDA(cudaMemcpyAsync(b->d_stats, &st, sizeof(st), cudaMemcpyHostToDevice, b->stream));
+    RCW_CUDA(cudaStreamSynchronize(b->stream));   // `host` and `st` are only valid during the call
+    b->step_index = h.step_index;
+    b->cfg.seed = h.seed;
+    b->cfg.env_id_offset = h.env_id_offset;
+    return enqueue_frame(b, kModeRender, nullptr);
+}
+
 int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int32_t* hit_dim,
                      float* dist, float* ray_dir) {
     if (int32_t rc = check_handle(b)) return rc;
@@ -981,6 +1107,7 @@ int32_t rcw_obs_layout(rcw_batch* b, size_t* env_stride_bytes, size_t* column_st
 }
 
 int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
+    NvtxRange nvtx("rcw_copy_obs");
     if (int32_t rc = check_handle(b)) return rc;
     if (!host) return fail(RCW_EINVAL, "host is null");
     if (env0 < 0 || n < 1 || env0 + n > b->cfg.num_envs)

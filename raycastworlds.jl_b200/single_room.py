@@ -214,6 +214,19 @@ class BatchedSingleRoom(AbstractGame):
         d = None if done is None else np.ascontiguousarray(done, np.uint8).reshape(n)
         _capi.check(self._lib.rcw_set_state(self._h, _ptr(p), _ptr(a), _ptr(g), _ptr(r), _ptr(d)))
 
+    def save_checkpoint(self) -> np.ndarray:
+        """Exact snapshot of the dynamic state (rcw_save_checkpoint) as a uint8 array."""
+        n = C.c_size_t()
+        _capi.check(self._lib.rcw_checkpoint_size(self._h, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        _capi.check(self._lib.rcw_save_checkpoint(self._h, _ptr(buf), n.value))
+        return buf
+
+    def load_checkpoint(self, buf):
+        """Restore a snapshot made by save_checkpoint() on a batch with the same configuration; re-renders."""
+        b = np.ascontiguousarray(np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray)) else buf, np.uint8)
+        _capi.check(self._lib.rcw_load_checkpoint(self._h, _ptr(b), b.size))
+
     def set_wall_map(self, wall_hw):
         """wall_hw: bool [H, W] — replaces tile_map[WALL, :, :] for every env of the batch."""
         w = np.asarray(wall_hw).astype(np.uint8)
