@@ -113,6 +113,7 @@ struct rcw_batch {
     uint32_t* d_wall_map = nullptr;      // wall layer shared by the batch
     uint32_t* d_wall_maps_env = nullptr; // [num_envs][map_words], allocated by rcw_set_wall_maps
     bool per_env_maps = false;
+    bool closed_border = true;           // every border tile of the active wall layer(s) is a wall
     StateRef st[2]{};
     int cur = 0;
     float* d_reward = nullptr;
@@ -167,6 +168,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.col_bytes = c.height_camera_view_pu * b->bpp;
     p.col_pitch = b->col_pitch;
     p.dda_flags = c.dda_flags;
+    p.closed_border = b->closed_border ? 1u : 0u;
     p.radius = c.player_radius_wu;
     p.incr = c.position_increment_wu;
     p.goal_reward = c.goal_reward;
@@ -186,6 +188,17 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
             p.palette[i] = col;
         }
     }
+    {   // what the renderer stores per column for each palette entry (see FrameParams::col_entry)
+        auto flat = [&](uint32_t col) { return c.obs_format != RCW_OBS_RGB8 || ((col ^ (col >> 8)) & 0xFFFFu) == 0; };
+        const bool cf = flat(p.palette[RCW_COLOR_CEILING]) && flat(p.palette[RCW_COLOR_FLOOR]);
+        for (int i = 0; i < 6; ++i) {
+            const bool slow = !(cf && flat(p.palette[i]));
+            const uint32_t col = p.palette[i];
+            const uint32_t word = c.obs_format == RCW_OBS_XRGB32 ? col : (col & 0xFFu) * 0x01010101u;
+            p.col_entry[i] = make_uint2(slow ? 0x80000000u : 0u, slow ? col : word);
+        }
+    }
+    p.gpe_magic = b->gpe >= 2 ? (~0ULL / (uint64_t)b->gpe) + 1ULL : 0ULL;
     p.dir_slot = b->dir_slot;
     p.dirs = b->d_dirs;
     p.ray_table = b->d_ray_table;
@@ -245,6 +258,7 @@ static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, 
     t.Hp = t.H * t.pu;
     t.Wp = t.W * t.pu;
     t.dda_flags = c.dda_flags;
+    t.closed_border = b->closed_border ? 1u : 0u;
     t.radius = c.player_radius_wu;
     for (int i = 0; i < 6; ++i) t.palette[i] = c.top_palette[i] & 0x00FFFFFFu;
     t.dir_slot = b->dir_slot;
@@ -610,13 +624,18 @@ int32_t rcw_set_wall_map(rcw_batch* b, const uint8_t* wall) {
     DeviceGuard g(b->device);
     const int H = b->cfg.height_tile_map_tu, W = b->cfg.width_tile_map_tu;
     std::vector<uint32_t> words((size_t)b->map_words, 0u);
+    bool closed = true;
     for (int j = 0; j < W; ++j)
-        for (int i = 0; i < H; ++i)
-            if (wall[(size_t)j * H + i]) words[(size_t)i * b->wpr + (j >> 5)] |= 1u << (j & 31);
+        for (int i = 0; i < H; ++i) {
+            const bool is_wall = wall[(size_t)j * H + i] != 0;
+            if (is_wall) words[(size_t)i * b->wpr + (j >> 5)] |= 1u << (j & 31);
+            else if (i == 0 || i == H - 1 || j == 0 || j == W - 1) closed = false;
+        }
     RCW_CUDA(cudaStreamSynchronize(b->stream));
     RCW_CUDA(cudaMemcpy(b->d_wall_map, words.data(), sizeof(uint32_t) * words.size(),
                         cudaMemcpyHostToDevice));
     b->per_env_maps = false;
+    b->closed_border = closed;
     return RCW_OK;
 }
 
@@ -628,6 +647,7 @@ int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls) {
     const size_t E = (size_t)b->cfg.num_envs, mw = (size_t)b->map_words, tiles = (size_t)H * W;
     if ((size_t)kWarpsPerCta * mw * 4 > 200 * 1024)
         return fail(RCW_ESIZE, "per-env tile maps of %dx%d do not fit in shared memory", H, W);
+    bool closed = true;
     std::vector<uint32_t> words;
     try {
         words.assign(E * mw, 0u);
@@ -638,14 +658,18 @@ int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls) {
         const uint8_t* w = walls + e * tiles;
         uint32_t* out = words.data() + e * mw;
         for (int j = 0; j < W; ++j)
-            for (int i = 0; i < H; ++i)
-                if (w[(size_t)j * H + i]) out[(size_t)i * b->wpr + (j >> 5)] |= 1u << (j & 31);
+            for (int i = 0; i < H; ++i) {
+                const bool is_wall = w[(size_t)j * H + i] != 0;
+                if (is_wall) out[(size_t)i * b->wpr + (j >> 5)] |= 1u << (j & 31);
+                else if (i == 0 || i == H - 1 || j == 0 || j == W - 1) closed = false;
+            }
     }
     RCW_CUDA(cudaStreamSynchronize(b->stream));
     if (!b->d_wall_maps_env) RCW_CUDA(dev_alloc(b, &b->d_wall_maps_env, E * mw, false));
     RCW_CUDA(cudaMemcpy(b->d_wall_maps_env, words.data(), sizeof(uint32_t) * words.size(),
                         cudaMemcpyHostToDevice));
     b->per_env_maps = true;
+    b->closed_border = closed;
     return RCW_OK;
 }
 

@@ -76,11 +76,16 @@ struct FrameParams {
     int32_t col_bytes;       // P * bytes per pixel
     int32_t col_pitch;       // bytes between consecutive columns: col_bytes rounded up to a multiple of 32
     uint32_t dda_flags;
+    uint32_t closed_border;  // every border tile of (every env's) wall layer is a wall: rays cannot leave the map
     // scalars of the reference constructor
     float radius, incr, goal_reward;
     float hl_num;            // camera_height_tile_wu * Float32(num_rays)   (single_room.jl:406)
     float two_s;             // 2 * semi_field_of_view_wu
     uint32_t palette[6];
+    uint2 col_entry[6];      // renderer's {slow << 31, colour word} of a column painted with palette entry k: the
+                             // word is the byte-replicated colour when entry k, ceiling and floor all have R == G == B
+                             // (or the format has whole-word pixels); otherwise the column takes the phase-rotated path
+    uint64_t gpe_magic;      // ceil(2^64 / gpe): item / gpe == umul64hi(item, gpe_magic), exact for 32-bit items (gpe >= 2)
     // tables
     int32_t dir_slot;        // >= 0: directions live in constant memory slot; < 0: use `dirs`
     const float2* dirs;      // [N] unit vectors (global copy, also the source of the ray table)
@@ -141,6 +146,7 @@ struct TopViewParams {
     int32_t pu;              // pu_per_tu
     int32_t Hp, Wp;          // H * pu, W * pu
     uint32_t dda_flags;
+    uint32_t closed_border;
     float radius;            // player_radius_wu
     uint32_t palette[6];     // RCW_TOP_COLOR_*
     int32_t dir_slot;

@@ -480,12 +480,48 @@ struct RayHit {
     bool is_wall;    // the hit tile is a wall (outside the map counts as wall); otherwise it is the goal
 };
 
+// The DDA walk itself, branch-free per step.  TIE_LE: decision D1 (advance along dimension 1 on a tie).
+// CLOSED: every border tile of the wall layer is a wall, so a ray can never leave the map and the probe
+// needs no bounds test (the default SingleRoom map; checked on the host for supplied maps).
+// A lane that has hit stays on its obstacle tile; the warp leaves together once no lane is still walking.
+template <bool TIE_LE, bool CLOSED>
+__device__ __forceinline__ void dda_walk(const uint32_t* s_map, int H, int W, int wpr, int gi0, int gj0, float dx,
+                                         float dy, int si, int sj, float& tx, float& ty, int& ti, int& tj, int& dim,
+                                         float& dist) {
+    // the tile the ray stands on is an obstacle: wall (outside the map counts as wall) or this env's goal
+    auto probe = [&]() {
+        bool wall;
+        if (CLOSED) {
+            wall = wall_bit(s_map, wpr, ti, tj);
+        } else {
+            const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
+            wall = !inside | wall_bit(s_map, wpr, inside ? ti : 0, inside ? tj : 0);
+        }
+        return wall | ((ti == gi0) & (tj == gj0));
+    };
+    bool stop = probe();
+#pragma unroll 1
+    while (__any_sync(0xFFFFFFFFu, !stop)) {
+        // kDdaStepsPerVote DDA steps per warp vote: a stopped lane just probes its own tile again
+#pragma unroll
+        for (int u = 0; u < kDdaStepsPerVote; ++u) {
+            const bool cmp = TIE_LE ? (tx <= ty) : (tx < ty);
+            const bool mx = !stop & cmp, my = !stop & !cmp;
+            dist = mx ? tx : (my ? ty : dist);
+            tx = mx ? __fadd_rn(tx, dx) : tx;
+            ty = my ? __fadd_rn(ty, dy) : ty;
+            ti += mx ? si : 0;
+            tj += my ? sj : 0;
+            dim = mx ? 1 : (my ? 2 : dim);
+            stop = probe();
+        }
+    }
+}
+
 // RayCaster.cast_ray contract for the ray rt = {ray_x, ray_y, |1/ray_x|, |1/ray_y|} from (x, y).
-// Must be called by all 32 lanes of a warp (lane <-> ray): a lane that has hit stays on its obstacle
-// tile, so "stopped" needs no extra state, and the warp leaves the loop together once no lane is still
-// walking (ballot early-exit).
+// Must be called by all 32 lanes of a warp (lane <-> ray).  `closed`: see dda_walk.
 __device__ __forceinline__ RayHit dda_cast(const uint32_t* s_map, int H, int W, int wpr, uint32_t dda_flags,
-                                           float x, float y, int gi0, int gj0, const float4 rt, int lane) {
+                                           bool closed, float x, float y, int gi0, int gj0, const float4 rt, int lane) {
     int ti = __float2int_rd(x), tj = __float2int_rd(y);
     const int si = rt.x < 0.0f ? -1 : 1, sj = rt.y < 0.0f ? -1 : 1;
     float tx = rt.x < 0.0f ? __fmul_rn(__fsub_rn(x, (float)ti), rt.z)
@@ -494,37 +530,17 @@ __device__ __forceinline__ RayHit dda_cast(const uint32_t* s_map, int H, int W, 
                            : __fmul_rn(__fsub_rn((float)(tj + 1), y), rt.w);
     int dim = 0;
     float dist = 0.0f;
-    const bool tie_le = (dda_flags & RCW_DDA_TIE_LE) != 0;
-    bool is_wall;   // the tile the ray stands on is a wall (outside the map counts as wall)
 #if RCW_EXP == 1
-    is_wall = true; dist = 1.0f + 0.01f * (float)lane; dim = 1 + (lane & 1);
+    dist = 1.0f + 0.01f * (float)lane; dim = 1 + (lane & 1);
 #else
     (void)lane;
-    // probe the tile the ray stands on: wall (outside the map counts as wall) or this env's goal
-    auto probe = [&]() {
-        const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
-        const int ci = inside ? ti : 0, cj = inside ? tj : 0;
-        is_wall = !inside | wall_bit(s_map, wpr, ci, cj);
-        return is_wall | ((ti == gi0) & (tj == gj0));
-    };
-    bool stop = probe();
-#pragma unroll 1
-    while (__any_sync(0xFFFFFFFFu, !stop)) {
-        // kDdaStepsPerVote DDA steps per warp vote: a stopped lane just probes its own tile again
-#pragma unroll
-        for (int u = 0; u < kDdaStepsPerVote; ++u) {
-            if (!stop) {
-                const bool take_x = (tx < ty) | (tie_le & (tx == ty));
-                dist = take_x ? tx : ty;
-                const float ax = __fadd_rn(tx, rt.z), ay = __fadd_rn(ty, rt.w);
-                tx = take_x ? ax : tx;
-                ty = take_x ? ty : ay;
-                ti += take_x ? si : 0;
-                tj += take_x ? 0 : sj;
-                dim = take_x ? 1 : 2;
-            }
-            stop = probe();
-        }
+    const bool tie_le = (dda_flags & RCW_DDA_TIE_LE) != 0;
+    if (closed) {
+        if (tie_le) dda_walk<true, true>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+        else dda_walk<false, true>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+    } else {
+        if (tie_le) dda_walk<true, false>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+        else dda_walk<false, false>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
     }
 #endif
     if ((dda_flags & RCW_DDA_DIST_POST) && dim != 0)
@@ -534,7 +550,9 @@ __device__ __forceinline__ RayHit dda_cast(const uint32_t* s_map, int H, int W, 
     h.tj = tj;
     h.dim = dim;
     h.dist = dist;
-    h.is_wall = is_wall;
+    // which layer stopped the ray: a wall (outside the map counts as wall), else this env's goal
+    const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
+    h.is_wall = !inside | wall_bit(s_map, wpr, inside ? ti : 0, inside ? tj : 0);
     return h;
 }
 
@@ -549,7 +567,7 @@ __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, cons
     const int gi0 = (int)(pose.goal & 0xFFFFu) - 1, gj0 = (int)(pose.goal >> 16) - 1;
     const int ray = g * 32 + lane;
     const float2 dir = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
-    const RayHit hit = dda_cast(s_map, p.H, p.W, p.wpr, p.dda_flags, pose.x, pose.y, gi0, gj0, rt, lane);
+    const RayHit hit = dda_cast(s_map, p.H, p.W, p.wpr, p.dda_flags, p.closed_border != 0, pose.x, pose.y, gi0, gj0, rt, lane);
     const int ti = hit.ti, tj = hit.tj, dim = hit.dim;
     const float dist = hit.dist;
     const bool is_wall = hit.is_wall;
@@ -713,27 +731,45 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
     const int n_iter = lane < n_sec ? ((n_sec - lane + 31) >> 5) : 0;
     int cl = lane / NS, sc = lane - cl * NS;
     const int adv_cl = 32 / NS, adv_sc = 32 - adv_cl * NS;
+    // the sectors of a pitched span are consecutive in memory: lane L writes sectors L, L + 32, ...
+    uint8_t* dst = span + (lane << 5);
+    if (!item_slow) {
+        const uint32_t ceil_w = PixelFormat<FMT>::flat_word(ceil_c), floor_w = PixelFormat<FMT>::flat_word(floor_c);
 #pragma unroll 2
-    for (int it = 0; it < n_iter; ++it) {
-        const uint2 info = colinfo[cl];
-        const int b1 = (int)(info.x & 0x7FFFFFFFu), b2 = CB - b1, ob = sc << 5;
-        const bool in_ceil = ob + 32 <= b1, in_floor = ob >= b2, in_wall = (ob >= b1) & (ob + 32 <= b2);
-        if (in_ceil | in_floor | in_wall) {
-            const uint32_t c = in_ceil ? ceil_c : (in_floor ? floor_c : (info.y & 0x00FFFFFFu));
-            uint8_t* const dst = span + cl * CP + ob;
-            if (!item_slow) {
-                const uint32_t w = PixelFormat<FMT>::flat_word(c);
+        for (int it = 0; it < n_iter; ++it) {
+            const uint2 info = colinfo[cl];
+            const int b1 = (int)info.x, b2 = CB - b1, ob = sc << 5, oe = ob + 32;
+            const bool in_ceil = oe <= b1, in_floor = ob >= b2, in_wall = (ob >= b1) & (oe <= b2);
+            if (in_ceil | in_floor | in_wall) {
+                const uint32_t w = in_ceil ? ceil_w : (in_floor ? floor_w : info.y);
                 const uint4 v = make_uint4(w, w, w, w);
                 store_stream32(dst, v, v);
-            } else {
-                store_stream32(dst, PixelFormat<FMT>::run16(c, ob), PixelFormat<FMT>::run16(c, ob + 16));
+            }
+            dst += 1024;
+            cl += adv_cl;
+            sc += adv_sc;
+            if (sc >= NS) {
+                sc -= NS;
+                ++cl;
             }
         }
-        cl += adv_cl;
-        sc += adv_sc;
-        if (sc >= NS) {
-            sc -= NS;
-            ++cl;
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) {
+            const uint2 info = colinfo[cl];
+            const int b1 = (int)(info.x & 0x7FFFFFFFu), b2 = CB - b1, ob = sc << 5;
+            const bool in_ceil = ob + 32 <= b1, in_floor = ob >= b2, in_wall = (ob >= b1) & (ob + 32 <= b2);
+            if (in_ceil | in_floor | in_wall) {
+                const uint32_t c = in_ceil ? ceil_c : (in_floor ? floor_c : (info.y & 0x00FFFFFFu));
+                store_stream32(dst, PixelFormat<FMT>::run16(c, ob), PixelFormat<FMT>::run16(c, ob + 16));
+            }
+            dst += 1024;
+            cl += adv_cl;
+            sc += adv_sc;
+            if (sc >= NS) {
+                sc -= NS;
+                ++cl;
+            }
         }
     }
     if (lane < ncols) {
@@ -754,16 +790,19 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
     }
 }
 
-// s_col entry of a column from its shade: single-colour vectors need no phase rotation when
-// R == G == B (RGB8) or always (XRGB32); otherwise the column takes the slow (funnel-shift) path
+// s_col entry of a column from its shade.  Single-colour vectors need no phase rotation when R == G == B
+// (RGB8) or always (XRGB32, GRAY8); otherwise the column takes the slow (funnel-shift) path.  Both cases
+// are worked out per palette entry on the host (FrameParams::col_entry).
 template <int FMT>
 __device__ __forceinline__ uint2 column_entry(const FrameParams& p, int pad, int cid, bool& slow) {
-    const uint32_t color = p.palette[cid];
-    slow = FMT == RCW_OBS_RGB8 &&
-           !(PixelFormat<FMT>::is_flat(color) && PixelFormat<FMT>::is_flat(p.palette[RCW_COLOR_CEILING]) &&
-             PixelFormat<FMT>::is_flat(p.palette[RCW_COLOR_FLOOR]));
-    return make_uint2((uint32_t)(pad * PixelFormat<FMT>::kBpp) | (slow ? 0x80000000u : 0u),
-                      slow ? color : PixelFormat<FMT>::flat_word(color));
+    const uint2 e = p.col_entry[cid];
+    slow = FMT == RCW_OBS_RGB8 && (e.x != 0u);
+    return make_uint2((uint32_t)(pad * PixelFormat<FMT>::kBpp) | e.x, e.y);
+}
+
+// item / gpe for the 32-bit work-item index (exact: FrameParams::gpe_magic)
+__device__ __forceinline__ uint32_t div_gpe(const FrameParams& p, uint32_t item) {
+    return p.gpe == 1 ? item : (uint32_t)__umul64hi((uint64_t)item, p.gpe_magic);
 }
 
 // STAGE: what one launch does for every (env, group of 32 rays) item, one warp per item
@@ -826,7 +865,7 @@ frame_kernel(const __grid_constant__ FrameParams p) {
     for (uint32_t base = blockIdx.x * kWarpsPerCta; base < n_items; base += round_stride, parity ^= 1u) {
         const uint32_t item = base + warp;
         const bool item_ok = item < n_items;
-        const uint32_t env_rel = (item_ok ? item : n_items - 1) / gpe;
+        const uint32_t env_rel = div_gpe(p, item_ok ? item : n_items - 1);
         const int g = (int)(item - env_rel * gpe);
         const int64_t env = p.env_first + env_rel;
         const int r0 = g * 32;
@@ -841,7 +880,7 @@ frame_kernel(const __grid_constant__ FrameParams p) {
             float4 rt;
             // lanes past the last ray shadow the last ray (same walk, nothing stored)
             const float4* const rt_lane = p.ray_table + min(r0 + lane, R - 1);
-            const uint32_t slot = env_rel - base / gpe;          // envs of this round, in order
+            const uint32_t slot = env_rel - div_gpe(p, base);    // envs of this round, in order
             const bool leader = item_ok && (warp == 0 || g == 0);
             const uint32_t* my_map = s_map;
             if (per_env_maps) {

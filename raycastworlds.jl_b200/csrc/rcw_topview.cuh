@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     for (int g = warp; g < groups; g += kTopThreads / 32) {
         const int ray = g * 32 + lane;
         const float4 rt = __ldg(p.ray_table + (size_t)au * (size_t)R + (size_t)min(ray, R - 1));
-        const RayHit hit = dda_cast(s_map, H, W, p.wpr, p.dda_flags, x, y, gi0, gj0, rt, lane);
+        const RayHit hit = dda_cast(s_map, H, W, p.wpr, p.dda_flags, p.closed_border != 0, x, y, gi0, gj0, rt, lane);
         // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
         const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
         const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
