@@ -198,7 +198,30 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
             p.col_entry[i] = make_uint2(slow ? 0x80000000u : 0u, slow ? col : word);
         }
     }
-    p.gpe_magic = b->gpe >= 2 ? (~0ULL / (uint64_t)b->gpe) + 1ULL : 0ULL;
+    if (b->gpe >= 2) {   // libdivide's branch-free u32 divider for d = gpe
+        const uint32_t d = (uint32_t)b->gpe;
+        uint32_t k = 31;
+        while (!(d >> k)) --k;                                   // floor(log2 d)
+        if ((d & (d - 1)) == 0) {
+            p.gpe_magic = 0;
+            p.gpe_shift = k - 1;
+        } else {
+            const uint64_t num = 1ULL << (32 + k);
+            uint64_t m = num / d;
+            const uint64_t rem = num % d;
+            m += m;
+            if (2 * rem >= d) m += 1;
+            p.gpe_magic = (uint32_t)(m + 1);                     // low 32 bits of the 33-bit multiplier
+            p.gpe_shift = k;
+        }
+    }
+    {   // renderer sweep units per column: mirror pairs of 64 bytes when col_bytes % 64 == 0, else 32-byte sectors
+        const int col_bytes = c.height_camera_view_pu * b->bpp;
+        const int U = (col_bytes & 63) == 0 ? (col_bytes >> 6) : (b->col_pitch >> 5);
+        p.unit_inv16 = U < 32 ? (uint32_t)((65536 + U - 1) / U) : 0u;
+        p.unit_adv_cl = 32 / U;
+        p.unit_adv_u = 32 % U;
+    }
     p.dir_slot = b->dir_slot;
     p.dirs = b->d_dirs;
     p.ray_table = b->d_ray_table;

@@ -85,7 +85,13 @@ struct FrameParams {
     uint2 col_entry[6];      // renderer's {slow << 31, colour word} of a column painted with palette entry k: the
                              // word is the byte-replicated colour when entry k, ceiling and floor all have R == G == B
                              // (or the format has whole-word pixels); otherwise the column takes the phase-rotated path
-    uint64_t gpe_magic;      // ceil(2^64 / gpe): item / gpe == umul64hi(item, gpe_magic), exact for 32-bit items (gpe >= 2)
+    uint32_t gpe_magic;      // item / gpe for any 32-bit item (gpe >= 2), branch-free round-up method (libdivide):
+    uint32_t gpe_shift;      //   t = umulhi(gpe_magic, n); q = (((n - t) >> 1) + t) >> gpe_shift
+    // the renderer sweeps units of 32 (mirror pairs: 64) bytes, U per column (render_span): lane L starts in
+    // column (L * unit_inv16) >> 16 and advances by (unit_adv_cl columns, unit_adv_u units) per iteration
+    uint32_t unit_inv16;     // U < 32 ? ceil(65536 / U) : 0
+    int32_t unit_adv_cl;     // 32 / U
+    int32_t unit_adv_u;      // 32 % U
     // tables
     int32_t dir_slot;        // >= 0: directions live in constant memory slot; < 0: use `dirs`
     const float2* dirs;      // [N] unit vectors (global copy, also the source of the ray table)

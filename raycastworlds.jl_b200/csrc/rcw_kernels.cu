@@ -655,8 +655,8 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
         const int HS = CB >> 6;                      // sector pairs per column
         const int n_sp = ncols * HS;
         const int n_iter = lane < n_sp ? ((n_sp - lane + 31) >> 5) : 0;
-        int cl = lane / HS, hs = lane - cl * HS;
-        const int adv_cl = 32 / HS, adv_hs = 32 - adv_cl * HS;
+        int cl = (int)(((uint32_t)lane * p.unit_inv16) >> 16), hs = lane - cl * HS;
+        const int adv_cl = p.unit_adv_cl, adv_hs = p.unit_adv_u;
         if (!item_slow) {
             const uint32_t ceil_w = PixelFormat<FMT>::flat_word(ceil_c), floor_w = PixelFormat<FMT>::flat_word(floor_c);
 #pragma unroll kPairUnroll
@@ -729,8 +729,8 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
     const int NS = CP >> 5;                          // sectors per column
     const int n_sec = ncols * NS;
     const int n_iter = lane < n_sec ? ((n_sec - lane + 31) >> 5) : 0;
-    int cl = lane / NS, sc = lane - cl * NS;
-    const int adv_cl = 32 / NS, adv_sc = 32 - adv_cl * NS;
+    int cl = (int)(((uint32_t)lane * p.unit_inv16) >> 16), sc = lane - cl * NS;
+    const int adv_cl = p.unit_adv_cl, adv_sc = p.unit_adv_u;
     // the sectors of a pitched span are consecutive in memory: lane L writes sectors L, L + 32, ...
     uint8_t* dst = span + (lane << 5);
     if (!item_slow) {
@@ -800,9 +800,11 @@ __device__ __forceinline__ uint2 column_entry(const FrameParams& p, int pad, int
     return make_uint2((uint32_t)(pad * PixelFormat<FMT>::kBpp) | e.x, e.y);
 }
 
-// item / gpe for the 32-bit work-item index (exact: FrameParams::gpe_magic)
-__device__ __forceinline__ uint32_t div_gpe(const FrameParams& p, uint32_t item) {
-    return p.gpe == 1 ? item : (uint32_t)__umul64hi((uint64_t)item, p.gpe_magic);
+// item / gpe for the 32-bit work-item index (exact for every n: FrameParams::gpe_magic / gpe_shift)
+__device__ __forceinline__ uint32_t div_gpe(const FrameParams& p, uint32_t n) {
+    if (p.gpe == 1) return n;
+    const uint32_t t = __umulhi(p.gpe_magic, n);
+    return (((n - t) >> 1) + t) >> p.gpe_shift;
 }
 
 // STAGE: what one launch does for every (env, group of 32 rays) item, one warp per item
