@@ -75,6 +75,10 @@ def test_single_room_redraws_the_top_view_every_act(rcw, oracle):
      dict(H=5, W=7, N=36, R=45, P=51, pu_per_tu=5)),       # 25 x 35 pixels: not a multiple of 8, ragged last sector
     (dict(height_tile_map_tu=12, width_tile_map_tu=9, num_rays=200, height_camera_view_pu=64, pu_per_tu=3),
      dict(H=12, W=9, R=200, P=64, pu_per_tu=3)),
+    (dict(height_tile_map_tu=6, width_tile_map_tu=5, num_rays=100, height_camera_view_pu=48, pu_per_tu=24),
+     dict(H=6, W=5, R=100, P=48, pu_per_tu=24)),            # one-tile sectors with a tile height that is not a power of two
+    (dict(height_tile_map_tu=7, width_tile_map_tu=10, num_rays=128, height_camera_view_pu=48, pu_per_tu=16),
+     dict(H=7, W=10, R=128, P=48, pu_per_tu=16)),
 ])
 def test_batched_rollout_with_top_view(rcw, oracle, kw, okw):
     n, seed, steps = 24, 21, 60
