@@ -211,6 +211,34 @@ function copy_obs(env::BatchedSingleRoom, e0 = 1, n = env.num_envs)
     return out
 end
 
+# host copy of the top views of envs e0:e0+n-1 (1-based): UInt32[H * pu, W * pu, n], the reference's top_view layout
+function copy_top_view(env::BatchedSingleRoom, height_pu::Integer, width_pu::Integer, e0 = 1, n = env.num_envs)
+    out = Array{UInt32}(undef, height_pu, width_pu, n)
+    GC.@preserve out begin
+        check(ccall((:rcw_copy_top_view, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
+                    env.handle, Int64(e0 - 1), Int64(n), out))
+    end
+    return out
+end
+
+# exact snapshot of the dynamic state (checkpoint / resume)
+function save_checkpoint(env::BatchedSingleRoom)
+    n = Ref{Csize_t}(0)
+    check(ccall((:rcw_checkpoint_size, LIB), Int32, (Ptr{Cvoid}, Ref{Csize_t}), env.handle, n))
+    buf = Vector{UInt8}(undef, n[])
+    GC.@preserve buf begin
+        check(ccall((:rcw_save_checkpoint, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t), env.handle, buf, n[]))
+    end
+    return buf
+end
+
+function load_checkpoint!(env::BatchedSingleRoom, buf::Vector{UInt8})
+    GC.@preserve buf begin
+        check(ccall((:rcw_load_checkpoint, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t), env.handle, buf, length(buf)))
+    end
+    return nothing
+end
+
 function episode_stats(env::BatchedSingleRoom; reset_counters = false)
     ep = Ref{Int64}(0); sr = Ref{Float64}(0); sl = Ref{Int64}(0)
     check(ccall((:rcw_episode_stats, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Float64}, Ref{Int64}, Int32),

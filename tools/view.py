@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Write the camera views of a few envs as PNG files (the non-interactive part of
+"""Write the camera views (and, with --top-view, the top views) of a few envs as PNG files (the non-interactive part of
 play!: the reference blits the transposed image, utils.jl:64-73).
     python tools/view.py --out gpurun_out/views --envs 4 --steps 40 [--format rgb8|xrgb32|gray8]
 """
@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--format", default="rgb8", choices=["rgb8", "xrgb32", "gray8"])
     ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--top-view", action="store_true", help="also dump update_top_view! (single_room.jl:446-483)")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     env = rcw.BatchedSingleRoom(args.envs, seed=args.seed, obs_format=args.format)
@@ -51,6 +52,15 @@ def main():
         path = os.path.join(args.out, f"env{e}_{args.format}.png")
         write_png(path, img)
         print(path, "pos", st["pos"][e], "dir", st["dir_au"][e], "goal", st["goal"][e])
+    if args.top_view:
+        env.render_top_view()
+        top = env.copy_top_view()             # uint32 [E, W*pu columns, H*pu rows]
+        for e in range(args.envs):
+            t = np.swapaxes(top[e], 0, 1)
+            img = np.stack([(t >> 16) & 255, (t >> 8) & 255, t & 255], -1).astype(np.uint8)
+            path = os.path.join(args.out, f"env{e}_top_view.png")
+            write_png(path, img)
+            print(path)
     env.close()
 
 
