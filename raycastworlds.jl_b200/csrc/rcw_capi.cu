@@ -89,6 +89,9 @@ static void release_dir_slot(int device, int slot) {
 // ------------------------------------------------------------------------------------------
 
 constexpr int kActionRing = 4;
+// env_kernel (one warp per env) is used for launches of at least this many envs: below it the grid of the
+// item kernel (one warp per 32-ray group) fills the 148 SMs better
+constexpr int64_t kEnvPerWarpMinEnvs = 2048;
 
 struct rcw_batch {
     rcw_config cfg{};
@@ -103,6 +106,8 @@ struct rcw_batch {
     int ctas_per_sm = 0;          // 0: one CTA per 8 items; >0: persistent grid of sm_count * this
     bool bulk = false;            // renderer: TMA bulk stores of whole bands (true) or per-lane vector stores
     bool split = false;           // one env-step = front launch + paint launch (true) or one fused launch
+    bool env_per_warp = false;    // narrow cameras (<= 128 rays): a warp owns a whole env (env_kernel) ...
+    int64_t env_per_warp_min = 0; // ... in launches of at least this many envs
     bool occ4 = false;            // fused kernel variant compiled for 32 instead of 24 warps per SM (front-bound steps)
     uint32_t* d_col_info = nullptr;
     int pat_stride = 0;
@@ -312,7 +317,8 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
         p.env_first = e0;
         p.env_count = E - e0 < b->obs_window ? E - e0 : b->obs_window;
         p.obs_slot0 = 0;
-        const LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, p.env_count)};
+        LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, p.env_count)};
+        sh.env_per_warp = b->env_per_warp && p.env_count >= b->env_per_warp_min;
         RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream));
         b->launches += b->split ? 2 : 1;
         // the reference's act!(env) / reset!(env) also redraw the top view (single_room.jl:329,337)
@@ -335,7 +341,8 @@ static int32_t enqueue_range_step(rcw_batch* b, const uint8_t* d_actions_env0, i
     p.env_first = env0;
     p.env_count = n;
     p.obs_slot0 = (uint32_t)(env0 % b->obs_window);
-    const LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, n)};
+    LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, n)};
+    sh.env_per_warp = b->env_per_warp && n >= b->env_per_warp_min;
     RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, sh, b->stream));
     RCW_CUDA(launch_commit_range(b->st[b->cur ^ 1], b->st[b->cur], env0, n, b->stream));
     b->launches += (b->split ? 2 : 1) + 1;
@@ -563,6 +570,16 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // registers are 2 % faster (profiles/README.md).
     b->occ4 = (32 * b->col_pitch < 20000) || ((int64_t)H * W >= 1024);
     if (const char* s = getenv("RCW_OCC")) b->occ4 = atoi(s) == 4;
+    // Small items (32 columns of at most 10 KB: narrow or one-byte-per-pixel cameras) are bound by act! and the
+    // DDA, not by the stores; a warp that owns the whole env needs no block barrier behind act! (env_kernel).
+    // Measured at 65,536 envs (GB/s, item kernel -> env kernel): RGB8 64x64 5091 -> 6053, 84x84 5397 -> 6887,
+    // 96x96 6224 -> 6971; GRAY8 84x84 2184 -> 2987, 128x128 3866 -> 5615, 160x120 3732 -> 5302, 256x192
+    // 5657 -> 7132, 512x256 7031 -> 7017.  Store-bound items lose: RGB8 128x128 (12 KB) 6897 -> 6756,
+    // 160x120 6701 -> 6113, 256x192 7366 -> 6305.
+    b->env_per_warp = b->gpe <= 8 && 32 * b->col_pitch <= 10240;
+    if (const char* s = getenv("RCW_ENV_PER_WARP")) b->env_per_warp = atoi(s) != 0;   // 1 forces it for any width
+    b->env_per_warp_min = kEnvPerWarpMinEnvs;
+    if (const char* s = getenv("RCW_ENV_PER_WARP_MIN")) b->env_per_warp_min = atoll(s);   // tests force the kernel on small batches
     b->obs_window = (c.obs_window_envs > 0 && c.obs_window_envs < E) ? c.obs_window_envs : E;
     b->obs_bytes = b->obs_env_stride * (size_t)b->obs_window;
     RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, false));

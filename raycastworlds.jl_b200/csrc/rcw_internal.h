@@ -176,6 +176,7 @@ struct LaunchShape {
     bool split;   // two launches (front, paint) instead of the fused kernel (measured alternative)
     bool occ4;    // fused kernel compiled for 4 CTAs per SM (steps bound by act! / DDA rather than by stores)
     int ctas;     // grid size
+    bool env_per_warp = false;   // small items: env_kernel, one warp = one env
 };
 cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);

@@ -999,6 +999,97 @@ frame_kernel(const __grid_constant__ FrameParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// small items: one warp = one env
+// ------------------------------------------------------------------------------------------
+// When an item (32 columns) is small — few rows or one byte per pixel — the step is bound by act! and the DDA,
+// not by the stores; the CTA barrier behind the env's leader warp then costs a fifth of the time
+// (profiles/README.md).  Here a warp owns a whole env: act! once, then its groups one after the other, the
+// ray-table row of the next group in flight while the current one is cast and painted.  No block barrier,
+// no pose exchange through shared memory, no item -> (env, group) arithmetic.
+template <int MODE, int FMT>
+__global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSmHi)
+env_kernel(const __grid_constant__ FrameParams p) {
+    extern __shared__ __align__(128) uint32_t s_dyn[];   // wall layer(s): one shared, or one slot per warp
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ __align__(8) uint64_t s_mbar_env[kWarpsPerCta];
+    __shared__ uint2 s_col[kWarpsPerCta][32];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool per_env_maps = p.map_env_stride != 0;
+    const uint32_t map_bytes = (uint32_t)p.map_words * 4u;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_mbar, 1);
+        if (per_env_maps)
+            for (int k = 0; k < kWarpsPerCta; ++k) mbar_init(&s_mbar_env[k], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !per_env_maps) {
+        mbar_arrive_expect_tx(&s_mbar, map_bytes);
+        bulk_copy_g2s(s_dyn, p.wall_map, map_bytes, &s_mbar);
+    }
+    const uint32_t env_rel = blockIdx.x * kWarpsPerCta + warp;
+    if (env_rel >= (uint32_t)p.env_count) return;     // (no block barrier below this point)
+    const int64_t env = p.env_first + env_rel;
+    const int R = p.R;
+    const uint32_t* my_map = s_dyn;
+    if (per_env_maps) {
+        my_map = s_dyn + (uint32_t)warp * (uint32_t)p.map_words;
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&s_mbar_env[warp], map_bytes);
+            bulk_copy_g2s(const_cast<uint32_t*>(my_map), p.wall_map + (size_t)env * p.map_env_stride, map_bytes,
+                          &s_mbar_env[warp]);
+        }
+    }
+    const float4* const rt_lane0 = p.ray_table + min(lane, R - 1);     // group 0
+    EnvPose pose;
+    float4 rt;
+    if (MODE == kModeStep) {
+        // loads first; the ray-table rows of the three directions the env can face after this step
+        const EnvInputs in = load_env_inputs(p, env);
+        const int au_m = in.au == 0 ? p.N - 1 : in.au - 1, au_p = in.au + 1 == p.N ? 0 : in.au + 1;
+        const float4 rt_m = __ldg(rt_lane0 + (size_t)au_m * (size_t)R);
+        const float4 rt_0 = __ldg(rt_lane0 + (size_t)in.au * (size_t)R);
+        const float4 rt_p = __ldg(rt_lane0 + (size_t)au_p * (size_t)R);
+        if (per_env_maps) mbar_wait(&s_mbar_env[warp], 0);
+        else mbar_wait(&s_mbar, 0);
+        pose = act_env(p, my_map, env, in, /*writer=*/true, lane);
+        if (pose.au == in.au) rt = rt_0;
+        else if (pose.au == au_m) rt = rt_m;
+        else if (pose.au == au_p) rt = rt_p;
+        else rt = __ldg(rt_lane0 + (size_t)pose.au * (size_t)R);       // auto-reset drew a new direction
+    } else {
+        pose.x = __ldg(p.in.pos_x + env);
+        pose.y = __ldg(p.in.pos_y + env);
+        pose.au = __ldg(p.in.dir_au + env);
+        pose.goal = __ldg(p.in.goal + env);
+        rt = __ldg(rt_lane0 + (size_t)pose.au * (size_t)R);
+        if (per_env_maps) mbar_wait(&s_mbar_env[warp], 0);
+        else mbar_wait(&s_mbar, 0);
+    }
+    uint32_t obs_slot = p.obs_slot0 + env_rel;
+    if (obs_slot >= p.obs_window) obs_slot -= p.obs_window;
+    uint8_t* const env_obs = p.obs + (size_t)obs_slot * p.obs_env_stride;
+    const float4* const rt_row = p.ray_table + (size_t)pose.au * (size_t)R;
+    const int gpe = p.gpe;
+    for (int g = 0; g < gpe; ++g) {
+        float4 rt_next = rt;
+        if (g + 1 < gpe) rt_next = __ldg(rt_row + min((g + 1) * 32 + lane, R - 1));
+        const ColumnShade cs = cast_and_shade<MODE>(p, my_map, pose, rt, g, lane, env_rel);
+        const int r0 = g * 32;
+        const int ncols = min(32, R - r0);
+        const int col0 = R - r0 - ncols;               // ray r paints column R-1-r
+        bool slow = false;
+        if (lane < ncols) s_col[warp][ncols - 1 - lane] = column_entry<FMT>(p, cs.pad, cs.cid, slow);
+        __syncwarp();
+        const bool item_slow = __any_sync(0xFFFFFFFFu, slow);
+        render_span<FMT>(p, s_col[warp], env_obs, col0 * p.col_pitch, ncols, lane, item_slow);
+        __syncwarp();                                  // s_col is rewritten by the next group
+        rt = rt_next;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // reset kernel: one thread per env (rare path)
 // ------------------------------------------------------------------------------------------
 
@@ -1095,6 +1186,26 @@ static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s
 
 }
 
+template <int MODE, int FMT>
+static cudaError_t launch_env_t(const FrameParams& p, cudaStream_t s) {
+    const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
+    const size_t smem = map_slots * (size_t)p.map_words * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(env_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned ctas = (unsigned)((p.env_count + kWarpsPerCta - 1) / kWarpsPerCta);
+    env_kernel<MODE, FMT><<<ctas, kThreadsPerCta, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_env_m(const FrameParams& p, int obs_format, cudaStream_t s) {
+    if (obs_format == RCW_OBS_GRAY8) return launch_env_t<MODE, RCW_OBS_GRAY8>(p, s);
+    if (obs_format == RCW_OBS_RGB8) return launch_env_t<MODE, RCW_OBS_RGB8>(p, s);
+    return launch_env_t<MODE, RCW_OBS_XRGB32>(p, s);
+}
+
 constexpr int kOcc = kCtasPerSmLo;
 
 // the shipped path (fused stage, lane-written sectors) exists for both register budgets
@@ -1123,6 +1234,8 @@ static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, const La
 cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s) {
     if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc>(p, sh.ctas, s);
     if (mode != kModeStep && mode != kModeRender) return cudaErrorInvalidValue;
+    if (sh.env_per_warp && !sh.split && !sh.bulk)
+        return mode == kModeStep ? launch_env_m<kModeStep>(p, obs_format, s) : launch_env_m<kModeRender>(p, obs_format, s);
     if (!sh.split)
         return mode == kModeStep ? launch_frame_m<kModeStep, kStageFused>(p, obs_format, sh, s)
                                  : launch_frame_m<kModeRender, kStageFused>(p, obs_format, sh, s);

@@ -1,0 +1,133 @@
+"""GPU parity tests of env_kernel (narrow cameras, one warp per env): the same comparisons against the oracle as
+the item kernel, with the kernel forced on small batches (RCW_ENV_PER_WARP_MIN=1), plus a batch large enough to
+take it by default, plus a check that both kernels produce identical bytes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rcw():
+    import raycastworlds_jl_b200 as m
+    return m
+
+
+@pytest.fixture()
+def forced(monkeypatch):
+    monkeypatch.setenv("RCW_ENV_PER_WARP", "1")
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_equals_oracle(env, ref, fmt="rgb8"):
+    st = env.get_state()
+    pos, au, goal = ref.states()
+    np.testing.assert_array_equal(bits(st["pos"]), bits(pos))
+    np.testing.assert_array_equal(st["dir_au"], au)
+    np.testing.assert_array_equal(st["goal"], goal)
+    r, d = ref.reward_done()
+    np.testing.assert_array_equal(st["reward"], r)
+    np.testing.assert_array_equal(st["done"], d)
+    want = {"rgb8": ref.obs_rgb8, "xrgb32": ref.obs_u32, "gray8": ref.obs_gray8}[fmt]()
+    np.testing.assert_array_equal(env.copy_obs(), want)
+    assert env.episode_stats() == ref.episode_stats()
+
+
+@pytest.mark.parametrize("R,P,fmt", [(84, 84, "rgb8"), (84, 84, "gray8"), (64, 64, "rgb8"), (128, 128, "xrgb32"),
+                                     (20, 33, "rgb8"), (45, 51, "xrgb32"), (100, 70, "gray8"), (97, 64, "rgb8")])
+def test_random_rollout_matches_oracle(rcw, oracle, forced, R, P, fmt):
+    n, seed, steps = 37, 100 + R, 120                       # 37 envs: the last CTA is ragged
+    env = rcw.BatchedSingleRoom(n, seed=seed, obs_format=fmt, num_rays=R, height_camera_view_pu=P)
+    ref = oracle.Batch(n, cfg=oracle.default_config(R=R, P=P), seed=seed)
+    assert_equals_oracle(env, ref, fmt)                     # the constructor's reset + render
+    env.step_random(steps)
+    ref.rollout(steps)
+    assert_equals_oracle(env, ref, fmt)
+    rng = np.random.default_rng(R)
+    for _ in range(10):                                     # explicit actions, biased towards moving forward
+        a = rng.choice([1, 1, 1, 2, 3, 4], size=n).astype(np.uint8)
+        env.act(a)
+        assert ref.step(a) == 0
+    assert_equals_oracle(env, ref, fmt)
+    rays = env.get_rays()                                   # the dump path stays on the item kernel
+    for e in (0, n - 1):
+        np.testing.assert_array_equal(rays["hit"][e], ref.world(e).ray_stop)
+    env.close()
+
+
+def test_goal_seeking_episodes_with_auto_reset(rcw, oracle, forced):
+    """Long rollout with many auto-resets on a small map (goals are hit often)."""
+    n, seed, steps = 64, 5, 1500
+    kw = dict(height_tile_map_tu=5, width_tile_map_tu=6, num_directions=32, num_rays=96, height_camera_view_pu=40)
+    env = rcw.BatchedSingleRoom(n, seed=seed, **kw)
+    ref = oracle.Batch(n, cfg=oracle.default_config(H=5, W=6, N=32, R=96, P=40), seed=seed)
+    env.step_random(steps)
+    ref.rollout(steps, threads=4)
+    assert ref.episode_stats()[0] > n
+    assert_equals_oracle(env, ref)
+    env.close()
+
+
+def test_per_env_maps_custom_palette_and_window(rcw, oracle, forced):
+    n, H, W, R, P, seed = 24, 9, 11, 90, 60, 13
+    rng = np.random.default_rng(4)
+    walls = np.zeros((n, H, W), bool)
+    walls[:, 0, :] = walls[:, -1, :] = walls[:, :, 0] = walls[:, :, -1] = True
+    walls[:, 2:-2, 2:-2] |= rng.random((n, H - 4, W - 4)) < 0.2
+    walls[3, 0, 2:6] = False                                  # an open border: the bounds-checked DDA variant
+    pal = [0x102030, 0x405060, 0x708090, 0xA0B0C0, 0xD0E0F0, 0x112233]   # no byte-replicated colour: phase-rotated path
+    kw = dict(height_tile_map_tu=H, width_tile_map_tu=W, num_rays=R, height_camera_view_pu=P)
+    env = rcw.BatchedSingleRoom(n, seed=seed, auto_reset=False, palette=pal, obs_window_envs=16, **kw)
+    env.set_wall_maps(walls)
+    cfg = oracle.default_config(H=H, W=W, R=R, P=P, palette=pal)
+    pos = np.stack([rng.uniform(1.2, H - 1.2, n), rng.uniform(1.2, W - 1.2, n)], 1).astype(np.float32)
+    au = rng.integers(0, 128, n).astype(np.int32)
+    goal = np.array([[H - 1, W - 1]] * n, np.int32)
+    for e in range(n):
+        walls[e, int(pos[e, 0]), int(pos[e, 1])] = False
+        walls[e, H - 2, W - 2] = False
+    env.set_wall_maps(walls)
+    env.set_state(pos=pos, dir_au=au, goal=goal)
+    worlds = []
+    for e in range(n):
+        w = oracle.World(cfg)
+        w.set_wall_map(walls[e])
+        w.set_state(pos[e, 0], pos[e, 1], au[e], goal[e, 0], goal[e, 1])
+        worlds.append(w)
+    for t in range(6):
+        a = rng.integers(1, 5, n).astype(np.uint8)
+        for w0 in (0, 16):                                    # window by window, like a learner
+            k = min(16, n - w0)
+            env.act_range(a[w0:w0 + k], w0)
+            got = env.copy_obs(w0, k)
+            for e in range(w0, w0 + k):
+                assert worlds[e].step(int(a[e])) == 0
+                np.testing.assert_array_equal(got[e - w0], worlds[e].obs_rgb8(), err_msg=f"step {t} env {e}")
+    st = env.get_state()
+    for e in range(n):
+        assert bits(st["pos"][e]).tolist() == bits(worlds[e].state()["pos"]).tolist()
+    env.close()
+
+
+def test_both_kernels_write_identical_bytes_and_default_selection(rcw, oracle, monkeypatch):
+    """4096 envs at 84 x 84 take env_kernel by default; RCW_ENV_PER_WARP=0 forces the item kernel."""
+    n, seed, steps = 4096, 3, 40
+    kw = dict(num_rays=84, height_camera_view_pu=84, obs_format="gray8")
+    a = rcw.BatchedSingleRoom(n, seed=seed, **kw)
+    monkeypatch.setenv("RCW_ENV_PER_WARP", "0")
+    b = rcw.BatchedSingleRoom(n, seed=seed, **kw)
+    a.step_random(steps)
+    b.step_random(steps)
+    np.testing.assert_array_equal(a.copy_obs(), b.copy_obs())
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        np.testing.assert_array_equal(sa[k], sb[k])
+    ref = oracle.Batch(8, cfg=oracle.default_config(R=84, P=84), seed=seed, env_id_offset=2000)
+    ref.rollout(steps)
+    np.testing.assert_array_equal(a.copy_obs(2000, 8), ref.obs_gray8())
+    a.close()
+    b.close()
