@@ -145,13 +145,16 @@ def cpu_port_rate(n_envs, kw, seconds, threads):
     cfg = orc.default_config(H=kw["height_tile_map_tu"], W=kw["width_tile_map_tu"],
                              N=kw["num_directions"], R=kw["num_rays"], P=kw["height_camera_view_pu"])
     b = orc.Batch(n_envs, cfg=cfg, seed=SEED)
+    b.rollout(2, threads=threads)                      # cold: thread start-up, first touch of the images
+    steps, chunk = 0, 8
     t0 = time.perf_counter()
-    b.rollout(1, threads=threads)
-    t1 = time.perf_counter() - t0
-    steps = int(max(2, min(400, seconds / max(t1, 1e-6))))
-    t0 = time.perf_counter()
-    b.rollout(steps, threads=threads)
-    dt = time.perf_counter() - t0
+    while True:
+        b.rollout(chunk, threads=threads)
+        steps += chunk
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+        chunk = int(max(8, min(4096, 0.25 * seconds * steps / dt)))   # about four more chunks
     return n_envs * steps / dt, steps, dt
 
 
