@@ -535,7 +535,11 @@ __device__ __forceinline__ RayHit dda_cast(const uint32_t* s_map, int H, int W, 
 #else
     (void)lane;
     const bool tie_le = (dda_flags & RCW_DDA_TIE_LE) != 0;
-    if (closed) {
+    // The unchecked walk is only safe from inside the map.  A player can be outside it: injected onto a border
+    // tile and stepped outwards, or carried over the border wall by an increment larger than a tile (the
+    // collision test looks at the candidate position only, collision_detection.jl:21-42).  Same pose in all lanes.
+    const bool start_inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
+    if (closed && start_inside) {
         if (tie_le) dda_walk<true, true>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
         else dda_walk<false, true>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
     } else {

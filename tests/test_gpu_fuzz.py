@@ -1,0 +1,181 @@
+"""Seeded random configurations, CUDA path versus the oracle: geometry, camera, formats, palettes, wall layers,
+DDA switches, auto-reset, both step kernels (item kernel / env kernel), the top view.  Every comparison is
+bit-exact.  The seeds are fixed, so a failure names a reproducible case."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rcw():
+    import raycastworlds_jl_b200 as m
+    return m
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def draw_case(seed):
+    rng = np.random.default_rng(seed)
+    H, W = int(rng.integers(3, 40)), int(rng.integers(3, 70))
+    if rng.random() < 0.3:
+        H, W = int(rng.integers(3, 9)), int(rng.integers(3, 9))
+    N = int(rng.choice([4, 7, 16, 36, 128, 256, 600]))
+    R = int(rng.choice([1, 2, 31, 32, 33, 45, 64, 84, 100, 128, 160, 257]))
+    P = int(rng.choice([1, 2, 7, 16, 21, 32, 51, 64, 84, 96, 120, 200]))
+    fmt = str(rng.choice(["rgb8", "xrgb32", "gray8"]))
+    radius = float(np.float32(rng.uniform(0.05, 0.45)))
+    incr = float(np.float32(rng.uniform(0.03, 0.6)))
+    sfov = float(np.float32(rng.uniform(0.2, 1.5)))
+    cam_h = float(np.float32(rng.uniform(0.3, 2.0)))
+    pal = None
+    if rng.random() < 0.4:
+        pal = [int(v) for v in rng.integers(0, 1 << 24, 6)]
+    return dict(H=H, W=W, N=N, R=R, P=P, fmt=fmt, radius=radius, incr=incr, sfov=sfov, cam_h=cam_h, pal=pal,
+                tie_le=bool(rng.integers(0, 2)), dist_post=bool(rng.integers(0, 2)),
+                maps=str(rng.choice(["default", "shared", "per_env"])), open_border=bool(rng.random() < 0.3),
+                env_kernel=bool(rng.integers(0, 2)), n=int(rng.integers(1, 41)), pu=int(rng.choice([1, 2, 3, 4, 8])),
+                seed=seed)
+
+
+@pytest.mark.parametrize("seed", range(72))
+def test_random_configuration_matches_oracle(rcw, oracle, monkeypatch, seed):
+    c = draw_case(1000 + seed)
+    rng = np.random.default_rng(5000 + seed)
+    monkeypatch.setenv("RCW_ENV_PER_WARP", "1" if c["env_kernel"] else "0")
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    n, H, W = c["n"], c["H"], c["W"]
+    kw = dict(height_tile_map_tu=H, width_tile_map_tu=W, num_directions=c["N"], num_rays=c["R"],
+              height_camera_view_pu=c["P"], player_radius_wu=c["radius"], position_increment_wu=c["incr"],
+              semi_field_of_view_wu=c["sfov"], camera_height_tile_wu=c["cam_h"], obs_format=c["fmt"],
+              dda_tie_le=c["tie_le"], dda_dist_post=c["dist_post"], pu_per_tu=c["pu"])
+    okw = dict(H=H, W=W, N=c["N"], R=c["R"], P=c["P"], radius=np.float32(c["radius"]), incr=np.float32(c["incr"]),
+               sfov=np.float32(c["sfov"]), cam_h=np.float32(c["cam_h"]), tie_le=int(c["tie_le"]),
+               dist_post=int(c["dist_post"]), pu_per_tu=c["pu"])
+    if c["pal"] is not None:
+        kw["palette"] = c["pal"]
+        okw["palette"] = c["pal"]
+    cfg = oracle.default_config(**okw)
+    want_obs = {"rgb8": "obs_rgb8", "xrgb32": "camera_view", "gray8": None}[c["fmt"]]
+
+    def gray(u32):
+        r, g, b = (u32 >> 16) & 255, (u32 >> 8) & 255, u32 & 255
+        return ((77 * r + 150 * g + 29 * b + 128) >> 8).astype(np.uint8)
+
+    def obs_of(w):
+        return gray(w.camera_view) if want_obs is None else (w.obs_rgb8() if want_obs == "obs_rgb8" else w.camera_view)
+
+    if c["maps"] == "default":
+        # Philox layouts, random policy, auto-reset: the batched semantics end to end
+        env = rcw.BatchedSingleRoom(n, seed=c["seed"], env_id_offset=77, **kw)
+        ref = oracle.Batch(n, cfg=cfg, seed=c["seed"], env_id_offset=77)
+        steps = int(rng.integers(1, 200))
+        env.step_random(steps)
+        ref.rollout(steps)
+        worlds = [ref.world(e) for e in range(n)]
+        r, d = ref.reward_done()
+        st = env.get_state()
+        np.testing.assert_array_equal(st["reward"], r)
+        np.testing.assert_array_equal(st["done"], d)
+        assert env.episode_stats() == ref.episode_stats()
+    else:
+        # host-supplied wall layers (one for the batch, or one per env), injected states, explicit actions
+        walls = np.zeros((n, H, W), bool)
+        walls[:, 0, :] = walls[:, -1, :] = walls[:, :, 0] = walls[:, :, -1] = True
+        if H > 4 and W > 4:
+            walls[:, 2:-2, 2:-2] |= rng.random((n, H - 4, W - 4)) < 0.15
+        if c["open_border"]:
+            walls[:, 0, 1:-1] &= rng.random((n, W - 2)) < 0.5
+            walls[:, 1:-1, -1] &= rng.random((n, H - 2)) < 0.5
+        if c["maps"] == "shared":
+            walls[:] = walls[0]
+        pos = np.stack([rng.uniform(0.05, H - 0.05, n), rng.uniform(0.05, W - 0.05, n)], 1).astype(np.float32)
+        au = rng.integers(0, c["N"], n).astype(np.int32)
+        goal = np.stack([rng.integers(1, H + 1, n), rng.integers(1, W + 1, n)], 1).astype(np.int32)
+        env = rcw.BatchedSingleRoom(n, seed=c["seed"], auto_reset=False, **kw)
+        if c["maps"] == "shared":
+            env.set_wall_map(walls[0])
+        else:
+            env.set_wall_maps(walls)
+        env.set_state(pos=pos, dir_au=au, goal=goal)
+        env.render()
+        worlds = []
+        for e in range(n):
+            w = oracle.World(cfg)
+            w.set_wall_map(walls[e])
+            w.set_state(pos[e, 0], pos[e, 1], au[e], goal[e, 0], goal[e, 1])
+            w.cast_rays()
+            w.update_camera_view()
+            worlds.append(w)
+        for _ in range(int(rng.integers(0, 25))):
+            a = rng.integers(1, 5, n).astype(np.uint8)
+            env.act(a)
+            for e in range(n):
+                assert worlds[e].step(int(a[e])) == 0
+        st = env.get_state()
+        np.testing.assert_array_equal(st["reward"], np.array([w.state()["reward"] for w in worlds], np.float32))
+        np.testing.assert_array_equal(st["done"], np.array([w.state()["done"] for w in worlds], np.uint8))
+
+    np.testing.assert_array_equal(bits(st["pos"]), bits(np.stack([w.state()["pos"] for w in worlds])), err_msg=str(c))
+    np.testing.assert_array_equal(st["dir_au"], np.array([w.state()["au"] for w in worlds], np.int32))
+    np.testing.assert_array_equal(st["goal"], np.stack([w.state()["goal"] for w in worlds]))
+    obs = env.copy_obs()
+    rays = env.get_rays()
+    for e in range(n):
+        np.testing.assert_array_equal(obs[e], obs_of(worlds[e]), err_msg=f"env {e} of {c}")
+        np.testing.assert_array_equal(rays["hit"][e], worlds[e].ray_stop, err_msg=f"env {e} of {c}")
+        np.testing.assert_array_equal(rays["dim"][e], worlds[e].ray_dim)
+        np.testing.assert_array_equal(bits(rays["dist"][e]), bits(worlds[e].ray_dist))
+    env.render_top_view()
+    top = env.copy_top_view()
+    for e in range(n):
+        worlds[e].update_top_view()
+        np.testing.assert_array_equal(top[e], worlds[e].top_view, err_msg=f"top view, env {e} of {c}")
+    env.close()
+
+
+@pytest.mark.parametrize("env_kernel", [0, 1])
+def test_player_carried_outside_the_map_is_defined(rcw, oracle, monkeypatch, env_kernel):
+    """An increment larger than a tile carries the player over the border wall (the collision test only looks at
+    the candidate position, collision_detection.jl:21-42), and a state injected onto a border tile can step
+    outwards.  Outside the map everything counts as wall: rays stop at once, the column is full height.  The
+    unchecked closed-border DDA must not be taken from there (found by the seeded fuzz test above)."""
+    monkeypatch.setenv("RCW_ENV_PER_WARP", str(env_kernel))
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    n = 6
+    kw = dict(num_rays=64, height_camera_view_pu=32, position_increment_wu=2.5, player_radius_wu=0.1, pu_per_tu=4)
+    env = rcw.BatchedSingleRoom(n, auto_reset=False, **kw)
+    cfg = oracle.default_config(R=64, P=32, incr=np.float32(2.5), radius=np.float32(0.1), pu_per_tu=4)
+    pos = np.array([[1.5, 1.5], [1.5, 1.5], [6.5, 14.5], [0.5, 7.5], [4.5, 0.2], [7.9, 15.9]], np.float32)
+    au = np.array([64, 96, 0, 64, 96, 16], np.int32)          # facing -i, -j, +i, -i, -j, diagonal
+    goal = np.array([[4, 8]] * n, np.int32)
+    env.set_state(pos=pos, dir_au=au, goal=goal)
+    env.render()
+    worlds = []
+    for e in range(n):
+        w = oracle.World(cfg)
+        w.set_state(pos[e, 0], pos[e, 1], au[e], 4, 8)
+        w.cast_rays()
+        w.update_camera_view()
+        worlds.append(w)
+    for a in (1, 1, 3, 1, 2, 2, 4, 1):
+        env.act(np.full(n, a, np.uint8))
+        for w in worlds:
+            assert w.step(a) == 0
+    st = env.get_state()
+    got = np.stack([w.state()["pos"] for w in worlds])
+    np.testing.assert_array_equal(bits(st["pos"]), bits(got))
+    assert (got < 0).any() or (got[:, 0] >= 8).any() or (got[:, 1] >= 16).any(), "somebody should have left the map"
+    obs = env.copy_obs()
+    rays = env.get_rays()
+    env.render_top_view()
+    top = env.copy_top_view()
+    for e, w in enumerate(worlds):
+        np.testing.assert_array_equal(obs[e], w.obs_rgb8())
+        np.testing.assert_array_equal(rays["hit"][e], w.ray_stop)
+        np.testing.assert_array_equal(bits(rays["dist"][e]), bits(w.ray_dist))
+        w.update_top_view()
+        np.testing.assert_array_equal(top[e], w.top_view)
+    env.close()
