@@ -179,3 +179,104 @@ def test_player_carried_outside_the_map_is_defined(rcw, oracle, monkeypatch, env
         w.update_top_view()
         np.testing.assert_array_equal(top[e], w.top_view)
     env.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_operation_sequences_with_windows(rcw, oracle, monkeypatch, seed):
+    """Random sequences of whole-batch steps, range steps (unaligned, wrapping the observation window), masked
+    resets to host layouts, partial set_state, and a checkpoint round trip through a fresh handle; afterwards the
+    whole state and every observation slot must equal the oracle's for the env rendered into it last."""
+    rng = np.random.default_rng(9000 + seed)
+    monkeypatch.setenv("RCW_ENV_PER_WARP", str(int(rng.integers(0, 2))))
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    n = int(rng.integers(2, 60))
+    K = int(rng.integers(1, n + 1)) if rng.random() < 0.8 else 0
+    R, P = int(rng.choice([20, 64, 84, 100, 160])), int(rng.choice([8, 21, 32, 64]))
+    fmt = str(rng.choice(["rgb8", "xrgb32", "gray8"]))
+    top = bool(rng.integers(0, 2))
+    kw = dict(num_rays=R, height_camera_view_pu=P, obs_format=fmt, auto_reset=False, obs_window_envs=K,
+              top_view=top, pu_per_tu=4)
+    cfg = oracle.default_config(R=R, P=P, pu_per_tu=4)
+    env = rcw.BatchedSingleRoom(n, seed=seed, **kw)
+    win = env.obs_window
+    # start from host layouts so that the oracle knows the state
+    def layouts():
+        g = np.stack([rng.integers(2, 8, n), rng.integers(2, 16, n)], 1).astype(np.int32)
+        p = np.stack([rng.integers(2, 8, n), rng.integers(2, 16, n)], 1).astype(np.int32)
+        p[(p == g).all(1)] = [2, 2]
+        g[(p == g).all(1)] = [3, 3]
+        return g, p, rng.integers(0, 128, n).astype(np.int32)
+    g, p, a = layouts()
+    env.reset(g, p, a)
+    worlds = []
+    for e in range(n):
+        w = oracle.World(cfg)
+        w.reset_to(g[e, 0], g[e, 1], p[e, 0], p[e, 1], a[e])
+        w.cast_rays()
+        w.update_camera_view()
+        worlds.append(w)
+    owner = {}
+    def rendered(envs):
+        for e in envs:
+            owner[e % win] = e
+    rendered(range(n))
+    for _ in range(int(rng.integers(3, 14))):
+        op = rng.choice(["act", "range", "range", "reset", "state", "checkpoint"])
+        if op == "act":
+            acts = rng.choice([1, 1, 2, 3, 4], size=n).astype(np.uint8)
+            env.act(acts)
+            for e in range(n):
+                assert worlds[e].step(int(acts[e])) == 0
+            rendered(range(n))
+        elif op == "range":
+            m = int(rng.integers(1, win + 1))
+            e0 = int(rng.integers(0, n - m + 1))
+            acts = rng.choice([1, 1, 2, 3, 4], size=m).astype(np.uint8)
+            env.act_range(acts, e0)
+            for k in range(m):
+                assert worlds[e0 + k].step(int(acts[k])) == 0
+            rendered(range(e0, e0 + m))
+        elif op == "reset":
+            g, p, a = layouts()
+            mask = (rng.random(n) < 0.4).astype(np.uint8)
+            env.reset(g, p, a, mask)
+            for e in np.nonzero(mask)[0]:
+                worlds[e].reset_to(g[e, 0], g[e, 1], p[e, 0], p[e, 1], a[e])
+                worlds[e].cast_rays()
+                worlds[e].update_camera_view()
+            rendered(range(n))                      # a reset re-renders the whole batch
+        elif op == "state":
+            au = rng.integers(0, 128, n).astype(np.int32)
+            env.set_state(dir_au=au)
+            env.render()
+            for e in range(n):
+                s = worlds[e].state()
+                worlds[e].set_state(s["pos"][0], s["pos"][1], au[e], s["goal"][0], s["goal"][1], s["reward"], int(s["done"]))
+                worlds[e].cast_rays()
+                worlds[e].update_camera_view()
+            rendered(range(n))
+        else:
+            blob = env.save_checkpoint()
+            env.close()
+            env = rcw.BatchedSingleRoom(n, seed=seed + 1, **kw)
+            env.load_checkpoint(blob)
+            rendered(range(n))
+    st = env.get_state()
+    np.testing.assert_array_equal(bits(st["pos"]), bits(np.stack([w.state()["pos"] for w in worlds])))
+    np.testing.assert_array_equal(st["dir_au"], np.array([w.state()["au"] for w in worlds], np.int32))
+    np.testing.assert_array_equal(st["goal"], np.stack([w.state()["goal"] for w in worlds]))
+    np.testing.assert_array_equal(st["reward"], np.array([w.state()["reward"] for w in worlds], np.float32))
+    np.testing.assert_array_equal(st["done"], np.array([w.state()["done"] for w in worlds], np.uint8))
+
+    def gray(u32):
+        r, g_, b = (u32 >> 16) & 255, (u32 >> 8) & 255, u32 & 255
+        return ((77 * r + 150 * g_ + 29 * b + 128) >> 8).astype(np.uint8)
+
+    for slot, e in owner.items():
+        w = worlds[e]
+        want = {"rgb8": w.obs_rgb8, "xrgb32": lambda: w.camera_view, "gray8": lambda: gray(w.camera_view)}[fmt]()
+        np.testing.assert_array_equal(env.copy_obs(e, 1)[0], want, err_msg=f"slot {slot} env {e}")
+        if top:
+            w.update_top_view()
+            np.testing.assert_array_equal(env.copy_top_view(e, 1)[0], w.top_view, err_msg=f"top view slot {slot} env {e}")
+    env.close()
