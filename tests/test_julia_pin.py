@@ -26,3 +26,6 @@ def test_oracle_matches_julia(oracle, golden, case):
         np.testing.assert_array_equal(w.ray_dim, ref[f"{case}_dim"][k])
         np.testing.assert_allclose(w.ray_dist, ref[f"{case}_dist"][k], rtol=1e-5)
         np.testing.assert_array_equal(w.camera_view, ref[f"{case}_image"][k])
+        if f"{case}_top" in ref:                      # pins the restated SimpleDraw shapes (line, circle) as well
+            w.update_top_view()
+            np.testing.assert_array_equal(w.top_view, ref[f"{case}_top"][k])

@@ -15,11 +15,11 @@ const SR = RCW.SingleRoomModule
 function world_for(case)
     case == "A" && return SR.SingleRoom()
     case == "B" && return SR.SingleRoom(height_tile_map_tu = 64, width_tile_map_tu = 64, num_directions = 256,
-                                        num_rays = 128, height_camera_view_pu = 96)
+                                        num_rays = 128, height_camera_view_pu = 96, pu_per_tu = 4)
     case == "C" && return SR.SingleRoom(height_tile_map_tu = 5, width_tile_map_tu = 7, num_directions = 36,
                                         num_rays = 45, height_camera_view_pu = 51, player_radius_wu = 0.2f0,
                                         position_increment_wu = 0.3f0, semi_field_of_view_wu = 0.5f0,
-                                        camera_height_tile_wu = 0.8f0)
+                                        camera_height_tile_wu = 0.8f0, pu_per_tu = 7)
     error("unknown case")
 end
 
@@ -43,10 +43,12 @@ function main(in_path, out_path)
         n, R = size(states, 1), length(env.world.ray_directions_wu)
         hit = zeros(Int32, n, R, 2); dim = zeros(Int32, n, R); dist = zeros(Float32, n, R)
         rdir = zeros(Float32, n, R, 2); img = zeros(UInt32, n, R, size(env.camera_view, 1))
+        top = zeros(UInt32, n, size(env.top_view, 2), size(env.top_view, 1))   # update_top_view! (SimpleDraw 0.3 shapes)
         for k in 1:n
             set_state!(env, states[k, 1], states[k, 2], au[k], goal[k, 1], goal[k, 2])
             RCW.cast_rays!(env.world)
             RCW.update_camera_view!(env)
+            RCW.update_top_view!(env)
             for i in 1:R
                 hit[k, i, 1] = env.world.ray_stop_position_tu[1, i]
                 hit[k, i, 2] = env.world.ray_stop_position_tu[2, i]
@@ -55,9 +57,10 @@ function main(in_path, out_path)
                 rdir[k, i, 1], rdir[k, i, 2] = env.world.ray_directions_wu[i]
             end
             img[k, :, :] = permutedims(env.camera_view)     # [column, row]
+            top[k, :, :] = permutedims(env.top_view)
         end
         out["$(case)_hit"] = hit; out["$(case)_dim"] = dim; out["$(case)_dist"] = dist
-        out["$(case)_ray_dir"] = rdir; out["$(case)_image"] = img
+        out["$(case)_ray_dir"] = rdir; out["$(case)_image"] = img; out["$(case)_top"] = top
         # act! trajectories
         init, actions = g["$(case)_act_init"], g["$(case)_act_actions"]
         ne, T = size(actions)
