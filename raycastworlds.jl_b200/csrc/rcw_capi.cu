@@ -106,6 +106,8 @@ struct rcw_batch {
     int ctas_per_sm = 0;          // 0: one CTA per 8 items; >0: persistent grid of sm_count * this
     bool bulk = false;            // renderer: TMA bulk stores of whole bands (true) or per-lane vector stores
     bool split = false;           // one env-step = front launch + paint launch (true) or one fused launch
+    bool no_packed_actions = false;  // RCW_PACKED_ACTIONS=0: always stage host actions through a device copy
+    PackedActions packed{};       // scratch for host actions delivered through the kernel parameters
     bool env_per_warp = false;    // narrow cameras (<= 128 rays): a warp owns a whole env (env_kernel) ...
     int64_t env_per_warp_min = 0; // ... in launches of at least this many envs
     bool occ4 = false;            // fused kernel variant compiled for 32 instead of 24 warps per SM (front-bound steps)
@@ -308,10 +310,31 @@ static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, 
 
 // One frame of the whole batch.  With an observation window the batch is rendered window by window
 // (one launch each, every frame still written to HBM); all launches read state `cur` and write `cur ^ 1`.
-static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
+// 2 bits per env into the kernel-parameter block (validated values 1..4)
+static void pack_actions(const uint8_t* actions, int64_t n, PackedActions& pa) {
+    int64_t k = 0;
+    for (int64_t w = 0; k + 16 <= n; ++w, k += 16) {
+        uint32_t v = 0;
+        for (int j = 0; j < 16; ++j) v |= (uint32_t)(actions[k + j] - 1u) << (2 * j);
+        pa.w[w] = v;
+    }
+    if (k < n) {
+        uint32_t v = 0;
+        for (int j = 0; k + j < n; ++j) v |= (uint32_t)(actions[k + j] - 1u) << (2 * j);
+        pa.w[k >> 4] = v;
+    }
+}
+
+// launches of at most kPackedActionEnvs envs on the fused path take host actions through the kernel parameters
+static bool packs_actions(const rcw_batch* b, int64_t env_count) {
+    return !b->split && !b->bulk && !b->no_packed_actions && env_count <= kPackedActionEnvs;
+}
+
+// h_actions != nullptr: validated host actions of the whole batch (d_actions is then ignored)
+static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions, const uint8_t* h_actions = nullptr) {
     FrameParams p;
     fill_frame_params(b, p);
-    p.actions = d_actions;
+    p.actions = h_actions ? nullptr : d_actions;
     const int64_t E = b->cfg.num_envs;
     for (int64_t e0 = 0; e0 < E; e0 += b->obs_window) {
         p.env_first = e0;
@@ -319,7 +342,12 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
         p.obs_slot0 = 0;
         LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, p.env_count)};
         sh.env_per_warp = b->env_per_warp && p.env_count >= b->env_per_warp_min;
-        RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream));
+        if (h_actions) {
+            pack_actions(h_actions + e0, p.env_count, b->packed);
+            RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream, &b->packed));
+        } else {
+            RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream));
+        }
         b->launches += b->split ? 2 : 1;
         // the reference's act!(env) / reset!(env) also redraw the top view (single_room.jl:329,337)
         if (b->cfg.top_view)
@@ -334,16 +362,23 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions) {
 
 // act! for the envs [env0, env0 + n) only: the launch reads state `cur` and writes `cur ^ 1` like a
 // full step, then the range is copied back so that `cur` stays the handle's one current buffer.
-static int32_t enqueue_range_step(rcw_batch* b, const uint8_t* d_actions_env0, int64_t env0, int64_t n) {
+// h_actions != nullptr: validated host actions of the range, delivered through the kernel parameters
+static int32_t enqueue_range_step(rcw_batch* b, const uint8_t* d_actions_env0, int64_t env0, int64_t n,
+                                  const uint8_t* h_actions = nullptr) {
     FrameParams p;
     fill_frame_params(b, p);
-    p.actions = d_actions_env0 - env0;   // the kernel indexes actions by env
+    p.actions = h_actions ? nullptr : d_actions_env0 - env0;   // the kernel indexes actions by env
     p.env_first = env0;
     p.env_count = n;
     p.obs_slot0 = (uint32_t)(env0 % b->obs_window);
     LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, n)};
     sh.env_per_warp = b->env_per_warp && n >= b->env_per_warp_min;
-    RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, sh, b->stream));
+    if (h_actions) {
+        pack_actions(h_actions, n, b->packed);
+        RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, sh, b->stream, &b->packed));
+    } else {
+        RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, sh, b->stream));
+    }
     RCW_CUDA(launch_commit_range(b->st[b->cur ^ 1], b->st[b->cur], env0, n, b->stream));
     b->launches += (b->split ? 2 : 1) + 1;
     if (b->cfg.top_view) return enqueue_top_view(b, b->st[b->cur], env0, n, p.obs_slot0);
@@ -578,6 +613,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // 160x120 6701 -> 6113, 256x192 7366 -> 6305.
     b->env_per_warp = b->gpe <= 8 && 32 * b->col_pitch <= 10240;
     if (const char* s = getenv("RCW_ENV_PER_WARP")) b->env_per_warp = atoi(s) != 0;   // 1 forces it for any width
+    if (const char* s = getenv("RCW_PACKED_ACTIONS")) b->no_packed_actions = atoi(s) == 0;
     b->env_per_warp_min = kEnvPerWarpMinEnvs;
     if (const char* s = getenv("RCW_ENV_PER_WARP_MIN")) b->env_per_warp_min = atoll(s);   // tests force the kernel on small batches
     b->obs_window = (c.obs_window_envs > 0 && c.obs_window_envs < E) ? c.obs_window_envs : E;
@@ -879,11 +915,36 @@ static int32_t stage_actions(rcw_batch* b, const uint8_t* actions, int64_t env0,
     return RCW_OK;
 }
 
+static bool is_device_pointer(const void* ptr) {
+    cudaPointerAttributes attr;
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, ptr);
+    if (pe != cudaSuccess) cudaGetLastError();
+    return pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+}
+
+// the reference's @assert (single_room.jl:140) for a host array
+static int32_t validate_host_actions(const uint8_t* actions, int64_t env0, int64_t n) {
+    uint32_t bad = 0;
+    for (int64_t k = 0; k < n; ++k) bad |= (uint32_t)((uint8_t)(actions[k] - 1u) > 3u);
+    if (bad)
+        for (int64_t k = 0; k < n; ++k)
+            if (actions[k] < 1 || actions[k] > 4)
+                return fail(RCW_EACTION, "Invalid action: %d (env %lld); actions must be in 1..4", (int)actions[k],
+                            (long long)(env0 + k));
+    return RCW_OK;
+}
+
 int32_t rcw_step(rcw_batch* b, const uint8_t* actions) {
     NvtxRange nvtx("rcw_step");
     if (int32_t rc = check_handle(b)) return rc;
     if (!actions) return fail(RCW_EINVAL, "actions is null (use rcw_step_random for the random policy)");
     DeviceGuard g(b->device);
+    const int64_t per_launch = b->cfg.num_envs < b->obs_window ? b->cfg.num_envs : b->obs_window;
+    if (packs_actions(b, per_launch) && !is_device_pointer(actions)) {
+        // host actions ride in the kernel parameters: no staging copy in front of the launch
+        if (int32_t rc = validate_host_actions(actions, 0, b->cfg.num_envs)) return rc;
+        return enqueue_frame(b, kModeStep, nullptr, actions);
+    }
     const uint8_t* d_actions = nullptr;
     if (int32_t rc = stage_actions(b, actions, 0, b->cfg.num_envs, &d_actions)) return rc;
     return enqueue_frame(b, kModeStep, d_actions);
@@ -900,6 +961,10 @@ int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64
         return fail(RCW_ESIZE, "a range of %lld envs does not fit the observation window of %lld",
                     (long long)n, (long long)b->obs_window);
     DeviceGuard g(b->device);
+    if (packs_actions(b, n) && !is_device_pointer(actions)) {
+        if (int32_t rc = validate_host_actions(actions, env0, n)) return rc;
+        return enqueue_range_step(b, nullptr, env0, n, actions);
+    }
     const uint8_t* d_actions = nullptr;
     if (int32_t rc = stage_actions(b, actions, env0, n, &d_actions)) return rc;
     return enqueue_range_step(b, d_actions, env0, n);

@@ -127,6 +127,15 @@ struct FrameParams {
     float* dump_dir;         // [n][R][2]
 };
 
+// Host-supplied actions of one launch, two bits per env (action - 1), passed by value in the kernel parameter
+// space (CUDA 12.1+: up to 32,764 bytes of parameters): no pinned staging, no host-to-device copy in front of
+// the kernel, the warps read their two bits with one constant-bank load.  Env k of the launch (relative to
+// FrameParams::env_first) is bits [2 (k mod 16), 2 (k mod 16) + 2) of w[k / 16].
+constexpr int kPackedActionEnvs = 32768;
+struct PackedActions {
+    uint32_t w[kPackedActionEnvs / 16];
+};
+
 struct ResetParams {
     int32_t H, W, wpr, N;
     const uint32_t* wall_map;
@@ -178,7 +187,9 @@ struct LaunchShape {
     int ctas;     // grid size
     bool env_per_warp = false;   // small items: env_kernel, one warp = one env
 };
-cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s);
+// packed != nullptr (step mode, fused path, env_count <= kPackedActionEnvs): the actions ride in the parameters
+cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s,
+                         const PackedActions* packed = nullptr);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);
 // state `from` -> state `to` for envs [env0, env0 + n): makes a range step visible in the buffer it read
 cudaError_t launch_commit_range(const StateRef& from, const StateRef& to, int64_t env0, int64_t n, cudaStream_t s);

@@ -355,14 +355,17 @@ struct EnvInputs {
     int action;
 };
 
-__device__ __forceinline__ EnvInputs load_env_inputs(const FrameParams& p, int64_t env) {
+// `pa`: the launch's actions packed into the kernel parameters (or nullptr); `env_rel`: env index in the launch
+__device__ __forceinline__ EnvInputs load_env_inputs(const FrameParams& p, int64_t env, const PackedActions* pa,
+                                                     uint32_t env_rel) {
     EnvInputs in;
     in.x = __ldg(p.in.pos_x + env);
     in.y = __ldg(p.in.pos_y + env);
     in.au = __ldg(p.in.dir_au + env);
     in.goal = __ldg(p.in.goal + env);
     in.episode = __ldg(p.in.episode + env);
-    in.action = p.actions ? (int)__ldg(p.actions + env) : 0;
+    if (pa) in.action = (int)((pa->w[env_rel >> 4] >> ((env_rel & 15u) * 2u)) & 3u) + 1;
+    else in.action = p.actions ? (int)__ldg(p.actions + env) : -1;   // -1: random policy
     return in;
 }
 
@@ -376,7 +379,7 @@ __device__ __forceinline__ EnvPose act_env(const FrameParams& p, const uint32_t*
     uint32_t episode = in.episode;
     int gi = (int)(in.goal & 0xFFFFu), gj = (int)(in.goal >> 16);
     const uint64_t env_id = p.env_id_offset + (uint64_t)env;
-    const int a = p.actions ? in.action : draw_action(p.seed, env_id, p.step_index);
+    const int a = in.action >= 0 ? in.action : draw_action(p.seed, env_id, p.step_index);
     const bool valid = (a >= 1) && (a <= 4);
     float reward = 0.0f;
     bool done = false;
@@ -824,9 +827,8 @@ enum : int { kStageFused = 0, kStageFront = 1, kStagePaint = 2 };
 // OCC = CTAs per SM the register allocation aims for.  20 warps per SM (91 registers) is best when the step
 // is bound by the store stream (default camera, RGB8 / XRGB32); 32 warps per SM (<= 64 registers) is 6-14 %
 // faster when act! and the DDA bound it (small frames, one-byte pixels, large maps) — profiles/README.md.
-template <int MODE, int FMT, bool BULK, int STAGE, int OCC>
-__global__ void __launch_bounds__(kThreadsPerCta, OCC)
-frame_kernel(const __grid_constant__ FrameParams p) {
+template <int MODE, int FMT, bool BULK, int STAGE>
+__device__ __forceinline__ void frame_body(const FrameParams& p, const PackedActions* pa) {
     extern __shared__ __align__(128) uint32_t s_dyn[];  // [pattern buffers (BULK)] [bit-packed wall layer]
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ __align__(8) uint64_t s_mbar_env[kWarpsPerCta];   // per-env wall layers: one per env slot
@@ -905,7 +907,7 @@ frame_kernel(const __grid_constant__ FrameParams p) {
                 // rows of the three directions the env can face after this step (turn right / keep /
                 // turn left), so the DDA does not start with a dependent L2 round trip.
                 EnvInputs in;
-                if (leader) in = load_env_inputs(p, env);
+                if (leader) in = load_env_inputs(p, env, pa, env_rel);
                 const int au_in = __ldg(p.in.dir_au + env);
                 const int au_m = au_in == 0 ? p.N - 1 : au_in - 1, au_p = au_in + 1 == p.N ? 0 : au_in + 1;
                 const float4 rt_m = __ldg(rt_lane + (size_t)au_m * (size_t)R);
@@ -1002,6 +1004,20 @@ frame_kernel(const __grid_constant__ FrameParams p) {
     if (BULK && kPaints) bulk_wait_group_read0();   // shared memory must outlive the TMA reads
 }
 
+// OCC = CTAs per SM the register allocation aims for (see above).
+template <int MODE, int FMT, bool BULK, int STAGE, int OCC>
+__global__ void __launch_bounds__(kThreadsPerCta, OCC)
+frame_kernel(const __grid_constant__ FrameParams p) {
+    frame_body<MODE, FMT, BULK, STAGE>(p, nullptr);
+}
+
+// the fused step with host-supplied actions packed into the parameters
+template <int FMT, int OCC>
+__global__ void __launch_bounds__(kThreadsPerCta, OCC)
+frame_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ PackedActions a) {
+    frame_body<kModeStep, FMT, false, kStageFused>(p, &a);
+}
+
 // ------------------------------------------------------------------------------------------
 // small items: one warp = one env
 // ------------------------------------------------------------------------------------------
@@ -1011,8 +1027,7 @@ frame_kernel(const __grid_constant__ FrameParams p) {
 // ray-table row of the next group in flight while the current one is cast and painted.  No block barrier,
 // no pose exchange through shared memory, no item -> (env, group) arithmetic.
 template <int MODE, int FMT>
-__global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSmHi)
-env_kernel(const __grid_constant__ FrameParams p) {
+__device__ __forceinline__ void env_body(const FrameParams& p, const PackedActions* pa) {
     extern __shared__ __align__(128) uint32_t s_dyn[];   // wall layer(s): one shared, or one slot per warp
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ __align__(8) uint64_t s_mbar_env[kWarpsPerCta];
@@ -1050,7 +1065,7 @@ env_kernel(const __grid_constant__ FrameParams p) {
     float4 rt;
     if (MODE == kModeStep) {
         // loads first; the ray-table rows of the three directions the env can face after this step
-        const EnvInputs in = load_env_inputs(p, env);
+        const EnvInputs in = load_env_inputs(p, env, pa, env_rel);
         const int au_m = in.au == 0 ? p.N - 1 : in.au - 1, au_p = in.au + 1 == p.N ? 0 : in.au + 1;
         const float4 rt_m = __ldg(rt_lane0 + (size_t)au_m * (size_t)R);
         const float4 rt_0 = __ldg(rt_lane0 + (size_t)in.au * (size_t)R);
@@ -1091,6 +1106,18 @@ env_kernel(const __grid_constant__ FrameParams p) {
         __syncwarp();                                  // s_col is rewritten by the next group
         rt = rt_next;
     }
+}
+
+template <int MODE, int FMT>
+__global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSmHi)
+env_kernel(const __grid_constant__ FrameParams p) {
+    env_body<MODE, FMT>(p, nullptr);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSmHi)
+env_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ PackedActions a) {
+    env_body<kModeStep, FMT>(p, &a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1203,6 +1230,38 @@ static cudaError_t launch_env_t(const FrameParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+template <int FMT>
+static cudaError_t launch_env_pa_t(const FrameParams& p, const PackedActions& pa, cudaStream_t s) {
+    const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
+    const size_t smem = map_slots * (size_t)p.map_words * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(env_kernel_pa<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned ctas = (unsigned)((p.env_count + kWarpsPerCta - 1) / kWarpsPerCta);
+    env_kernel_pa<FMT><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
+    return cudaGetLastError();
+}
+
+template <int FMT, int OCC>
+static cudaError_t launch_frame_pa_t(const FrameParams& p, const PackedActions& pa, int ctas, cudaStream_t s) {
+    const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
+    const size_t smem = map_slots * (size_t)p.map_words * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(frame_kernel_pa<FMT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    frame_kernel_pa<FMT, OCC><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
+    return cudaGetLastError();
+}
+
+template <int FMT>
+static cudaError_t launch_packed(const FrameParams& p, const PackedActions& pa, const LaunchShape& sh, cudaStream_t s) {
+    if (sh.env_per_warp) return launch_env_pa_t<FMT>(p, pa, s);
+    return sh.occ4 ? launch_frame_pa_t<FMT, kCtasPerSmHi>(p, pa, sh.ctas, s)
+                   : launch_frame_pa_t<FMT, kCtasPerSmLo>(p, pa, sh.ctas, s);
+}
+
 template <int MODE>
 static cudaError_t launch_env_m(const FrameParams& p, int obs_format, cudaStream_t s) {
     if (obs_format == RCW_OBS_GRAY8) return launch_env_t<MODE, RCW_OBS_GRAY8>(p, s);
@@ -1235,7 +1294,14 @@ static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, const La
 }
 
 // split = false: one fused launch.  split = true: two launches (front, then paint) through p.col_info.
-cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s) {
+cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s,
+                         const PackedActions* packed) {
+    if (packed) {
+        if (mode != kModeStep || sh.split || sh.bulk || p.env_count > kPackedActionEnvs) return cudaErrorInvalidValue;
+        if (obs_format == RCW_OBS_GRAY8) return launch_packed<RCW_OBS_GRAY8>(p, *packed, sh, s);
+        if (obs_format == RCW_OBS_RGB8) return launch_packed<RCW_OBS_RGB8>(p, *packed, sh, s);
+        return launch_packed<RCW_OBS_XRGB32>(p, *packed, sh, s);
+    }
     if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc>(p, sh.ctas, s);
     if (mode != kModeStep && mode != kModeRender) return cudaErrorInvalidValue;
     if (sh.env_per_warp && !sh.split && !sh.bulk)

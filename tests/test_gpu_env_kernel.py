@@ -131,3 +131,30 @@ def test_both_kernels_write_identical_bytes_and_default_selection(rcw, oracle, m
     np.testing.assert_array_equal(a.copy_obs(2000, 8), ref.obs_gray8())
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("n", [32768, 32769, 40000])
+def test_host_actions_around_the_parameter_capacity(rcw, oracle, n):
+    """Host action arrays ride in the kernel parameters up to 32,768 envs per launch (2 bits each); larger
+    launches stage them through a device copy.  Both sides of the limit against the oracle, sampled."""
+    seed, steps = 17, 6
+    kw = dict(num_rays=32, height_camera_view_pu=16, obs_format="gray8")
+    env = rcw.BatchedSingleRoom(n, seed=seed, **kw)
+    rng = np.random.default_rng(n)
+    actions = rng.choice([1, 1, 2, 3, 4], size=(steps, n)).astype(np.uint8)
+    for t in range(steps):
+        env.act(actions[t])
+    st = env.get_state()
+    for s0 in (0, 16380, 32760, n - 8):
+        ref = oracle.Batch(8, cfg=oracle.default_config(R=32, P=16), seed=seed, env_id_offset=s0)
+        for t in range(steps):
+            assert ref.step(actions[t, s0:s0 + 8]) == 0
+        pos, au, goal = ref.states()
+        np.testing.assert_array_equal(bits(st["pos"][s0:s0 + 8]), bits(pos))
+        np.testing.assert_array_equal(st["dir_au"][s0:s0 + 8], au)
+        np.testing.assert_array_equal(env.copy_obs(s0, 8), ref.obs_gray8())
+    bad = actions[0].copy()
+    bad[n - 1] = 5
+    with pytest.raises(AssertionError):
+        env.act(bad)
+    env.close()

@@ -46,6 +46,7 @@ def test_random_configuration_matches_oracle(rcw, oracle, monkeypatch, seed):
     rng = np.random.default_rng(5000 + seed)
     monkeypatch.setenv("RCW_ENV_PER_WARP", "1" if c["env_kernel"] else "0")
     monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    monkeypatch.setenv("RCW_PACKED_ACTIONS", str(seed % 2))      # host actions: kernel parameters / staged copy
     n, H, W = c["n"], c["H"], c["W"]
     kw = dict(height_tile_map_tu=H, width_tile_map_tu=W, num_directions=c["N"], num_rays=c["R"],
               height_camera_view_pu=c["P"], player_radius_wu=c["radius"], position_increment_wu=c["incr"],
@@ -189,6 +190,7 @@ def test_random_operation_sequences_with_windows(rcw, oracle, monkeypatch, seed)
     rng = np.random.default_rng(9000 + seed)
     monkeypatch.setenv("RCW_ENV_PER_WARP", str(int(rng.integers(0, 2))))
     monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    monkeypatch.setenv("RCW_PACKED_ACTIONS", str(int(rng.integers(0, 2))))
     n = int(rng.integers(2, 60))
     K = int(rng.integers(1, n + 1)) if rng.random() < 0.8 else 0
     R, P = int(rng.choice([20, 64, 84, 100, 160])), int(rng.choice([8, 21, 32, 64]))
