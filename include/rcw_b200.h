@@ -151,7 +151,8 @@ int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls);
  * [num_envs] int32; the player is placed at the tile centre (i-0.5, j-0.5).  All three NULL =>
  * the layout is drawn on the device (uniform interior goal, uniform empty player tile by
  * rejection, uniform direction — same draw order as the reference).  Sets reward=0,
- * done=false, then casts and renders. */
+ * done=false, then casts and renders the envs that were reset (the observations of the others still
+ * belong to their unchanged state).  Does not block: host arrays are staged before the call returns. */
 int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij,
                   const int32_t* dir_au, const uint8_t* mask);
 

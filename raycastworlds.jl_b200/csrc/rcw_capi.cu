@@ -134,6 +134,11 @@ struct rcw_batch {
     int64_t obs_window = 0;       // env slots of the observation buffer (num_envs unless cfg.obs_window_envs)
     int col_pitch = 0;            // bytes between consecutive columns of an observation (multiple of 32)
     size_t obs_bytes = 0;
+    // rcw_reset scratch (host layouts and mask), allocated on first use
+    int32_t* d_reset_goal = nullptr;
+    int32_t* d_reset_player = nullptr;
+    int32_t* d_reset_dir = nullptr;
+    uint8_t* d_reset_mask = nullptr;
     // top view (update_top_view!): allocated when first drawn
     uint8_t* d_top = nullptr;
     size_t top_env_stride = 0;
@@ -269,7 +274,8 @@ static int grid_for(const rcw_batch* b, int64_t env_count) {
 }
 
 // update_top_view! for envs [env0, env0 + n) from state `st`, into the slots that start at slot0.
-static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, int64_t n, uint32_t slot0) {
+static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, int64_t n, uint32_t slot0,
+                                const uint8_t* d_mask = nullptr) {
     const rcw_config& c = b->cfg;
     if (!b->d_top) {
         const size_t px = (size_t)c.height_tile_map_tu * c.pu_per_tu * (size_t)c.width_tile_map_tu * c.pu_per_tu;
@@ -297,6 +303,7 @@ static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, 
     t.wall_map = b->per_env_maps ? b->d_wall_maps_env : b->d_wall_map;
     t.map_env_stride = b->per_env_maps ? (uint32_t)b->map_words : 0u;
     t.st = st;
+    t.mask = d_mask;
     t.top = b->d_top;
     t.env_stride = b->top_env_stride;
     t.window = (uint32_t)b->obs_window;
@@ -331,10 +338,13 @@ static bool packs_actions(const rcw_batch* b, int64_t env_count) {
 }
 
 // h_actions != nullptr: validated host actions of the whole batch (d_actions is then ignored)
-static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions, const uint8_t* h_actions = nullptr) {
+// d_render_mask (kModeRender): redraw only the envs whose byte is nonzero
+static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions, const uint8_t* h_actions = nullptr,
+                             const uint8_t* d_render_mask = nullptr) {
     FrameParams p;
     fill_frame_params(b, p);
     p.actions = h_actions ? nullptr : d_actions;
+    p.render_mask = mode == kModeRender ? d_render_mask : nullptr;
     const int64_t E = b->cfg.num_envs;
     for (int64_t e0 = 0; e0 < E; e0 += b->obs_window) {
         p.env_first = e0;
@@ -351,7 +361,8 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions, c
         b->launches += b->split ? 2 : 1;
         // the reference's act!(env) / reset!(env) also redraw the top view (single_room.jl:329,337)
         if (b->cfg.top_view)
-            if (int32_t rc = enqueue_top_view(b, mode == kModeStep ? p.out : p.in, e0, p.env_count, 0)) return rc;
+            if (int32_t rc = enqueue_top_view(b, mode == kModeStep ? p.out : p.in, e0, p.env_count, 0, p.render_mask))
+                return rc;
     }
     if (mode == kModeStep) {
         b->cur ^= 1;
@@ -811,12 +822,6 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
     const int64_t E = c.num_envs;
     int32_t *d_goal = nullptr, *d_player = nullptr, *d_dir = nullptr;
     uint8_t* d_mask = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_goal);
-        cudaFree(d_player);
-        cudaFree(d_dir);
-        cudaFree(d_mask);
-    };
     if (any) {
         for (int64_t e = 0; e < E; ++e) {
             if (mask && !mask[e]) continue;
@@ -829,25 +834,24 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
                 return fail(RCW_EINVAL, "env %lld: direction %d outside 0..%d", (long long)e,
                             dir_au[e], c.num_directions - 1);
         }
-        cudaError_t e1 = cudaMalloc((void**)&d_goal, sizeof(int32_t) * 2 * (size_t)E);
-        cudaError_t e2 = cudaMalloc((void**)&d_player, sizeof(int32_t) * 2 * (size_t)E);
-        cudaError_t e3 = cudaMalloc((void**)&d_dir, sizeof(int32_t) * (size_t)E);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-            cleanup();
-            cudaGetLastError();
-            return fail(RCW_ENOMEM, "device allocation for reset layouts failed");
+        // the scratch buffers live as long as the handle; copies from pageable host memory are staged before
+        // cudaMemcpyAsync returns, copies and kernels are ordered by the handle's stream: no blocking here
+        if (!b->d_reset_goal) {
+            RCW_CUDA(dev_alloc(b, &b->d_reset_goal, 2 * (size_t)E, false));
+            RCW_CUDA(dev_alloc(b, &b->d_reset_player, 2 * (size_t)E, false));
+            RCW_CUDA(dev_alloc(b, &b->d_reset_dir, (size_t)E, false));
         }
-        cudaMemcpyAsync(d_goal, goal_ij, sizeof(int32_t) * 2 * (size_t)E, cudaMemcpyHostToDevice, b->stream);
-        cudaMemcpyAsync(d_player, player_ij, sizeof(int32_t) * 2 * (size_t)E, cudaMemcpyHostToDevice, b->stream);
-        cudaMemcpyAsync(d_dir, dir_au, sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, b->stream);
+        d_goal = b->d_reset_goal;
+        d_player = b->d_reset_player;
+        d_dir = b->d_reset_dir;
+        RCW_CUDA(cudaMemcpyAsync(d_goal, goal_ij, sizeof(int32_t) * 2 * (size_t)E, cudaMemcpyHostToDevice, b->stream));
+        RCW_CUDA(cudaMemcpyAsync(d_player, player_ij, sizeof(int32_t) * 2 * (size_t)E, cudaMemcpyHostToDevice, b->stream));
+        RCW_CUDA(cudaMemcpyAsync(d_dir, dir_au, sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, b->stream));
     }
     if (mask) {
-        if (cudaMalloc((void**)&d_mask, (size_t)E) != cudaSuccess) {
-            cleanup();
-            cudaGetLastError();
-            return fail(RCW_ENOMEM, "device allocation for the reset mask failed");
-        }
-        cudaMemcpyAsync(d_mask, mask, (size_t)E, cudaMemcpyHostToDevice, b->stream);
+        if (!b->d_reset_mask) RCW_CUDA(dev_alloc(b, &b->d_reset_mask, (size_t)E, false));
+        d_mask = b->d_reset_mask;
+        RCW_CUDA(cudaMemcpyAsync(d_mask, mask, (size_t)E, cudaMemcpyHostToDevice, b->stream));
     }
     ResetParams rp;
     memset(&rp, 0, sizeof(rp));
@@ -869,16 +873,10 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
     rp.player_ij = d_player;
     rp.dir_au = d_dir;
     rp.mask = d_mask;
-    cudaError_t le = launch_reset(rp, b->stream);
+    RCW_CUDA(launch_reset(rp, b->stream));
     b->launches += 1;
-    if (any || mask) {
-        // the temporaries are host-visible only through this call: drain before freeing
-        cudaError_t se = cudaStreamSynchronize(b->stream);
-        cleanup();
-        if (le == cudaSuccess) le = se;
-    }
-    RCW_CUDA(le);
-    return enqueue_frame(b, kModeRender, nullptr);
+    // only the envs that were reset are redrawn (the others' observations are still those of their state)
+    return enqueue_frame(b, kModeRender, nullptr, nullptr, d_mask);
 }
 
 // The actions of envs [env0, env0 + n) as a device pointer to the first of them.  A device array is used

@@ -103,6 +103,7 @@ struct FrameParams {
     uint32_t* col_info;      // [num_envs][R] pad | palette index << 16, column order (split launches)
     // state
     StateRef in, out;
+    const uint8_t* render_mask;  // kModeRender only: nonzero = redraw this env (nullptr: all) — masked resets
     const uint8_t* actions;  // device, 1..4 per env; nullptr => random policy
     float* reward;
     uint8_t* done;
@@ -170,6 +171,7 @@ struct TopViewParams {
     const uint32_t* wall_map;
     uint32_t map_env_stride;
     StateRef st;             // the state to draw
+    const uint8_t* mask;     // nonzero = draw this env (nullptr: all)
     uint8_t* top;            // [window][env_stride] bytes; one env = uint32 [Wp][Hp], row fastest
     size_t env_stride;       // bytes, multiple of 128
     uint32_t window, slot0;  // env_first + k lives in slot (slot0 + k) mod window

@@ -880,6 +880,10 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
         const int ncols = min(32, R - r0);
         const int col0 = R - r0 - ncols;               // first column of the span (ray r paints column R-1-r)
 
+        // a masked render (after a masked reset) redraws only the chosen envs; the decision is per env, so
+        // all warps of an env — including the one that stages its wall layer — agree
+        if (MODE == kModeRender && STAGE == kStageFused && p.render_mask && !__ldg(p.render_mask + env)) continue;
+
         ColumnShade cs;
         cs.pad = 0;
         cs.cid = RCW_COLOR_WALL_1;
@@ -1002,6 +1006,9 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
         __syncwarp();   // s_col is rewritten in the next round
     }
     if (BULK && kPaints) bulk_wait_group_read0();   // shared memory must outlive the TMA reads
+    // a thread that never needed the staged wall layer (all its items skipped or out of range) still waits for
+    // the bulk copy: shared memory must not be released while the copy is in flight
+    if (!staged) mbar_wait(&s_mbar, 0);
 }
 
 // OCC = CTAs per SM the register allocation aims for (see above).
@@ -1047,9 +1054,15 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
         mbar_arrive_expect_tx(&s_mbar, map_bytes);
         bulk_copy_g2s(s_dyn, p.wall_map, map_bytes, &s_mbar);
     }
+    // (no block barrier below this point)  A warp without work still waits for the CTA's bulk copy, so that shared
+    // memory is not released while the copy is in flight.
     const uint32_t env_rel = blockIdx.x * kWarpsPerCta + warp;
-    if (env_rel >= (uint32_t)p.env_count) return;     // (no block barrier below this point)
     const int64_t env = p.env_first + env_rel;
+    if (env_rel >= (uint32_t)p.env_count ||
+        (MODE == kModeRender && p.render_mask && !__ldg(p.render_mask + env))) {       // out of range / masked render
+        if (!per_env_maps) mbar_wait(&s_mbar, 0);
+        return;
+    }
     const int R = p.R;
     const uint32_t* my_map = s_dyn;
     if (per_env_maps) {

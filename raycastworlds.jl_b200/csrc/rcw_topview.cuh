@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
 
     const uint32_t env_rel = blockIdx.x;
     const int64_t env = p.env_first + env_rel;
+    if (p.mask && !__ldg(p.mask + env)) return;               // masked redraw: the whole CTA leaves
 
     // ---- this env's wall layer: one TMA bulk copy; planes cleared and tables built meanwhile
     if (tid == 0) {

@@ -158,3 +158,51 @@ def test_host_actions_around_the_parameter_capacity(rcw, oracle, n):
     with pytest.raises(AssertionError):
         env.act(bad)
     env.close()
+
+
+@pytest.mark.parametrize("env_kernel", [0, 1])
+def test_masked_reset_redraws_only_the_reset_envs(rcw, oracle, monkeypatch, env_kernel):
+    """rcw_reset with a mask redraws the envs it reset and leaves the other observations (and top views)
+    byte for byte as they were; it does not block and reuses its device scratch from call to call."""
+    monkeypatch.setenv("RCW_ENV_PER_WARP", str(env_kernel))
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    n = 50
+    kw = dict(num_rays=96, height_camera_view_pu=40, top_view=True, pu_per_tu=4, auto_reset=False)
+    env = rcw.BatchedSingleRoom(n, seed=8, **kw)
+    cfg = oracle.default_config(R=96, P=40, pu_per_tu=4)
+    env.step_random(30)
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        before_obs, before_top, before = env.copy_obs(), env.copy_top_view(), env.get_state()
+        mask = (rng.random(n) < 0.3).astype(np.uint8)
+        g = np.stack([rng.integers(2, 8, n), rng.integers(2, 16, n)], 1).astype(np.int32)
+        p = np.stack([rng.integers(2, 8, n), rng.integers(2, 16, n)], 1).astype(np.int32)
+        p[(p == g).all(1)] = [2, 2]
+        g[(p == g).all(1)] = [3, 3]
+        a = rng.integers(0, 128, n).astype(np.int32)
+        env.reset(g, p, a, mask)
+        obs, top, st = env.copy_obs(), env.copy_top_view(), env.get_state()
+        keep = mask == 0
+        np.testing.assert_array_equal(obs[keep], before_obs[keep])
+        np.testing.assert_array_equal(top[keep], before_top[keep])
+        np.testing.assert_array_equal(bits(st["pos"][keep]), bits(before["pos"][keep]))
+        for e in np.nonzero(mask)[0]:
+            w = oracle.World(cfg)
+            w.reset_to(g[e, 0], g[e, 1], p[e, 0], p[e, 1], a[e])
+            w.cast_rays()
+            w.update_camera_view()
+            w.update_top_view()
+            np.testing.assert_array_equal(obs[e], w.obs_rgb8())
+            np.testing.assert_array_equal(top[e], w.top_view)
+            assert st["reward"][e] == 0 and st["done"][e] == 0
+        env.step_random(5)
+    # a mask of zeros redraws nothing; a Philox reset under a mask draws new layouts only there
+    before_obs = env.copy_obs()
+    env.reset(mask=np.zeros(n, np.uint8))
+    np.testing.assert_array_equal(env.copy_obs(), before_obs)
+    mask = np.zeros(n, np.uint8)
+    mask[7] = mask[49] = 1
+    env.reset(mask=mask)
+    after = env.copy_obs()
+    np.testing.assert_array_equal(after[mask == 0], before_obs[mask == 0])
+    env.close()

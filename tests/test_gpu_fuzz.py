@@ -246,7 +246,7 @@ def test_random_operation_sequences_with_windows(rcw, oracle, monkeypatch, seed)
                 worlds[e].reset_to(g[e, 0], g[e, 1], p[e, 0], p[e, 1], a[e])
                 worlds[e].cast_rays()
                 worlds[e].update_camera_view()
-            rendered(range(n))                      # a reset re-renders the whole batch
+            rendered(np.nonzero(mask)[0].tolist())  # a masked reset re-renders the envs it reset
         elif op == "state":
             au = rng.integers(0, 128, n).astype(np.int32)
             env.set_state(dir_au=au)
