@@ -282,3 +282,38 @@ def test_random_operation_sequences_with_windows(rcw, oracle, monkeypatch, seed)
             w.update_top_view()
             np.testing.assert_array_equal(env.copy_top_view(e, 1)[0], w.top_view, err_msg=f"top view slot {slot} env {e}")
     env.close()
+
+
+@pytest.mark.parametrize("env_kernel", [0, 1])
+def test_huge_tile_map_needs_opt_in_shared_memory(rcw, oracle, monkeypatch, env_kernel):
+    """1200 x 1000 tiles: the bit-packed wall layer is 150 KB, above the 48 KB of shared memory a kernel gets
+    without opting in.  Every step kernel variant (item / env kernel, actions from the parameters, the random
+    policy, render) and the reset draw must handle it; rays walk hundreds of tiles."""
+    monkeypatch.setenv("RCW_ENV_PER_WARP", str(env_kernel))
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    n, H, W, seed = 5, 1200, 1000, 2
+    kw = dict(height_tile_map_tu=H, width_tile_map_tu=W, num_directions=64, num_rays=70, height_camera_view_pu=24,
+              position_increment_wu=0.45)
+    env = rcw.BatchedSingleRoom(n, seed=seed, **kw)
+    ref = oracle.Batch(n, cfg=oracle.default_config(H=H, W=W, N=64, R=70, P=24, incr=np.float32(0.45)), seed=seed)
+    env.step_random(12)
+    ref.rollout(12)
+    rng = np.random.default_rng(1)
+    for _ in range(6):
+        a = rng.integers(1, 5, n).astype(np.uint8)
+        env.act(a)
+        assert ref.step(a) == 0
+    st = env.get_state()
+    pos, au, goal = ref.states()
+    np.testing.assert_array_equal(bits(st["pos"]), bits(pos))
+    np.testing.assert_array_equal(st["goal"], goal)
+    np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    rays = env.get_rays()
+    assert rays["dist"].max() > 100, "some ray should cross a good part of the map"
+    for e in range(n):
+        np.testing.assert_array_equal(rays["hit"][e], ref.world(e).ray_stop)
+        np.testing.assert_array_equal(bits(rays["dist"][e]), bits(ref.world(e).ray_dist))
+    env.close()
+    with pytest.raises(rcw.RcwError) as ei:                       # 3000 x 3000 tiles: 1.1 MB, does not fit an SM
+        rcw.BatchedSingleRoom(1, height_tile_map_tu=3000, width_tile_map_tu=3000)
+    assert ei.value.code == rcw._capi.RCW_ESIZE
