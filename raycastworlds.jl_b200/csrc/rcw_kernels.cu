@@ -7,7 +7,7 @@
 // Mapping.  A work item is (env, group of 32 consecutive rays) and belongs to one warp:
 // lane <-> ray for the DDA, then all 32 lanes stream the group's 32 observation columns, which
 // are contiguous in memory (ray i paints column R-i+1, single_room.jl:431), in whole 32-byte
-// sectors with 256-bit stores.  The eight warps of a CTA take eight consecutive items, so a CTA
+// sectors with 256-bit stores.  The four warps of a CTA take four consecutive items, so a CTA
 // writes one contiguous span of the observation buffer.  The path is bound by HBM writes (393 KB
 // per env-step at the default resolution versus a few hundred bytes of state), so everything else
 // is arranged to keep the store stream dense and complete: the wall layer is staged into shared
@@ -16,6 +16,10 @@
 // from an L2-resident table (prefetched for the three directions the env can face next), act! /
 // auto-reset run once per env of a CTA and reach the other warps through shared memory, and the
 // state they read is double-buffered so that the warps of an env in other CTAs never race.
+// When the items are small (narrow or one-byte-per-pixel cameras) the step is bound by act! and the DDA
+// instead, and env_kernel gives a whole env to one warp (no block barrier behind act!).  Host-supplied
+// actions of up to 32,768 envs ride in the kernel parameters (frame_kernel_pa / env_kernel_pa).
+// rcw_topview.cuh (included below) draws the reference's top view.
 //
 // Arithmetic.  Every binary32 operation that the reference performs is written with an explicit
 // round-to-nearest intrinsic (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn), which the compiler
