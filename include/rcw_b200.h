@@ -114,7 +114,14 @@ typedef struct rcw_config {
                                         doubles the HBM writes of a step                                       */
     int32_t  pu_per_tu;              /* pixels per tile of the top view, default 32 (single_room.jl:269)       */
     uint32_t top_palette[6];         /* 0x00RRGGBB, indices RCW_TOP_COLOR_*                                    */
-    uint32_t reserved[4];            /* must be zero                                           */
+    int32_t  frame_stack;            /* 0 or 1 (default): one frame per env.  K > 1 (up to 64): the observation buffer
+                                        keeps the K most recent frames of every env in a ring — [env][K][columns][rows]
+                                        — and every rcw_step / rcw_step_random writes the next ring position, so a
+                                        learner that stacks frames reads them in place instead of copying K - 1 old
+                                        frames per step.  rcw_obs_frames tells which position is
+                                        the newest.  Resets and rcw_render overwrite the newest frame; not combinable
+                                        with obs_window_envs / rcw_step_range.                                     */
+    uint32_t reserved[3];            /* must be zero                                           */
 } rcw_config;
 
 typedef struct rcw_batch rcw_batch; /* opaque */
@@ -223,6 +230,14 @@ int32_t rcw_obs_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_
  * 256 px).  env_stride_bytes is a multiple of 128.  rcw_copy_obs removes the padding. */
 int32_t rcw_obs_layout(rcw_batch* b, size_t* env_stride_bytes, size_t* column_stride_bytes,
                        size_t* column_bytes, int32_t* bytes_per_pixel);
+
+/* Frame ring of the observation buffer (rcw_config.frame_stack): number of ring positions K, the position
+ * the newest frame is in, and the distance in bytes between consecutive positions of one env (the frame with
+ * age a, 0 = newest, is at position (newest - a) mod K; env_stride_bytes of rcw_obs_layout spans all K). */
+int32_t rcw_obs_frames(rcw_batch* b, int32_t* frame_stack, int32_t* newest, size_t* frame_stride_bytes);
+
+/* rcw_copy_obs for the frame of the given age (0 = newest ... frame_stack - 1 = oldest). */
+int32_t rcw_copy_obs_frame(rcw_batch* b, int64_t env0, int64_t n, int32_t age, void* host);
 
 /* Blocking copy of the observations of envs [env0, env0+n) to host memory, densely packed
  * (n * num_rays * height_px * bytes_per_pixel).  With an observation window n must not exceed it and

@@ -24,7 +24,7 @@ SYMBOLS = (
     "rcw_step", "rcw_step_range", "rcw_step_random", "rcw_render",
     "rcw_render_top_view", "rcw_top_view_device_ptr", "rcw_copy_top_view", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
     "rcw_checkpoint_size", "rcw_save_checkpoint", "rcw_load_checkpoint",
-    "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
+    "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_obs_frames", "rcw_copy_obs_frame", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
     "rcw_sync", "rcw_last_error",
 )
 
@@ -54,7 +54,8 @@ class RcwConfig(C.Structure):
         ("top_view", C.c_int32),
         ("pu_per_tu", C.c_int32),
         ("top_palette", C.c_uint32 * 6),
-        ("reserved", C.c_uint32 * 4),
+        ("frame_stack", C.c_int32),
+        ("reserved", C.c_uint32 * 3),
     ]
 
 
@@ -107,6 +108,8 @@ def load() -> C.CDLL:
         "rcw_obs_device_ptr": (i32, [vp, P(vp), P(C.c_size_t), P(C.c_size_t)]),
         "rcw_obs_layout": (i32, [vp, P(C.c_size_t), P(C.c_size_t), P(C.c_size_t), P(i32)]),
         "rcw_copy_obs": (i32, [vp, i64, i64, vp]),
+        "rcw_obs_frames": (i32, [vp, P(i32), P(i32), P(C.c_size_t)]),
+        "rcw_copy_obs_frame": (i32, [vp, i64, i64, i32, vp]),
         "rcw_episode_stats": (i32, [vp, P(i64), P(C.c_double), P(i64), i32]),
         "rcw_launch_count": (i32, [vp, P(i64)]),
         "rcw_stream": (i32, [vp, P(vp)]),

@@ -130,7 +130,10 @@ struct rcw_batch {
     DeviceStats* d_stats = nullptr;
     uint8_t* d_actions = nullptr;
     uint8_t* d_obs = nullptr;
-    size_t obs_env_stride = 0;
+    size_t obs_env_stride = 0;    // bytes between consecutive envs (all ring positions of an env)
+    size_t frame_stride = 0;      // bytes between consecutive ring positions of one env (rcw_config.frame_stack)
+    int frame_stack = 1;
+    int frame_newest = 0;         // ring position of the newest frame
     int64_t obs_window = 0;       // env slots of the observation buffer (num_envs unless cfg.obs_window_envs)
     int col_pitch = 0;            // bytes between consecutive columns of an observation (multiple of 32)
     size_t obs_bytes = 0;
@@ -250,7 +253,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.ep_return = b->d_ep_return;
     p.ep_length = b->d_ep_length;
     p.stats = b->d_stats;
-    p.obs = b->d_obs;
+    p.obs = b->d_obs + (size_t)b->frame_newest * b->frame_stride;
     p.obs_env_stride = b->obs_env_stride;
     p.obs_window = (uint32_t)b->obs_window;
     p.obs_slot0 = 0;
@@ -341,6 +344,7 @@ static bool packs_actions(const rcw_batch* b, int64_t env_count) {
 // d_render_mask (kModeRender): redraw only the envs whose byte is nonzero
 static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions, const uint8_t* h_actions = nullptr,
                              const uint8_t* d_render_mask = nullptr) {
+    if (mode == kModeStep) b->frame_newest = (b->frame_newest + 1) % b->frame_stack;   // a step writes the next ring position
     FrameParams p;
     fill_frame_params(b, p);
     p.actions = h_actions ? nullptr : d_actions;
@@ -606,7 +610,9 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // ---- observations ---------------------------------------------------------------------------
     // every column starts on a 32-byte sector, every env on a 128-byte line (see rcw_obs_layout)
     b->col_pitch = (P * b->bpp + 31) & ~31;
-    b->obs_env_stride = (((size_t)R * b->col_pitch) + 127) & ~(size_t)127;
+    b->frame_stack = c.frame_stack > 1 ? c.frame_stack : 1;
+    b->frame_stride = (((size_t)R * b->col_pitch) + 127) & ~(size_t)127;
+    b->obs_env_stride = b->frame_stride * (size_t)b->frame_stack;
     // Grid shape: one CTA per 8 items and the hardware scheduler balances the tail (measured best once
     // the register budget below is chosen per geometry; RCW_CTAS_PER_SM > 0 caps the grid and loops).
     if (b->ctas_per_sm < 0) b->ctas_per_sm = 0;
@@ -629,7 +635,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     if (const char* s = getenv("RCW_ENV_PER_WARP_MIN")) b->env_per_warp_min = atoll(s);   // tests force the kernel on small batches
     b->obs_window = (c.obs_window_envs > 0 && c.obs_window_envs < E) ? c.obs_window_envs : E;
     b->obs_bytes = b->obs_env_stride * (size_t)b->obs_window;
-    RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, false));
+    RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, /*zero=*/b->frame_stack > 1));   // older ring positions start black
     return RCW_OK;
 }
 
@@ -659,6 +665,9 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
     if (cfg->dda_flags & ~(uint32_t)(RCW_DDA_TIE_LE | RCW_DDA_DIST_POST))
         return fail(RCW_EINVAL, "unknown dda_flags 0x%x", cfg->dda_flags);
     if (cfg->obs_window_envs < 0) return fail(RCW_EINVAL, "obs_window_envs must be >= 0");
+    if (cfg->frame_stack < 0 || cfg->frame_stack > 64) return fail(RCW_EINVAL, "frame_stack must be in 0..64");
+    if (cfg->frame_stack > 1 && cfg->obs_window_envs > 0 && cfg->obs_window_envs < cfg->num_envs)
+        return fail(RCW_EINVAL, "frame_stack cannot be combined with an observation window");
     if (cfg->pu_per_tu < 1 || cfg->pu_per_tu > 1024) return fail(RCW_EINVAL, "pu_per_tu must be in 1..1024");
     if (cfg->top_view != 0 && cfg->top_view != 1) return fail(RCW_EINVAL, "top_view must be 0 or 1");
     const int bpp = cfg->obs_format == RCW_OBS_RGB8 ? 3 : (cfg->obs_format == RCW_OBS_XRGB32 ? 4 : 1);
@@ -958,6 +967,9 @@ int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64
     if (n > b->obs_window)
         return fail(RCW_ESIZE, "a range of %lld envs does not fit the observation window of %lld",
                     (long long)n, (long long)b->obs_window);
+    if (b->frame_stack > 1)
+        return fail(RCW_EINVAL, "rcw_step_range cannot be used with a frame ring (frame_stack = %d): the ring "
+                    "position is shared by the batch", b->frame_stack);
     DeviceGuard g(b->device);
     if (packs_actions(b, n) && !is_device_pointer(actions)) {
         if (int32_t rc = validate_host_actions(actions, env0, n)) return rc;
@@ -1233,7 +1245,15 @@ int32_t rcw_obs_layout(rcw_batch* b, size_t* env_stride_bytes, size_t* column_st
     return RCW_OK;
 }
 
-int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
+int32_t rcw_obs_frames(rcw_batch* b, int32_t* frame_stack, int32_t* newest, size_t* frame_stride_bytes) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (frame_stack) *frame_stack = b->frame_stack;
+    if (newest) *newest = b->frame_newest;
+    if (frame_stride_bytes) *frame_stride_bytes = b->frame_stride;
+    return RCW_OK;
+}
+
+int32_t rcw_copy_obs_frame(rcw_batch* b, int64_t env0, int64_t n, int32_t age, void* host) {
     NvtxRange nvtx("rcw_copy_obs");
     if (int32_t rc = check_handle(b)) return rc;
     if (!host) return fail(RCW_EINVAL, "host is null");
@@ -1243,18 +1263,25 @@ int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
     if (n > b->obs_window)
         return fail(RCW_ESIZE, "%lld envs requested, the observation window holds %lld", (long long)n,
                     (long long)b->obs_window);
+    if (age < 0 || age >= b->frame_stack)
+        return fail(RCW_ESIZE, "frame age %d outside 0..%d", age, b->frame_stack - 1);
     DeviceGuard g(b->device);
     const size_t R = (size_t)b->cfg.num_rays, col_bytes = (size_t)b->cfg.height_camera_view_pu * b->bpp;
     const int64_t slot0 = env0 % b->obs_window;
     if (slot0 + n > b->obs_window) {   // the range wraps around the window: two pieces
         const int64_t n1 = b->obs_window - slot0;
-        if (int32_t rc = rcw_copy_obs(b, env0, n1, host)) return rc;
-        return rcw_copy_obs(b, env0 + n1, n - n1, static_cast<uint8_t*>(host) + (size_t)n1 * R * col_bytes);
+        if (int32_t rc = rcw_copy_obs_frame(b, env0, n1, age, host)) return rc;
+        return rcw_copy_obs_frame(b, env0 + n1, n - n1, age, static_cast<uint8_t*>(host) + (size_t)n1 * R * col_bytes);
     }
-    const uint8_t* src = b->d_obs + (size_t)slot0 * b->obs_env_stride;
+    const int pos = (b->frame_newest - age + b->frame_stack) % b->frame_stack;
+    const uint8_t* src = b->d_obs + (size_t)slot0 * b->obs_env_stride + (size_t)pos * b->frame_stride;
     uint8_t* dst = static_cast<uint8_t*>(host);
     if (col_bytes == (size_t)b->col_pitch && R * col_bytes == b->obs_env_stride) {
         RCW_CUDA(cudaMemcpyAsync(dst, src, R * col_bytes * (size_t)n, cudaMemcpyDeviceToHost, b->stream));
+    } else if (col_bytes == (size_t)b->col_pitch) {
+        // dense frames, envs apart (frame ring or padded env stride): one 2-D copy, a row per env
+        RCW_CUDA(cudaMemcpy2DAsync(dst, R * col_bytes, src, b->obs_env_stride, R * col_bytes, (size_t)n,
+                                   cudaMemcpyDeviceToHost, b->stream));
     } else if (R * (size_t)b->col_pitch == b->obs_env_stride) {
         // pitched columns, envs back to back: one 2-D copy over all columns
         RCW_CUDA(cudaMemcpy2DAsync(dst, col_bytes, src, (size_t)b->col_pitch, col_bytes, R * (size_t)n,
@@ -1266,6 +1293,10 @@ int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
                                        cudaMemcpyDeviceToHost, b->stream));
     }
     return sync_and_check(b);
+}
+
+int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {
+    return rcw_copy_obs_frame(b, env0, n, 0, host);
 }
 
 int32_t rcw_episode_stats(rcw_batch* b, int64_t* episodes, double* sum_return, int64_t* sum_length,

@@ -50,7 +50,8 @@ struct RcwConfig
     top_view::Int32
     pu_per_tu::Int32
     top_palette::NTuple{6, UInt32}
-    reserved::NTuple{4, UInt32}
+    frame_stack::Int32
+    reserved::NTuple{3, UInt32}
 end
 
 last_error() = unsafe_string(ccall((:rcw_last_error, LIB), Cstring, ()))
@@ -95,6 +96,7 @@ function BatchedSingleRoom(;
         obs_window_envs = 0,
         top_view = false,
         pu_per_tu = 32,
+        frame_stack = 1,
     )
     T === Float32 || error("librcw_b200 computes in Float32 (the reference default, single_room.jl:43)")
 
@@ -115,7 +117,8 @@ function BatchedSingleRoom(;
                         Float32(position_increment_wu), Float32(semi_field_of_view_wu),
                         Float32(camera_height_tile_wu), Float32(goal_reward), Int32(obs_format),
                         Int32(auto_reset), UInt64(seed), palette, UInt32(0), Int32(obs_window_envs),
-                        Int32(top_view), Int32(pu_per_tu), top_palette, ntuple(_ -> UInt32(0), 4)))
+                        Int32(top_view), Int32(pu_per_tu), top_palette, Int32(frame_stack),
+                        ntuple(_ -> UInt32(0), 3)))
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve directions begin
         check(ccall((:rcw_create, LIB), Int32, (Ref{RcwConfig}, Ptr{Float32}, Ref{Ptr{Cvoid}}),

@@ -49,7 +49,8 @@ class BatchedSingleRoom(AbstractGame):
     (the observation buffer holds only that many env slots, env e in slot e mod K — for batches whose
     observations exceed HBM; see `act_range`), `top_view` (redraw the top view inside every step /
     reset / render like the reference's act!(env), single_room.jl:333-340; off by default for a batch),
-    `pu_per_tu` (:269) and `top_palette`.
+    `pu_per_tu` (:269) and `top_palette`, and `frame_stack` (K > 1: the observation buffer keeps the K most
+    recent frames of every env in a ring that every step advances; see `obs_frames()`).
     """
 
     def __init__(self, num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int = 8,
@@ -61,7 +62,8 @@ class BatchedSingleRoom(AbstractGame):
                  seed: int = 0, env_id_offset: int = 0,
                  directions_wu: Optional[np.ndarray] = None, palette: Optional[Sequence[int]] = None,
                  dda_tie_le: bool = False, dda_dist_post: bool = False, obs_window_envs: int = 0,
-                 top_view: bool = False, pu_per_tu: int = 32, top_palette: Optional[Sequence[int]] = None):
+                 top_view: bool = False, pu_per_tu: int = 32, top_palette: Optional[Sequence[int]] = None,
+                 frame_stack: int = 1):
         self._lib = _capi.load()
         self._h = C.c_void_p()
         cfg = _capi.default_config()
@@ -90,6 +92,7 @@ class BatchedSingleRoom(AbstractGame):
         cfg.dda_flags = (_capi.RCW_DDA_TIE_LE if dda_tie_le else 0) | (
             _capi.RCW_DDA_DIST_POST if dda_dist_post else 0)
         cfg.obs_window_envs = int(obs_window_envs)
+        cfg.frame_stack = int(frame_stack)
         cfg.top_view = int(bool(top_view))
         cfg.pu_per_tu = int(pu_per_tu)
         if top_palette is not None:
@@ -104,6 +107,7 @@ class BatchedSingleRoom(AbstractGame):
         self.cfg = cfg
         self.num_envs = int(num_envs)
         self.obs_window = int(obs_window_envs) if 0 < int(obs_window_envs) < int(num_envs) else int(num_envs)
+        self.frame_stack = max(1, int(frame_stack))
         self.obs_format = obs_format
         self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1}[obs_format]
 
@@ -272,6 +276,12 @@ class BatchedSingleRoom(AbstractGame):
         _capi.check(self._lib.rcw_obs_layout(self._h, C.byref(es), C.byref(cs), C.byref(cbytes), C.byref(bpp)))
         return es.value, cs.value, cbytes.value, bpp.value
 
+    def obs_frames(self):
+        """(frame_stack, newest ring position, frame_stride_bytes) — rcw_obs_frames."""
+        k, newest, stride = C.c_int32(), C.c_int32(), C.c_size_t()
+        _capi.check(self._lib.rcw_obs_frames(self._h, C.byref(k), C.byref(newest), C.byref(stride)))
+        return k.value, newest.value, stride.value
+
     def obs_tensor(self):
         """Zero-copy torch view of the device observation buffer, shape obs_shape (borrowed: valid
         until the next act/reset/render, like the reference's aliased `state`, single_room.jl:576).
@@ -285,6 +295,14 @@ class BatchedSingleRoom(AbstractGame):
         holder = _CudaBuffer(ptr, total, self)
         flat = torch.as_tensor(holder, device=torch.device("cuda", self.cfg.device))
         slots = self.obs_window
+        if self.frame_stack > 1:
+            # the whole ring: [env, ring position, ...]; obs_frames()[1] is the newest position
+            k, _, fs = self.obs_frames()
+            if self.obs_format == "rgb8":
+                return torch.as_strided(flat, (slots, k, R, P, 3), (env_stride, fs, col_stride, 3, 1))
+            if self.obs_format == "gray8":
+                return torch.as_strided(flat, (slots, k, R, P), (env_stride, fs, col_stride, 1))
+            return torch.as_strided(flat.view(torch.int32), (slots, k, R, P), (env_stride // 4, fs // 4, col_stride // 4, 1))
         if self.obs_format == "rgb8":
             return torch.as_strided(flat, (slots, R, P, 3), (env_stride, col_stride, 3, 1))
         if self.obs_format == "gray8":
@@ -299,15 +317,16 @@ class BatchedSingleRoom(AbstractGame):
         t = self.obs_tensor()
         return t.permute(0, 3, 1, 2) if self.obs_format == "rgb8" else t.unsqueeze(1)
 
-    def copy_obs(self, env0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None):
-        """Blocking device->host copy of the observations of envs [env0, env0+n)."""
+    def copy_obs(self, env0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None, age: int = 0):
+        """Blocking device->host copy of the observations of envs [env0, env0+n); with a frame ring, `age`
+        selects the frame (0 = newest)."""
         n = min(self.num_envs - env0, self.obs_window) if n is None else n
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
         shape = (n, R, P, 3) if self.obs_format == "rgb8" else (n, R, P)
         dtype = np.uint32 if self.obs_format == "xrgb32" else np.uint8
         if out is None:
             out = np.empty(shape, dtype)
-        _capi.check(self._lib.rcw_copy_obs(self._h, env0, n, _ptr(out)))
+        _capi.check(self._lib.rcw_copy_obs_frame(self._h, env0, n, int(age), _ptr(out)))
         return out
 
     # -- top view (single_room.jl:342-372, 446-483) -----------------------------------------------------
