@@ -233,7 +233,7 @@ def run_b200(args):
     offset = rank * n
     env = rcw.BatchedSingleRoom(n, device=local, seed=SEED, env_id_offset=offset,
                                 obs_format=args.obs_format, obs_window_envs=args.obs_window_envs,
-                                top_view=args.top_view, **kw)
+                                top_view=args.top_view, result_ring=2, **kw)
     windowed = env.obs_window < n
     stream = torch.cuda.ExternalStream(env.cuda_stream(), device=dev)
     K, W = args.steps, args.warmup
@@ -274,11 +274,16 @@ def run_b200(args):
     total_ms = rcw.max_over_ranks(total_ms, device=dev if world > 1 else None)
     value = world * n * K / (total_ms * 1e-3)
 
-    # ---- end to end through the public API with HOST buffers: pinned host actions -> H2D -> step
-    #      -> D2H of reward + done, every step; observations stay in HBM for the learner
-    #      (rcw_obs_device_ptr, the reference's aliased `state`).  A second figure also pulls the
-    #      whole observation to the host each step (PCIe-bound).
+    # ---- end to end through the public API with HOST buffers, every step: pinned host actions in (they ride in
+    #      the kernel parameters: H2D inside the launch), the step, reward + done of every env back in host memory
+    #      (the kernel writes them through to the pinned result ring: D2H inside the launch) and read by the host.
+    #      Observations stay in HBM for the learner (rcw_obs_device_ptr, the reference's aliased `state`).
+    #      `e2e`: the host enqueues step k + 1 before it reads the results of step k (result_ring = 2), which a
+    #      rollout loop may do because its actions come from the observations, not from the rewards;
+    #      `e2e_lockstep`: the host reads the results of step k before it enqueues step k + 1.
+    #      A third figure also pulls the whole observation to the host each step (PCIe-bound).
     e2e = None
+    e2e_lockstep = None
     e2e_obs = None
     if not args.no_e2e:
         rng = np.random.default_rng(SEED + rank)
@@ -287,20 +292,40 @@ def run_b200(args):
         actions[:] = rng.integers(1, 5, size=(K, n), dtype=np.uint8)
         r_host = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
         d_host = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
-        for k in range(min(W, K)):
-            env.act(actions[k])
-            env.reward_done(r_host, d_host)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(K):
-            env.act(actions[k])
-            env.reward_done(r_host, d_host)
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        dt = rcw.max_over_ranks(dt, device=dev if world > 1 else None)
-        e2e = {"value": world * n * K / dt, "unit": UNIT, "h2d_bytes_per_step": n,
-               "d2h_bytes_per_step": n * 5, "ms_per_step": 1e3 * dt / K,
-               "note": "host actions in, host reward+done out, every step; observations stay in HBM"}
+
+        def run_e2e(lag):
+            ret, fin, pending = 0.0, 0, []
+            for k in range(K):
+                pending.append(env.act_async(actions[k]))
+                if len(pending) > lag:
+                    r, d = env.wait(pending.pop(0))
+                    ret += float(r.sum())
+                    fin += int(np.count_nonzero(d))
+            for t in pending:
+                r, d = env.wait(t)
+                ret += float(r.sum())
+                fin += int(np.count_nonzero(d))
+            return ret, fin
+
+        results = {}
+        for name, lag in (("e2e", 1), ("e2e_lockstep", 0)):
+            for k in range(min(W, K)):
+                env.wait(env.act_async(actions[k]))
+            env.sync()
+            barrier()
+            t0 = time.perf_counter()
+            ret, fin = run_e2e(lag)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            dt = rcw.max_over_ranks(dt, device=dev if world > 1 else None)
+            results[name] = {"value": world * n * K / dt, "unit": UNIT, "h2d_bytes_per_step": n,
+                             "d2h_bytes_per_step": n * 5, "ms_per_step": 1e3 * dt / K,
+                             "episodes_finished_rank0": fin, "sum_reward_rank0": ret}
+        e2e, e2e_lockstep = results["e2e"], results["e2e_lockstep"]
+        e2e["note"] = ("host actions in, reward + done of every env out to host memory and summed by the host, every "
+                       "step; step k + 1 is enqueued before the results of step k are read (rcw_step_async / rcw_wait, "
+                       "result_ring = 2); observations stay in HBM")
+        e2e_lockstep["note"] = "as e2e, but the results of step k are read before step k + 1 is enqueued"
     if not args.no_e2e and not windowed:
         Ko = max(1, min(K, 5))
         obs_host = torch.empty(env.obs_shape, dtype=torch.int32 if args.obs_format == "xrgb32" else torch.uint8)
@@ -350,7 +375,7 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": min(n, env_window) * bytes_per_step_env,
                 "launch_ms": launch_ms / (-(-n // env_window)), "peak_source": peak_src,
             },
-            "e2e": e2e, "e2e_obs_to_host": e2e_obs,
+            "e2e": e2e, "e2e_lockstep": e2e_lockstep, "e2e_obs_to_host": e2e_obs,
             "gpu_launches": launches,
             "clocks": clocks,
             "episodes": {"finished": stats[0], "sum_return": stats[1], "sum_length": stats[2]},

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RCW_ABI_VERSION 2
+#define RCW_ABI_VERSION 3
 
 typedef enum rcw_status {
     RCW_OK      = 0,
@@ -121,7 +121,13 @@ typedef struct rcw_config {
                                         frames per step.  rcw_obs_frames tells which position is
                                         the newest.  Resets and rcw_render overwrite the newest frame; not combinable
                                         with obs_window_envs / rcw_step_range.                                     */
-    uint32_t reserved[3];            /* must be zero                                           */
+    int32_t  result_ring;            /* 0 (default): none.  D in 1..64: rcw_step_async is available — the step kernel
+                                        also writes every env's reward and done straight into slot (ticket mod D) of a
+                                        pinned host ring (mapped memory: no copy is enqueued behind the kernel), and
+                                        rcw_wait(ticket) hands out the slot once that step has finished.  With D >= 2 a
+                                        host loop can enqueue step k + 1 before it reads the results of step k, so the
+                                        device never idles while the host wakes up.                               */
+    uint32_t reserved[2];            /* must be zero                                           */
 } rcw_config;
 
 typedef struct rcw_batch rcw_batch; /* opaque */
@@ -169,6 +175,20 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
  * and nothing is enqueued; for a device array the offending env is left untouched and the
  * error is reported by the next blocking call. */
 int32_t rcw_step(rcw_batch* b, const uint8_t* actions);
+
+/* rcw_step whose rewards and terminations also land in host memory without a copy (rcw_config.result_ring = D >= 1).
+ * *ticket numbers the steps enqueued this way (0, 1, 2, ...).  Only enqueues; on an error (RCW_EACTION for a host
+ * array, ...) nothing is enqueued and no ticket is consumed. */
+int32_t rcw_step_async(rcw_batch* b, const uint8_t* actions, int64_t* ticket);
+
+/* Blocks until the step of `ticket` has finished (later steps may still be running), then returns pointers to its
+ * reward [num_envs] f32 and done [num_envs] u8 inside the pinned result ring — what rcw_get_state would have
+ * returned right after that step (terminal reward / done survive the same-step auto-reset).  The memory is
+ * read-only for the caller and stays valid until D further rcw_step_async calls have been made, when the slot is
+ * written again; a ticket older than that => RCW_EINVAL.  An env whose device-side action was outside 1..4 keeps
+ * its previous reward / done; that error is reported by the next blocking call other than rcw_wait.
+ * Either pointer may be NULL. */
+int32_t rcw_wait(rcw_batch* b, int64_t ticket, const float** reward, const uint8_t** done);
 
 /* rcw_step for the envs [env0, env0 + n) only; the other envs keep their state, reward and done.
  * actions: [n] (actions[k] belongs to env env0 + k), host or device pointer, 1..4 as in rcw_step.

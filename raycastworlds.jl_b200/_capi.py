@@ -16,12 +16,12 @@ LIB_PATH = os.environ.get("RCW_LIB") or os.path.join(_PKG, "lib", "librcw_b200.s
 RCW_OK, RCW_EINVAL, RCW_EACTION, RCW_ECUDA, RCW_ENOMEM, RCW_ESIZE = 0, -1, -2, -3, -4, -5
 RCW_OBS_RGB8, RCW_OBS_XRGB32, RCW_OBS_GRAY8 = 0, 1, 2
 RCW_DDA_TIE_LE, RCW_DDA_DIST_POST = 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/rcw_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_set_wall_maps", "rcw_reset",
-    "rcw_step", "rcw_step_range", "rcw_step_random", "rcw_render",
+    "rcw_step", "rcw_step_async", "rcw_wait", "rcw_step_range", "rcw_step_random", "rcw_render",
     "rcw_render_top_view", "rcw_top_view_device_ptr", "rcw_copy_top_view", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
     "rcw_checkpoint_size", "rcw_save_checkpoint", "rcw_load_checkpoint",
     "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_obs_frames", "rcw_copy_obs_frame", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
@@ -55,7 +55,8 @@ class RcwConfig(C.Structure):
         ("pu_per_tu", C.c_int32),
         ("top_palette", C.c_uint32 * 6),
         ("frame_stack", C.c_int32),
-        ("reserved", C.c_uint32 * 3),
+        ("result_ring", C.c_int32),
+        ("reserved", C.c_uint32 * 2),
     ]
 
 
@@ -93,6 +94,8 @@ def load() -> C.CDLL:
         "rcw_set_wall_maps": (i32, [vp, vp]),
         "rcw_reset": (i32, [vp, vp, vp, vp, vp]),
         "rcw_step": (i32, [vp, vp]),
+        "rcw_step_async": (i32, [vp, vp, P(i64)]),
+        "rcw_wait": (i32, [vp, i64, P(vp), P(vp)]),
         "rcw_step_range": (i32, [vp, vp, i64, i64]),
         "rcw_step_random": (i32, [vp, i32]),
         "rcw_render": (i32, [vp]),

@@ -151,6 +151,15 @@ struct rcw_batch {
     int ring = 0;
     DeviceStats* h_stats = nullptr;  // pinned
     uint8_t* h_reward_done = nullptr; // pinned staging: reward f32[E] followed by done u8[E]
+    // result ring (rcw_config.result_ring = D): D slots of {reward f32[E], done u8[E]} in pinned, mapped host
+    // memory that the step kernel of rcw_step_async writes through to; one event per slot marks its step done
+    int result_ring = 0;
+    uint8_t* h_results = nullptr;     // host address of slot 0
+    uint8_t* d_results = nullptr;     // the same memory as the device sees it
+    size_t result_slot_bytes = 0;     // 5 * E rounded up to 128
+    cudaEvent_t result_ready[64]{};
+    int64_t next_ticket = 0;
+    int result_slot = -1;             // >= 0 while rcw_step_async enqueues its step
     bool device_actions_pending = false;  // a device-side action array was used since the last check
     // counters
     uint64_t step_index = 0;
@@ -250,6 +259,11 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.actions = nullptr;
     p.reward = b->d_reward;
     p.done = b->d_done;
+    if (b->result_slot >= 0) {
+        uint8_t* slot = b->d_results + (size_t)b->result_slot * b->result_slot_bytes;
+        p.host_reward = reinterpret_cast<float*>(slot);
+        p.host_done = slot + (size_t)c.num_envs * 4;
+    }
     p.ep_return = b->d_ep_return;
     p.ep_length = b->d_ep_length;
     p.stats = b->d_stats;
@@ -503,6 +517,9 @@ int32_t rcw_destroy(rcw_batch* b) {
     }
     if (b->h_stats) cudaFreeHost(b->h_stats);
     if (b->h_reward_done) cudaFreeHost(b->h_reward_done);
+    if (b->h_results) cudaFreeHost(b->h_results);
+    for (cudaEvent_t ev : b->result_ready)
+        if (ev) cudaEventDestroy(ev);
     if (b->stream) cudaStreamDestroy(b->stream);
     release_dir_slot(b->device, b->dir_slot);
     cudaGetLastError();
@@ -606,6 +623,16 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     }
     RCW_CUDA(cudaMallocHost((void**)&b->h_stats, sizeof(DeviceStats)));
     RCW_CUDA(cudaMallocHost((void**)&b->h_reward_done, (size_t)E * 5));
+    b->result_ring = c.result_ring;
+    if (b->result_ring > 0) {
+        b->result_slot_bytes = ((size_t)E * 5 + 127) & ~(size_t)127;
+        RCW_CUDA(cudaHostAlloc((void**)&b->h_results, b->result_slot_bytes * (size_t)b->result_ring,
+                               cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(b->h_results, 0, b->result_slot_bytes * (size_t)b->result_ring);
+        RCW_CUDA(cudaHostGetDevicePointer((void**)&b->d_results, b->h_results, 0));
+        for (int i = 0; i < b->result_ring; ++i)
+            RCW_CUDA(cudaEventCreateWithFlags(&b->result_ready[i], cudaEventDisableTiming));
+    }
 
     // ---- observations ---------------------------------------------------------------------------
     // every column starts on a 32-byte sector, every env on a 128-byte line (see rcw_obs_layout)
@@ -666,6 +693,7 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
         return fail(RCW_EINVAL, "unknown dda_flags 0x%x", cfg->dda_flags);
     if (cfg->obs_window_envs < 0) return fail(RCW_EINVAL, "obs_window_envs must be >= 0");
     if (cfg->frame_stack < 0 || cfg->frame_stack > 64) return fail(RCW_EINVAL, "frame_stack must be in 0..64");
+    if (cfg->result_ring < 0 || cfg->result_ring > 64) return fail(RCW_EINVAL, "result_ring must be in 0..64");
     if (cfg->frame_stack > 1 && cfg->obs_window_envs > 0 && cfg->obs_window_envs < cfg->num_envs)
         return fail(RCW_EINVAL, "frame_stack cannot be combined with an observation window");
     if (cfg->pu_per_tu < 1 || cfg->pu_per_tu > 1024) return fail(RCW_EINVAL, "pu_per_tu must be in 1..1024");
@@ -955,6 +983,41 @@ int32_t rcw_step(rcw_batch* b, const uint8_t* actions) {
     const uint8_t* d_actions = nullptr;
     if (int32_t rc = stage_actions(b, actions, 0, b->cfg.num_envs, &d_actions)) return rc;
     return enqueue_frame(b, kModeStep, d_actions);
+}
+
+int32_t rcw_step_async(rcw_batch* b, const uint8_t* actions, int64_t* ticket) {
+    NvtxRange nvtx("rcw_step_async");
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!ticket) return fail(RCW_EINVAL, "ticket is null");
+    if (b->result_ring < 1)
+        return fail(RCW_EINVAL, "rcw_step_async needs a result ring (rcw_config.result_ring >= 1)");
+    if (b->split || b->bulk)
+        return fail(RCW_EINVAL, "rcw_step_async is not available on the RCW_SPLIT / RCW_RENDER_PATH=bulk variants");
+    const int slot = (int)(b->next_ticket % b->result_ring);
+    b->result_slot = slot;
+    const int32_t rc = rcw_step(b, actions);
+    b->result_slot = -1;
+    if (rc) return rc;   // nothing was enqueued (null / invalid host actions): no ticket is consumed
+    DeviceGuard g(b->device);
+    RCW_CUDA(cudaEventRecord(b->result_ready[slot], b->stream));
+    *ticket = b->next_ticket++;
+    return RCW_OK;
+}
+
+int32_t rcw_wait(rcw_batch* b, int64_t ticket, const float** reward, const uint8_t** done) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (b->result_ring < 1) return fail(RCW_EINVAL, "no result ring (rcw_config.result_ring >= 1)");
+    if (ticket < 0 || ticket >= b->next_ticket)
+        return fail(RCW_EINVAL, "ticket %lld was not issued (next is %lld)", (long long)ticket, (long long)b->next_ticket);
+    if (ticket + b->result_ring < b->next_ticket)
+        return fail(RCW_EINVAL, "ticket %lld is too old: its slot of the %d-deep result ring was reused by step %lld",
+                    (long long)ticket, b->result_ring, (long long)(ticket + b->result_ring));
+    const int slot = (int)(ticket % b->result_ring);
+    RCW_CUDA(cudaEventSynchronize(b->result_ready[slot]));
+    const uint8_t* base = b->h_results + (size_t)slot * b->result_slot_bytes;
+    if (reward) *reward = reinterpret_cast<const float*>(base);
+    if (done) *done = base + (size_t)b->cfg.num_envs * 4;
+    return RCW_OK;
 }
 
 int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64_t n) {

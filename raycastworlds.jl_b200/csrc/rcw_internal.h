@@ -107,6 +107,8 @@ struct FrameParams {
     const uint8_t* actions;  // device, 1..4 per env; nullptr => random policy
     float* reward;
     uint8_t* done;
+    float* host_reward;      // kModeStep, optional: slot of the pinned, mapped result ring (rcw_step_async) that the
+    uint8_t* host_done;      //   env's writer lane also stores reward / done to — no copy behind the kernel
     float* ep_return;
     uint32_t* ep_length;
     DeviceStats* stats;

@@ -462,8 +462,16 @@ __device__ __forceinline__ EnvPose act_env(const FrameParams& p, const uint32_t*
             p.done[env] = done ? 1 : 0;
             p.ep_return[env] = ep_return;
             p.ep_length[env] = ep_length;
+            if (p.host_reward) {   // write-through to the result ring in host memory (posted PCIe writes)
+                p.host_reward[env] = reward;
+                p.host_done[env] = done ? 1 : 0;
+            }
         } else {
             atomicExch(&p.stats->bad_action, 1);
+            if (p.host_reward) {   // the env was not stepped: its previous reward / done stand
+                p.host_reward[env] = p.reward[env];
+                p.host_done[env] = p.done[env];
+            }
         }
     }
     return pose;

@@ -51,7 +51,8 @@ struct RcwConfig
     pu_per_tu::Int32
     top_palette::NTuple{6, UInt32}
     frame_stack::Int32
-    reserved::NTuple{3, UInt32}
+    result_ring::Int32
+    reserved::NTuple{2, UInt32}
 end
 
 last_error() = unsafe_string(ccall((:rcw_last_error, LIB), Cstring, ()))
@@ -97,6 +98,7 @@ function BatchedSingleRoom(;
         top_view = false,
         pu_per_tu = 32,
         frame_stack = 1,
+        result_ring = 0,
     )
     T === Float32 || error("librcw_b200 computes in Float32 (the reference default, single_room.jl:43)")
 
@@ -118,7 +120,7 @@ function BatchedSingleRoom(;
                         Float32(camera_height_tile_wu), Float32(goal_reward), Int32(obs_format),
                         Int32(auto_reset), UInt64(seed), palette, UInt32(0), Int32(obs_window_envs),
                         Int32(top_view), Int32(pu_per_tu), top_palette, Int32(frame_stack),
-                        ntuple(_ -> UInt32(0), 3)))
+                        Int32(result_ring), ntuple(_ -> UInt32(0), 2)))
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve directions begin
         check(ccall((:rcw_create, LIB), Int32, (Ref{RcwConfig}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
@@ -155,6 +157,27 @@ function RCW.act!(env::BatchedSingleRoom, actions::Vector{UInt8})
     return nothing
 end
 RCW.act!(env::BatchedSingleRoom, actions::AbstractVector{<:Integer}) = RCW.act!(env, convert(Vector{UInt8}, actions))
+
+# act! whose rewards / terminations also land in the pinned result ring (`result_ring = D >= 1`); returns the
+# step's ticket.  With D >= 2, enqueue step k + 1 before `wait_results(env, k)`: the device never idles.
+function act_async!(env::BatchedSingleRoom, actions::Vector{UInt8})
+    length(actions) == env.num_envs || throw(DimensionMismatch("one action per env"))
+    ticket = Ref{Int64}(0)
+    GC.@preserve actions begin
+        check(ccall((:rcw_step_async, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Ref{Int64}), env.handle, actions, ticket))
+    end
+    return ticket[]
+end
+
+# blocks until the step of `ticket` has finished; (reward, done) are views of the pinned ring (not owned by Julia),
+# valid until `result_ring` further act_async! calls
+function wait_results(env::BatchedSingleRoom, ticket::Integer)
+    r = Ref{Ptr{Float32}}(C_NULL)
+    d = Ref{Ptr{UInt8}}(C_NULL)
+    check(ccall((:rcw_wait, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Float32}}, Ref{Ptr{UInt8}}),
+                env.handle, Int64(ticket), r, d))
+    return unsafe_wrap(Array, r[], env.num_envs; own = false), unsafe_wrap(Array, d[], env.num_envs; own = false)
+end
 
 # act! for the envs env0+1 : env0+length(actions) only (0-based env0); with an observation window
 # (`obs_window_envs`) this is how a learner walks a batch whose observations do not fit in HBM

@@ -50,7 +50,9 @@ class BatchedSingleRoom(AbstractGame):
     observations exceed HBM; see `act_range`), `top_view` (redraw the top view inside every step /
     reset / render like the reference's act!(env), single_room.jl:333-340; off by default for a batch),
     `pu_per_tu` (:269) and `top_palette`, and `frame_stack` (K > 1: the observation buffer keeps the K most
-    recent frames of every env in a ring that every step advances; see `obs_frames()`).
+    recent frames of every env in a ring that every step advances; see `obs_frames()`), and `result_ring`
+    (D >= 1: `act_async` / `wait` — the step kernel writes rewards and terminations straight into a pinned host
+    ring, and with D >= 2 the host can enqueue step k + 1 before it reads the results of step k).
     """
 
     def __init__(self, num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int = 8,
@@ -63,7 +65,7 @@ class BatchedSingleRoom(AbstractGame):
                  directions_wu: Optional[np.ndarray] = None, palette: Optional[Sequence[int]] = None,
                  dda_tie_le: bool = False, dda_dist_post: bool = False, obs_window_envs: int = 0,
                  top_view: bool = False, pu_per_tu: int = 32, top_palette: Optional[Sequence[int]] = None,
-                 frame_stack: int = 1):
+                 frame_stack: int = 1, result_ring: int = 0):
         self._lib = _capi.load()
         self._h = C.c_void_p()
         cfg = _capi.default_config()
@@ -93,6 +95,7 @@ class BatchedSingleRoom(AbstractGame):
             _capi.RCW_DDA_DIST_POST if dda_dist_post else 0)
         cfg.obs_window_envs = int(obs_window_envs)
         cfg.frame_stack = int(frame_stack)
+        cfg.result_ring = int(result_ring)
         cfg.top_view = int(bool(top_view))
         cfg.pu_per_tu = int(pu_per_tu)
         if top_palette is not None:
@@ -108,12 +111,17 @@ class BatchedSingleRoom(AbstractGame):
         self.num_envs = int(num_envs)
         self.obs_window = int(obs_window_envs) if 0 < int(obs_window_envs) < int(num_envs) else int(num_envs)
         self.frame_stack = max(1, int(frame_stack))
+        self.result_ring = int(result_ring)
+        self._result_views = {}
+        self._ticket = C.c_int64()
+        self._wait_r, self._wait_d = C.c_void_p(), C.c_void_p()
         self.obs_format = obs_format
         self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1}[obs_format]
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            self._result_views = {}   # views of the pinned result ring die with the handle
             self._lib.rcw_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -157,6 +165,48 @@ class BatchedSingleRoom(AbstractGame):
             a = a.astype(np.uint8)
         a = np.ascontiguousarray(a)
         _capi.check(self._lib.rcw_step(self._h, _ptr(a)))
+
+    def act_async(self, actions) -> int:
+        """`act` whose rewards / terminations also land in the pinned result ring (rcw_step_async; needs
+        `result_ring >= 1`).  Returns the step's ticket for `wait`.  `actions`: uint8 host array [num_envs]
+        (or anything `act` accepts)."""
+        cai = getattr(actions, "__cuda_array_interface__", None)
+        if cai is not None:
+            if cai["typestr"] not in ("|u1", "<u1") or int(np.prod(cai["shape"])) != self.num_envs:
+                raise ValueError("device actions must be uint8 [num_envs]")
+            ptr = C.c_void_p(cai["data"][0])
+        else:
+            a = actions if isinstance(actions, np.ndarray) else np.asarray(actions)
+            if a.dtype != np.uint8:
+                if ((a < 1) | (a > NUM_ACTIONS)).any():
+                    bad = a[(a < 1) | (a > NUM_ACTIONS)].reshape(-1)[0]
+                    raise _capi.InvalidActionError(_capi.RCW_EACTION, f"Invalid action: {bad}")
+                a = a.astype(np.uint8)
+            if a.size != self.num_envs:
+                raise ValueError("actions must hold one value per env")
+            a = np.ascontiguousarray(a)
+            ptr = a.ctypes.data
+        rc = self._lib.rcw_step_async(self._h, ptr, C.byref(self._ticket))
+        if rc:
+            _capi.check(rc)
+        return self._ticket.value
+
+    def wait(self, ticket: int):
+        """Blocks until the step of `ticket` has finished; returns (reward f32 [num_envs], done u8 [num_envs]) as
+        read-only views of the pinned result ring, valid until `result_ring` further `act_async` calls."""
+        rc = self._lib.rcw_wait(self._h, int(ticket), C.byref(self._wait_r), C.byref(self._wait_d))
+        if rc:
+            _capi.check(rc)
+        key = self._wait_r.value
+        views = self._result_views.get(key)
+        if views is None:
+            n = self.num_envs
+            r = np.ctypeslib.as_array(C.cast(self._wait_r, C.POINTER(C.c_float)), shape=(n,))
+            d = np.ctypeslib.as_array(C.cast(self._wait_d, C.POINTER(C.c_uint8)), shape=(n,))
+            r.flags.writeable = False
+            d.flags.writeable = False
+            views = self._result_views[key] = (r, d)
+        return views
 
     def act_range(self, actions, env0: int, n: Optional[int] = None):
         """act! for the envs [env0, env0 + n) only (rcw_step_range): `actions` holds n values in 1..4,

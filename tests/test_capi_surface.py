@@ -53,7 +53,7 @@ def test_config_struct_layout_and_defaults():
     assert cfg.player_radius_wu == 0.125 and cfg.position_increment_wu == 0.125
     assert cfg.semi_field_of_view_wu == pytest.approx(2 / 3, rel=1e-7)
     assert list(cfg.palette) == [0xFFFFFF, 0x404040, 0x808080, 0xC0C0C0, 0x800000, 0xC00000]
-    assert (cfg.obs_window_envs, cfg.top_view, cfg.pu_per_tu, cfg.frame_stack) == (0, 0, 32, 0)  # :269; the top view is opt-in for a batch
+    assert (cfg.obs_window_envs, cfg.top_view, cfg.pu_per_tu, cfg.frame_stack, cfg.result_ring) == (0, 0, 32, 0, 0)  # :269; the top view is opt-in for a batch
     assert list(cfg.top_palette) == [0xFFFFFF, 0xFF0000, 0x000000, 0xCCCCCC, 0x808080, 0xC0C0C0]  # :288-290, 364-367
     assert _capi.load().rcw_version() == _capi.ABI_VERSION
 
@@ -67,7 +67,7 @@ def test_validation_errors_without_gpu():
     assert b"struct_size" in lib.rcw_last_error()
     for field, value in [("num_envs", 0), ("height_tile_map_tu", 2), ("player_radius_wu", 0.6),
                          ("obs_format", 7), ("num_rays", 0), ("dda_flags", 8), ("obs_window_envs", -1), ("pu_per_tu", 0),
-                         ("top_view", 2), ("frame_stack", 65)]:
+                         ("top_view", 2), ("frame_stack", 65), ("result_ring", 65), ("result_ring", -1)]:
         cfg = _capi.default_config()
         setattr(cfg, field, value)
         assert lib.rcw_create(C.byref(cfg), None, C.byref(h)) == _capi.RCW_EINVAL, field
