@@ -39,6 +39,7 @@ int main(int argc, char** argv) {
     cfg.seed = seed;
     cfg.num_rays = 96;
     cfg.height_camera_view_pu = 64;
+    cfg.result_ring = 2;   /* rewards / terminations arrive in pinned host memory, read one step behind */
 
     /* a struct from a different ABI revision is refused, not misread */
     rcw_config bad = cfg;
@@ -62,9 +63,23 @@ int main(int argc, char** argv) {
     actions[n - 1] = 7;
     if (rcw_step(b, actions) != RCW_EACTION) return 4;
 
+    double ring_reward = 0;
+    long ring_done = 0;
     for (int s = 1; s <= steps; ++s) {
         for (int64_t e = 0; e < n; ++e) actions[e] = (uint8_t)(1 + ((e + s) % 7 == 0 ? 2 : 0) + ((e * 31 + s) % 11 == 0 ? 1 : 0));
-        CHECK(rcw_step(b, actions));
+        /* enqueue step s, then read the results of step s - 1 while step s runs */
+        int64_t ticket;
+        CHECK(rcw_step_async(b, actions, &ticket));
+        if (ticket != s - 1) return 6;
+        if (ticket > 0) {
+            const float* r;
+            const uint8_t* d;
+            CHECK(rcw_wait(b, ticket - 1, &r, &d));
+            for (int64_t e = 0; e < n; ++e) {
+                ring_reward += r[e];
+                ring_done += d[e];
+            }
+        }
         if (s % 10 == 0 || s == steps) {
             CHECK(rcw_get_state(b, pos, dir, NULL, NULL, done));
             CHECK(rcw_copy_obs(b, 0, 1, obs));
@@ -80,6 +95,17 @@ int main(int argc, char** argv) {
             CHECK(rcw_episode_stats(b, &episodes, &sum_return, &sum_length, 0));
             printf("%d %.6f %.6f %ld %lld %u\n", s, sx, sy, sd, (long long)episodes, fnv1a(obs, dense));
         }
+    }
+    {
+        const float* r;
+        const uint8_t* d;
+        CHECK(rcw_wait(b, steps - 1, &r, &d));
+        for (int64_t e = 0; e < n; ++e) {
+            ring_reward += r[e];
+            ring_done += d[e];
+        }
+        if (rcw_wait(b, steps, &r, &d) != RCW_EINVAL) return 7;   /* not issued */
+        printf("ring %.6f %ld\n", ring_reward, ring_done);
     }
     int64_t launches;
     CHECK(rcw_launch_count(b, &launches));

@@ -49,11 +49,16 @@ def test_c_host_matches_oracle(host_binary, oracle):
     r = subprocess.run([host_binary, str(n), str(steps), str(seed)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lines = [ln.split() for ln in r.stdout.strip().splitlines()]
+    ring = lines.pop()
     assert [int(ln[0]) for ln in lines] == [10, 20, 30, 40, 50, 60]
     ref = oracle.Batch(n, cfg=oracle.default_config(R=96, P=64), seed=seed)
     k = 0
+    sum_reward, sum_done = 0.0, 0
     for s in range(1, steps + 1):
         assert ref.step(actions_of(n, s)) == 0
+        rew, don = ref.reward_done()
+        sum_reward += float(rew.sum())
+        sum_done += int(don.sum())
         if s % 10 == 0:
             pos, au, _ = ref.states()
             step, sx, sy, sd, episodes, crc = lines[k]
@@ -63,3 +68,5 @@ def test_c_host_matches_oracle(host_binary, oracle):
             assert int(episodes) == ref.episode_stats()[0]
             assert int(crc) == fnv1a(ref.world(0).obs_rgb8())
             k += 1
+    # every step's rewards / terminations as read from the pinned result ring (rcw_step_async / rcw_wait)
+    assert ring[0] == "ring" and float(ring[1]) == sum_reward and int(ring[2]) == sum_done
