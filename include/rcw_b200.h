@@ -49,8 +49,16 @@ typedef enum rcw_status {
 typedef enum rcw_obs_format {
     RCW_OBS_RGB8   = 0, /* uint8  [num_envs][num_rays columns][height_px][3]  (R,G,B bytes of the reference pixel) */
     RCW_OBS_XRGB32 = 1, /* uint32 [num_envs][num_rays columns][height_px]     (bit-identical to the reference's UInt32 pixels) */
-    RCW_OBS_GRAY8  = 2  /* uint8  [num_envs][num_rays columns][height_px]     learner-facing: BT.601 luma of the reference
+    RCW_OBS_GRAY8  = 2, /* uint8  [num_envs][num_rays columns][height_px]     learner-facing: BT.601 luma of the reference
                            pixel, (77 R + 150 G + 29 B + 128) >> 8; a third of the RGB8 write */
+    RCW_OBS_COLUMNS = 3 /* uint32 [num_envs][num_rays columns]: the camera view BEFORE it is expanded into pixels —
+                           what update_camera_view! decides per ray (single_room.jl:404-439): word = pad | cid << 16,
+                           pad = rows of ceiling = rows of floor (0: the whole column has the wall colour; the wall
+                           band has height_px - 2 pad rows), cid = RCW_COLOR_WALL_1 .. RCW_COLOR_GOAL_2.  Lossless
+                           (rcw_expand_columns reproduces the pixel image bit for bit) at 4 bytes per column instead
+                           of height_px * 3: 2 KB instead of 393 KB per default frame, for replay buffers that
+                           rasterise only the frames they sample.  NOT rendered pixels: steps in
+                           this format are bound by act! and the DDA, not by HBM writes. */
     /* dense on the host (rcw_copy_obs); on the device columns may be pitched, see rcw_obs_layout */
 } rcw_obs_format;
 
@@ -243,7 +251,8 @@ int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int
  * total_bytes covers obs_window_envs env slots when a window is configured, num_envs otherwise. */
 int32_t rcw_obs_device_ptr(rcw_batch* b, void** dptr, size_t* total_bytes, size_t* env_stride_bytes);
 
-/* Device layout of the observation buffer.  One env = num_rays columns; one column = height_px
+/* Device layout of the observation buffer.  (RCW_OBS_COLUMNS: one env = num_rays uint32 words, column_bytes =
+ * column_stride_bytes = bytes_per_pixel = 4.)  One env = num_rays columns; one column = height_px
  * pixels (column_bytes) followed by padding up to column_stride_bytes, a multiple of 32, so that
  * every column starts on a 32-byte sector and the renderer only ever writes whole sectors
  * (column_stride_bytes == column_bytes whenever column_bytes is a multiple of 32, e.g. the default
@@ -263,6 +272,19 @@ int32_t rcw_copy_obs_frame(rcw_batch* b, int64_t env0, int64_t n, int32_t age, v
  * (n * num_rays * height_px * bytes_per_pixel).  With an observation window n must not exceed it and
  * the copy returns what the slots (env0 + k) mod K hold — the caller knows which envs it rendered last. */
 int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host);
+
+/* Rasterise camera views stored as RCW_OBS_COLUMNS words: the second half of update_camera_view!
+ * (single_room.jl:413-441) as a pure store stream.  columns: DEVICE pointer to n envs' words,
+ * columns_env_stride_bytes apart (0 => dense, num_rays * 4) — the handle's own observations
+ * (rcw_obs_device_ptr of a RCW_OBS_COLUMNS handle) or records a learner kept in its replay buffer; the handle only
+ * supplies the geometry (num_rays, height_px) and the palette, so any handle of that geometry can expand them.
+ * dst: DEVICE pointer to n images in pixel_format (RGB8 / XRGB32 / GRAY8) laid out as rcw_expanded_layout says
+ * (columns pitched to 32 bytes, envs to 128; dense whenever height_px * bytes_per_pixel is a multiple of 32 and
+ * num_rays * that a multiple of 128, e.g. the default camera).  Only enqueues (on the handle's stream). */
+int32_t rcw_expand_columns(rcw_batch* b, const uint32_t* columns, size_t columns_env_stride_bytes, int64_t n,
+                           int32_t pixel_format, void* dst);
+int32_t rcw_expanded_layout(rcw_batch* b, int32_t pixel_format, size_t* env_stride_bytes,
+                            size_t* column_stride_bytes, size_t* column_bytes);
 
 /* ---- top view (single_room.jl:342-372, 446-483) ------------------------ */
 

@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         "orc_ray_dir": (vp, [vp]),
         "orc_camera_view": (vp, [vp]),
         "orc_wall_heights": (None, [vp, vp]),
+        "orc_camera_columns": (None, [vp, vp]),
         "orc_obs_rgb8": (None, [vp, vp]),
         "orc_philox4x32_10": (None, [vp, vp, vp]),
         "orc_draw_layout": (None, [vp, u64, u64, C.c_uint32, vp, vp, vp]),
@@ -234,6 +235,12 @@ class World:
         self.L.orc_wall_heights(self.p, out.ctypes.data)
         return out
 
+    def camera_columns(self):
+        """[R] uint32, pad | palette index << 16 per image column: the camera view before it becomes pixels."""
+        out = np.empty(self.cfg.R, np.uint32)
+        self.L.orc_camera_columns(self.p, out.ctypes.data)
+        return out
+
     def obs_rgb8(self):
         out = np.empty((self.cfg.R, self.cfg.P, 3), np.uint8)
         self.L.orc_obs_rgb8(self.p, out.ctypes.data)
@@ -309,6 +316,12 @@ class Batch:
         out = np.empty((self.num_envs, self.cfg.R, self.cfg.P, 3), np.uint8)
         for e in range(self.num_envs):
             out[e] = self.world(e).obs_rgb8()
+        return out
+
+    def obs_columns(self):
+        out = np.empty((self.num_envs, self.cfg.R), np.uint32)
+        for e in range(self.num_envs):
+            out[e] = self.world(e).camera_columns()
         return out
 
     def obs_gray8(self):

@@ -384,6 +384,25 @@ void orc_update_camera_view(orc_world* w) {
     }
 }
 
+/* The camera view before it is expanded into pixels (the batched engine's RCW_OBS_COLUMNS format, no reference
+ * counterpart): per image column k = R - i + 1 (:431) the two decisions update_camera_view! takes for ray i —
+ * the rows of ceiling = rows of floor, pad = (P - h) / 2 (:436), 0 when the whole column has the wall colour
+ * (h >= P - 1, :433), and the colour as an index into the palette (2/3: wall hit across dimension 1 / 2, 4/5: goal;
+ * :417-428).  word = pad | index << 16. */
+void orc_camera_columns(const orc_world* w, uint32_t* out) {
+    const int R = w->cfg.R, P = w->cfg.P, H = w->cfg.H;
+    for (int i = 1; i <= R; ++i) {
+        const int h = height_line_pu(w, i - 1);
+        const int dim = w->ray_dim[i - 1];
+        const int ih = w->ray_stop[2 * (i - 1) + 0], jh = w->ray_stop[2 * (i - 1) + 1];
+        int is_wall = 1;
+        if (ih >= 1 && ih <= H && jh >= 1 && jh <= w->cfg.W) is_wall = w->wall[(ih - 1) + H * (jh - 1)];
+        const uint32_t cid = is_wall ? (dim == 1 ? 2u : 3u) : (dim == 1 ? 4u : 5u);
+        const uint32_t pad = h >= P - 1 ? 0u : (uint32_t)((P - h) / 2);
+        out[R - i] = pad | (cid << 16);
+    }
+}
+
 /* ---- top view (single_room.jl:342-372, 446-483) ------------------------------------------------
  * The shapes are drawn by SimpleDraw.jl 0.3 [EXT, not vendored, no Manifest]: FilledRectangle(position,
  * height, width), Line(point1, point2), Circle(position, diameter).  Restated here from the algorithms

@@ -62,6 +62,7 @@ int32_t orc_is_player_colliding(const orc_world* w, int32_t layer /*1 wall, 2 go
 int32_t orc_act(orc_world* w, int32_t action);   /* returns 0, or -2 for an invalid action */
 void orc_cast_rays(orc_world* w);
 void orc_update_camera_view(orc_world* w);
+void orc_camera_columns(const orc_world* w, uint32_t* out);   /* [R] pad | palette index << 16, column order */
 int32_t orc_step(orc_world* w, int32_t action);  /* act -> cast_rays -> update_camera_view */
 /* update_top_view!(env) (single_room.jl:446-483) from the rays of the last orc_cast_rays.  The drawing
  * primitives come from the un-vendored package SimpleDraw.jl 0.3 (Project.toml) and are restated from their

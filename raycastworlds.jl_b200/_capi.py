@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RCW_LIB") or os.path.join(_PKG, "lib", "librcw_b200.so")
 
 RCW_OK, RCW_EINVAL, RCW_EACTION, RCW_ECUDA, RCW_ENOMEM, RCW_ESIZE = 0, -1, -2, -3, -4, -5
-RCW_OBS_RGB8, RCW_OBS_XRGB32, RCW_OBS_GRAY8 = 0, 1, 2
+RCW_OBS_RGB8, RCW_OBS_XRGB32, RCW_OBS_GRAY8, RCW_OBS_COLUMNS = 0, 1, 2, 3
 RCW_DDA_TIE_LE, RCW_DDA_DIST_POST = 1, 2
 ABI_VERSION = 3
 
@@ -24,7 +24,7 @@ SYMBOLS = (
     "rcw_step", "rcw_step_async", "rcw_wait", "rcw_step_range", "rcw_step_random", "rcw_render",
     "rcw_render_top_view", "rcw_top_view_device_ptr", "rcw_copy_top_view", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
     "rcw_checkpoint_size", "rcw_save_checkpoint", "rcw_load_checkpoint",
-    "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_obs_frames", "rcw_copy_obs_frame", "rcw_copy_obs", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
+    "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_obs_frames", "rcw_copy_obs_frame", "rcw_copy_obs", "rcw_expand_columns", "rcw_expanded_layout", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
     "rcw_sync", "rcw_last_error",
 )
 
@@ -111,6 +111,8 @@ def load() -> C.CDLL:
         "rcw_obs_device_ptr": (i32, [vp, P(vp), P(C.c_size_t), P(C.c_size_t)]),
         "rcw_obs_layout": (i32, [vp, P(C.c_size_t), P(C.c_size_t), P(C.c_size_t), P(i32)]),
         "rcw_copy_obs": (i32, [vp, i64, i64, vp]),
+        "rcw_expand_columns": (i32, [vp, vp, C.c_size_t, i64, i32, vp]),
+        "rcw_expanded_layout": (i32, [vp, i32, P(C.c_size_t), P(C.c_size_t), P(C.c_size_t)]),
         "rcw_obs_frames": (i32, [vp, P(i32), P(i32), P(C.c_size_t)]),
         "rcw_copy_obs_frame": (i32, [vp, i64, i64, i32, vp]),
         "rcw_episode_stats": (i32, [vp, P(i64), P(C.c_double), P(i64), i32]),

@@ -178,8 +178,21 @@ static cudaError_t dev_alloc(rcw_batch* b, T** out, size_t count, bool zero = tr
     return e;
 }
 
-static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
+static int bytes_per_pixel(int fmt) { return fmt == RCW_OBS_RGB8 ? 3 : (fmt == RCW_OBS_GRAY8 ? 1 : 4); }
+
+// bytes of one column of an observation: the pixels of the column, or its one RCW_OBS_COLUMNS word
+static int column_bytes(const rcw_batch* b) {
+    return b->cfg.obs_format == RCW_OBS_COLUMNS ? 4 : b->cfg.height_camera_view_pu * b->bpp;
+}
+
+// pixel_fmt: the format the renderer fields are prepared for (-1: the handle's own; rcw_expand_columns paints
+// a format of the caller's choice; a RCW_OBS_COLUMNS step paints nothing)
+static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt = -1) {
     const rcw_config& c = b->cfg;
+    if (pixel_fmt < 0) pixel_fmt = c.obs_format == RCW_OBS_COLUMNS ? (int)RCW_OBS_RGB8 : c.obs_format;
+    const int px_bpp = bytes_per_pixel(pixel_fmt);
+    const int px_col_bytes = c.height_camera_view_pu * px_bpp;
+    const int px_col_pitch = (px_col_bytes + 31) & ~31;
     memset(&p, 0, sizeof(p));
     p.H = c.height_tile_map_tu;
     p.W = c.width_tile_map_tu;
@@ -189,8 +202,8 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.R = c.num_rays;
     p.P = c.height_camera_view_pu;
     p.gpe = b->gpe;
-    p.col_bytes = c.height_camera_view_pu * b->bpp;
-    p.col_pitch = b->col_pitch;
+    p.col_bytes = px_col_bytes;
+    p.col_pitch = px_col_pitch;
     p.dda_flags = c.dda_flags;
     p.closed_border = b->closed_border ? 1u : 0u;
     p.radius = c.player_radius_wu;
@@ -204,7 +217,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.two_s = two_s;
     for (int i = 0; i < 6; ++i) {
         const uint32_t col = c.palette[i] & 0x00FFFFFFu;
-        if (c.obs_format == RCW_OBS_GRAY8) {
+        if (pixel_fmt == RCW_OBS_GRAY8) {
             // BT.601 luma of the reference pixel, replicated so the colour is "flat" for the renderer
             const uint32_t y = (77u * ((col >> 16) & 255u) + 150u * ((col >> 8) & 255u) + 29u * (col & 255u) + 128u) >> 8;
             p.palette[i] = y * 0x00010101u;
@@ -213,12 +226,12 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
         }
     }
     {   // what the renderer stores per column for each palette entry (see FrameParams::col_entry)
-        auto flat = [&](uint32_t col) { return c.obs_format != RCW_OBS_RGB8 || ((col ^ (col >> 8)) & 0xFFFFu) == 0; };
+        auto flat = [&](uint32_t col) { return pixel_fmt != RCW_OBS_RGB8 || ((col ^ (col >> 8)) & 0xFFFFu) == 0; };
         const bool cf = flat(p.palette[RCW_COLOR_CEILING]) && flat(p.palette[RCW_COLOR_FLOOR]);
         for (int i = 0; i < 6; ++i) {
             const bool slow = !(cf && flat(p.palette[i]));
             const uint32_t col = p.palette[i];
-            const uint32_t word = c.obs_format == RCW_OBS_XRGB32 ? col : (col & 0xFFu) * 0x01010101u;
+            const uint32_t word = pixel_fmt == RCW_OBS_XRGB32 ? col : (col & 0xFFu) * 0x01010101u;
             p.col_entry[i] = make_uint2(slow ? 0x80000000u : 0u, slow ? col : word);
         }
     }
@@ -240,8 +253,8 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
         }
     }
     {   // renderer sweep units per column: mirror pairs of 64 bytes when col_bytes % 64 == 0, else 32-byte sectors
-        const int col_bytes = c.height_camera_view_pu * b->bpp;
-        const int U = (col_bytes & 63) == 0 ? (col_bytes >> 6) : (b->col_pitch >> 5);
+        const int col_bytes = px_col_bytes;
+        const int U = (col_bytes & 63) == 0 ? (col_bytes >> 6) : (px_col_pitch >> 5);
         p.unit_inv16 = U < 32 ? (uint32_t)((65536 + U - 1) / U) : 0u;
         p.unit_adv_cl = 32 / U;
         p.unit_adv_u = 32 % U;
@@ -254,6 +267,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.patterns = b->d_patterns;
     p.pat_stride = b->pat_stride;
     p.col_info = b->d_col_info;
+    p.col_info_stride = (uint32_t)c.num_rays;
     p.in = b->st[b->cur];
     p.out = b->st[b->cur ^ 1];
     p.actions = nullptr;
@@ -269,6 +283,10 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p) {
     p.stats = b->d_stats;
     p.obs = b->d_obs + (size_t)b->frame_newest * b->frame_stride;
     p.obs_env_stride = b->obs_env_stride;
+    if (c.obs_format == RCW_OBS_COLUMNS) {   // the front stage's column words are the observation
+        p.col_info = reinterpret_cast<uint32_t*>(p.obs);
+        p.col_info_stride = (uint32_t)(b->obs_env_stride / 4);
+    }
     p.obs_window = (uint32_t)b->obs_window;
     p.obs_slot0 = 0;
     p.num_envs = c.num_envs;
@@ -351,7 +369,8 @@ static void pack_actions(const uint8_t* actions, int64_t n, PackedActions& pa) {
 
 // launches of at most kPackedActionEnvs envs on the fused path take host actions through the kernel parameters
 static bool packs_actions(const rcw_batch* b, int64_t env_count) {
-    return !b->split && !b->bulk && !b->no_packed_actions && env_count <= kPackedActionEnvs;
+    return (b->cfg.obs_format == RCW_OBS_COLUMNS || (!b->split && !b->bulk)) && !b->no_packed_actions &&
+           env_count <= kPackedActionEnvs;
 }
 
 // h_actions != nullptr: validated host actions of the whole batch (d_actions is then ignored)
@@ -362,7 +381,7 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions, c
     FrameParams p;
     fill_frame_params(b, p);
     p.actions = h_actions ? nullptr : d_actions;
-    p.render_mask = mode == kModeRender ? d_render_mask : nullptr;
+    p.render_mask = (mode == kModeRender && !b->split) ? d_render_mask : nullptr;   // (a split launch redraws every env)
     const int64_t E = b->cfg.num_envs;
     for (int64_t e0 = 0; e0 < E; e0 += b->obs_window) {
         p.env_first = e0;
@@ -577,7 +596,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
 
     // ---- single-colour pattern buffers for the bulk renderer: palette entry k repeated as the
     //      observation's byte stream (RGB8: R,G,B,R,...; XRGB32: little-endian 0x00RRGGBB words) ----
-    const int col_bytes = P * b->bpp;
+    const int col_bytes = column_bytes(b);
     b->pat_stride = ((col_bytes < 3072 ? col_bytes : 3072) + 32 + 15) & ~15;
     // Renderer: lane-written whole sectors (default) or TMA bulk stores of the bands.  The bulk path
     // is kept as a measured alternative (profiles/): its per-lane UBLKCP issue serialises and its
@@ -585,6 +604,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     b->bulk = false;
     if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0 && c.obs_format != RCW_OBS_GRAY8;
     if (const char* s = getenv("RCW_SPLIT")) b->split = atoi(s) != 0;
+    if (c.obs_format == RCW_OBS_COLUMNS) b->bulk = b->split = false;   // nothing is painted
     if (b->split) RCW_CUDA(dev_alloc(b, &b->d_col_info, (size_t)E * (size_t)R));   // 4 B per column, two-launch path only
     {
         std::vector<uint8_t> pat((size_t)6 * b->pat_stride);
@@ -636,7 +656,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
 
     // ---- observations ---------------------------------------------------------------------------
     // every column starts on a 32-byte sector, every env on a 128-byte line (see rcw_obs_layout)
-    b->col_pitch = (P * b->bpp + 31) & ~31;
+    b->col_pitch = c.obs_format == RCW_OBS_COLUMNS ? 4 : (P * b->bpp + 31) & ~31;
     b->frame_stack = c.frame_stack > 1 ? c.frame_stack : 1;
     b->frame_stride = (((size_t)R * b->col_pitch) + 127) & ~(size_t)127;
     b->obs_env_stride = b->frame_stride * (size_t)b->frame_stack;
@@ -655,7 +675,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // 96x96 6224 -> 6971; GRAY8 84x84 2184 -> 2987, 128x128 3866 -> 5615, 160x120 3732 -> 5302, 256x192
     // 5657 -> 7132, 512x256 7031 -> 7017.  Store-bound items lose: RGB8 128x128 (12 KB) 6897 -> 6756,
     // 160x120 6701 -> 6113, 256x192 7366 -> 6305.
-    b->env_per_warp = b->gpe <= 8 && 32 * b->col_pitch <= 10240;
+    b->env_per_warp = b->gpe <= 8 && 32 * b->col_pitch <= 10240 && c.obs_format != RCW_OBS_COLUMNS;
     if (const char* s = getenv("RCW_ENV_PER_WARP")) b->env_per_warp = atoi(s) != 0;   // 1 forces it for any width
     if (const char* s = getenv("RCW_PACKED_ACTIONS")) b->no_packed_actions = atoi(s) == 0;
     b->env_per_warp_min = kEnvPerWarpMinEnvs;
@@ -683,7 +703,8 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
         return fail(RCW_EINVAL, "num_rays and height_camera_view_pu must be positive");
     if (cfg->height_camera_view_pu > 32767)
         return fail(RCW_EINVAL, "height_camera_view_pu must be below 32768");
-    if (cfg->obs_format != RCW_OBS_RGB8 && cfg->obs_format != RCW_OBS_XRGB32 && cfg->obs_format != RCW_OBS_GRAY8)
+    if (cfg->obs_format != RCW_OBS_RGB8 && cfg->obs_format != RCW_OBS_XRGB32 && cfg->obs_format != RCW_OBS_GRAY8 &&
+        cfg->obs_format != RCW_OBS_COLUMNS)
         return fail(RCW_EINVAL, "unknown obs_format %d", cfg->obs_format);
     if (cfg->num_envs < 1) return fail(RCW_EINVAL, "num_envs must be positive");
     if (!(cfg->player_radius_wu > 0.0f) || !(cfg->player_radius_wu < 0.5f))
@@ -698,7 +719,7 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
         return fail(RCW_EINVAL, "frame_stack cannot be combined with an observation window");
     if (cfg->pu_per_tu < 1 || cfg->pu_per_tu > 1024) return fail(RCW_EINVAL, "pu_per_tu must be in 1..1024");
     if (cfg->top_view != 0 && cfg->top_view != 1) return fail(RCW_EINVAL, "top_view must be 0 or 1");
-    const int bpp = cfg->obs_format == RCW_OBS_RGB8 ? 3 : (cfg->obs_format == RCW_OBS_XRGB32 ? 4 : 1);
+    const int bpp = bytes_per_pixel(cfg->obs_format);   // RCW_OBS_COLUMNS: the 4 bytes of a column word
     const int gpe = (cfg->num_rays + 31) / 32;
     if ((int64_t)cfg->num_rays * cfg->height_camera_view_pu * bpp >= (1LL << 30))
         return fail(RCW_ESIZE, "one observation must be smaller than 1 GiB");
@@ -1303,7 +1324,7 @@ int32_t rcw_obs_layout(rcw_batch* b, size_t* env_stride_bytes, size_t* column_st
     if (int32_t rc = check_handle(b)) return rc;
     if (env_stride_bytes) *env_stride_bytes = b->obs_env_stride;
     if (column_stride_bytes) *column_stride_bytes = (size_t)b->col_pitch;
-    if (column_bytes) *column_bytes = (size_t)b->cfg.height_camera_view_pu * b->bpp;
+    if (column_bytes) *column_bytes = (size_t)::column_bytes(b);
     if (bytes_per_pixel) *bytes_per_pixel = b->bpp;
     return RCW_OK;
 }
@@ -1329,7 +1350,7 @@ int32_t rcw_copy_obs_frame(rcw_batch* b, int64_t env0, int64_t n, int32_t age, v
     if (age < 0 || age >= b->frame_stack)
         return fail(RCW_ESIZE, "frame age %d outside 0..%d", age, b->frame_stack - 1);
     DeviceGuard g(b->device);
-    const size_t R = (size_t)b->cfg.num_rays, col_bytes = (size_t)b->cfg.height_camera_view_pu * b->bpp;
+    const size_t R = (size_t)b->cfg.num_rays, col_bytes = (size_t)column_bytes(b);
     const int64_t slot0 = env0 % b->obs_window;
     if (slot0 + n > b->obs_window) {   // the range wraps around the window: two pieces
         const int64_t n1 = b->obs_window - slot0;
@@ -1356,6 +1377,51 @@ int32_t rcw_copy_obs_frame(rcw_batch* b, int64_t env0, int64_t n, int32_t age, v
                                        cudaMemcpyDeviceToHost, b->stream));
     }
     return sync_and_check(b);
+}
+
+int32_t rcw_expanded_layout(rcw_batch* b, int32_t pixel_format, size_t* env_stride_bytes,
+                            size_t* column_stride_bytes, size_t* column_bytes) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (pixel_format != RCW_OBS_RGB8 && pixel_format != RCW_OBS_XRGB32 && pixel_format != RCW_OBS_GRAY8)
+        return fail(RCW_EINVAL, "pixel_format must be RCW_OBS_RGB8, RCW_OBS_XRGB32 or RCW_OBS_GRAY8");
+    const size_t cb = (size_t)b->cfg.height_camera_view_pu * bytes_per_pixel(pixel_format);
+    const size_t pitch = (cb + 31) & ~(size_t)31;
+    if (column_bytes) *column_bytes = cb;
+    if (column_stride_bytes) *column_stride_bytes = pitch;
+    if (env_stride_bytes) *env_stride_bytes = ((size_t)b->cfg.num_rays * pitch + 127) & ~(size_t)127;
+    return RCW_OK;
+}
+
+int32_t rcw_expand_columns(rcw_batch* b, const uint32_t* columns, size_t columns_env_stride_bytes, int64_t n,
+                           int32_t pixel_format, void* dst) {
+    NvtxRange nvtx("rcw_expand_columns");
+    if (int32_t rc = check_handle(b)) return rc;
+    size_t env_stride = 0;
+    if (int32_t rc = rcw_expanded_layout(b, pixel_format, &env_stride, nullptr, nullptr)) return rc;
+    if (!columns || !dst) return fail(RCW_EINVAL, "columns / dst is null");
+    if (!is_device_pointer(columns) || !is_device_pointer(dst))
+        return fail(RCW_EINVAL, "columns and dst must be device pointers");
+    if (columns_env_stride_bytes == 0) columns_env_stride_bytes = (size_t)b->cfg.num_rays * 4;
+    if (columns_env_stride_bytes % 4 || columns_env_stride_bytes < (size_t)b->cfg.num_rays * 4 ||
+        columns_env_stride_bytes / 4 > 0xFFFFFFFFull)
+        return fail(RCW_EINVAL, "columns_env_stride_bytes must be a multiple of 4 and at least num_rays * 4");
+    if (n < 1 || n * b->gpe >= (1LL << 31) || n > 0xFFFFFFFFLL)
+        return fail(RCW_ESIZE, "n = %lld out of range", (long long)n);
+    if ((uintptr_t)dst % 32) return fail(RCW_EINVAL, "dst must be 32-byte aligned");
+    DeviceGuard g(b->device);
+    FrameParams p;
+    fill_frame_params(b, p, pixel_format);
+    p.col_info = const_cast<uint32_t*>(columns);
+    p.col_info_stride = (uint32_t)(columns_env_stride_bytes / 4);
+    p.obs = static_cast<uint8_t*>(dst);
+    p.obs_env_stride = env_stride;
+    p.obs_window = (uint32_t)n;
+    p.obs_slot0 = 0;
+    p.env_first = 0;
+    p.env_count = n;
+    RCW_CUDA(launch_expand_columns(p, pixel_format, grid_for(b, n), b->stream));
+    b->launches += 1;
+    return RCW_OK;
 }
 
 int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host) {

@@ -100,7 +100,9 @@ struct FrameParams {
     uint32_t map_env_stride; // words between the wall layers of consecutive envs; 0 = one layer shared by all
     const uint8_t* patterns; // [6][pat_stride] single-colour byte runs, one per palette entry (bulk renderer)
     int32_t pat_stride;      // bytes, multiple of 16: min(col_bytes, 3072) + 32 rounded up
-    uint32_t* col_info;      // [num_envs][R] pad | palette index << 16, column order (split launches)
+    uint32_t* col_info;      // [env slots][col_info_stride] pad | palette index << 16, column order: the
+                             // RCW_OBS_COLUMNS observation itself, or the hand-over of a split launch
+    uint32_t col_info_stride;// words between consecutive env slots of col_info (>= R)
     // state
     StateRef in, out;
     const uint8_t* render_mask;  // kModeRender only: nonzero = redraw this env (nullptr: all) — masked resets
@@ -194,6 +196,8 @@ struct LaunchShape {
 // packed != nullptr (step mode, fused path, env_count <= kPackedActionEnvs): the actions ride in the parameters
 cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s,
                          const PackedActions* packed = nullptr);
+// RCW_OBS_COLUMNS -> pixels: p.col_info (column words of p.env_count envs) painted into p.obs in pixel_format
+cudaError_t launch_expand_columns(const FrameParams& p, int pixel_format, int ctas, cudaStream_t s);
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);
 // state `from` -> state `to` for envs [env0, env0 + n): makes a range step visible in the buffer it read
 cudaError_t launch_commit_range(const StateRef& from, const StateRef& to, int64_t env0, int64_t n, cudaStream_t s);

@@ -894,7 +894,11 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
 
         // a masked render (after a masked reset) redraws only the chosen envs; the decision is per env, so
         // all warps of an env — including the one that stages its wall layer — agree
-        if (MODE == kModeRender && STAGE == kStageFused && p.render_mask && !__ldg(p.render_mask + env)) continue;
+        if (MODE == kModeRender && STAGE != kStagePaint && p.render_mask && !__ldg(p.render_mask + env)) continue;
+
+        // the env's slot in the observation buffer (a window of obs_window envs; the whole batch by default)
+        uint32_t obs_slot = p.obs_slot0 + env_rel;
+        if (obs_slot >= p.obs_window) obs_slot -= p.obs_window;
 
         ColumnShade cs;
         cs.pad = 0;
@@ -966,7 +970,7 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
             if (STAGE == kStageFront) {
                 // column order, so the paint launch reads its 32 columns with one coalesced load
                 if (lane < ncols)
-                    p.col_info[(size_t)env * (size_t)R + (size_t)(col0 + ncols - 1 - lane)] =
+                    p.col_info[(size_t)obs_slot * p.col_info_stride + (size_t)(col0 + ncols - 1 - lane)] =
                         (uint32_t)cs.pad | ((uint32_t)cs.cid << 16);
                 continue;
             }
@@ -978,16 +982,13 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
             }
         }
 
-        // the env's slot in the observation buffer (a window of obs_window envs; the whole batch by default)
-        uint32_t obs_slot = p.obs_slot0 + env_rel;
-        if (obs_slot >= p.obs_window) obs_slot -= p.obs_window;
         uint8_t* const env_obs = p.obs + (size_t)obs_slot * p.obs_env_stride;
         const int B0 = col0 * p.col_pitch;             // byte span of the warp's columns in the env image
         int my_col = ncols - 1 - lane;                 // span column of this lane's ray
         if (STAGE == kStagePaint) {
             my_col = lane;                             // the info array is already in column order
             if (lane < ncols) {
-                const uint32_t info = __ldg(p.col_info + (size_t)env * (size_t)R + (size_t)(col0 + lane));
+                const uint32_t info = __ldg(p.col_info + (size_t)obs_slot * p.col_info_stride + (size_t)(col0 + lane));
                 cs.pad = (int)(info & 0xFFFFu);
                 cs.cid = (int)(info >> 16);
             }
@@ -1030,11 +1031,11 @@ frame_kernel(const __grid_constant__ FrameParams p) {
     frame_body<MODE, FMT, BULK, STAGE>(p, nullptr);
 }
 
-// the fused step with host-supplied actions packed into the parameters
-template <int FMT, int OCC>
+// the step (fused, or the front stage alone: RCW_OBS_COLUMNS) with host-supplied actions packed into the parameters
+template <int FMT, int OCC, int STAGE = kStageFused>
 __global__ void __launch_bounds__(kThreadsPerCta, OCC)
 frame_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ PackedActions a) {
-    frame_body<kModeStep, FMT, false, kStageFused>(p, &a);
+    frame_body<kModeStep, FMT, false, STAGE>(p, &a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1268,15 +1269,15 @@ static cudaError_t launch_env_pa_t(const FrameParams& p, const PackedActions& pa
     return cudaGetLastError();
 }
 
-template <int FMT, int OCC>
+template <int FMT, int OCC, int STAGE = kStageFused>
 static cudaError_t launch_frame_pa_t(const FrameParams& p, const PackedActions& pa, int ctas, cudaStream_t s) {
     const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
     const size_t smem = map_slots * (size_t)p.map_words * 4;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(frame_kernel_pa<FMT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(frame_kernel_pa<FMT, OCC, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    frame_kernel_pa<FMT, OCC><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
+    frame_kernel_pa<FMT, OCC, STAGE><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
     return cudaGetLastError();
 }
 
@@ -1321,6 +1322,18 @@ static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, const La
 // split = false: one fused launch.  split = true: two launches (front, then paint) through p.col_info.
 cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s,
                          const PackedActions* packed) {
+    if (obs_format == RCW_OBS_COLUMNS) {
+        // the observation is the front stage's output: {rows of ceiling, palette index} per column, no pixels;
+        // act! + DDA bound it, so it runs at the front-bound register budget
+        if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc>(p, sh.ctas, s);
+        if (packed) {
+            if (mode != kModeStep || p.env_count > kPackedActionEnvs) return cudaErrorInvalidValue;
+            return launch_frame_pa_t<RCW_OBS_RGB8, kCtasPerSmHi, kStageFront>(p, *packed, sh.ctas, s);
+        }
+        if (mode == kModeStep) return launch_frame_t<kModeStep, RCW_OBS_RGB8, false, kStageFront, kCtasPerSmHi>(p, sh.ctas, s);
+        if (mode == kModeRender) return launch_frame_t<kModeRender, RCW_OBS_RGB8, false, kStageFront, kCtasPerSmHi>(p, sh.ctas, s);
+        return cudaErrorInvalidValue;
+    }
     if (packed) {
         if (mode != kModeStep || sh.split || sh.bulk || p.env_count > kPackedActionEnvs) return cudaErrorInvalidValue;
         if (obs_format == RCW_OBS_GRAY8) return launch_packed<RCW_OBS_GRAY8>(p, *packed, sh, s);
@@ -1339,6 +1352,13 @@ cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const L
                         : launch_frame_t<kModeRender, RCW_OBS_RGB8, false, kStageFront, kOcc>(p, sh.ctas, s);
     if (e != cudaSuccess) return e;
     return launch_frame_m<kModeRender, kStagePaint>(p, obs_format, sh, s);
+}
+
+cudaError_t launch_expand_columns(const FrameParams& p, int pixel_format, int ctas, cudaStream_t s) {
+    LaunchShape sh{false, true, false, ctas};
+    if (pixel_format != RCW_OBS_RGB8 && pixel_format != RCW_OBS_XRGB32 && pixel_format != RCW_OBS_GRAY8)
+        return cudaErrorInvalidValue;
+    return launch_frame_m<kModeRender, kStagePaint>(p, pixel_format, sh, s);
 }
 
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s) {

@@ -30,6 +30,10 @@ NUM_ACTIONS = 4  # single_room.jl:19
 ACTION_NAMES = ("MOVE_FORWARD", "MOVE_BACKWARD", "TURN_LEFT", "TURN_RIGHT")  # single_room.jl:486
 
 
+_FORMATS = (("rgb8", _capi.RCW_OBS_RGB8), ("xrgb32", _capi.RCW_OBS_XRGB32), ("gray8", _capi.RCW_OBS_GRAY8),
+            ("columns", _capi.RCW_OBS_COLUMNS))
+
+
 class AbstractGame:
     """src/RayCastWorlds.jl:5"""
 
@@ -82,7 +86,7 @@ class BatchedSingleRoom(AbstractGame):
         cfg.semi_field_of_view_wu = float(np.float32(semi_field_of_view_wu))
         cfg.camera_height_tile_wu = float(np.float32(camera_height_tile_wu))
         cfg.goal_reward = float(np.float32(goal_reward))
-        fmt = {"rgb8": _capi.RCW_OBS_RGB8, "xrgb32": _capi.RCW_OBS_XRGB32, "gray8": _capi.RCW_OBS_GRAY8}
+        fmt = dict(_FORMATS)
         if obs_format not in fmt:
             raise ValueError(f"obs_format must be one of {sorted(fmt)}")
         cfg.obs_format = fmt[obs_format]
@@ -116,7 +120,7 @@ class BatchedSingleRoom(AbstractGame):
         self._ticket = C.c_int64()
         self._wait_r, self._wait_d = C.c_void_p(), C.c_void_p()
         self.obs_format = obs_format
-        self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1}[obs_format]
+        self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1, "columns": 4}[obs_format]
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -313,6 +317,8 @@ class BatchedSingleRoom(AbstractGame):
         fastest index, as in the reference's Array{UInt32}(P, R).  env slots = num_envs unless an
         observation window was configured."""
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
+        if self.obs_format == "columns":
+            return (self.obs_window, R)      # one uint32 word per column: pad | palette index << 16
         return (self.obs_window, R, P, 3) if self.obs_format == "rgb8" else (self.obs_window, R, P)
 
     def obs_device_ptr(self):
@@ -345,6 +351,12 @@ class BatchedSingleRoom(AbstractGame):
         holder = _CudaBuffer(ptr, total, self)
         flat = torch.as_tensor(holder, device=torch.device("cuda", self.cfg.device))
         slots = self.obs_window
+        if self.obs_format == "columns":
+            words = flat.view(torch.int32)
+            if self.frame_stack > 1:
+                k, _, fs = self.obs_frames()
+                return torch.as_strided(words, (slots, k, R), (env_stride // 4, fs // 4, 1))
+            return torch.as_strided(words, (slots, R), (env_stride // 4, 1))
         if self.frame_stack > 1:
             # the whole ring: [env, ring position, ...]; obs_frames()[1] is the newest position
             k, _, fs = self.obs_frames()
@@ -364,16 +376,54 @@ class BatchedSingleRoom(AbstractGame):
         """The same buffer as a [N, C, num_rays, height_px] torch view for convolutional learners: the
         image is presented transposed (camera columns along torch's "height"), which is exactly torch's
         channels_last memory format whenever the columns are not pitched — no copy, no permute kernel."""
+        if self.obs_format == "columns":
+            raise ValueError("the columns format holds no pixels; expand_columns() rasterises it")
         t = self.obs_tensor()
         return t.permute(0, 3, 1, 2) if self.obs_format == "rgb8" else t.unsqueeze(1)
+
+    def expand_columns(self, columns=None, pixel_format: str = "rgb8"):
+        """Rasterise camera views kept as column words (obs_format="columns") into pixels on the device
+        (rcw_expand_columns).  `columns`: CUDA int32 / uint32 tensor [n, num_rays] (rows may be strided) — e.g. a
+        minibatch gathered from a replay buffer; None: this handle's own newest observations.  Returns a torch
+        view [n, num_rays, height_px(, 3)] (uint8; int32 for "xrgb32") of a freshly allocated device buffer, on
+        the handle's stream."""
+        import torch
+
+        if pixel_format not in ("rgb8", "xrgb32", "gray8"):
+            raise ValueError("pixel_format must be rgb8, xrgb32 or gray8")
+        dev = torch.device("cuda", self.cfg.device)
+        R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
+        if columns is None:
+            if self.obs_format != "columns":
+                raise ValueError("this handle's observations are pixels already")
+            ptr, _, env_stride = self.obs_device_ptr()
+            k, newest, fs = self.obs_frames()
+            src, src_stride, n = ptr + newest * fs, env_stride, self.obs_window
+        else:
+            if columns.dim() != 2 or columns.shape[1] != R or columns.stride(1) != 1 or columns.element_size() != 4:
+                raise ValueError("columns must be a 32-bit [n, num_rays] CUDA tensor with contiguous rows")
+            src, src_stride, n = columns.data_ptr(), columns.stride(0) * 4, columns.shape[0]
+        es, cs, cb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _capi.check(self._lib.rcw_expanded_layout(self._h, dict(_FORMATS)[pixel_format], C.byref(es), C.byref(cs), C.byref(cb)))
+        es, cs = es.value, cs.value
+        stream = torch.cuda.ExternalStream(self.cuda_stream(), device=dev)
+        with torch.cuda.stream(stream):
+            buf = torch.empty(n * es, dtype=torch.uint8, device=dev)
+        _capi.check(self._lib.rcw_expand_columns(self._h, C.c_void_p(src), src_stride, n, dict(_FORMATS)[pixel_format],
+                                                 C.c_void_p(buf.data_ptr())))
+        if pixel_format == "rgb8":
+            return torch.as_strided(buf, (n, R, P, 3), (es, cs, 3, 1))
+        if pixel_format == "gray8":
+            return torch.as_strided(buf, (n, R, P), (es, cs, 1))
+        return torch.as_strided(buf.view(torch.int32), (n, R, P), (es // 4, cs // 4, 1))
 
     def copy_obs(self, env0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None, age: int = 0):
         """Blocking device->host copy of the observations of envs [env0, env0+n); with a frame ring, `age`
         selects the frame (0 = newest)."""
         n = min(self.num_envs - env0, self.obs_window) if n is None else n
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
-        shape = (n, R, P, 3) if self.obs_format == "rgb8" else (n, R, P)
-        dtype = np.uint32 if self.obs_format == "xrgb32" else np.uint8
+        shape = (n, R, P, 3) if self.obs_format == "rgb8" else ((n, R) if self.obs_format == "columns" else (n, R, P))
+        dtype = np.uint32 if self.obs_format in ("xrgb32", "columns") else np.uint8
         if out is None:
             out = np.empty(shape, dtype)
         _capi.check(self._lib.rcw_copy_obs_frame(self._h, env0, n, int(age), _ptr(out)))
