@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
-    ap.add_argument("--obs-format", choices=["rgb8", "xrgb32", "gray8"], default="rgb8")
+    ap.add_argument("--obs-format", choices=["rgb8", "xrgb32", "gray8", "columns"], default="rgb8")
     ap.add_argument("--map", choices=["default", "large"], default="default",
                     help="default: 8x16 tiles / 128 directions; large: 64x64 / 256 (BASELINE config 5)")
     ap.add_argument("--rays", type=int, default=512, help="num_rays = observation width (default 512)")
@@ -238,6 +238,8 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(env.cuda_stream(), device=dev)
     K, W = args.steps, args.warmup
     bytes_per_step_env = kw["num_rays"] * kw["height_camera_view_pu"] * env.bytes_per_pixel
+    if args.obs_format == "columns":   # 4 bytes per column: not rendered pixels, the step is bound by act! + DDA
+        bytes_per_step_env = kw["num_rays"] * 4
     if args.top_view:
         bytes_per_step_env += 4 * int(np.prod(env.top_view_shape[1:]))
 
@@ -328,9 +330,9 @@ def run_b200(args):
         e2e_lockstep["note"] = "as e2e, but the results of step k are read before step k + 1 is enqueued"
     if not args.no_e2e and not windowed:
         Ko = max(1, min(K, 5))
-        obs_host = torch.empty(env.obs_shape, dtype=torch.int32 if args.obs_format == "xrgb32" else torch.uint8)
+        obs_host = torch.empty(env.obs_shape, dtype=torch.int32 if args.obs_format in ("xrgb32", "columns") else torch.uint8)
         obs_host = obs_host.pin_memory().numpy()
-        if args.obs_format == "xrgb32":
+        if args.obs_format in ("xrgb32", "columns"):
             obs_host = obs_host.view(np.uint32)
         barrier()
         t0 = time.perf_counter()
@@ -365,7 +367,9 @@ def run_b200(args):
                 "envs_per_gpu": n, "obs_bytes_per_env_step": bytes_per_step_env,
                 "obs_window_envs": env_window, "launches_per_step": -(-n // env_window) * (2 if args.top_view else 1),
                 "top_view": bool(args.top_view),
-                "l2": f"each step writes {n * bytes_per_step_env / 1e9:.2f} GB of observations, larger than the 126 MB L2; no flush needed",
+                "l2": (f"each step writes {n * bytes_per_step_env / 1e9:.2f} GB of observations, larger than the 126 MB L2; no flush needed"
+                       if n * bytes_per_step_env > 126e6 else
+                       f"each step writes {n * bytes_per_step_env / 1e6:.1f} MB of observations: L2-resident, the step is bound by act! + DDA (issue), not by HBM"),
                 "seed": SEED,
             },
             "roofline": {

@@ -675,7 +675,8 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // 96x96 6224 -> 6971; GRAY8 84x84 2184 -> 2987, 128x128 3866 -> 5615, 160x120 3732 -> 5302, 256x192
     // 5657 -> 7132, 512x256 7031 -> 7017.  Store-bound items lose: RGB8 128x128 (12 KB) 6897 -> 6756,
     // 160x120 6701 -> 6113, 256x192 7366 -> 6305.
-    b->env_per_warp = b->gpe <= 8 && 32 * b->col_pitch <= 10240 && c.obs_format != RCW_OBS_COLUMNS;
+    b->env_per_warp = b->gpe <= 8 && 32 * b->col_pitch <= 10240;
+    if (c.obs_format == RCW_OBS_COLUMNS) b->env_per_warp = true;   // nothing is painted: act! + DDA only, any width
     if (const char* s = getenv("RCW_ENV_PER_WARP")) b->env_per_warp = atoi(s) != 0;   // 1 forces it for any width
     if (const char* s = getenv("RCW_PACKED_ACTIONS")) b->no_packed_actions = atoi(s) == 0;
     b->env_per_warp_min = kEnvPerWarpMinEnvs;

@@ -1046,7 +1046,8 @@ frame_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ P
 // (profiles/README.md).  Here a warp owns a whole env: act! once, then its groups one after the other, the
 // ray-table row of the next group in flight while the current one is cast and painted.  No block barrier,
 // no pose exchange through shared memory, no item -> (env, group) arithmetic.
-template <int MODE, int FMT>
+// WORDS: the observation is the column words themselves (RCW_OBS_COLUMNS): nothing is painted.
+template <int MODE, int FMT, bool WORDS = false>
 __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActions* pa) {
     extern __shared__ __align__(128) uint32_t s_dyn[];   // wall layer(s): one shared, or one slot per warp
     __shared__ __align__(8) uint64_t s_mbar;
@@ -1124,6 +1125,13 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
         const int r0 = g * 32;
         const int ncols = min(32, R - r0);
         const int col0 = R - r0 - ncols;               // ray r paints column R-1-r
+        if (WORDS) {
+            if (lane < ncols)
+                p.col_info[(size_t)obs_slot * p.col_info_stride + (size_t)(col0 + ncols - 1 - lane)] =
+                    (uint32_t)cs.pad | ((uint32_t)cs.cid << 16);
+            rt = rt_next;
+            continue;
+        }
         bool slow = false;
         if (lane < ncols) s_col[warp][ncols - 1 - lane] = column_entry<FMT>(p, cs.pad, cs.cid, slow);
         __syncwarp();
@@ -1134,16 +1142,16 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
     }
 }
 
-template <int MODE, int FMT>
+template <int MODE, int FMT, bool WORDS = false>
 __global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSmHi)
 env_kernel(const __grid_constant__ FrameParams p) {
-    env_body<MODE, FMT>(p, nullptr);
+    env_body<MODE, FMT, WORDS>(p, nullptr);
 }
 
-template <int FMT>
+template <int FMT, bool WORDS = false>
 __global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSmHi)
 env_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ PackedActions a) {
-    env_body<kModeStep, FMT>(p, &a);
+    env_body<kModeStep, FMT, WORDS>(p, &a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1243,29 +1251,29 @@ static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s
 
 }
 
-template <int MODE, int FMT>
+template <int MODE, int FMT, bool WORDS = false>
 static cudaError_t launch_env_t(const FrameParams& p, cudaStream_t s) {
     const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
     const size_t smem = map_slots * (size_t)p.map_words * 4;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(env_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(env_kernel<MODE, FMT, WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const unsigned ctas = (unsigned)((p.env_count + kWarpsPerCta - 1) / kWarpsPerCta);
-    env_kernel<MODE, FMT><<<ctas, kThreadsPerCta, smem, s>>>(p);
+    env_kernel<MODE, FMT, WORDS><<<ctas, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-template <int FMT>
+template <int FMT, bool WORDS = false>
 static cudaError_t launch_env_pa_t(const FrameParams& p, const PackedActions& pa, cudaStream_t s) {
     const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
     const size_t smem = map_slots * (size_t)p.map_words * 4;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(env_kernel_pa<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(env_kernel_pa<FMT, WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const unsigned ctas = (unsigned)((p.env_count + kWarpsPerCta - 1) / kWarpsPerCta);
-    env_kernel_pa<FMT><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
+    env_kernel_pa<FMT, WORDS><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
     return cudaGetLastError();
 }
 
@@ -1328,8 +1336,11 @@ cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const L
         if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc>(p, sh.ctas, s);
         if (packed) {
             if (mode != kModeStep || p.env_count > kPackedActionEnvs) return cudaErrorInvalidValue;
+            if (sh.env_per_warp) return launch_env_pa_t<RCW_OBS_RGB8, true>(p, *packed, s);
             return launch_frame_pa_t<RCW_OBS_RGB8, kCtasPerSmHi, kStageFront>(p, *packed, sh.ctas, s);
         }
+        if (sh.env_per_warp && mode == kModeStep) return launch_env_t<kModeStep, RCW_OBS_RGB8, true>(p, s);
+        if (sh.env_per_warp && mode == kModeRender) return launch_env_t<kModeRender, RCW_OBS_RGB8, true>(p, s);
         if (mode == kModeStep) return launch_frame_t<kModeStep, RCW_OBS_RGB8, false, kStageFront, kCtasPerSmHi>(p, sh.ctas, s);
         if (mode == kModeRender) return launch_frame_t<kModeRender, RCW_OBS_RGB8, false, kStageFront, kCtasPerSmHi>(p, sh.ctas, s);
         return cudaErrorInvalidValue;

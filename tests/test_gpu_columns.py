@@ -38,10 +38,13 @@ def _engine_kwargs(g):
     return {names[k]: (float(v) if isinstance(v, np.floating) else v) for k, v in g.items()}
 
 
+@pytest.mark.parametrize("env_kernel", [0, 1])
 @pytest.mark.parametrize("geo", GEOMETRIES)
-def test_columns_match_oracle_and_expand_to_the_pixel_image(rcw, oracle, geo):
+def test_columns_match_oracle_and_expand_to_the_pixel_image(rcw, oracle, monkeypatch, geo, env_kernel):
     import torch
 
+    monkeypatch.setenv("RCW_ENV_PER_WARP", str(env_kernel))      # both step kernels: one warp per env / per 32 rays
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
     n, seed = 37, 21
     env = rcw.BatchedSingleRoom(n, seed=seed, obs_format="columns", **_engine_kwargs(geo))
     ref = oracle.Batch(n, cfg=oracle.default_config(**geo), seed=seed)
@@ -96,7 +99,10 @@ def test_expand_records_from_a_replay_buffer_on_a_pixel_handle(rcw, oracle):
     pixels.close()
 
 
-def test_columns_with_frame_ring_window_masked_reset_and_checkpoint(rcw, oracle):
+@pytest.mark.parametrize("env_kernel", [0, 1])
+def test_columns_with_frame_ring_window_masked_reset_and_checkpoint(rcw, oracle, monkeypatch, env_kernel):
+    monkeypatch.setenv("RCW_ENV_PER_WARP", str(env_kernel))
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
     n, seed, K = 24, 8, 3
     env = rcw.BatchedSingleRoom(n, seed=seed, obs_format="columns", num_rays=64, height_camera_view_pu=32, frame_stack=K)
     ref = oracle.Batch(n, cfg=oracle.default_config(R=64, P=32), seed=seed)
