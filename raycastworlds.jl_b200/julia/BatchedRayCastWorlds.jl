@@ -24,6 +24,11 @@ const RCW_OK = Int32(0)
 const RCW_EACTION = Int32(-2)
 const RCW_OBS_RGB8 = Int32(0)
 const RCW_OBS_XRGB32 = Int32(1)
+const RCW_OBS_GRAY8 = Int32(2)      # BT.601 luma of the reference pixel, one byte per pixel
+const RCW_OBS_COLUMNS = Int32(3)    # one UInt32 per ray column: pad | colour id << 16 (see expand_columns)
+const RCW_ABI_VERSION = Int32(3)
+
+version() = ccall((:rcw_version, LIB), Int32, ())
 
 # mirrors `struct rcw_config` (include/rcw_b200.h); isbits, same field order and C layout
 struct RcwConfig
@@ -68,6 +73,8 @@ end
 mutable struct BatchedSingleRoom <: RCW.AbstractGame
     handle::Ptr{Cvoid}
     num_envs::Int
+    height_tile_map_tu::Int
+    width_tile_map_tu::Int
     num_rays::Int
     height_camera_view_pu::Int
     obs_format::Int32
@@ -101,6 +108,7 @@ function BatchedSingleRoom(;
         result_ring = 0,
     )
     T === Float32 || error("librcw_b200 computes in Float32 (the reference default, single_room.jl:43)")
+    version() == RCW_ABI_VERSION || error("librcw_b200 ABI $(version()), this binding was written for $(RCW_ABI_VERSION)")
 
     # the reference's own direction table (single_room.jl:65-69), so that cos/sin come from Julia
     directions = Matrix{Float32}(undef, 2, num_directions)
@@ -126,7 +134,8 @@ function BatchedSingleRoom(;
         check(ccall((:rcw_create, LIB), Int32, (Ref{RcwConfig}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
                     cfg, directions, handle))
     end
-    env = BatchedSingleRoom(handle[], num_envs, num_rays, height_camera_view_pu, Int32(obs_format),
+    env = BatchedSingleRoom(handle[], num_envs, height_tile_map_tu, width_tile_map_tu, num_rays,
+                            height_camera_view_pu, Int32(obs_format),
                             Float32(goal_reward), zeros(Float32, num_envs), zeros(UInt8, num_envs))
     finalizer(e -> (e.handle != C_NULL && ccall((:rcw_destroy, LIB), Int32, (Ptr{Cvoid},), e.handle); e.handle = C_NULL), env)
     return env
@@ -226,15 +235,71 @@ function obs_device_ptr(env::BatchedSingleRoom)
     return ptr[], Int(total[]), Int(stride[])
 end
 
-# host copy of the observations of envs e0:e0+n-1 (1-based): UInt8[3, P, R, n] or UInt32[P, R, n]
-function copy_obs(env::BatchedSingleRoom, e0 = 1, n = env.num_envs)
+# dense host array for n envs in the handle's observation format:
+# RGB8 UInt8[3, P, R, n] | XRGB32 UInt32[P, R, n] (the reference's camera_view, :300) | GRAY8 UInt8[P, R, n] | COLUMNS UInt32[R, n]
+function _host_obs(env::BatchedSingleRoom, n, fmt = env.obs_format)
     P, R = env.height_camera_view_pu, env.num_rays
-    out = env.obs_format == RCW_OBS_RGB8 ? Array{UInt8}(undef, 3, P, R, n) : Array{UInt32}(undef, P, R, n)
+    fmt == RCW_OBS_RGB8 && return Array{UInt8}(undef, 3, P, R, n)
+    fmt == RCW_OBS_XRGB32 && return Array{UInt32}(undef, P, R, n)
+    fmt == RCW_OBS_GRAY8 && return Array{UInt8}(undef, P, R, n)
+    return Array{UInt32}(undef, R, n)
+end
+
+# host copy of the observations of envs e0:e0+n-1 (1-based)
+function copy_obs(env::BatchedSingleRoom, e0 = 1, n = env.num_envs)
+    out = _host_obs(env, n)
     GC.@preserve out begin
         check(ccall((:rcw_copy_obs, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
                     env.handle, Int64(e0 - 1), Int64(n), out))
     end
     return out
+end
+
+# the same for the frame of the given age of a frame ring (`frame_stack = K`): 0 = newest ... K - 1 = oldest
+function copy_obs_frame(env::BatchedSingleRoom, age::Integer, e0 = 1, n = env.num_envs)
+    out = _host_obs(env, n)
+    GC.@preserve out begin
+        check(ccall((:rcw_copy_obs_frame, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Cvoid}),
+                    env.handle, Int64(e0 - 1), Int64(n), Int32(age), out))
+    end
+    return out
+end
+
+# (frame_stack K, newest ring position (0-based), bytes between two positions of one env): the frame with
+# age a is at position mod(newest - a, K) of every env of the device buffer
+function obs_frames(env::BatchedSingleRoom)
+    k = Ref{Int32}(0); newest = Ref{Int32}(0); stride = Ref{Csize_t}(0)
+    check(ccall((:rcw_obs_frames, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ref{Csize_t}),
+                env.handle, k, newest, stride))
+    return Int(k[]), Int(newest[]), Int(stride[])
+end
+
+# device layout of one env of the observation buffer:
+# (env_stride_bytes, column_stride_bytes, column_bytes, bytes_per_pixel); columns are pitched to 32 bytes
+function obs_layout(env::BatchedSingleRoom)
+    es = Ref{Csize_t}(0); cs = Ref{Csize_t}(0); cb = Ref{Csize_t}(0); bpp = Ref{Int32}(0)
+    check(ccall((:rcw_obs_layout, LIB), Int32, (Ptr{Cvoid}, Ref{Csize_t}, Ref{Csize_t}, Ref{Csize_t}, Ref{Int32}),
+                env.handle, es, cs, cb, bpp))
+    return Int(es[]), Int(cs[]), Int(cb[]), Int(bpp[])
+end
+
+# Column words -> pixels on the device (the second half of update_camera_view!, single_room.jl:413-441).
+# `columns`: device pointer to n envs' UInt32 words (this handle's own observations when it was created with
+# obs_format = RCW_OBS_COLUMNS, or records a replay buffer kept), `columns_env_stride` bytes apart (0 = dense);
+# `dst`: device pointer to n images in `pixel_format`, laid out as `expanded_layout` says.  Only enqueues.
+function expand_columns!(env::BatchedSingleRoom, dst::Ptr{Cvoid}, columns::Ptr{Cvoid}, n::Integer;
+                         pixel_format = RCW_OBS_RGB8, columns_env_stride = 0)
+    check(ccall((:rcw_expand_columns, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Int64, Int32, Ptr{Cvoid}),
+                env.handle, columns, Csize_t(columns_env_stride), Int64(n), Int32(pixel_format), dst))
+    return nothing
+end
+
+# (env_stride_bytes, column_stride_bytes, column_bytes) of the images expand_columns! writes
+function expanded_layout(env::BatchedSingleRoom, pixel_format = RCW_OBS_RGB8)
+    es = Ref{Csize_t}(0); cs = Ref{Csize_t}(0); cb = Ref{Csize_t}(0)
+    check(ccall((:rcw_expanded_layout, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Csize_t}, Ref{Csize_t}, Ref{Csize_t}),
+                env.handle, Int32(pixel_format), es, cs, cb))
+    return Int(es[]), Int(cs[]), Int(cb[])
 end
 
 # host copy of the top views of envs e0:e0+n-1 (1-based): UInt32[H * pu, W * pu, n], the reference's top_view layout
@@ -245,6 +310,101 @@ function copy_top_view(env::BatchedSingleRoom, height_pu::Integer, width_pu::Int
                     env.handle, Int64(e0 - 1), Int64(n), out))
     end
     return out
+end
+
+# borrowed device pointer of the top views: UInt32 [env slots][W * pu columns][H * pu rows]
+function top_view_device_ptr(env::BatchedSingleRoom)
+    ptr = Ref{Ptr{Cvoid}}(C_NULL); total = Ref{Csize_t}(0); stride = Ref{Csize_t}(0)
+    check(ccall((:rcw_top_view_device_ptr, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Csize_t}, Ref{Csize_t}),
+                env.handle, ptr, total, stride))
+    return ptr[], Int(total[]), Int(stride[])
+end
+
+# ---- world fields (parity injection / inspection): the reference reads and writes them as
+#      world.player_position_wu, .player_direction_au, .goal_position, .reward, .done (single_room.jl:21-40)
+
+# (pos 2 x n Float32 [wu], dir n Int32 [au, 0-based], goal 2 x n Int32 [1-based tile], reward n Float32, done n UInt8)
+function get_state(env::BatchedSingleRoom)
+    n = env.num_envs
+    pos = Matrix{Float32}(undef, 2, n); dir = Vector{Int32}(undef, n); goal = Matrix{Int32}(undef, 2, n)
+    r = Vector{Float32}(undef, n); d = Vector{UInt8}(undef, n)
+    GC.@preserve pos dir goal r d begin
+        check(ccall((:rcw_get_state, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{UInt8}),
+                    env.handle, pos, dir, goal, r, d))
+    end
+    return (pos = pos, dir = dir, goal = goal, reward = r, done = d)
+end
+
+_ptr_or_null(::Nothing, T) = Ptr{T}(C_NULL)
+_ptr_or_null(a::Array{T}, ::Type{T}) where {T} = pointer(a)
+
+# overwrite any subset of the fields (`nothing` = keep); does not re-render: follow with RCW.cast_rays!(env)
+function set_state!(env::BatchedSingleRoom; pos = nothing, dir = nothing, goal = nothing, reward = nothing, done = nothing)
+    GC.@preserve pos dir goal reward done begin
+        check(ccall((:rcw_set_state, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{UInt8}),
+                    env.handle, _ptr_or_null(pos, Float32), _ptr_or_null(dir, Int32), _ptr_or_null(goal, Int32),
+                    _ptr_or_null(reward, Float32), _ptr_or_null(done, UInt8)))
+    end
+    return nothing
+end
+
+# world.ray_stop_position_tu (2 x R x n), ray_hit_dimension (R x n), ray_distance_wu (R x n), ray_directions_wu
+# (2 x R x n) of envs e0:e0+n-1 (1-based), single_room.jl:29-31,39 — debug / parity only
+function get_rays(env::BatchedSingleRoom, e0 = 1, n = env.num_envs)
+    R = env.num_rays
+    hit = Array{Int32}(undef, 2, R, n); dim = Matrix{Int32}(undef, R, n)
+    dist = Matrix{Float32}(undef, R, n); ray = Array{Float32}(undef, 2, R, n)
+    GC.@preserve hit dim dist ray begin
+        check(ccall((:rcw_get_rays, LIB), Int32,
+                    (Ptr{Cvoid}, Int64, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}),
+                    env.handle, Int64(e0 - 1), Int64(n), hit, dim, dist, ray))
+    end
+    return (hit = hit, dim = dim, dist = dist, ray = ray)
+end
+
+# tile_map[WALL, :, :] (single_room.jl:55-60) supplied by the host.  `wall`: H x W (one layer shared by the
+# batch) or H x W x num_envs (one per env), nonzero / true = wall; Julia's column-major order is the ABI's.
+# Does not re-render: follow with RCW.reset!(env) or RCW.cast_rays!(env).
+function set_wall_map!(env::BatchedSingleRoom, wall::AbstractArray{<:Union{Bool, Integer}})
+    H, W = env.height_tile_map_tu, env.width_tile_map_tu
+    bytes = convert(Array{UInt8}, wall .!= 0)
+    if size(bytes) == (H, W)
+        GC.@preserve bytes check(ccall((:rcw_set_wall_map, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), env.handle, bytes))
+    elseif size(bytes) == (H, W, env.num_envs)
+        GC.@preserve bytes check(ccall((:rcw_set_wall_maps, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), env.handle, bytes))
+    else
+        throw(DimensionMismatch("wall layer must be $(H) x $(W) or $(H) x $(W) x $(env.num_envs)"))
+    end
+    return nothing
+end
+
+# reset!(env) for the envs whose mask entry is true only (the others keep state and observation)
+function reset_masked!(env::BatchedSingleRoom, mask::AbstractVector{Bool})
+    length(mask) == env.num_envs || throw(DimensionMismatch("one mask entry per env"))
+    m = convert(Vector{UInt8}, mask)
+    GC.@preserve m begin
+        check(ccall((:rcw_reset, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}),
+                    env.handle, C_NULL, C_NULL, C_NULL, m))
+    end
+    return nothing
+end
+
+# blocks until everything enqueued on the handle has finished (and reports a deferred RCW_EACTION)
+sync(env::BatchedSingleRoom) = check(ccall((:rcw_sync, LIB), Int32, (Ptr{Cvoid},), env.handle))
+
+# the handle's cudaStream_t, e.g. to build a CUDA.CuStream for work that must follow the step
+function cuda_stream(env::BatchedSingleRoom)
+    s = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rcw_stream, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), env.handle, s))
+    return s[]
+end
+
+function launch_count(env::BatchedSingleRoom)
+    n = Ref{Int64}(0)
+    check(ccall((:rcw_launch_count, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), env.handle, n))
+    return n[]
 end
 
 # exact snapshot of the dynamic state (checkpoint / resume)
