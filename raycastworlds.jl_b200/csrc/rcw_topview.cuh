@@ -30,9 +30,11 @@ __device__ __forceinline__ void plane_set(uint32_t* plane, int i, int j, int Hp,
 }
 
 __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_constant__ TopViewParams p) {
-    // [wall layer][ray plane][player plane][palette 8 x u32][row info u16][column info u16][row-sector info u16][tile code u8]
+    // [wall layer][ray plane][player plane][palette 8 x u32][line list R x int2][tile colour (W + 1) x H u32]
+    // [row info u16][column info u16][row-sector info u16][column offset u16]
     extern __shared__ __align__(128) uint32_t s_top[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_nlines;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, Hp = p.Hp, Wp = p.Wp, pu = p.pu, R = p.R;
     const uint32_t SB = plane_col_bits(Hp);                    // bits per plane column
@@ -41,10 +43,12 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     uint32_t* const s_ray = s_map + p.map_words;
     uint32_t* const s_player = s_ray + plane_words;
     uint32_t* const s_pal = s_player + plane_words;
-    uint16_t* const s_row = reinterpret_cast<uint16_t*>(s_pal + 8);                // [Hp] tile row | border << 15
+    int2* const s_line = reinterpret_cast<int2*>(s_pal + 8);                       // [R] end pixels of the distinct segments
+    uint32_t* const s_tilec = reinterpret_cast<uint32_t*>(s_line + R);             // [W + 1][H] tile colour; column W = border colour
+    uint16_t* const s_row = reinterpret_cast<uint16_t*>(s_tilec + (size_t)(W + 1) * H);   // [Hp] tile row | border << 15
     uint16_t* const s_colinfo = s_row + ((Hp + 1) & ~1);                           // [Wp] tile column | border << 15
     uint16_t* const s_rowsec = s_colinfo + ((Wp + 1) & ~1);                        // [Hp / 8] tile row | first px border << 14 | last << 15
-    uint8_t* const s_tile = reinterpret_cast<uint8_t*>(s_rowsec + (((Hp >> 3) + 2) & ~1)); // [W][H] colour code of the tile
+    uint16_t* const s_coloff = s_rowsec + (((Hp >> 3) + 2) & ~1);                  // [Wp] H * tile column, or H * W for a border column
 
     const uint32_t env_rel = blockIdx.x;
     const int64_t env = p.env_first + env_rel;
@@ -52,6 +56,7 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
 
     // ---- this env's wall layer: one TMA bulk copy; planes cleared and tables built meanwhile
     if (tid == 0) {
+        s_nlines = 0u;
         mbar_init(&s_bar, 1);
         mbar_arrive_expect_tx(&s_bar, (uint32_t)p.map_words * 4u);
         bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.map_words * 4u, &s_bar);
@@ -71,7 +76,9 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     }
     for (int j = tid; j < Wp; j += kTopThreads) {
         const int t = j / pu, r = j - t * pu;
-        s_colinfo[j] = (uint16_t)(t | ((r == 0 || r == pu - 1) ? 0x8000 : 0));
+        const bool border = r == 0 || r == pu - 1;
+        s_colinfo[j] = (uint16_t)(t | (border ? 0x8000 : 0));
+        s_coloff[j] = (uint16_t)(H * (border ? W : t));
     }
     for (int q = tid; q < (Hp >> 3); q += kTopThreads) {        // used when pu % 8 == 0: a sector lies in one tile
         const int i = q << 3, t = i / pu, r = i - t * pu;
@@ -81,13 +88,16 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     mbar_wait(&s_bar, 0);
 
     // ---- draw_tile_map! colour of every tile: findfirst over the layers WALL, GOAL (:355-360)
-    for (int t = tid; t < H * W; t += kTopThreads) {
+    for (int t = tid; t < H * (W + 1); t += kTopThreads) {
         const int j0 = t / H, i0 = t - j0 * H;
-        s_tile[t] = wall_bit(s_map, p.wpr, i0, j0) ? RCW_TOP_COLOR_WALL
-                                                   : ((i0 == gi0 && j0 == gj0) ? RCW_TOP_COLOR_GOAL : RCW_TOP_COLOR_EMPTY);
+        int code = RCW_TOP_COLOR_BORDER;                      // pseudo tile column W: what a border column of the image shows
+        if (j0 < W)
+            code = wall_bit(s_map, p.wpr, i0, j0) ? RCW_TOP_COLOR_WALL
+                                                  : ((i0 == gi0 && j0 == gj0) ? RCW_TOP_COLOR_GOAL : RCW_TOP_COLOR_EMPTY);
+        s_tilec[t] = p.palette[code];
     }
 
-    // ---- the ray segments (:474-478): lane <-> ray, Bresenham into the ray plane
+    // ---- the ray segments (:474-478), first half: lane <-> ray, where each ray stops, as a pixel
     const float fpu = (float)pu;
     const int ip = wu_to_pu(x, fpu), jp = wu_to_pu(y, fpu);           // :469
     const int groups = (R + 31) >> 5;
@@ -98,40 +108,66 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
         const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
         const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
-        // [EXT SimpleDraw] Line(point1, point2): Bresenham, all octants, both end points drawn; the walk
-        // reaches (i2, j2) after exactly max(|di|, |dj|) steps.  The warp walks its 32 lines in lock step up
-        // to the longest one.  lane <-> ray, and adjacent rays share most of their pixels (they leave the same
-        // pixel with slopes that differ by 1/400): a lane whose pixel equals its lower neighbour's leaves the
-        // shared-memory atomic to that neighbour.
-        const int di = abs(i2 - ip), dj = -abs(j2 - jp);
+        // All segments start at the player's pixel, and neighbouring rays stop a fraction of a pixel apart (0.2 - 0.6
+        // px at the usual distances): a ray whose stop pixel equals its lower neighbour's draws exactly the same
+        // pixels and is dropped here.  The distinct segments (about 4 in 10 at the defaults) are appended to one
+        // list per env — their order only decides which lane sets a shared bit, not the picture.
+        const int i2_below = __shfl_up_sync(0xFFFFFFFFu, i2, 1), j2_below = __shfl_up_sync(0xFFFFFFFFu, j2, 1);
+        const bool distinct = (ray < R) & ((lane == 0) | (i2 != i2_below) | (j2 != j2_below));
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, distinct);
+        uint32_t base = 0u;
+        if (lane == 0) base = atomicAdd(&s_nlines, (uint32_t)__popc(ballot));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (distinct) s_line[base + (uint32_t)__popc(ballot & ((1u << lane) - 1u))] = make_int2(i2, j2);
+    }
+    __syncthreads();          // the list is complete (and every tile colour written)
+
+    // ---- second half: lane <-> distinct segment.  [EXT SimpleDraw] Line(point1, point2): Bresenham, all octants,
+    //      both end points drawn; the walk reaches the end after exactly max(|di|, |dj|) steps, the major axis
+    //      advancing in every one of them (the all-octant form `e2 = 2 err; if e2 >= dj ...; if e2 <= di ...`
+    //      reduces to that), so one decision variable suffices: with M / m the larger / smaller of |di|, |dj| and
+    //      F = 2 err' - M (err' = err for |di| >= |dj|, -err otherwise; F starts at M - 2 m), the minor axis steps
+    //      iff F <= 0, and F += step ? 2 (M - m) : -2 m — the same pixels, ties included, in both octant families.
+    //      The warp walks its 32 segments in lock step up to the longest one; a lane whose pixel equals its lower
+    //      neighbour's (neighbouring segments share their first pixels) leaves the shared-memory atomic to it.
+    const int n_lines = (int)s_nlines;
+    for (int l0 = warp * 32; l0 < n_lines; l0 += kTopThreads) {
+        const bool have = l0 + lane < n_lines;
+        const int2 end = s_line[min(l0 + lane, n_lines - 1)];
+        const int i2 = end.x, j2 = end.y;
+        const int di = abs(i2 - ip), dj = abs(j2 - jp);
         const int si = ip < i2 ? 1 : -1, sj = jp < j2 ? 1 : -1;
-        const int n = ray < R ? max(di, -dj) : -1;                // steps of this lane's line; -1: no line
+        const int n = have ? max(di, dj) : -1;                    // steps of this lane's segment; -1: none
         const int n_max = __reduce_max_sync(0xFFFFFFFFu, n);
         const int n_below = __shfl_up_sync(0xFFFFFFFFu, n, 1);
         // both end points inside the image => every pixel of the line is (it stays in their bounding box)
         const bool clip = (ip < 1) | (ip > Hp) | (jp < 1) | (jp > Wp) | (i2 < 1) | (i2 > Hp) | (j2 < 1) | (j2 > Wp);
-        int err = di + dj;
-        if (!__any_sync(0xFFFFFFFFu, clip && n >= 0)) {
+        if (!__any_sync(0xFFFFFFFFu, clip && have)) {
+            const bool i_major = di >= dj;
+            const int M = max(di, dj), m = min(di, dj);
+            const int bit_si = si, bit_sj = sj * (int)SB;       // bit index steps of the two axes
+            const int adv_major = i_major ? bit_si : bit_sj, adv_both = bit_si + bit_sj;
+            const int f_stay = -2 * m, f_step = 2 * (M - m);
+            const int n_dup = lane > 0 ? n_below : -1;          // the lower neighbour still draws while k <= n_dup
+            int F = M - 2 * m;
             uint32_t idx = (uint32_t)(jp - 1) * SB + (uint32_t)(ip - 1);
-            const int idx_si = si, idx_sj = sj * (int)SB;
 #pragma unroll 2
             for (int k = 0; k <= n_max; ++k) {
                 const uint32_t below = __shfl_up_sync(0xFFFFFFFFu, idx, 1);
-                const bool dup = (lane > 0) & (k <= n_below) & (below == idx);
+                const bool dup = (k <= n_dup) & (below == idx);
                 if ((k <= n) & !dup) atomicOr(s_ray + (idx >> 5), 1u << (idx & 31u));
-                const int e2 = 2 * err;
-                const bool step_i = e2 >= dj, step_j = e2 <= di;
-                err += (step_i ? dj : 0) + (step_j ? di : 0);
-                idx += (uint32_t)((step_i ? idx_si : 0) + (step_j ? idx_sj : 0));
+                const bool step = F <= 0;
+                F += step ? f_step : f_stay;
+                idx += (uint32_t)(step ? adv_both : adv_major);
             }
-        } else if (n >= 0) {
-            int i = ip, j = jp;
+        } else if (have) {
+            int i = ip, j = jp, err = di - dj;
             for (int k = n;; --k) {
                 plane_set(s_ray, i, j, Hp, Wp, SB);
                 if (k == 0) break;
                 const int e2 = 2 * err;
-                if (e2 >= dj) {
-                    err += dj;
+                if (e2 >= -dj) {
+                    err -= dj;
                     i += si;
                 }
                 if (e2 <= di) {
@@ -182,11 +218,42 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         const uint32_t SPC = (uint32_t)Hp >> 3, SBy = SB >> 3;   // sectors / plane bytes per column
         uint32_t j0 = (uint32_t)tid / SPC, q = (uint32_t)tid - j0 * SPC;
         const uint32_t adv_j = kTopThreads / SPC, adv_q = kTopThreads - adv_j * SPC;
+        if (adv_q == 0) {
+            // the CTA covers whole columns per sweep (256 % (Hp / 8) == 0, e.g. the default 256 rows): a thread
+            // stays on its rows, so the tile row and the border ends of its sectors are fixed
+            const uint32_t rs = s_rowsec[q];
+            const uint32_t* const tile_row = s_tilec + (rs & 0x3FFFu);
+            const bool border_first = (rs & 0x4000u) != 0u, border_last = (rs & 0x8000u) != 0u;
+            const uint8_t* rayp = ray_bytes + q + j0 * SBy;
+            const uint8_t* playerp = player_bytes + q + j0 * SBy;
+            uint8_t* dst = img + ((size_t)tid << 5);
+#pragma unroll 2
+            for (; j0 < (uint32_t)Wp; j0 += adv_j) {
+                const uint32_t base = tile_row[s_coloff[j0]];
+                const uint32_t rb = *rayp, pb = *playerp;
+                uint32_t px[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) px[k] = base;
+                if (border_first) px[0] = border_c;
+                if (border_last) px[7] = border_c;
+                if (rb | pb) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        px[k] = ((rb >> k) & 1u) ? ray_c : px[k];
+                        px[k] = ((pb >> k) & 1u) ? player_c : px[k];
+                    }
+                }
+                store_stream32(dst, make_uint4(px[0], px[1], px[2], px[3]), make_uint4(px[4], px[5], px[6], px[7]));
+                rayp += adv_j * SBy;
+                playerp += adv_j * SBy;
+                dst += (size_t)kTopThreads << 5;
+            }
+            return;
+        }
 #pragma unroll 2
         for (uint32_t s = tid; s < n_sec; s += kTopThreads) {
-            const uint32_t rs = s_rowsec[q], cinfo = s_colinfo[j0];
-            const uint32_t tile_c = s_pal[s_tile[(rs & 0x3FFFu) + (uint32_t)H * (cinfo & 0x7FFFu)]];
-            const uint32_t base = (cinfo & 0x8000u) ? border_c : tile_c;
+            const uint32_t rs = s_rowsec[q];
+            const uint32_t base = s_tilec[(rs & 0x3FFFu) + s_coloff[j0]];
             const uint32_t rb = ray_bytes[j0 * SBy + q], pb = player_bytes[j0 * SBy + q];
             uint32_t px[8];
 #pragma unroll
@@ -220,8 +287,7 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         for (int k = 0; k < 8; ++k) {
             const uint32_t jc = min(j0, (uint32_t)Wp - 1u);
             const uint32_t rinfo = s_row[i0], cinfo = s_colinfo[jc];
-            const uint32_t code = s_tile[(rinfo & 0x7FFFu) + (uint32_t)H * (cinfo & 0x7FFFu)];
-            uint32_t c = ((rinfo | cinfo) & 0x8000u) ? border_c : s_pal[code];
+            uint32_t c = ((rinfo | cinfo) & 0x8000u) ? border_c : s_tilec[(rinfo & 0x7FFFu) + (uint32_t)H * (cinfo & 0x7FFFu)];
             const uint32_t bit = jc * SB + i0;
             c = ((s_ray[bit >> 5] >> (bit & 31u)) & 1u) ? ray_c : c;
             c = ((s_player[bit >> 5] >> (bit & 31u)) & 1u) ? player_c : c;
@@ -236,15 +302,16 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     }
 }
 
-size_t top_view_smem_bytes(int H, int W, int pu, int map_words) {
+size_t top_view_smem_bytes(int H, int W, int R, int pu, int map_words) {
     const size_t Hp = (size_t)H * pu, Wp = (size_t)W * pu;
     const size_t plane_words = (Wp * (plane_col_bits((int)Hp) >> 5) + 1) & ~(size_t)1;
-    return (size_t)map_words * 4 + 2 * plane_words * 4 + 8 * 4 + 2 * ((Hp + 1) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1) +
-           2 * (((Hp >> 3) + 2) & ~(size_t)1) + (((size_t)H * W + 15) & ~(size_t)15);
+    return (size_t)map_words * 4 + 2 * plane_words * 4 + 8 * 4 + (size_t)R * 8 + (size_t)(W + 1) * H * 4 +
+           2 * ((Hp + 1) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1) + 2 * (((Hp >> 3) + 2) & ~(size_t)1) +
+           2 * ((Wp + 1) & ~(size_t)1);
 }
 
 cudaError_t launch_top_view(const TopViewParams& p, cudaStream_t s) {
-    const size_t smem = top_view_smem_bytes(p.H, p.W, p.pu, p.map_words);
+    const size_t smem = top_view_smem_bytes(p.H, p.W, p.R, p.pu, p.map_words);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(top_view_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
