@@ -470,7 +470,7 @@ static int32_t check_top_view_fits(const rcw_config& c) {
     const int64_t Hp = (int64_t)c.height_tile_map_tu * c.pu_per_tu, Wp = (int64_t)c.width_tile_map_tu * c.pu_per_tu;
     const int map_words = ((c.height_tile_map_tu * ((c.width_tile_map_tu + 31) / 32) + 3) / 4) * 4;
     if (Hp > 32767 || Wp > 32767 || Hp * Wp >= (1LL << 28) ||
-        top_view_smem_bytes(c.height_tile_map_tu, c.width_tile_map_tu, c.num_rays, c.pu_per_tu, map_words) > 200 * 1024)
+        top_view_smem_bytes(c.height_tile_map_tu, c.width_tile_map_tu, c.num_rays, c.pu_per_tu, c.player_radius_wu, map_words) > 200 * 1024)
         return fail(RCW_ESIZE, "a top view of %lldx%lld pixels does not fit the renderer's shared memory; "
                     "lower pu_per_tu", (long long)Hp, (long long)Wp);
     return RCW_OK;

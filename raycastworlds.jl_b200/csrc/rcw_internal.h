@@ -201,7 +201,7 @@ cudaError_t launch_expand_columns(const FrameParams& p, int pixel_format, int ct
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s);
 // state `from` -> state `to` for envs [env0, env0 + n): makes a range step visible in the buffer it read
 cudaError_t launch_commit_range(const StateRef& from, const StateRef& to, int64_t env0, int64_t n, cudaStream_t s);
-size_t top_view_smem_bytes(int H, int W, int R, int pu, int map_words);
+size_t top_view_smem_bytes(int H, int W, int R, int pu, float radius, int map_words);
 cudaError_t launch_top_view(const TopViewParams& p, cudaStream_t s);
 cudaError_t upload_dir_slot(int slot, const float2* host_dirs, int n, cudaStream_t s);
 

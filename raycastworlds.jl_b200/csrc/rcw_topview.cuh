@@ -7,10 +7,11 @@
 // is not vendored: they are restated from the algorithms that package documents (Bresenham line over all
 // octants, midpoint circle), every pixel bounds-checked — UNPINNED like the DDA.
 //
-// One CTA draws one env.  The image is never read back from HBM: rays and circle are rasterised into two
-// bit planes in shared memory (one bit per pixel each, atomicOr), then the CTA streams the whole image out
-// once, in whole 32-byte sectors, composing every pixel as circle > ray > tile border > tile colour — the
-// draw order of the reference (:472, :474-478, :480).  512 KB per env at the defaults: HBM-write bound.
+// One CTA draws one env.  The image is never read back from HBM: the ray segments are rasterised into a bit
+// plane in shared memory (one bit per pixel, atomicOr), the circle into a small bitmap of its bounding box,
+// then the CTA streams the whole image out once, in whole 32-byte sectors, composing every pixel as
+// circle > ray > tile border > tile colour — the draw order of the reference (:472, :474-478, :480).
+// 512 KB per env at the defaults: HBM-write bound.
 
 constexpr int kTopThreads = 256;
 
@@ -29,23 +30,32 @@ __device__ __forceinline__ void plane_set(uint32_t* plane, int i, int j, int Hp,
     }
 }
 
-__global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_constant__ TopViewParams p) {
-    // [wall layer][ray plane][player plane][palette 8 x u32][line list R x int2][tile colour (W + 1) x H u32]
+// The player's circle lives in a bitmap of its bounding box: D = 2 rp + 1 columns of D bits (rp = radius in pixels),
+// each column in CW = ceil(D / 32) words; local pixel (ci, cj) = (i - ip + rp, j - jp + rp).
+__host__ __device__ __forceinline__ uint32_t circle_words(int rp) {
+    const uint32_t D = 2u * (uint32_t)rp + 1u;
+    return D * ((D + 31u) >> 5);
+}
+
+__global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_constant__ TopViewParams p) {
+    // [wall layer][ray plane][palette 8 x u32][line list R x int2][tile colour (W + 1) x H u32][circle bitmap]
     // [row info u16][column info u16][row-sector info u16][column offset u16]
     extern __shared__ __align__(128) uint32_t s_top[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_nlines;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, Hp = p.Hp, Wp = p.Wp, pu = p.pu, R = p.R;
+    const float fpu = (float)pu;
+    const int rp = wu_to_pu(p.radius, fpu);                    // :470, the same for every env
     const uint32_t SB = plane_col_bits(Hp);                    // bits per plane column
-    const uint32_t plane_words = ((uint32_t)Wp * (SB >> 5) + 1u) & ~1u;   // even: the two planes are cleared as uint4
+    const uint32_t plane_words = ((uint32_t)Wp * (SB >> 5) + 3u) & ~3u;   // the plane is cleared as uint4
     uint32_t* const s_map = s_top;
     uint32_t* const s_ray = s_map + p.map_words;
-    uint32_t* const s_player = s_ray + plane_words;
-    uint32_t* const s_pal = s_player + plane_words;
+    uint32_t* const s_pal = s_ray + plane_words;
     int2* const s_line = reinterpret_cast<int2*>(s_pal + 8);                       // [R] end pixels of the distinct segments
     uint32_t* const s_tilec = reinterpret_cast<uint32_t*>(s_line + R);             // [W + 1][H] tile colour; column W = border colour
-    uint16_t* const s_row = reinterpret_cast<uint16_t*>(s_tilec + (size_t)(W + 1) * H);   // [Hp] tile row | border << 15
+    uint32_t* const s_circ = s_tilec + (size_t)(W + 1) * H;                        // [2 rp + 1][CW] the circle's bounding box
+    uint16_t* const s_row = reinterpret_cast<uint16_t*>(s_circ + circle_words(rp));   // [Hp] tile row | border << 15
     uint16_t* const s_colinfo = s_row + ((Hp + 1) & ~1);                           // [Wp] tile column | border << 15
     uint16_t* const s_rowsec = s_colinfo + ((Wp + 1) & ~1);                        // [Hp / 8] tile row | first px border << 14 | last << 15
     uint16_t* const s_coloff = s_rowsec + (((Hp >> 3) + 2) & ~1);                  // [Wp] H * tile column, or H * W for a border column
@@ -62,8 +72,8 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.map_words * 4u, &s_bar);
     }
     {
-        uint4* const z = reinterpret_cast<uint4*>(s_ray);       // both planes, contiguous, 16-byte aligned
-        for (uint32_t k = tid; k < plane_words >> 1; k += kTopThreads) z[k] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* const z = reinterpret_cast<uint4*>(s_ray);       // 16-byte aligned: map_words is a multiple of 4
+        for (uint32_t k = tid; k < plane_words >> 2; k += kTopThreads) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
     const float x = __ldg(p.st.pos_x + env), y = __ldg(p.st.pos_y + env);
     const int au = __ldg(p.st.dir_au + env);
@@ -84,7 +94,29 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         const int i = q << 3, t = i / pu, r = i - t * pu;
         s_rowsec[q] = (uint16_t)(t | (r == 0 ? 0x4000 : 0) | (r + 7 == pu - 1 ? 0x8000 : 0));
     }
-    __syncthreads();          // mbarrier initialised, planes cleared
+    // ---- the player (:480): [EXT SimpleDraw] Circle(Point(i - r, j - r), 2r + 1) = midpoint circle of radius r,
+    //      drawn by one thread of the last warp while the others build the tables
+    const uint32_t CW = (2u * (uint32_t)rp + 32u) >> 5;        // words per column of the circle bitmap
+    if (tid == kTopThreads - 1) {
+        for (uint32_t k = 0; k < circle_words(rp); ++k) s_circ[k] = 0u;
+        auto set = [&](int da, int db) {                        // pixel (ip + da, jp + db)
+            const uint32_t ci = (uint32_t)(da + rp), cj = (uint32_t)(db + rp);
+            s_circ[cj * CW + (ci >> 5)] |= 1u << (ci & 31u);
+        };
+        int a = 0, b = rp, d = 1 - rp;
+        while (a <= b) {
+            set(a, b), set(-a, b), set(a, -b), set(-a, -b);
+            set(b, a), set(-b, a), set(b, -a), set(-b, -a);
+            if (d < 0) {
+                d += 2 * a + 3;
+            } else {
+                d += 2 * (a - b) + 5;
+                b -= 1;
+            }
+            a += 1;
+        }
+    }
+    __syncthreads();          // mbarrier initialised, plane cleared
     mbar_wait(&s_bar, 0);
 
     // ---- draw_tile_map! colour of every tile: findfirst over the layers WALL, GOAL (:355-360)
@@ -98,7 +130,6 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     }
 
     // ---- the ray segments (:474-478), first half: lane <-> ray, where each ray stops, as a pixel
-    const float fpu = (float)pu;
     const int ip = wu_to_pu(x, fpu), jp = wu_to_pu(y, fpu);           // :469
     const int groups = (R + 31) >> 5;
     for (int g = warp; g < groups; g += kTopThreads / 32) {
@@ -178,28 +209,6 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         }
     }
 
-    // ---- the player (:480): [EXT SimpleDraw] Circle(Point(i - r, j - r), 2r + 1) = midpoint circle of radius r
-    if (tid == 0) {
-        const int rp = wu_to_pu(p.radius, fpu);                        // :470
-        int a = 0, b = rp, d = 1 - rp;
-        while (a <= b) {
-            plane_set(s_player, ip + a, jp + b, Hp, Wp, SB);
-            plane_set(s_player, ip - a, jp + b, Hp, Wp, SB);
-            plane_set(s_player, ip + a, jp - b, Hp, Wp, SB);
-            plane_set(s_player, ip - a, jp - b, Hp, Wp, SB);
-            plane_set(s_player, ip + b, jp + a, Hp, Wp, SB);
-            plane_set(s_player, ip - b, jp + a, Hp, Wp, SB);
-            plane_set(s_player, ip + b, jp - a, Hp, Wp, SB);
-            plane_set(s_player, ip - b, jp - a, Hp, Wp, SB);
-            if (d < 0) {
-                d += 2 * a + 3;
-            } else {
-                d += 2 * (a - b) + 5;
-                b -= 1;
-            }
-            a += 1;
-        }
-    }
     __syncthreads();
 
     // ---- stream the image out: one 32-byte sector (8 consecutive pixels of the column-major image) per
@@ -208,78 +217,15 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
     if (slot >= p.window) slot -= p.window;
     uint8_t* const img = p.top + (size_t)slot * p.env_stride;
     const uint8_t* const ray_bytes = reinterpret_cast<const uint8_t*>(s_ray);
-    const uint8_t* const player_bytes = reinterpret_cast<const uint8_t*>(s_player);
     const uint32_t border_c = s_pal[RCW_TOP_COLOR_BORDER], ray_c = s_pal[RCW_TOP_COLOR_RAY],
                    player_c = s_pal[RCW_TOP_COLOR_PLAYER];
     const uint32_t L = (uint32_t)Hp * (uint32_t)Wp;          // pixels
     const uint32_t n_sec = (L + 7u) >> 3;
-    if (((Hp | pu) & 7) == 0) {
-        // a sector lies inside one tile of one image column: one colour, borders only at its two ends
-        const uint32_t SPC = (uint32_t)Hp >> 3, SBy = SB >> 3;   // sectors / plane bytes per column
-        uint32_t j0 = (uint32_t)tid / SPC, q = (uint32_t)tid - j0 * SPC;
-        const uint32_t adv_j = kTopThreads / SPC, adv_q = kTopThreads - adv_j * SPC;
-        if (adv_q == 0) {
-            // the CTA covers whole columns per sweep (256 % (Hp / 8) == 0, e.g. the default 256 rows): a thread
-            // stays on its rows, so the tile row and the border ends of its sectors are fixed
-            const uint32_t rs = s_rowsec[q];
-            const uint32_t* const tile_row = s_tilec + (rs & 0x3FFFu);
-            const bool border_first = (rs & 0x4000u) != 0u, border_last = (rs & 0x8000u) != 0u;
-            const uint8_t* rayp = ray_bytes + q + j0 * SBy;
-            const uint8_t* playerp = player_bytes + q + j0 * SBy;
-            uint8_t* dst = img + ((size_t)tid << 5);
-#pragma unroll 2
-            for (; j0 < (uint32_t)Wp; j0 += adv_j) {
-                const uint32_t base = tile_row[s_coloff[j0]];
-                const uint32_t rb = *rayp, pb = *playerp;
-                uint32_t px[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) px[k] = base;
-                if (border_first) px[0] = border_c;
-                if (border_last) px[7] = border_c;
-                if (rb | pb) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        px[k] = ((rb >> k) & 1u) ? ray_c : px[k];
-                        px[k] = ((pb >> k) & 1u) ? player_c : px[k];
-                    }
-                }
-                store_stream32(dst, make_uint4(px[0], px[1], px[2], px[3]), make_uint4(px[4], px[5], px[6], px[7]));
-                rayp += adv_j * SBy;
-                playerp += adv_j * SBy;
-                dst += (size_t)kTopThreads << 5;
-            }
-            return;
-        }
-#pragma unroll 2
-        for (uint32_t s = tid; s < n_sec; s += kTopThreads) {
-            const uint32_t rs = s_rowsec[q];
-            const uint32_t base = s_tilec[(rs & 0x3FFFu) + s_coloff[j0]];
-            const uint32_t rb = ray_bytes[j0 * SBy + q], pb = player_bytes[j0 * SBy + q];
-            uint32_t px[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) px[k] = base;
-            if (rs & 0x4000u) px[0] = border_c;
-            if (rs & 0x8000u) px[7] = border_c;
-            if (rb | pb) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    px[k] = ((rb >> k) & 1u) ? ray_c : px[k];
-                    px[k] = ((pb >> k) & 1u) ? player_c : px[k];
-                }
-            }
-            store_stream32(img + ((size_t)s << 5), make_uint4(px[0], px[1], px[2], px[3]),
-                           make_uint4(px[4], px[5], px[6], px[7]));
-            j0 += adv_j;
-            q += adv_q;
-            if (q >= SPC) {
-                q -= SPC;
-                ++j0;
-            }
-        }
-        return;
-    }
-    // any size: pixel by pixel through the row / column tables
-    for (uint32_t s = tid; s < n_sec; s += kTopThreads) {
+    const int ci0 = ip - 1 - rp, cj0 = jp - 1 - rp;          // 0-based image position of the circle bitmap's corner
+    const uint32_t D = 2u * (uint32_t)rp + 1u;
+
+    // sector s of any image size, pixel by pixel through the row / column tables, circle included
+    auto store_sector_by_pixel = [&](uint32_t s) {
         const uint32_t idx0 = s << 3;
         uint32_t j0 = idx0 / (uint32_t)Hp, i0 = idx0 - j0 * (uint32_t)Hp;
         uint32_t px[8];
@@ -290,7 +236,8 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
             uint32_t c = ((rinfo | cinfo) & 0x8000u) ? border_c : s_tilec[(rinfo & 0x7FFFu) + (uint32_t)H * (cinfo & 0x7FFFu)];
             const uint32_t bit = jc * SB + i0;
             c = ((s_ray[bit >> 5] >> (bit & 31u)) & 1u) ? ray_c : c;
-            c = ((s_player[bit >> 5] >> (bit & 31u)) & 1u) ? player_c : c;
+            const uint32_t ci = i0 - (uint32_t)ci0, cj = jc - (uint32_t)cj0;
+            if (ci < D && cj < D && ((s_circ[cj * CW + (ci >> 5)] >> (ci & 31u)) & 1u)) c = player_c;
             px[k] = (idx0 + (uint32_t)k < L) ? c : 0u;    // bytes behind the last pixel are padding
             if (++i0 == (uint32_t)Hp) {                    // next column of the image
                 i0 = 0;
@@ -299,19 +246,98 @@ __global__ void __launch_bounds__(kTopThreads) top_view_kernel(const __grid_cons
         }
         store_stream32(img + ((size_t)s << 5), make_uint4(px[0], px[1], px[2], px[3]),
                        make_uint4(px[4], px[5], px[6], px[7]));
+    };
+
+    if (((Hp | pu) & 7) != 0) {
+        for (uint32_t s = tid; s < n_sec; s += kTopThreads) store_sector_by_pixel(s);
+        return;
+    }
+
+    // pu and Hp multiples of 8: a sector lies inside one tile of one image column — one colour, borders only at
+    // its two ends.  The sweep leaves the circle out; the few sectors it touches are rewritten afterwards.
+    {
+        const uint32_t SPC = (uint32_t)Hp >> 3, SBy = SB >> 3;   // sectors / plane bytes per column
+        uint32_t j0 = (uint32_t)tid / SPC, q = (uint32_t)tid - j0 * SPC;
+        const uint32_t adv_j = kTopThreads / SPC, adv_q = kTopThreads - adv_j * SPC;
+        if (adv_q == 0) {
+            // the CTA covers whole columns per sweep (256 % (Hp / 8) == 0, e.g. the default 256 rows): a thread
+            // stays on its rows, so the tile row and the border ends of its sectors are fixed
+            const uint32_t rs = s_rowsec[q];
+            const uint32_t* const tile_row = s_tilec + (rs & 0x3FFFu);
+            const bool border_first = (rs & 0x4000u) != 0u, border_last = (rs & 0x8000u) != 0u;
+            const uint8_t* rayp = ray_bytes + q + j0 * SBy;
+            uint8_t* dst = img + ((size_t)tid << 5);
+#pragma unroll 2
+            for (; j0 < (uint32_t)Wp; j0 += adv_j) {
+                const uint32_t base = tile_row[s_coloff[j0]];
+                const uint32_t rb = *rayp;
+                uint32_t px[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) px[k] = base;
+                if (border_first) px[0] = border_c;
+                if (border_last) px[7] = border_c;
+                if (rb) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) px[k] = ((rb >> k) & 1u) ? ray_c : px[k];
+                }
+                store_stream32(dst, make_uint4(px[0], px[1], px[2], px[3]), make_uint4(px[4], px[5], px[6], px[7]));
+                rayp += adv_j * SBy;
+                dst += (size_t)kTopThreads << 5;
+            }
+        } else {
+#pragma unroll 2
+            for (uint32_t s = tid; s < n_sec; s += kTopThreads) {
+                const uint32_t rs = s_rowsec[q];
+                const uint32_t base = s_tilec[(rs & 0x3FFFu) + s_coloff[j0]];
+                const uint32_t rb = ray_bytes[j0 * SBy + q];
+                uint32_t px[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) px[k] = base;
+                if (rs & 0x4000u) px[0] = border_c;
+                if (rs & 0x8000u) px[7] = border_c;
+                if (rb) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) px[k] = ((rb >> k) & 1u) ? ray_c : px[k];
+                }
+                store_stream32(img + ((size_t)s << 5), make_uint4(px[0], px[1], px[2], px[3]),
+                               make_uint4(px[4], px[5], px[6], px[7]));
+                j0 += adv_j;
+                q += adv_q;
+                if (q >= SPC) {
+                    q -= SPC;
+                    ++j0;
+                }
+            }
+        }
+    }
+    // the circle: the sectors under its bounding box once more, now complete.  The barrier orders the two stores
+    // of such a sector (both by this CTA), so the later one is what memory keeps.
+    __syncthreads();
+    {
+        const int j_lo = max(cj0, 0), j_hi = min(cj0 + 2 * rp, Wp - 1);
+        const int i_lo = max(ci0, 0), i_hi = min(ci0 + 2 * rp, Hp - 1);
+        if (j_lo <= j_hi && i_lo <= i_hi) {
+            const uint32_t q_lo = (uint32_t)i_lo >> 3, nq = ((uint32_t)i_hi >> 3) - q_lo + 1u;
+            const uint32_t n_fix = (uint32_t)(j_hi - j_lo + 1) * nq;
+            for (uint32_t t = tid; t < n_fix; t += kTopThreads) {
+                const uint32_t c = t / nq, k = t - c * nq;
+                store_sector_by_pixel(((uint32_t)j_lo + c) * ((uint32_t)Hp >> 3) + q_lo + k);
+            }
+        }
     }
 }
 
-size_t top_view_smem_bytes(int H, int W, int R, int pu, int map_words) {
+size_t top_view_smem_bytes(int H, int W, int R, int pu, float radius, int map_words) {
     const size_t Hp = (size_t)H * pu, Wp = (size_t)W * pu;
-    const size_t plane_words = (Wp * (plane_col_bits((int)Hp) >> 5) + 1) & ~(size_t)1;
-    return (size_t)map_words * 4 + 2 * plane_words * 4 + 8 * 4 + (size_t)R * 8 + (size_t)(W + 1) * H * 4 +
-           2 * ((Hp + 1) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1) + 2 * (((Hp >> 3) + 2) & ~(size_t)1) +
-           2 * ((Wp + 1) & ~(size_t)1);
+    const size_t plane_words = (Wp * (plane_col_bits((int)Hp) >> 5) + 3) & ~(size_t)3;
+    const int rp = (int)floorf(radius * (float)pu) + 1;          // wu_to_pu(radius, pu)
+    return (size_t)map_words * 4 + plane_words * 4 + 8 * 4 + (size_t)R * 8 + (size_t)(W + 1) * H * 4 +
+           (size_t)circle_words(rp) * 4 + 2 * ((Hp + 1) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1) +
+           2 * (((Hp >> 3) + 2) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1);
 }
 
 cudaError_t launch_top_view(const TopViewParams& p, cudaStream_t s) {
-    const size_t smem = top_view_smem_bytes(p.H, p.W, p.R, p.pu, p.map_words);
+    const size_t smem = top_view_smem_bytes(p.H, p.W, p.R, p.pu, p.radius, p.map_words);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(top_view_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
