@@ -101,3 +101,17 @@ def test_action_validation_in_host_mirror():
     assert rcw.NUM_ACTIONS == 4
     assert rcw.ACTION_NAMES == ("MOVE_FORWARD", "MOVE_BACKWARD", "TURN_LEFT", "TURN_RIGHT")
     assert issubclass(rcw.InvalidActionError, AssertionError)
+
+
+def test_julia_binding_covers_the_header():
+    """The Julia file cannot run here (no julia binary); what can be checked is that it binds every entry point the
+    header declares (rcw_config_init excepted: the binding fills the struct itself) and that its mirror of
+    rcw_config lists the C fields in the C order."""
+    jl = open(os.path.join(ROOT, "raycastworlds.jl_b200", "julia", "BatchedRayCastWorlds.jl")).read()
+    bound = set(re.findall(r"\(:(rcw_[a-z_0-9]+), LIB\)", jl))
+    assert bound == set(header_functions()) - {"rcw_config_init"}
+    struct = jl[jl.index("struct RcwConfig"):]
+    struct = struct[:struct.index("\nend")]
+    julia_fields = re.findall(r"^\s+([a-z_0-9]+)::", struct, flags=re.M)
+    assert julia_fields == [name for name, _ in _capi.RcwConfig._fields_]
+    assert f"const RCW_ABI_VERSION = Int32({_capi.ABI_VERSION})" in jl
