@@ -1,10 +1,15 @@
 """Seeded random configurations, CUDA path versus the oracle: geometry, camera, formats, palettes, wall layers,
 DDA switches, auto-reset, both step kernels (item kernel / env kernel), the top view.  Every comparison is
 bit-exact.  The seeds are fixed, so a failure names a reproducible case."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+# RCW_FUZZ_BASE=k shifts every seed by 1000 k: fresh cases for an extended run (the default set stays reproducible)
+BASE = 1000 * int(os.environ.get("RCW_FUZZ_BASE", "0"))
 
 
 @pytest.fixture(scope="module")
@@ -36,14 +41,15 @@ def draw_case(seed):
     return dict(H=H, W=W, N=N, R=R, P=P, fmt=fmt, radius=radius, incr=incr, sfov=sfov, cam_h=cam_h, pal=pal,
                 tie_le=bool(rng.integers(0, 2)), dist_post=bool(rng.integers(0, 2)),
                 maps=str(rng.choice(["default", "shared", "per_env"])), open_border=bool(rng.random() < 0.3),
-                env_kernel=bool(rng.integers(0, 2)), n=int(rng.integers(1, 41)), pu=int(rng.choice([1, 2, 3, 4, 8])),
+                env_kernel=bool(rng.integers(0, 2)), n=int(rng.integers(1, 41)),
+                pu=int(rng.choice([1, 2, 3, 4, 8] if seed < 100000 else [1, 3, 8, 8, 16, 24])),
                 seed=seed)
 
 
 @pytest.mark.parametrize("seed", range(72))
 def test_random_configuration_matches_oracle(rcw, oracle, monkeypatch, seed):
-    c = draw_case(1000 + seed)
-    rng = np.random.default_rng(5000 + seed)
+    c = draw_case(BASE + 1000 + seed)
+    rng = np.random.default_rng(BASE + 5000 + seed)
     monkeypatch.setenv("RCW_ENV_PER_WARP", "1" if c["env_kernel"] else "0")
     monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
     monkeypatch.setenv("RCW_PACKED_ACTIONS", str(seed % 2))      # host actions: kernel parameters / staged copy
@@ -129,6 +135,9 @@ def test_random_configuration_matches_oracle(rcw, oracle, monkeypatch, seed):
         np.testing.assert_array_equal(rays["hit"][e], worlds[e].ray_stop, err_msg=f"env {e} of {c}")
         np.testing.assert_array_equal(rays["dim"][e], worlds[e].ray_dim)
         np.testing.assert_array_equal(bits(rays["dist"][e]), bits(worlds[e].ray_dist))
+    if H * W * c["pu"] ** 2 > 600_000:       # beyond the top view renderer's shared memory (RCW_ESIZE): not this test
+        env.close()
+        return
     env.render_top_view()
     top = env.copy_top_view()
     for e in range(n):

@@ -157,3 +157,39 @@ def test_top_view_window_and_errors(rcw, oracle):
     with pytest.raises(rcw.RcwError):
         big.render_top_view()
     big.close()
+
+
+@pytest.mark.parametrize("H,W,pu,radius,rays", [
+    (4, 6, 32, 0.125, 96),      # 128 rows = 16 sectors per column: a thread keeps its rows (256 % 16 == 0)
+    (8, 5, 8, 0.3, 64),         # 64 rows = 8 sectors per column
+    (5, 7, 40, 0.45, 130),      # 200 rows = 25 sectors per column (256 % 25 != 0); circle radius 19 px: two bitmap words per column
+    (3, 9, 24, 0.4, 40),        # 72 rows = 9 sectors per column, tiles three sectors high
+    (9, 4, 64, 0.49, 33),       # 576 rows; circle radius 32 px
+])
+def test_one_tile_sector_sweeps_and_circle_rewrite(rcw, oracle, H, W, pu, radius, rays):
+    """The image sizes whose sectors lie inside one tile (pu and H * pu multiples of 8) take the fast sweeps and
+    write the circle afterwards (the sectors under its bounding box a second time).  Borderless maps let the
+    player stand at the image's edges: the circle is clipped there."""
+    kw = dict(height_tile_map_tu=H, width_tile_map_tu=W, num_rays=rays, height_camera_view_pu=32, pu_per_tu=pu,
+              player_radius_wu=radius, num_directions=24)
+    cfg = oracle.default_config(H=H, W=W, R=rays, P=32, pu_per_tu=pu, radius=np.float32(radius), N=24)
+    pos = np.array([[H / 2, W / 2], [0.05, 0.07], [H - 0.02, W - 0.3], [0.3, W - 0.01], [H - 0.4, 0.2],
+                    [H / 2 + 0.01, 0.5], [0.5, W / 2], [0.0, 0.0], [H - 0.001, W - 0.001]], np.float32)
+    n = len(pos)
+    au = (np.arange(n, dtype=np.int32) * 5) % 24
+    goal = np.tile(np.array([[2, 2]], np.int32), (n, 1))
+    walls = np.zeros((n, H, W), bool)                           # no walls at all: every ray leaves the map
+    walls[0, 0, :] = walls[0, -1, :] = walls[0, :, 0] = walls[0, :, -1] = True   # env 0: the usual closed room
+    env = rcw.BatchedSingleRoom(n, seed=3, auto_reset=False, **kw)
+    env.set_wall_maps(walls)
+    env.set_state(pos=pos, dir_au=au, goal=goal)
+    env.render_top_view()
+    top = env.copy_top_view()
+    for e in range(n):
+        w = oracle.World(cfg)
+        w.set_wall_map(walls[e])
+        w.set_state(pos[e, 0], pos[e, 1], au[e], goal[e, 0], goal[e, 1])
+        w.cast_rays()
+        w.update_top_view()
+        np.testing.assert_array_equal(top[e], w.top_view, err_msg=f"env {e}")
+    env.close()
