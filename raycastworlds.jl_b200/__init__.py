@@ -8,7 +8,8 @@ Because the directory name contains a dot, import it through the repo-root shim:
 from . import _capi, sharding  # noqa: F401
 from ._capi import InvalidActionError, RcwError  # noqa: F401
 from .single_room import (  # noqa: F401
-    ACTION_NAMES, NUM_ACTIONS, AbstractGame, BatchedSingleRoom, RLBaseEnv, SingleRoom, act,
-    action_space, get_action_names, is_terminated, reset, reward, state, state_space,
+    ACTION_KEYS, ACTION_NAMES, CAMERA_VIEW, NUM_ACTIONS, NUM_VIEWS, TOP_VIEW, AbstractGame, BatchedSingleRoom,
+    RLBaseEnv, SingleRoom, act, action_space, get_action_keys, get_action_names, is_terminated, play, reset, reward,
+    state, state_space,
 )
 from .sharding import max_over_ranks, reduce_episode_stats, shard_envs  # noqa: F401

@@ -28,6 +28,8 @@ from . import _capi
 
 NUM_ACTIONS = 4  # single_room.jl:19
 ACTION_NAMES = ("MOVE_FORWARD", "MOVE_BACKWARD", "TURN_LEFT", "TURN_RIGHT")  # single_room.jl:486
+ACTION_KEYS = ("W", "S", "A", "D")  # single_room.jl:485 (MFB.KB_KEY_W, KB_KEY_S, KB_KEY_A, KB_KEY_D)
+NUM_VIEWS, CAMERA_VIEW, TOP_VIEW = 2, 1, 2  # single_room.jl:237-239
 
 
 _FORMATS = (("rgb8", _capi.RCW_OBS_RGB8), ("xrgb32", _capi.RCW_OBS_XRGB32), ("gray8", _capi.RCW_OBS_GRAY8),
@@ -602,6 +604,55 @@ def act(env, action):
 
 def get_action_names(env):
     return (env.env if isinstance(env, RLBaseEnv) else env).get_action_names()
+
+
+def get_action_keys(env):
+    """get_action_keys(env) (single_room.jl:485): the keys play! binds to the four actions."""
+    return ACTION_KEYS
+
+
+def play(game: "SingleRoom", keys, on_frame=None):
+    """play!(game) (single_room.jl:488-572) without the MiniFB window: the same key handling, driven by an iterable
+    of key names instead of keyboard events.  W / S / A / D act, R resets (and zeroes the step
+    count), V switches between camera view and top view (clearing the frame buffer, :533-534), Q closes; any
+    other key is reported and ignored (:540).  After every key the current view is copied into the frame buffer
+    like copy_image_to_frame_buffer! does (utils.jl:64-73: the window shows image[i, j] at row i, column j) and
+    `on_frame(frame_buffer, info)` is called, info = what the reference prints with @show (:549-551).
+    Returns (frame_buffer, info) as they stand when the keys run out or Q is pressed.
+    frame_buffer: uint32 [max(view heights), max(view widths)] (:503-506)."""
+    if not isinstance(game, SingleRoom):
+        raise TypeError("play drives one SingleRoom, like the reference")
+    camera, top = game.camera_view, game.top_view
+    frame_buffer = np.zeros((max(top.shape[0], camera.shape[0]), max(top.shape[1], camera.shape[1])), np.uint32)
+    current_view, steps_taken = CAMERA_VIEW, 0
+
+    def blit():
+        image = game.camera_view if current_view == CAMERA_VIEW else game.top_view
+        frame_buffer[:image.shape[0], :image.shape[1]] = image
+
+    blit()                                                        # :512-517
+    info = dict(key=None, steps_taken=0, reward=game.world.reward, done=game.world.done, view=current_view, warning=None)
+    for key in keys:
+        key, warning = str(key).upper(), None
+        if key == "Q":                                            # :525-527
+            break
+        elif key == "R":                                          # :528-530
+            game.reset()
+            steps_taken = 0
+        elif key == "V":                                          # :531-534
+            current_view = current_view % NUM_VIEWS + 1           # mod1(current_view + 1, NUM_VIEWS)
+            frame_buffer[:] = 0
+        elif key in ACTION_KEYS:                                  # :535-538
+            game.act(ACTION_KEYS.index(key) + 1)
+            steps_taken += 1
+        else:
+            warning = f"No keybinding exists for {key}"           # :540
+        blit()                                                    # :543-547
+        info = dict(key=key, steps_taken=steps_taken, reward=game.world.reward, done=game.world.done,
+                    view=current_view, warning=warning)
+        if on_frame is not None:
+            on_frame(frame_buffer, info)
+    return frame_buffer, info
 
 
 def state(env: RLBaseEnv):

@@ -193,3 +193,35 @@ def test_one_tile_sector_sweeps_and_circle_rewrite(rcw, oracle, H, W, pu, radius
         w.update_top_view()
         np.testing.assert_array_equal(top[e], w.top_view, err_msg=f"env {e}")
     env.close()
+
+
+def test_play_drives_the_key_bindings_without_a_window(rcw, oracle):
+    """play!(game) (single_room.jl:488-572) headless: W/S/A/D act, R resets, V toggles the view and clears the frame
+    buffer, unknown keys are reported, Q stops; the frame buffer holds the current view like
+    copy_image_to_frame_buffer! leaves it (utils.jl:64-73)."""
+    assert rcw.get_action_keys(None) == ("W", "S", "A", "D")                          # :485
+    game = rcw.SingleRoom(seed=5, num_rays=96, height_camera_view_pu=40, pu_per_tu=8)   # camera 40 x 96, top view 64 x 128
+    ref = oracle.Batch(1, cfg=oracle.default_config(R=96, P=40, pu_per_tu=8), seed=5, auto_reset=False)
+    frames = []
+    fb, info = rcw.play(game, "wwdxsaVwwa", on_frame=lambda f, i: frames.append((f.copy(), i)))
+    assert fb.shape == (64, 128) and fb.dtype == np.uint32                            # max of the two views, :503-506
+    assert [i["key"] for _, i in frames] == list("WWDXSAVWWA")
+    assert frames[3][1]["warning"] == "No keybinding exists for X" and frames[3][1]["steps_taken"] == 3
+    assert info["steps_taken"] == 8 and info["view"] == rcw.TOP_VIEW
+    for a in [1, 1, 4, 2, 3]:                                                        # W W D (X) S A
+        ref.step(np.array([a], np.uint8))
+    w = ref.world(0)
+    np.testing.assert_array_equal(frames[5][0][:40, :96], w.camera_view.T)           # camera view after six keys
+    assert not frames[5][0][40:].any() and not frames[5][0][:, 96:].any()            # the rest of the buffer stays zero
+    for a in [1, 1, 3]:
+        ref.step(np.array([a], np.uint8))
+    w = ref.world(0)
+    w.update_top_view()
+    np.testing.assert_array_equal(fb, w.top_view.T)                                   # V: top view fills the buffer
+    assert info["reward"] == w.state()["reward"] and bool(info["done"]) == bool(w.state()["done"])
+    fb2, info2 = rcw.play(game, ["r", "q", "w"])                                      # R resets the count, Q stops before W
+    assert info2["key"] == "R" and info2["steps_taken"] == 0 and info2["view"] == rcw.CAMERA_VIEW
+    np.testing.assert_array_equal(fb2[:40, :96], game.camera_view)
+    with pytest.raises(TypeError):
+        rcw.play(rcw.BatchedSingleRoom, "w")
+    game.close()
