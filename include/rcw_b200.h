@@ -173,7 +173,8 @@ int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls);
  * the layout is drawn on the device (uniform interior goal, uniform empty player tile by
  * rejection, uniform direction — same draw order as the reference).  Sets reward=0,
  * done=false, then casts and renders the envs that were reset (the observations of the others still
- * belong to their unchanged state).  Does not block: host arrays are staged before the call returns. */
+ * belong to their unchanged state).  Does not block for pageable host arrays (they are staged before the call
+ * returns); pinned / registered host arrays are waited for, so the caller may reuse them at once either way. */
 int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij,
                   const int32_t* dir_au, const uint8_t* mask);
 
@@ -280,7 +281,10 @@ int32_t rcw_copy_obs(rcw_batch* b, int64_t env0, int64_t n, void* host);
  * supplies the geometry (num_rays, height_px) and the palette, so any handle of that geometry can expand them.
  * dst: DEVICE pointer to n images in pixel_format (RGB8 / XRGB32 / GRAY8) laid out as rcw_expanded_layout says
  * (columns pitched to 32 bytes, envs to 128; dense whenever height_px * bytes_per_pixel is a multiple of 32 and
- * num_rays * that a multiple of 128, e.g. the default camera).  Only enqueues (on the handle's stream). */
+ * num_rays * that a multiple of 128, e.g. the default camera).  Only enqueues (on the handle's stream).
+ * The words are validated on the device: a palette index outside RCW_COLOR_WALL_1..RCW_COLOR_GOAL_2 or a pad
+ * above height_px / 2 (a stale or uninitialised replay row) is clamped into range — nothing is written outside
+ * the word's own column — and the next blocking call on the handle returns RCW_EINVAL once. */
 int32_t rcw_expand_columns(rcw_batch* b, const uint32_t* columns, size_t columns_env_stride_bytes, int64_t n,
                            int32_t pixel_format, void* dst);
 int32_t rcw_expanded_layout(rcw_batch* b, int32_t pixel_format, size_t* env_stride_bytes,

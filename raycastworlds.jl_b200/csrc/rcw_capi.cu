@@ -51,15 +51,42 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
         }                                                                                      \
     } while (0)
 
+// Is the primary context of `dev` alive?  cudaGetDevice() answers 0 on a thread that never selected a device, and
+// since CUDA 12 cudaSetDevice(0) CREATES that context (hundreds of MB and a slice of GPU 0 in every rank of a
+// plain-C / Julia host that runs one process per GPU with cfg.device = rank and never calls cudaSetDevice
+// itself).  The driver entry point is fetched through the runtime, so the library does not link libcuda.
+static bool primary_context_active(int dev) {
+    typedef int (*fn_t)(int /*CUdevice*/, unsigned int*, int*);
+    static fn_t fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxGetState", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<fn_t>(f);
+    }();
+    if (!fn) return true;   // cannot tell: behave as before
+    unsigned int flags = 0;
+    int active = 0;
+    if (fn(dev, &flags, &active) != 0) return true;
+    return active != 0;
+}
+
+// Selects the handle's device for the duration of a call.  The caller's device is restored only when it
+// differs AND already has a context (see above): a guard never creates a context on a device the host did not use.
 struct DeviceGuard {
     int prev = -1;
     bool ok = false;
+    bool restore = false;
     explicit DeviceGuard(int dev) {
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        ok = cudaSetDevice(dev) == cudaSuccess;
+        restore = prev >= 0 && prev != dev && primary_context_active(prev);
+        ok = (prev == dev && primary_context_active(dev)) || cudaSetDevice(dev) == cudaSuccess;
     }
     ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
+        if (restore) cudaSetDevice(prev);
     }
 };
 
@@ -161,6 +188,7 @@ struct rcw_batch {
     int64_t next_ticket = 0;
     int result_slot = -1;             // >= 0 while rcw_step_async enqueues its step
     bool device_actions_pending = false;  // a device-side action array was used since the last check
+    bool expand_pending = false;          // rcw_expand_columns ran since the last check (caller-supplied words)
     // counters
     uint64_t step_index = 0;
     int64_t launches = 0;
@@ -442,18 +470,22 @@ static int32_t check_handle(const rcw_batch* b) {
 static int32_t sync_and_check(rcw_batch* b, bool need_stats = false) {
     // the stats block is only fetched when somebody needs it: the caller, or a device-side action
     // array whose values could not be validated on the host
-    const bool fetch = need_stats || b->device_actions_pending;
+    const bool fetch = need_stats || b->device_actions_pending || b->expand_pending;
     if (fetch)
         RCW_CUDA(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost,
                                  b->stream));
     RCW_CUDA(cudaStreamSynchronize(b->stream));
+    if (fetch) b->device_actions_pending = b->expand_pending = false;
     if (fetch && b->h_stats->bad_action) {
         RCW_CUDA(cudaMemsetAsync(&b->d_stats->bad_action, 0, sizeof(int), b->stream));
-        b->device_actions_pending = false;
         return fail(RCW_EACTION, "a device-side action array held a value outside 1..4; "
                                  "the affected envs were not stepped");
     }
-    if (fetch) b->device_actions_pending = false;
+    if (fetch && b->h_stats->bad_columns) {
+        RCW_CUDA(cudaMemsetAsync(&b->d_stats->bad_columns, 0, sizeof(int), b->stream));
+        return fail(RCW_EINVAL, "rcw_expand_columns read a column word outside the format (palette index not in "
+                                "2..5 or more ceiling rows than half the column); the word was clamped");
+    }
     return RCW_OK;
 }
 
@@ -724,6 +756,8 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
     const int gpe = (cfg->num_rays + 31) / 32;
     if ((int64_t)cfg->num_rays * cfg->height_camera_view_pu * bpp >= (1LL << 30))
         return fail(RCW_ESIZE, "one observation must be smaller than 1 GiB");
+    if ((int64_t)cfg->num_directions * cfg->num_rays >= (1LL << 31))
+        return fail(RCW_ESIZE, "num_directions * num_rays must be below 2^31 (the ray table is indexed with 32 bits)");
     if (cfg->num_envs * gpe >= (1LL << 31))
         return fail(RCW_ESIZE, "num_envs * ceil(num_rays/32) must be below 2^31 per handle");
     if ((int64_t)((H * ((W + 31) / 32) + 3) / 4) * 16 > 200 * 1024)
@@ -869,6 +903,14 @@ int32_t rcw_render(rcw_batch* b) {
     return enqueue_frame(b, kModeRender, nullptr);
 }
 
+static bool is_pinned_host(const void* ptr) {
+    if (!ptr) return false;
+    cudaPointerAttributes attr;
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, ptr);
+    if (pe != cudaSuccess) cudaGetLastError();
+    return pe == cudaSuccess && attr.type == cudaMemoryTypeHost;
+}
+
 int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij,
                   const int32_t* dir_au, const uint8_t* mask) {
     NvtxRange nvtx("rcw_reset");
@@ -895,6 +937,7 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
         }
         // the scratch buffers live as long as the handle; copies from pageable host memory are staged before
         // cudaMemcpyAsync returns, copies and kernels are ordered by the handle's stream: no blocking here
+        // (pinned / registered arrays: see below)
         if (!b->d_reset_goal) {
             RCW_CUDA(dev_alloc(b, &b->d_reset_goal, 2 * (size_t)E, false));
             RCW_CUDA(dev_alloc(b, &b->d_reset_player, 2 * (size_t)E, false));
@@ -912,6 +955,11 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
         d_mask = b->d_reset_mask;
         RCW_CUDA(cudaMemcpyAsync(d_mask, mask, (size_t)E, cudaMemcpyHostToDevice, b->stream));
     }
+    // "staged before cudaMemcpyAsync returns" only holds for pageable memory: the DMA engine reads pinned or
+    // registered host arrays (torch pinned tensors, cudaHostRegister) when the copy executes.  The header promises
+    // that host pointers are only touched during the call, so wait for those copies here.
+    if (is_pinned_host(goal_ij) || is_pinned_host(player_ij) || is_pinned_host(dir_au) || is_pinned_host(mask))
+        RCW_CUDA(cudaStreamSynchronize(b->stream));
     ResetParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.H = c.height_tile_map_tu;
@@ -1422,6 +1470,7 @@ int32_t rcw_expand_columns(rcw_batch* b, const uint32_t* columns, size_t columns
     p.env_count = n;
     RCW_CUDA(launch_expand_columns(p, pixel_format, grid_for(b, n), b->stream));
     b->launches += 1;
+    b->expand_pending = true;   // the words are the caller's: a bad one is clamped and reported by the next blocking call
     return RCW_OK;
 }
 

@@ -49,7 +49,8 @@ struct DeviceStats {
     unsigned long long sum_length;
     double sum_return;
     int bad_action;   // set when a device-side action array held a value outside 1..4
-    int pad;
+    int bad_columns;  // set when rcw_expand_columns read a column word with a palette index outside
+                      // RCW_COLOR_WALL_1..RCW_COLOR_GOAL_2 or more ceiling rows than half the column (clamped)
 };
 
 // Struct-of-arrays environment state in HBM.  The fields every warp of an env reads

@@ -991,6 +991,14 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
                 const uint32_t info = __ldg(p.col_info + (size_t)obs_slot * p.col_info_stride + (size_t)(col0 + lane));
                 cs.pad = (int)(info & 0xFFFFu);
                 cs.cid = (int)(info >> 16);
+                // the words may come from a caller's replay buffer: a stale or uninitialised row must not index
+                // outside the palette or paint outside its column — clamp, and leave a sticky flag for the host
+                const bool bad = (cs.cid < RCW_COLOR_WALL_1) | (cs.cid > RCW_COLOR_GOAL_2) | (cs.pad > (p.P >> 1));
+                if (bad) {
+                    cs.cid = min(max(cs.cid, (int)RCW_COLOR_WALL_1), (int)RCW_COLOR_GOAL_2);
+                    cs.pad = min(cs.pad, p.P >> 1);
+                    if (p.stats) atomicExch(&p.stats->bad_columns, 1);
+                }
             }
         }
 
@@ -1231,7 +1239,7 @@ __global__ void build_ray_table_kernel(const float2* __restrict__ dirs, int N, i
 
 cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov, float4* table,
                                    cudaStream_t s) {
-    const int n = N * R;
+    const int n = N * R;   // rcw_create rejects N * R >= 2^31
     build_ray_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(dirs, N, R, sfov, table);
     return cudaGetLastError();
 }

@@ -160,3 +160,49 @@ def test_columns_errors(rcw):
     with pytest.raises(ValueError):
         col.obs_tensor_nchw()
     col.close()
+
+
+@pytest.mark.parametrize("fmt", ["rgb8", "xrgb32", "gray8"])
+@pytest.mark.parametrize("shape", [(64, 32), (45, 51), (512, 256)])
+def test_expand_clamps_garbage_words_and_reports_them(rcw, fmt, shape):
+    """Words from a caller's replay buffer may be stale or uninitialised: a palette index outside 2..5 or a pad
+    above height_px / 2 is clamped (nothing is written outside the word's own column: guard bytes around the
+    destination stay intact) and the next blocking call reports RCW_EINVAL once."""
+    import ctypes as C
+
+    import torch
+
+    R, P = shape
+    n = 5
+    env = rcw.BatchedSingleRoom(2, num_rays=R, height_camera_view_pu=P)
+    rng = np.random.default_rng(R * 1000 + P)
+    words = rng.integers(0, 2 ** 32, size=(n, R), dtype=np.uint64).astype(np.uint32)
+    words[0, 0] = 0xFFFFFFFF
+    words[1, R - 1] = (200 << 16) | 0xFFFF
+    words[2, 1] = (3 << 16) | (P // 2 + 1)                      # valid colour, pad one row too many
+    es, cs, cb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    code = {"rgb8": 0, "xrgb32": 1, "gray8": 2}[fmt]
+    assert env._lib.rcw_expanded_layout(env._h, code, C.byref(es), C.byref(cs), C.byref(cb)) == 0
+    guard = 1 << 20
+    buf = torch.full((guard + n * es.value + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    src = torch.from_numpy(words.view(np.int32)).cuda()
+    dst = buf.data_ptr() + guard
+    assert dst % 32 == 0
+    assert env._lib.rcw_expand_columns(env._h, src.data_ptr(), 0, n, code, dst) == 0
+    rc = env._lib.rcw_sync(env._h)
+    assert rc == rcw._capi.RCW_EINVAL, env._lib.rcw_last_error()
+    assert env._lib.rcw_sync(env._h) == 0                      # reported once
+    host = buf.cpu().numpy()
+    assert (host[:guard] == 0xA5).all() and (host[guard + n * es.value:] == 0xA5).all()
+    # the picture is that of the clamped words
+    cid = np.clip(words >> 16, 2, 5)
+    pad = np.minimum(words & 0xFFFF, P // 2)
+    clamped = (pad | (cid << 16)).astype(np.uint32)
+    src2 = torch.from_numpy(clamped.view(np.int32)).cuda()
+    want = env.expand_columns(src2, pixel_format=fmt)
+    assert env._lib.rcw_sync(env._h) == 0                      # valid words: no report
+    bpp = {"rgb8": 3, "xrgb32": 4, "gray8": 1}[fmt]
+    got = torch.as_strided(buf[guard:guard + n * es.value], (n, R, P * bpp), (es.value, cs.value, 1))
+    want_b = want.contiguous().view(torch.uint8).reshape(n, R, P * bpp)
+    assert torch.equal(got, want_b)
+    env.close()
