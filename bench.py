@@ -4,19 +4,36 @@
     python bench.py --gpus 1 --steps 200 --warmup 20
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps 5 --warmup 1      # CPU arm (oracle port, all cores)
+    python bench.py --impl reference --steps 20 --warmup 5     # CPU arm (oracle port, all cores)
 
 A step = one random-policy env-step of every env of the batch: act! (+ same-step auto-reset), the
 512-ray DDA and the full 256x512 RGB8 observation written to HBM (BASELINE.json configs[1]:
 4096 envs per GPU, default camera).  One step is exactly one kernel launch.  Weak scaling: every
 rank owns `--envs-per-gpu` envs, global env ids key the RNG, no collective on the step path.
 Rank 0 prints ONE JSON line.
+
+The timed region is exactly K steps between two CUDA events on the handle's stream (barrier +
+synchronize on both sides, max over ranks); it is repeated until at least `--min-seconds` of timed
+launches have run and the MEDIAN region is reported (`timing` tells how many and their spread), so that
+the clock samples come from timed launches even at the driver's --steps 20 (4.6 ms of work).
+
+The other BASELINE configs ride in the same line under `configs` (short device-timed runs, each with
+its own roofline fraction and clocks): at N = 1 config 4 (65,536 envs), config 5 (64x64 map, 256
+directions, 262,144 envs), the reference's own UInt32 pixel format, two reduced resolutions and
+step + top view; at N > 1 config 3 (2^20 envs sharded over the N GPUs, through an observation window
+where one GPU's share does not fit in HBM) and the 128x128 reduced-resolution figure.
+
+`--impl reference` times the CPU port of the reference (oracle/, C, pthreads over envs — Julia is
+not in the image) on the SAME config, writing the SAME frame format, under both loop schedules
+(step-major: every env once per step; env-major: each thread runs its envs through all K steps, the
+analogue of Threads.@threads over envs) and reports the FASTER one as value / e2e.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -29,12 +46,13 @@ if ROOT not in sys.path:
 METRIC = "rendered env-steps/sec"
 UNIT = "env-steps/s"
 SEED = 0x5EED
+BPP = {"rgb8": 3, "xrgb32": 4, "gray8": 1, "columns": 4}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
@@ -49,18 +67,44 @@ def parse_args():
     ap.add_argument("--top-view", action="store_true",
                     help="also redraw the top view inside every step (the reference's act!(env), single_room.jl:337); "
                          "not part of the north-star path, a second kernel launch and 512 KB more per env-step")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="repeat the K-step timed region until this much timed work has run; the median is reported")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE configs)")
+    ap.add_argument("--reference-seconds", type=float, default=8.0,
+                    help="--impl reference: timed work per loop schedule")
     return ap.parse_args()
 
 
-def workload(args):
+def geometry(map_name="default", rays=512, height=256):
     kw = dict(height_tile_map_tu=8, width_tile_map_tu=16, num_directions=128)
-    if args.map == "large":
+    if map_name == "large":
         kw = dict(height_tile_map_tu=64, width_tile_map_tu=64, num_directions=256)
-    kw.update(num_rays=args.rays, height_camera_view_pu=args.height)
+    kw.update(num_rays=rays, height_camera_view_pu=height)
     return kw
+
+
+def frame_bytes(kw, fmt):
+    if fmt == "columns":   # 4 bytes per column: not rendered pixels, the step is bound by act! + DDA
+        return kw["num_rays"] * 4
+    return kw["num_rays"] * kw["height_camera_view_pu"] * BPP[fmt]
+
+
+def config_block(n_per_gpu, n_gpus, kw, fmt, map_name, top_view=False):
+    """The `config` object — built the same way by BOTH arms so that the driver can compare them."""
+    baseline = (n_per_gpu, map_name, kw["num_rays"], kw["height_camera_view_pu"], fmt, top_view) == \
+               (4096, "default", 512, 256, "rgb8", False)
+    return {
+        "workload": (f"BatchedSingleRoom {n_per_gpu} envs per GPU x {n_gpus} GPU(s), "
+                     f"{kw['height_tile_map_tu']}x{kw['width_tile_map_tu']} tiles, {kw['num_directions']} directions, "
+                     f"{kw['num_rays']} rays x {kw['height_camera_view_pu']} px {fmt}, random policy + auto-reset"
+                     + (" + top view" if top_view else "")
+                     + (" (BASELINE.json configs[1] per GPU)" if baseline else "")),
+        "envs_per_gpu": n_per_gpu, "n_gpus": n_gpus, "obs_format": fmt,
+        "obs_bytes_per_env_step": frame_bytes(kw, fmt), "seed": SEED,
+    }
 
 
 def mem_peaks():
@@ -89,23 +133,20 @@ class ClockSampler:
             self.thread.start()
         except OSError:
             self.proc = None
+        return self
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=3)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
+    def mark(self):
+        """Number of samples so far (to split one sampler's stream into windows)."""
+        return len(self.lines)
+
+    def summary(self, first=0, last=None):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        sm, smax, power, reasons = [], [], [], set()
+        for _, ln in self.lines[first:last]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -119,91 +160,194 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no samples"]}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power),
                 "samples": len(sm), "reasons": sorted(reasons)}
 
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+
 
 def measured_traffic(n_envs, kw, fmt):
-    """DRAM bytes (read + write) of one launch of the step kernel, from the committed
-    `ncu --set full` capture of this workload (profiles/traffic.json), or None."""
+    """DRAM bytes (read + write) of ONE launch of the step kernel at this exact workload, taken from a committed
+    `ncu --set full` capture (profiles/traffic.json names the capture), or None when this workload has none."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     key = f"{n_envs}x{kw['num_rays']}x{kw['height_camera_view_pu']}x{fmt}x{kw['height_tile_map_tu']}x{kw['width_tile_map_tu']}"
     try:
         with open(path) as f:
-            return json.load(f).get(key)
+            d = json.load(f)
     except OSError:
-        return None
+        return None, None
+    v = d.get(key)
+    if isinstance(v, dict):
+        return v.get("bytes"), v.get("source")
+    return v, ("profiles/r01_step_kernel_final.md" if v is not None else None)
 
 
-def cpu_port_rate(n_envs, kw, seconds, threads):
-    """Env-steps/s of the CPU oracle (C restatement of the reference, pthreads over envs) on a
-    bounded sample: the same batch, as many whole steps as fit in about `seconds`."""
-    from oracle import oracle as orc
+# --------------------------------------------------------------------------------------------
+# CPU arm
+# --------------------------------------------------------------------------------------------
 
-    cfg = orc.default_config(H=kw["height_tile_map_tu"], W=kw["width_tile_map_tu"],
-                             N=kw["num_directions"], R=kw["num_rays"], P=kw["height_camera_view_pu"])
-    b = orc.Batch(n_envs, cfg=cfg, seed=SEED)
-    b.rollout(2, threads=threads)                      # cold: thread start-up, first touch of the images
-    steps, chunk = 0, 8
-    t0 = time.perf_counter()
-    while True:
-        b.rollout(chunk, threads=threads)
-        steps += chunk
-        dt = time.perf_counter() - t0
-        if dt >= seconds:
-            break
-        chunk = int(max(8, min(4096, 0.25 * seconds * steps / dt)))   # about four more chunks
-    return n_envs * steps / dt, steps, dt
+ORACLE_RENDER = {"rgb8": "rgb8", "xrgb32": "xrgb32", "gray8": "gray8", "columns": "none"}
+
+
+def oracle_cfg(orc, kw):
+    return orc.default_config(H=kw["height_tile_map_tu"], W=kw["width_tile_map_tu"], N=kw["num_directions"],
+                              R=kw["num_rays"], P=kw["height_camera_view_pu"])
+
+
+def cpu_schedules(orc, m, kw, fmt, K, W, seconds, threads):
+    """Env-steps/s of the CPU port on `m` envs of the workload under both loop schedules.  A timed region is K
+    steps of the m envs; regions repeat until `seconds` of timed work per schedule; the median region counts."""
+    render = ORACLE_RENDER[fmt]
+    out = {}
+    for name in ("step_major", "env_major"):
+        b = orc.Batch(m, cfg=oracle_cfg(orc, kw), seed=SEED)
+
+        def region(k):
+            if name == "step_major":
+                for _ in range(k):
+                    b.rollout(1, threads=threads, render=render)
+            else:
+                b.rollout(k, threads=threads, render=render)
+
+        region(max(1, W))
+        times, t_all = [], time.perf_counter()
+        while True:
+            t0 = time.perf_counter()
+            region(K)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_all >= seconds and len(times) >= 3 or len(times) >= 2000:
+                break
+        med = statistics.median(times)
+        out[name] = {"value": m * K / med, "region_s_median": med, "region_s_min": min(times),
+                     "region_s_max": max(times), "regions": len(times)}
+        del b
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  Julia is absent from this image and the DDA
-    lives in un-vendored RayCaster.jl, so this times the oracle port (C restatement, pthreads over
-    envs = the analogue of Threads.@threads over envs) with every host core, on the same config."""
+    """--impl reference: the reference's CPU path.  Julia is absent from this image and the DDA lives in
+    un-vendored RayCaster.jl, so this times the oracle port (C restatement, pthreads over envs = the analogue of
+    Threads.@threads over envs) with every host core, on the same config and frame format as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as orc
 
-    kw = workload(args)
-    n = args.envs_per_gpu
+    kw = geometry(args.map, args.rays, args.height)
+    n, G = args.envs_per_gpu, args.gpus
+    fmt = args.obs_format
     threads = os.cpu_count() or 1
-    cfg = orc.default_config(H=kw["height_tile_map_tu"], W=kw["width_tile_map_tu"],
-                             N=kw["num_directions"], R=kw["num_rays"], P=kw["height_camera_view_pu"])
-    # bounded sample: a step is one random-policy step of `m` of the batch's n envs, m chosen so that
-    # warmup + steps stay within about two minutes on this host
-    probe = orc.Batch(min(n, 4 * threads), cfg=cfg, seed=SEED)
-    t0 = time.perf_counter()
-    probe.rollout(2, threads=threads)
-    per_env_step = (time.perf_counter() - t0) / (2 * probe.num_envs)
-    del probe
-    budget = 120.0
-    m = int(min(n, max(threads, budget / (per_env_step * max(1, args.steps + args.warmup)))))
-    b = orc.Batch(m, cfg=cfg, seed=SEED)
-    for _ in range(args.warmup):
-        b.rollout(1, threads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        b.rollout(1, threads=threads)
-    dt = time.perf_counter() - t0
-    value = m * args.steps / dt
-    sample = (f"{m} of the {n} envs per step x {args.steps} steps in {dt:.1f} s, UInt32 camera view, "
-              f"{threads} pthreads over envs")
+    # bounded sample of the N-GPU workload: m of its n * G envs (the port keeps a UInt32 and a byte image per env
+    # in host memory; 8192 envs = 7 GB), every step of the timed region steps all m of them
+    m = int(min(n * G, 8192))
+    sched = cpu_schedules(orc, m, kw, fmt, args.steps, args.warmup, args.reference_seconds, threads)
+    best = max(sched, key=lambda k: sched[k]["value"])
+    value = sched[best]["value"]
+    sample = (f"{m} of the workload's {n * G} envs, regions of {args.steps} steps repeated for "
+              f"{args.reference_seconds:.0f} s per schedule, {fmt} frames written directly, {threads} pthreads over "
+              f"envs; value = the faster schedule ({best})")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"BatchedSingleRoom {n} envs, {kw['height_tile_map_tu']}x{kw['width_tile_map_tu']} tiles, "
-                               f"{kw['num_rays']} rays x {kw['height_camera_view_pu']} px, random policy + auto-reset",
-                   "note": "CPU oracle port of the reference (C, -O2, pthreads over envs); Julia is not in the image"},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sched[best]["region_s_median"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_block(n, G, kw, fmt, args.map, args.top_view),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "schedules": sched,
+        "note": ("CPU oracle port of the reference (C, -O2, pthreads over envs); Julia is not in the image.  "
+                 "step_major = every env once per step (frames stream through the host caches), env_major = each "
+                 "thread runs its envs through all steps of a region (cache-resident frames)"),
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+
+class Timer:
+    """K-step regions on one handle, CUDA events on the handle's stream, max over ranks, median of regions."""
+
+    def __init__(self, torch, dist, rcw, dev, world):
+        self.torch, self.dist, self.rcw, self.dev, self.world = torch, dist, rcw, dev, world
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, values):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def device_regions(self, env, K, min_seconds, max_regions=400):
+        """Median (over regions, each the max over ranks) milliseconds of K back-to-back step launches."""
+        torch = self.torch
+        stream = torch.cuda.ExternalStream(env.cuda_stream(), device=self.dev)
+
+        def one():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.barrier()
+            e0.record(stream)
+            env.step_random(K)
+            e1.record(stream)
+            env.sync()
+            self.barrier()
+            return e0.elapsed_time(e1)
+
+        first = self.max_over_ranks([one()])[0]
+        n_more = int(min(max_regions, max(2, -(-min_seconds * 1e3 // max(first, 1e-3)))))   # the same on every rank
+        times = self.max_over_ranks([first] + [one() for _ in range(n_more)])
+        return times
+
+
+def summarize(times_ms):
+    return {"regions": len(times_ms), "region_ms_median": statistics.median(times_ms), "region_ms_min": min(times_ms),
+            "region_ms_max": max(times_ms), "timed_total_s": sum(times_ms) * 1e-3}
+
+
+def run_side_config(T, rcw, sampler, label, n, kw, fmt, K, W, min_seconds, peak, local, offset, window=0,
+                    top_view=False, note=None):
+    """One entry of the `configs` block: its own handle, W warm-up steps, K-step regions, median."""
+    env = rcw.BatchedSingleRoom(n, device=local, seed=SEED, env_id_offset=offset, obs_format=fmt,
+                                obs_window_envs=window, top_view=top_view, **kw)
+    try:
+        env.step_random(W)
+        env.sync()
+        m0 = sampler.mark() if sampler else 0
+        l0 = env.launch_count()
+        times = T.device_regions(env, K, min_seconds)
+        launches = env.launch_count() - l0
+        med = statistics.median(times)
+        bytes_env = frame_bytes(kw, fmt)
+        if top_view:
+            bytes_env += 4 * kw["height_tile_map_tu"] * 32 * kw["width_tile_map_tu"] * 32
+        achieved = n * bytes_env / (med / K * 1e-3) / 1e9
+        out = {"workload": label, "envs_per_gpu": n, "obs_format": fmt, "obs_bytes_per_env_step": bytes_env,
+               "obs_window_envs": env.obs_window, "steps": K, "warmup": W,
+               "value": T.world * n * K / (med * 1e-3), "unit": UNIT, "ms_per_step": med / K,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
+               "gpu_launches_per_region": launches // len(times), "timing": summarize(times)}
+        if sampler:
+            out["clocks"] = sampler.summary(m0, sampler.mark())
+        if note:
+            out["note"] = note
+        return out
+    finally:
+        env.close()
 
 
 def run_b200(args):
@@ -222,59 +366,35 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    T = Timer(torch, dist, rcw, dev, world)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    kw = workload(args)
+    kw = geometry(args.map, args.rays, args.height)
+    fmt = args.obs_format
     n = args.envs_per_gpu
     offset = rank * n
-    env = rcw.BatchedSingleRoom(n, device=local, seed=SEED, env_id_offset=offset,
-                                obs_format=args.obs_format, obs_window_envs=args.obs_window_envs,
-                                top_view=args.top_view, result_ring=2, **kw)
-    windowed = env.obs_window < n
-    stream = torch.cuda.ExternalStream(env.cuda_stream(), device=dev)
     K, W = args.steps, args.warmup
-    bytes_per_step_env = kw["num_rays"] * kw["height_camera_view_pu"] * env.bytes_per_pixel
-    if args.obs_format == "columns":   # 4 bytes per column: not rendered pixels, the step is bound by act! + DDA
-        bytes_per_step_env = kw["num_rays"] * 4
+    peak, peak_src = mem_peaks()
+    env = rcw.BatchedSingleRoom(n, device=local, seed=SEED, env_id_offset=offset, obs_format=fmt,
+                                obs_window_envs=args.obs_window_envs, top_view=args.top_view, result_ring=2, **kw)
+    windowed = env.obs_window < n
+    bytes_per_step_env = frame_bytes(kw, fmt)
     if args.top_view:
         bytes_per_step_env += 4 * int(np.prod(env.top_view_shape[1:]))
 
-    # ---- device-resident throughput: K launches back to back, CUDA events on the handle's stream
+    # ---- device-resident throughput: regions of K launches back to back, CUDA events on the handle's stream
     env.step_random(W)
     env.sync()
-    events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    sampler = ClockSampler(local).start() if rank == 0 else None
     launches0 = env.launch_count()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    events[0].record(stream)
-    for k in range(K):
-        env.step_random(1)
-        events[k + 1].record(stream)
-    env.sync()
-    barrier()
-    launches = env.launch_count() - launches0
+    m0 = sampler.mark() if sampler else 0
+    times = T.device_regions(env, K, args.min_seconds)
     clocks = None
-    if rank == 0:
-        # nvidia-smi needs ~100 ms to deliver its first sample: when the timed region was shorter, keep
-        # the same load running (untimed) until a few samples exist, and say so
-        extra_t0 = time.perf_counter()
-        while len(sampler.lines) < 3 and time.perf_counter() - extra_t0 < 2.0:
-            env.step_random(20)
-            env.sync()
-        extra_ms = 1e3 * (time.perf_counter() - extra_t0)
-        clocks = sampler.stop()
-        clocks["sampled"] = ("during the timed region" if extra_ms < 1.0 else
-                             f"timed region + {extra_ms:.0f} ms of the same launches right after it")
-    total_ms = events[0].elapsed_time(events[K])
-    per_launch_ms = [events[k].elapsed_time(events[k + 1]) for k in range(K)]
-    total_ms = rcw.max_over_ranks(total_ms, device=dev if world > 1 else None)
-    value = world * n * K / (total_ms * 1e-3)
+    if sampler:
+        clocks = sampler.summary(m0, sampler.mark())
+        clocks["sampled"] = f"during the {len(times)} timed regions ({sum(times) * 1e-3:.2f} s of timed launches)"
+    launches_per_region = (env.launch_count() - launches0) // len(times)
+    region_ms = statistics.median(times)
+    value = world * n * K / (region_ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers, every step: pinned host actions in (they ride in
     #      the kernel parameters: H2D inside the launch), the step, reward + done of every env back in host memory
@@ -284,9 +404,7 @@ def run_b200(args):
     #      rollout loop may do because its actions come from the observations, not from the rewards;
     #      `e2e_lockstep`: the host reads the results of step k before it enqueues step k + 1.
     #      A third figure also pulls the whole observation to the host each step (PCIe-bound).
-    e2e = None
-    e2e_lockstep = None
-    e2e_obs = None
+    e2e = e2e_lockstep = e2e_obs = None
     if not args.no_e2e:
         rng = np.random.default_rng(SEED + rank)
         pinned = torch.empty((K, n), dtype=torch.uint8).pin_memory()
@@ -314,35 +432,42 @@ def run_b200(args):
             for k in range(min(W, K)):
                 env.wait(env.act_async(actions[k]))
             env.sync()
-            barrier()
-            t0 = time.perf_counter()
-            ret, fin = run_e2e(lag)
-            torch.cuda.synchronize(dev)
-            dt = time.perf_counter() - t0
-            dt = rcw.max_over_ranks(dt, device=dev if world > 1 else None)
+
+            def one():
+                T.barrier()
+                t0 = time.perf_counter()
+                ret, fin = run_e2e(lag)
+                torch.cuda.synchronize(dev)
+                return time.perf_counter() - t0, ret, fin
+
+            first, ret, fin = one()
+            first = T.max_over_ranks([first])[0]
+            n_more = int(min(400, max(2, -(-args.min_seconds // max(first, 1e-6)))))
+            dts = T.max_over_ranks([first] + [one()[0] for _ in range(n_more)])
+            dt = statistics.median(dts)
             results[name] = {"value": world * n * K / dt, "unit": UNIT, "h2d_bytes_per_step": n,
-                             "d2h_bytes_per_step": n * 5, "ms_per_step": 1e3 * dt / K,
-                             "episodes_finished_rank0": fin, "sum_reward_rank0": ret}
+                             "d2h_bytes_per_step": n * 5, "ms_per_step": 1e3 * dt / K, "regions": len(dts),
+                             "region_ms_min": 1e3 * min(dts), "region_ms_max": 1e3 * max(dts),
+                             "episodes_finished_rank0_first_region": fin, "sum_reward_rank0_first_region": ret}
         e2e, e2e_lockstep = results["e2e"], results["e2e_lockstep"]
         e2e["note"] = ("host actions in, reward + done of every env out to host memory and summed by the host, every "
                        "step; step k + 1 is enqueued before the results of step k are read (rcw_step_async / rcw_wait, "
-                       "result_ring = 2); observations stay in HBM")
+                       "result_ring = 2); observations stay in HBM; median of wall-clock regions of K steps")
         e2e_lockstep["note"] = "as e2e, but the results of step k are read before step k + 1 is enqueued"
     if not args.no_e2e and not windowed:
         Ko = max(1, min(K, 5))
-        obs_host = torch.empty(env.obs_shape, dtype=torch.int32 if args.obs_format in ("xrgb32", "columns") else torch.uint8)
+        obs_host = torch.empty(env.obs_shape, dtype=torch.int32 if fmt in ("xrgb32", "columns") else torch.uint8)
         obs_host = obs_host.pin_memory().numpy()
-        if args.obs_format in ("xrgb32", "columns"):
+        if fmt in ("xrgb32", "columns"):
             obs_host = obs_host.view(np.uint32)
-        barrier()
+        T.barrier()
         t0 = time.perf_counter()
         for k in range(Ko):
             env.act(actions[k])
             env.reward_done(r_host, d_host)
             env.copy_obs(out=obs_host)
         torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        dt = rcw.max_over_ranks(dt, device=dev if world > 1 else None)
+        dt = T.max_over_ranks([time.perf_counter() - t0])[0]
         e2e_obs = {"value": world * n * Ko / dt, "unit": UNIT, "steps": Ko, "h2d_bytes_per_step": n,
                    "d2h_bytes_per_step": n * 5 + n * bytes_per_step_env,
                    "note": "as e2e plus the full observation copied to pinned host memory every step"}
@@ -352,45 +477,89 @@ def run_b200(args):
     stats = rcw.reduce_episode_stats(stats, device=dev if world > 1 else None)
     env.close()
 
+    # ---- the other BASELINE configs, short device-timed runs (every rank takes part at N > 1)
+    side = {}
+    if not args.no_configs and (args.map, args.rays, args.height, fmt, args.top_view) == ("default", 512, 256, "rgb8", False):
+        Ks, Ws, secs = max(5, min(K, 20)), max(3, min(W, 5)), 0.3
+        g_def, g_large = geometry(), geometry("large")
+        runs = []
+        if world == 1:
+            runs = [
+                ("config4_65536_envs", "BASELINE.json configs[3]: 512 rays x 256 px, 65,536 envs, rgb8 (25.8 GB of frames per step)",
+                 65536, g_def, "rgb8", 0, False),
+                ("config5_large_map_262144_envs", "BASELINE.json configs[4]: 64x64 tiles, 256 directions, 262,144 envs, rgb8 "
+                 "(103 GB of frames per step, all resident)", 262144, g_large, "rgb8", 0, False),
+                ("xrgb32_4096_envs", "configs[1] in the reference's own pixel format (UInt32, single_room.jl:300)",
+                 4096, g_def, "xrgb32", 0, False),
+                ("step_plus_top_view_4096_envs", "configs[1] + update_top_view! in every step: the reference's full "
+                 "act!(env) sequence (single_room.jl:333-340); 917,504 B per env-step", 4096, g_def, "rgb8", 0, True),
+                ("reduced_128x128_rgb8_65536_envs", "REDUCED RESOLUTION (not the default camera): 128 rays x 128 px rgb8",
+                 65536, geometry(rays=128, height=128), "rgb8", 0, False),
+                ("reduced_84x84_gray8_65536_envs", "REDUCED RESOLUTION (not the default camera): 84 rays x 84 px gray8",
+                 65536, geometry(rays=84, height=84), "gray8", 0, False),
+            ]
+        else:
+            share = (1 << 20) // world
+            fits = share * frame_bytes(g_def, "rgb8") < 150e9
+            runs = [
+                ("config3_1M_envs_sharded", f"BASELINE.json configs[2]: 2^20 envs over {world} GPUs = {share} envs per GPU, "
+                 "default camera rgb8" + ("" if fits else "; one GPU's frames (206 GB) exceed HBM: rendered through a "
+                                          "131,072-slot observation window, every frame still written to HBM"),
+                 share, g_def, "rgb8", 0 if fits else 131072, False),
+                ("reduced_128x128_rgb8_65536_envs_per_gpu", "REDUCED RESOLUTION (not the default camera): 128 rays x 128 px "
+                 "rgb8, 65,536 envs per GPU", 65536, geometry(rays=128, height=128), "rgb8", 0, False),
+            ]
+        for key, label, n_s, g, f, win, tv in runs:
+            try:
+                side[key] = run_side_config(T, rcw, sampler, label, n_s, g, f, Ks, Ws, secs, peak, local,
+                                            rank * n_s, window=win, top_view=tv)
+            except Exception as exc:   # a side run must never take the headline down with it
+                side[key] = {"workload": label, "error": f"{type(exc).__name__}: {exc}"}
+    if sampler:
+        sampler.stop()
+
     if rank == 0:
-        peak, peak_src = mem_peaks()
-        launch_ms = sum(per_launch_ms) / len(per_launch_ms)
-        achieved = n * bytes_per_step_env / (launch_ms * 1e-3) / 1e9
+        launch_ms = region_ms / K / (-(-n // env_window))
+        achieved = min(n, env_window) * bytes_per_step_env / (launch_ms * 1e-3) / 1e9
+        traffic, traffic_src = (None, None) if args.top_view else measured_traffic(n, kw, fmt)
+        cfg = config_block(n, world, kw, fmt, args.map, args.top_view)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": region_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"BatchedSingleRoom {n} envs per GPU, {kw['height_tile_map_tu']}x{kw['width_tile_map_tu']} tiles, "
-                            f"{kw['num_directions']} directions, {kw['num_rays']} rays x {kw['height_camera_view_pu']} px "
-                            f"{args.obs_format}, random policy + auto-reset" + (" (BASELINE.json configs[1])" if (n, args.map, args.rays, args.height) == (4096, "default", 512, 256) else ""),
-                "envs_per_gpu": n, "obs_bytes_per_env_step": bytes_per_step_env,
-                "obs_window_envs": env_window, "launches_per_step": -(-n // env_window) * (2 if args.top_view else 1),
-                "top_view": bool(args.top_view),
-                "l2": (f"each step writes {n * bytes_per_step_env / 1e9:.2f} GB of observations, larger than the 126 MB L2; no flush needed"
-                       if n * bytes_per_step_env > 126e6 else
-                       f"each step writes {n * bytes_per_step_env / 1e6:.1f} MB of observations: L2-resident, the step is bound by act! + DDA (issue), not by HBM"),
-                "seed": SEED,
-            },
+            "config": cfg,
+            "timing": dict(summarize(times), obs_window_envs=env_window,
+                           launches_per_step=-(-n // env_window) * (2 if args.top_view else 1),
+                           l2=(f"each step writes {n * bytes_per_step_env / 1e9:.2f} GB of observations, larger than the 126 MB L2; no flush needed"
+                               if n * bytes_per_step_env > 126e6 else
+                               f"each step writes {n * bytes_per_step_env / 1e6:.1f} MB of observations: L2-resident, the step is bound by act! + DDA (issue), not by HBM"),
+                           rule="value = median over regions of (K steps / region time); region time = max over ranks"),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None if args.top_view else measured_traffic(n, kw, args.obs_format),
+                "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "rcw::frame_kernel<kModeStep, fused>" + (" + rcw::top_view_kernel" if args.top_view else ""),
                 "algorithmic_bytes_per_launch": min(n, env_window) * bytes_per_step_env,
-                "launch_ms": launch_ms / (-(-n // env_window)), "peak_source": peak_src,
+                "launch_ms": launch_ms, "peak_source": peak_src,
             },
             "e2e": e2e, "e2e_lockstep": e2e_lockstep, "e2e_obs_to_host": e2e_obs,
-            "gpu_launches": launches,
+            "gpu_launches": launches_per_region,
             "clocks": clocks,
             "episodes": {"finished": stats[0], "sum_return": stats[1], "sum_length": stats[2]},
+            "configs": side,
         }
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as orc
+
             threads = os.cpu_count() or 1
-            rate, steps, dt = cpu_port_rate(min(n, 1024), kw, args.cpu_baseline_seconds, threads)
+            m = min(n, 1024)
+            sched = cpu_schedules(orc, m, kw, fmt, K, 2, args.cpu_baseline_seconds / 2, threads)
+            best = max(sched, key=lambda k: sched[k]["value"])
             line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"{min(n, 1024)} envs x {steps} steps of the same workload in {dt:.1f} s "
-                          "(C restatement of the reference, pthreads over envs, UInt32 camera view)"}
+                "value": sched[best]["value"], "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{m} envs of the same workload, regions of {K} steps for {args.cpu_baseline_seconds / 2:.0f} s per "
+                          f"schedule (C restatement of the reference, pthreads over envs, {fmt} frames written "
+                          f"directly); value = the faster schedule ({best})",
+                "schedules": {k: v["value"] for k, v in sched.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
         "orc_wall_heights": (None, [vp, vp]),
         "orc_camera_columns": (None, [vp, vp]),
         "orc_obs_rgb8": (None, [vp, vp]),
+        "orc_update_camera_view_bytes": (None, [vp, i32]),
+        "orc_frame_bytes": (vp, [vp]),
         "orc_philox4x32_10": (None, [vp, vp, vp]),
         "orc_draw_layout": (None, [vp, u64, u64, C.c_uint32, vp, vp, vp]),
         "orc_draw_action": (i32, [u64, u64, u64]),
@@ -246,6 +248,13 @@ class World:
         self.L.orc_obs_rgb8(self.p, out.ctypes.data)
         return out
 
+    def frame_bytes(self, fmt: str):
+        """The camera view rendered directly in the engine's byte formats ("rgb8": [R, P, 3], "gray8": [R, P])."""
+        code = {"rgb8": 2, "gray8": 3}[fmt]
+        self.L.orc_update_camera_view_bytes(self.p, code)
+        shape = (self.cfg.R, self.cfg.P, 3) if fmt == "rgb8" else (self.cfg.R, self.cfg.P)
+        return _view(self.L.orc_frame_bytes(self.p), shape, np.uint8).copy()
+
     def draw_layout(self, seed, env_id, episode):
         g = np.empty(2, np.int32)
         p = np.empty(2, np.int32)
@@ -285,8 +294,11 @@ class Batch:
         a = np.ascontiguousarray(actions, np.uint8)
         return int(self.L.orc_batch_step(self.p, a.ctypes.data, threads))
 
+    RENDER = {False: 0, True: 1, None: 0, "none": 0, "xrgb32": 1, "rgb8": 2, "gray8": 3}
+
     def rollout(self, n_steps, threads=1, render=True):
-        self.L.orc_batch_rollout(self.p, int(n_steps), int(threads), int(bool(render)))
+        """render: False / True (the reference's UInt32 camera view) or "xrgb32" | "rgb8" | "gray8" (bench arm)."""
+        self.L.orc_batch_rollout(self.p, int(n_steps), int(threads), self.RENDER[render])
 
     def reward_done(self):
         r = np.empty(self.num_envs, np.float32)

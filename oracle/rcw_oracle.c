@@ -30,6 +30,7 @@ struct orc_world {
     float* ray_dir;      /* ray_directions_wu [R][2] */
     uint32_t* camera;    /* camera_view [R columns][P rows], row fastest (Array{UInt32}(P,R)) */
     uint32_t* top;       /* top_view [W*pu columns][H*pu rows], row fastest (Array{UInt32}(H*pu, W*pu), :302) */
+    uint8_t* frame8;     /* Part B: the camera view written directly as RGB8 / GRAY8 bytes (bench arm), lazily allocated */
 };
 
 /* ------------------------------------------------------------------------------------- */
@@ -118,6 +119,7 @@ void orc_destroy(orc_world* w) {
     free(w->ray_dir);
     free(w->camera);
     free(w->top);
+    free(w->frame8);
     free(w);
 }
 
@@ -529,6 +531,55 @@ void orc_obs_rgb8(const orc_world* w, uint8_t* out) {
 /* Part B — batched semantics of the new engine (DESIGN.md "Batched semantics")           */
 /* ------------------------------------------------------------------------------------- */
 
+/* update_camera_view! (single_room.jl:374-444) writing the engine's byte formats directly instead of UInt32
+ * pixels, so that the CPU arm of bench.py stores the same bytes per frame as the GPU arm: fmt 2 = RGB8 (bytes
+ * R, G, B of the reference pixel, 3 per pixel), fmt 3 = GRAY8 (BT.601 luma, 1 per pixel).  Same bands, same
+ * column order; the result equals orc_obs_rgb8 / the luma of orc_camera_view (tested). */
+static void fill_pixels(uint8_t* dst, int n_px, uint32_t color, int fmt) {
+    if (fmt == 3) {
+        const uint32_t y = (77u * ((color >> 16) & 255u) + 150u * ((color >> 8) & 255u) + 29u * (color & 255u) + 128u) >> 8;
+        memset(dst, (int)y, (size_t)n_px);
+        return;
+    }
+    const uint8_t r = (uint8_t)(color >> 16), g = (uint8_t)(color >> 8), b = (uint8_t)color;
+    if (r == g && g == b) {
+        memset(dst, r, (size_t)n_px * 3);
+        return;
+    }
+    for (int k = 0; k < n_px; ++k) {
+        dst[3 * k + 0] = r;
+        dst[3 * k + 1] = g;
+        dst[3 * k + 2] = b;
+    }
+}
+
+void orc_update_camera_view_bytes(orc_world* w, int32_t fmt) {
+    const int R = w->cfg.R, P = w->cfg.P, H = w->cfg.H;
+    const int bpp = fmt == 3 ? 1 : 3;
+    if (!w->frame8) w->frame8 = (uint8_t*)calloc((size_t)R * P * 3, 1);
+    const uint32_t ceiling = w->cfg.palette[0], floorc = w->cfg.palette[1];
+    for (int i = 1; i <= R; ++i) {
+        const int h = height_line_pu(w, i - 1);
+        const int dim = w->ray_dim[i - 1];
+        const int ih = w->ray_stop[2 * (i - 1) + 0], jh = w->ray_stop[2 * (i - 1) + 1];
+        int is_wall = 1;
+        if (ih >= 1 && ih <= H && jh >= 1 && jh <= w->cfg.W) is_wall = w->wall[(ih - 1) + H * (jh - 1)];
+        const uint32_t color = is_wall ? (dim == 1 ? w->cfg.palette[2] : w->cfg.palette[3])
+                                       : (dim == 1 ? w->cfg.palette[4] : w->cfg.palette[5]);
+        uint8_t* col = w->frame8 + (size_t)(R - i) * P * bpp; /* k = R - i + 1 (:431) */
+        if (h >= P - 1) {
+            fill_pixels(col, P, color, fmt);
+        } else {
+            const int pad = (P - h) / 2;
+            fill_pixels(col, pad, ceiling, fmt);
+            fill_pixels(col + (size_t)pad * bpp, P - 2 * pad, color, fmt);
+            fill_pixels(col + (size_t)(P - pad) * bpp, pad, floorc, fmt);
+        }
+    }
+}
+
+const uint8_t* orc_frame_bytes(const orc_world* w) { return w->frame8; }
+
 /* Philox4x32-10, Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11). */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
@@ -702,7 +753,8 @@ static int32_t batch_step_env(orc_batch* b, int64_t e, int32_t action, uint64_t 
         }
     }
     orc_cast_rays(w);
-    if (render) orc_update_camera_view(w);
+    if (render == 1) orc_update_camera_view(w);                 /* the reference's UInt32 pixels */
+    else if (render >= 2) orc_update_camera_view_bytes(w, render); /* 2: RGB8, 3: GRAY8 (the engine's formats) */
     return 0;
 }
 

@@ -83,6 +83,9 @@ void orc_wall_heights(const orc_world* w, int32_t* height_line_pu /* [R], per ra
 void orc_obs_rgb8(const orc_world* w, uint8_t* out /* [R][P][3] */);
 
 /* ---- Part B: batched semantics of the new engine (no reference counterpart) ----------- */
+/* the camera view in the engine's byte formats (fmt 2 = RGB8 [R][P][3], 3 = GRAY8 [R][P]), written directly */
+void orc_update_camera_view_bytes(orc_world* w, int32_t fmt);
+const uint8_t* orc_frame_bytes(const orc_world* w);
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* layout draw of episode `episode` of global env `env_id` */
 void orc_draw_layout(const orc_world* w, uint64_t seed, uint64_t env_id, uint32_t episode,
@@ -99,7 +102,8 @@ void orc_batch_reset(orc_batch* b);                       /* Philox layouts, epi
 /* one step of every env; actions NULL => random policy.  threads >= 1 (pthreads over envs). */
 int32_t orc_batch_step(orc_batch* b, const uint8_t* actions, int32_t threads);
 /* n random-policy steps with `threads` pthreads, each env stepped independently
- * (env-major loop: the analogue of Threads.@threads over envs).  render=0 skips the camera view. */
+ * (env-major loop: the analogue of Threads.@threads over envs).  render: 0 skips the camera view, 1 = the
+ * reference's UInt32 pixels, 2 = RGB8 bytes, 3 = GRAY8 bytes written directly (orc_update_camera_view_bytes). */
 void orc_batch_rollout(orc_batch* b, int32_t n_steps, int32_t threads, int32_t render);
 void orc_batch_episode_stats(const orc_batch* b, int64_t* episodes, double* sum_return,
                              int64_t* sum_length);

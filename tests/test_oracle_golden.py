@@ -54,3 +54,22 @@ def test_act_trajectories_match_golden(oracle, golden, case):
             n_done += s["done"]
     if case == "A":
         assert n_done > 0, "fixture should contain goal hits"
+
+
+@pytest.mark.parametrize("case", ["A", "C"])
+def test_byte_formats_written_directly_equal_the_converted_uint32_view(oracle, golden, case):
+    """bench.py's CPU arm writes RGB8 / GRAY8 frames directly (orc_update_camera_view_bytes) so that both arms
+    store the same bytes per frame; the bytes must be those of the reference's UInt32 picture."""
+    kw = dict(GOLDEN_CONFIGS[case])
+    if case == "C":
+        kw["palette"] = [0x112233, 0x445566, 0x778899, 0xAABBCC, 0xDD1122, 0x3344EE]
+    w = oracle.World(oracle.default_config(**kw))
+    states, au, goal = golden[f"{case}_states"], golden[f"{case}_au"], golden[f"{case}_goal"]
+    for k in range(0, len(states), 3):
+        w.set_state(states[k, 0], states[k, 1], au[k], goal[k, 0], goal[k, 1])
+        w.cast_rays()
+        w.update_camera_view()
+        np.testing.assert_array_equal(w.frame_bytes("rgb8"), w.obs_rgb8())
+        c = w.camera_view
+        luma = ((77 * ((c >> 16) & 255) + 150 * ((c >> 8) & 255) + 29 * (c & 255) + 128) >> 8).astype(np.uint8)
+        np.testing.assert_array_equal(w.frame_bytes("gray8"), luma)
