@@ -148,6 +148,10 @@ struct rcw_batch {
     uint32_t* d_wall_maps_env = nullptr; // [num_envs][map_words], allocated by rcw_set_wall_maps
     bool per_env_maps = false;
     bool closed_border = true;           // every border tile of the active wall layer(s) is a wall
+    bool room = true;                    // the shared wall layer is exactly the border of the map (SingleRoom's own map,
+                                         // single_room.jl:57-60): kernels without a wall layer in shared memory (RoomMap)
+    bool room_allowed = true;            // RCW_ROOM=0 keeps every launch on the bit-packed wall layer (tests, A/B)
+    uint8_t* d_col_table = nullptr;      // ready-made columns for env_kernel's table renderer (small columns only)
     StateRef st[2]{};
     int cur = 0;
     float* d_reward = nullptr;
@@ -234,6 +238,8 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
     p.col_pitch = px_col_pitch;
     p.dda_flags = c.dda_flags;
     p.closed_border = b->closed_border ? 1u : 0u;
+    p.room = (b->room && b->room_allowed && !b->per_env_maps) ? 1u : 0u;
+    p.col_table = (pixel_fmt == c.obs_format) ? b->d_col_table : nullptr;
     p.radius = c.player_radius_wu;
     p.incr = c.position_increment_wu;
     p.goal_reward = c.goal_reward;
@@ -286,6 +292,10 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
         p.unit_inv16 = U < 32 ? (uint32_t)((65536 + U - 1) / U) : 0u;
         p.unit_adv_cl = 32 / U;
         p.unit_adv_u = 32 % U;
+        const int NS = px_col_pitch >> 5;
+        p.sec_inv16 = NS < 32 ? (uint32_t)((65536 + NS - 1) / NS) : 0u;
+        p.sec_adv_cl = 32 / NS;
+        p.sec_adv_u = 32 % NS;
     }
     p.dir_slot = b->dir_slot;
     p.dirs = b->d_dirs;
@@ -334,6 +344,15 @@ static int grid_for(const rcw_batch* b, int64_t env_count) {
         if (ctas > cap) ctas = cap;
     }
     return (int)(ctas < 1 ? 1 : ctas);
+}
+
+// how a step / render launch of n envs is shaped
+static LaunchShape shape_for(const rcw_batch* b, int64_t n) {
+    LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, n)};
+    sh.env_per_warp = b->env_per_warp && n >= b->env_per_warp_min;
+    sh.room = b->room && b->room_allowed && !b->per_env_maps;
+    sh.table = sh.env_per_warp && b->d_col_table != nullptr;
+    return sh;
 }
 
 // update_top_view! for envs [env0, env0 + n) from state `st`, into the slots that start at slot0.
@@ -415,8 +434,7 @@ static int32_t enqueue_frame(rcw_batch* b, int mode, const uint8_t* d_actions, c
         p.env_first = e0;
         p.env_count = E - e0 < b->obs_window ? E - e0 : b->obs_window;
         p.obs_slot0 = 0;
-        LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, p.env_count)};
-        sh.env_per_warp = b->env_per_warp && p.env_count >= b->env_per_warp_min;
+        const LaunchShape sh = shape_for(b, p.env_count);
         if (h_actions) {
             pack_actions(h_actions + e0, p.env_count, b->packed);
             RCW_CUDA(launch_frame(p, mode, b->cfg.obs_format, sh, b->stream, &b->packed));
@@ -447,8 +465,7 @@ static int32_t enqueue_range_step(rcw_batch* b, const uint8_t* d_actions_env0, i
     p.env_first = env0;
     p.env_count = n;
     p.obs_slot0 = (uint32_t)(env0 % b->obs_window);
-    LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, n)};
-    sh.env_per_warp = b->env_per_warp && n >= b->env_per_warp_min;
+    const LaunchShape sh = shape_for(b, n);
     if (h_actions) {
         pack_actions(h_actions, n, b->packed);
         RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, sh, b->stream, &b->packed));
@@ -716,6 +733,45 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     b->obs_window = (c.obs_window_envs > 0 && c.obs_window_envs < E) ? c.obs_window_envs : E;
     b->obs_bytes = b->obs_env_stride * (size_t)b->obs_window;
     RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, /*zero=*/b->frame_stack > 1));   // older ring positions start black
+    if (const char* s = getenv("RCW_ROOM")) b->room_allowed = atoi(s) != 0;
+    // ---- ready-made columns (env_kernel's table renderer) ------------------------------------------
+    // update_camera_view! paints one of (P / 2 + 1) x 4 possible columns (rows of ceiling = rows of floor x
+    // wall / goal colour per hit dimension, single_room.jl:417-439).  When they are small, all of them together
+    // fit the L1 / L2 caches, and painting a column is copying it.  Built here with the renderer's own rules
+    // (pixel bytes per format, the pitch padding behind the last row continues the floor).
+    {
+        const size_t table_bytes = (size_t)(P / 2 + 1) * 4 * (size_t)b->col_pitch;
+        size_t limit = 64 * 1024;
+        if (const char* s = getenv("RCW_COL_TABLE_KB")) limit = (size_t)atoll(s) * 1024;   // 0 disables the table
+        if (b->env_per_warp && c.obs_format != RCW_OBS_COLUMNS && table_bytes <= limit) {
+            uint32_t pal[6];
+            for (int i = 0; i < 6; ++i) {
+                const uint32_t col = c.palette[i] & 0x00FFFFFFu;
+                pal[i] = c.obs_format == RCW_OBS_GRAY8
+                             ? ((77u * ((col >> 16) & 255u) + 150u * ((col >> 8) & 255u) + 29u * (col & 255u) + 128u) >> 8) * 0x00010101u
+                             : col;
+            }
+            auto pixel_byte = [&](uint32_t col, int k) -> uint8_t {   // byte k of a pixel of colour 0x00RRGGBB
+                if (c.obs_format == RCW_OBS_RGB8) return (uint8_t)(col >> (16 - 8 * k));
+                if (c.obs_format == RCW_OBS_XRGB32) return (uint8_t)(col >> (8 * k));
+                return (uint8_t)col;
+            };
+            std::vector<uint8_t> tab(table_bytes);
+            for (int pad = 0; pad <= P / 2; ++pad)
+                for (int k = 0; k < 4; ++k) {
+                    uint8_t* colp = tab.data() + ((size_t)pad * 4 + k) * b->col_pitch;
+                    for (int ob = 0; ob < b->col_pitch; ++ob) {
+                        const int row = ob / b->bpp;
+                        const uint32_t col = row < pad ? pal[RCW_COLOR_CEILING]
+                                                       : (row < P - pad ? pal[RCW_COLOR_WALL_1 + k] : pal[RCW_COLOR_FLOOR]);
+                        colp[ob] = pixel_byte(col, ob - row * b->bpp);
+                    }
+                }
+            RCW_CUDA(dev_alloc(b, &b->d_col_table, table_bytes, false));
+            RCW_CUDA(cudaMemcpyAsync(b->d_col_table, tab.data(), table_bytes, cudaMemcpyHostToDevice, b->stream));
+            RCW_CUDA(cudaStreamSynchronize(b->stream));
+        }
+    }
     return RCW_OK;
 }
 
@@ -804,18 +860,21 @@ int32_t rcw_set_wall_map(rcw_batch* b, const uint8_t* wall) {
     DeviceGuard g(b->device);
     const int H = b->cfg.height_tile_map_tu, W = b->cfg.width_tile_map_tu;
     std::vector<uint32_t> words((size_t)b->map_words, 0u);
-    bool closed = true;
+    bool closed = true, interior_walls = false;
     for (int j = 0; j < W; ++j)
         for (int i = 0; i < H; ++i) {
             const bool is_wall = wall[(size_t)j * H + i] != 0;
+            const bool border = i == 0 || i == H - 1 || j == 0 || j == W - 1;
             if (is_wall) words[(size_t)i * b->wpr + (j >> 5)] |= 1u << (j & 31);
-            else if (i == 0 || i == H - 1 || j == 0 || j == W - 1) closed = false;
+            if (is_wall && !border) interior_walls = true;
+            if (!is_wall && border) closed = false;
         }
     RCW_CUDA(cudaStreamSynchronize(b->stream));
     RCW_CUDA(cudaMemcpy(b->d_wall_map, words.data(), sizeof(uint32_t) * words.size(),
                         cudaMemcpyHostToDevice));
     b->per_env_maps = false;
     b->closed_border = closed;
+    b->room = closed && !interior_walls;
     return RCW_OK;
 }
 
@@ -850,6 +909,7 @@ int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls) {
                         cudaMemcpyHostToDevice));
     b->per_env_maps = true;
     b->closed_border = closed;
+    b->room = false;
     return RCW_OK;
 }
 
@@ -1346,7 +1406,8 @@ int32_t rcw_get_rays(rcw_batch* b, int64_t env0, int64_t n, int32_t* hit_ij, int
     p.dump_dim = d_dim;
     p.dump_dist = d_dist;
     p.dump_dir = d_dir;
-    const LaunchShape sh{false, false, false, grid_for(b, n)};
+    LaunchShape sh{false, false, false, grid_for(b, n)};
+    sh.room = p.room != 0;
     cudaError_t e = launch_frame(p, kModeRays, b->cfg.obs_format, sh, b->stream);
     b->launches += 1;
     if (e == cudaSuccess && hit_ij) e = cudaMemcpyAsync(hit_ij, d_hit, cnt * 8, cudaMemcpyDeviceToHost, b->stream);

@@ -93,6 +93,12 @@ struct FrameParams {
     uint32_t unit_inv16;     // U < 32 ? ceil(65536 / U) : 0
     int32_t unit_adv_cl;     // 32 / U
     int32_t unit_adv_u;      // 32 % U
+    // the same for U = col_pitch / 32 sectors per column (table renderer of env_kernel)
+    uint32_t sec_inv16;
+    int32_t sec_adv_cl, sec_adv_u;
+    const uint8_t* col_table;// [P / 2 + 1 rows of ceiling][4 colours WALL_1..GOAL_2][col_pitch] ready-made pitched columns
+                             // (nullptr: none — the table is only built for small columns, LaunchShape::table)
+    uint32_t room;           // the wall layer is exactly the border of the map (and H, W <= 32767): RoomMap kernels
     // tables
     int32_t dir_slot;        // >= 0: directions live in constant memory slot; < 0: use `dirs`
     const float2* dirs;      // [N] unit vectors (global copy, also the source of the ray table)
@@ -193,6 +199,8 @@ struct LaunchShape {
     bool occ4;    // fused kernel compiled for 4 CTAs per SM (steps bound by act! / DDA rather than by stores)
     int ctas;     // grid size
     bool env_per_warp = false;   // small items: env_kernel, one warp = one env
+    bool room = false;           // wall layer == border of the map: kernels without a map in shared memory (RoomMap)
+    bool table = false;          // env_kernel copies ready-made columns out of FrameParams::col_table
 };
 // packed != nullptr (step mode, fused path, env_count <= kPackedActionEnvs): the actions ride in the parameters
 cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s,

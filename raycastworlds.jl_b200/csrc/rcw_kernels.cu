@@ -26,6 +26,8 @@
 // never contracts into FMAs, so positions, hit tiles, hit sides and distances are bit-identical
 // to the CPU restatement (the file is also compiled with -fmad=false).
 
+#include <type_traits>
+
 #include "rcw_internal.h"
 
 namespace rcw {
@@ -106,10 +108,22 @@ constexpr uint32_t kStreamAction = 0x41u;
 
 __device__ __forceinline__ uint32_t uniform_below(uint32_t u, uint32_t n) { return __umulhi(u, n); }
 
-// wall layer probe, 0-based tile, caller guarantees the tile is inside the map
-__device__ __forceinline__ bool wall_bit(const uint32_t* map, int wpr, int i0, int j0) {
-    return (map[i0 * wpr + (j0 >> 5)] >> (j0 & 31)) & 1u;
-}
+// The wall layer as the kernels see it (0-based tiles; the caller guarantees the tile is inside the map).
+// BitsMap: bit-packed words, bit j0 of row i0 — any map, staged in shared memory (or read from global memory
+// by the reset kernel).  RoomMap: the border tiles are walls and nothing else is — the map every SingleRoom of
+// the reference has (single_room.jl:57-60); it needs no memory at all, and its DDA counts down to the border
+// instead of probing (dda_walk_room).  The host picks the view per launch (FrameParams::room).
+struct BitsMap {
+    const uint32_t* w;
+    int wpr;
+    __device__ __forceinline__ bool wall(int i0, int j0) const { return (w[i0 * wpr + (j0 >> 5)] >> (j0 & 31)) & 1u; }
+};
+struct RoomMap {
+    int H1, W1;   // H - 1, W - 1
+    __device__ __forceinline__ bool wall(int i0, int j0) const {
+        return ((unsigned)(i0 - 1) >= (unsigned)(H1 - 1)) | ((unsigned)(j0 - 1) >= (unsigned)(W1 - 1));
+    }
+};
 
 // Uniform random policy: action in 1..4 for (global env id, global step index).
 __device__ __forceinline__ int draw_action(uint64_t seed, uint64_t env_id, uint64_t step) {
@@ -123,7 +137,8 @@ __device__ __forceinline__ int draw_action(uint64_t seed, uint64_t env_id, uint6
 // Layout of a new episode, in the draw order of reset! (single_room.jl:120,124,128):
 // goal_i in 2..H-1, goal_j in 2..W-1, player tile uniform over all tiles with rejection while a
 // wall or the goal is on it (utils.jl:23-37,52-58), direction in 0..N-1.  All outputs 1-based.
-__device__ inline void draw_layout(const uint32_t* map, int H, int W, int wpr, int N, uint64_t seed,
+template <class Map>
+__device__ inline void draw_layout(const Map& map, int H, int W, int N, uint64_t seed,
                                    uint64_t env_id, uint32_t episode, int& gi, int& gj, int& pi,
                                    int& pj, int& au) {
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -139,7 +154,7 @@ __device__ inline void draw_layout(const uint32_t* map, int H, int W, int wpr, i
         const uint32_t lin = uniform_below(draw, (uint32_t)(H * W));  // CartesianIndices, i fastest
         pi = (int)(lin % (uint32_t)H) + 1;
         pj = (int)(lin / (uint32_t)H) + 1;
-        const bool occupied = wall_bit(map, wpr, pi - 1, pj - 1) || (pi == gi && pj == gj);
+        const bool occupied = map.wall(pi - 1, pj - 1) || (pi == gi && pj == gj);
         if (!occupied || t == max_tries) break;
         const int word = (int)(t & 3);
         if (word == 0) {
@@ -375,9 +390,10 @@ __device__ __forceinline__ EnvInputs load_env_inputs(const FrameParams& p, int64
 
 // single_room.jl:139-191 (+ same-step auto-reset and episode bookkeeping of the batched engine).
 // `writer` is true in the one warp of the whole grid that owns the env's persistent state.
-__device__ __forceinline__ EnvPose act_env(const FrameParams& p, const uint32_t* s_map, int64_t env,
+template <class Map>
+__device__ __forceinline__ EnvPose act_env(const FrameParams& p, const Map& map, int64_t env,
                                            const EnvInputs& in, bool writer, int lane) {
-    const int H = p.H, W = p.W, wpr = p.wpr;
+    const int H = p.H, W = p.W;
     float x = in.x, y = in.y;
     int au = in.au;
     uint32_t episode = in.episode;
@@ -401,7 +417,7 @@ __device__ __forceinline__ EnvPose act_env(const FrameParams& p, const uint32_t*
             bool hit_goal = false, hit_wall = false;
             if (lane < 9 && ti >= 1 && ti <= H && tj >= 1 && tj <= W) {
                 const bool is_goal = (ti == gi) && (tj == gj);
-                const bool is_wall = wall_bit(s_map, wpr, ti - 1, tj - 1);
+                const bool is_wall = map.wall(ti - 1, tj - 1);
                 if (is_goal || is_wall) {
                     const bool c = circle_hits_tile(nx, ny, ti, tj, p.radius);
                     hit_goal = is_goal && c;
@@ -441,7 +457,7 @@ __device__ __forceinline__ EnvPose act_env(const FrameParams& p, const uint32_t*
         if (p.auto_reset) {
             episode += 1u;
             int pi, pj;
-            draw_layout(s_map, H, W, wpr, p.N, p.seed, env_id, episode, gi, gj, pi, pj, au);
+            draw_layout(map, H, W, p.N, p.seed, env_id, episode, gi, gj, pi, pj, au);
             x = __fsub_rn((float)pi, 0.5f);   // tile centre (single_room.jl:125)
             y = __fsub_rn((float)pj, 0.5f);
         }
@@ -499,18 +515,18 @@ struct RayHit {
 // CLOSED: every border tile of the wall layer is a wall, so a ray can never leave the map and the probe
 // needs no bounds test (the default SingleRoom map; checked on the host for supplied maps).
 // A lane that has hit stays on its obstacle tile; the warp leaves together once no lane is still walking.
-template <bool TIE_LE, bool CLOSED>
-__device__ __forceinline__ void dda_walk(const uint32_t* s_map, int H, int W, int wpr, int gi0, int gj0, float dx,
+template <bool TIE_LE, bool CLOSED, class Map>
+__device__ __forceinline__ void dda_walk(const Map& map, int H, int W, int gi0, int gj0, float dx,
                                          float dy, int si, int sj, float& tx, float& ty, int& ti, int& tj, int& dim,
                                          float& dist) {
     // the tile the ray stands on is an obstacle: wall (outside the map counts as wall) or this env's goal
     auto probe = [&]() {
         bool wall;
         if (CLOSED) {
-            wall = wall_bit(s_map, wpr, ti, tj);
+            wall = map.wall(ti, tj);
         } else {
             const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
-            wall = !inside | wall_bit(s_map, wpr, inside ? ti : 0, inside ? tj : 0);
+            wall = !inside | map.wall(inside ? ti : 0, inside ? tj : 0);
         }
         return wall | ((ti == gi0) & (tj == gj0));
     };
@@ -533,9 +549,47 @@ __device__ __forceinline__ void dda_walk(const uint32_t* s_map, int H, int W, in
     }
 }
 
+// The same walk through a room (RoomMap: walls on the border only), from a start tile inside the map.  The side
+// distances, the comparison, the order of the steps and therefore tile, dimension and distance are those of
+// dda_walk; what changes is the probe.  A ray that walks away from an interior tile can only meet the border
+// it walks towards, so instead of looking tiles up the lane counts the steps left to that border in each
+// dimension — both counts in one register, (ci << 16) | cj, decremented by 0x10000 or 1 — and stops when either
+// reaches zero (one subtract and one mask test: a half that is zero borrows) or when the pair equals the
+// goal's (one compare).  No shared memory, no address arithmetic: 11 instructions per step instead of ~30.
+template <bool TIE_LE>
+__device__ __forceinline__ void dda_walk_room(const RoomMap& map, int gi0, int gj0, float dx, float dy, int si,
+                                              int sj, float& tx, float& ty, int& ti, int& tj, int& dim, float& dist) {
+    // steps left until the border tile in the direction of travel (H, W <= 32767: FrameParams::room)
+    const int ci0 = si > 0 ? map.H1 - ti : ti, cj0 = sj > 0 ? map.W1 - tj : tj;
+    const int gci = si > 0 ? map.H1 - gi0 : gi0, gcj = sj > 0 ? map.W1 - gj0 : gj0;
+    uint32_t cnt = ((uint32_t)ci0 << 16) | (uint32_t)cj0;
+    // a goal outside 0..32767 in either dimension can never be met: give it a pair no count reaches
+    const bool goal_in = ((unsigned)gci < 0x8000u) & ((unsigned)gcj < 0x8000u);
+    const uint32_t gcnt = goal_in ? (((uint32_t)gci << 16) | (uint32_t)gcj) : 0xFFFFFFFFu;
+    bool stop = map.wall(ti, tj) | (cnt == gcnt);     // the start tile itself: any border tile is a wall
+#pragma unroll 1
+    while (__any_sync(0xFFFFFFFFu, !stop)) {
+#pragma unroll
+        for (int u = 0; u < kDdaStepsPerVote; ++u) {
+            const bool cmp = TIE_LE ? (tx <= ty) : (tx < ty);
+            const bool mx = !stop & cmp, my = !stop & !cmp;
+            dist = mx ? tx : (my ? ty : dist);
+            tx = mx ? __fadd_rn(tx, dx) : tx;
+            ty = my ? __fadd_rn(ty, dy) : ty;
+            cnt -= mx ? 0x10000u : (my ? 1u : 0u);
+            dim = mx ? 1 : (my ? 2 : dim);
+            stop |= (((cnt - 0x00010001u) & 0x80008000u) != 0u) | (cnt == gcnt);   // (sticky: a lane that stopped on its start tile)
+        }
+    }
+    const int ci = (int)(cnt >> 16), cj = (int)(cnt & 0xFFFFu);
+    ti = si > 0 ? map.H1 - ci : ci;
+    tj = sj > 0 ? map.W1 - cj : cj;
+}
+
 // RayCaster.cast_ray contract for the ray rt = {ray_x, ray_y, |1/ray_x|, |1/ray_y|} from (x, y).
 // Must be called by all 32 lanes of a warp (lane <-> ray).  `closed`: see dda_walk.
-__device__ __forceinline__ RayHit dda_cast(const uint32_t* s_map, int H, int W, int wpr, uint32_t dda_flags,
+template <class Map>
+__device__ __forceinline__ RayHit dda_cast(const Map& map, int H, int W, uint32_t dda_flags,
                                            bool closed, float x, float y, int gi0, int gj0, const float4 rt, int lane) {
     int ti = __float2int_rd(x), tj = __float2int_rd(y);
     const int si = rt.x < 0.0f ? -1 : 1, sj = rt.y < 0.0f ? -1 : 1;
@@ -554,12 +608,19 @@ __device__ __forceinline__ RayHit dda_cast(const uint32_t* s_map, int H, int W, 
     // tile and stepped outwards, or carried over the border wall by an increment larger than a tile (the
     // collision test looks at the candidate position only, collision_detection.jl:21-42).  Same pose in all lanes.
     const bool start_inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
-    if (closed && start_inside) {
-        if (tie_le) dda_walk<true, true>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
-        else dda_walk<false, true>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+    if constexpr (std::is_same<Map, RoomMap>::value) {
+        if (start_inside) {
+            if (tie_le) dda_walk_room<true>(map, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+            else dda_walk_room<false>(map, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+        }   // from outside the map every tile counts as wall: the ray stops where it stands (dim 0, dist 0)
     } else {
-        if (tie_le) dda_walk<true, false>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
-        else dda_walk<false, false>(s_map, H, W, wpr, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+        if (closed && start_inside) {
+            if (tie_le) dda_walk<true, true>(map, H, W, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+            else dda_walk<false, true>(map, H, W, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+        } else {
+            if (tie_le) dda_walk<true, false>(map, H, W, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+            else dda_walk<false, false>(map, H, W, gi0, gj0, rt.z, rt.w, si, sj, tx, ty, ti, tj, dim, dist);
+        }
     }
 #endif
     if ((dda_flags & RCW_DDA_DIST_POST) && dim != 0)
@@ -571,14 +632,14 @@ __device__ __forceinline__ RayHit dda_cast(const uint32_t* s_map, int H, int W, 
     h.dist = dist;
     // which layer stopped the ray: a wall (outside the map counts as wall), else this env's goal
     const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
-    h.is_wall = !inside | wall_bit(s_map, wpr, inside ? ti : 0, inside ? tj : 0);
+    h.is_wall = !inside | map.wall(inside ? ti : 0, inside ? tj : 0);
     return h;
 }
 
 // cast_rays! for the 32 rays [32 g, 32 g + 32) of an env (single_room.jl:195-231) and the height /
 // colour of every ray's column (:404-429).  lane <-> ray.  Optionally dumps the ray results.
-template <int MODE>
-__device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, const uint32_t* s_map,
+template <int MODE, class Map>
+__device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, const Map& map,
                                                       const EnvPose& pose, const float4 rt, int g, int lane,
                                                       uint32_t env_rel) {
     const int R = p.R, P = p.P;
@@ -586,7 +647,7 @@ __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, cons
     const int gi0 = (int)(pose.goal & 0xFFFFu) - 1, gj0 = (int)(pose.goal >> 16) - 1;
     const int ray = g * 32 + lane;
     const float2 dir = p.dir_slot >= 0 ? c_dirs[p.dir_slot][au] : __ldg(p.dirs + au);
-    const RayHit hit = dda_cast(s_map, p.H, p.W, p.wpr, p.dda_flags, p.closed_border != 0, pose.x, pose.y, gi0, gj0, rt, lane);
+    const RayHit hit = dda_cast(map, p.H, p.W, p.dda_flags, p.closed_border != 0, pose.x, pose.y, gi0, gj0, rt, lane);
     const int ti = hit.ti, tj = hit.tj, dim = hit.dim;
     const float dist = hit.dist;
     const bool is_wall = hit.is_wall;
@@ -839,7 +900,19 @@ enum : int { kStageFused = 0, kStageFront = 1, kStagePaint = 2 };
 // OCC = CTAs per SM the register allocation aims for.  20 warps per SM (91 registers) is best when the step
 // is bound by the store stream (default camera, RGB8 / XRGB32); 32 warps per SM (<= 64 registers) is 6-14 %
 // faster when act! and the DDA bound it (small frames, one-byte pixels, large maps) — profiles/README.md.
-template <int MODE, int FMT, bool BULK, int STAGE>
+// ROOM: the wall layer is the border of the map and nothing else (RoomMap): nothing is staged in shared memory.
+template <bool ROOM>
+struct MapOf {
+    using type = BitsMap;
+    __device__ static __forceinline__ BitsMap make(const FrameParams& p, const uint32_t* words) { return BitsMap{words, p.wpr}; }
+};
+template <>
+struct MapOf<true> {
+    using type = RoomMap;
+    __device__ static __forceinline__ RoomMap make(const FrameParams& p, const uint32_t*) { return RoomMap{p.H - 1, p.W - 1}; }
+};
+
+template <int MODE, int FMT, bool BULK, int STAGE, bool ROOM = false>
 __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedActions* pa) {
     extern __shared__ __align__(128) uint32_t s_dyn[];  // [pattern buffers (BULK)] [bit-packed wall layer]
     __shared__ __align__(8) uint64_t s_mbar;
@@ -851,16 +924,17 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
     const int warp = threadIdx.x >> 5;
     constexpr bool kPaints = STAGE != kStageFront && MODE != kModeRays;
     constexpr bool kCasts = STAGE != kStagePaint;
+    constexpr bool kStagesMap = kCasts && !ROOM;         // the DDA / act! read a bit-packed wall layer from shared memory
 
     // ---- stage the wall layer (and the pattern buffers): TMA bulk copies, completion on mbarriers.
     // A wall layer shared by the batch is copied once per CTA here; per-env wall layers
     // (map_env_stride != 0) are copied per env of the round by that env's first warp, below.
     const uint32_t pat_bytes = (BULK && kPaints) ? 6u * (uint32_t)p.pat_stride : 0u;
     uint32_t* const s_map = s_dyn + pat_bytes / 4;
-    const bool per_env_maps = kCasts && p.map_env_stride != 0;
+    const bool per_env_maps = kStagesMap && p.map_env_stride != 0;
     const uint32_t map_bytes = (uint32_t)p.map_words * 4u;
-    const uint32_t shared_bytes = (kCasts && !per_env_maps) ? map_bytes : 0u;
-    if (kCasts || pat_bytes) {
+    const uint32_t shared_bytes = (kStagesMap && !per_env_maps) ? map_bytes : 0u;
+    if (kStagesMap || pat_bytes) {
         if (threadIdx.x == 0) {
             mbar_init(&s_mbar, 1);
             if (per_env_maps)
@@ -939,7 +1013,7 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
                 }
                 if (per_env_maps) mbar_wait(&s_mbar_env[slot], 0);
                 if (leader) {
-                    pose = act_env(p, my_map, env, in, /*writer=*/g == 0, lane);
+                    pose = act_env(p, MapOf<ROOM>::make(p, my_map), env, in, /*writer=*/g == 0, lane);
                     if (lane == 0) s_env[parity][slot] = pose;
                 }
                 __syncthreads();
@@ -965,7 +1039,7 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
                 if (per_env_maps) mbar_wait(&s_mbar_env[slot], 0);
             }
             if (!item_ok) continue;   // (no block barrier below this point)
-            cs = cast_and_shade<MODE>(p, my_map, pose, rt, g, lane, env_rel);
+            cs = cast_and_shade<MODE>(p, MapOf<ROOM>::make(p, my_map), pose, rt, g, lane, env_rel);
             if (MODE == kModeRays) continue;
             if (STAGE == kStageFront) {
                 // column order, so the paint launch reads its 32 columns with one coalesced load
@@ -1033,17 +1107,17 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
 }
 
 // OCC = CTAs per SM the register allocation aims for (see above).
-template <int MODE, int FMT, bool BULK, int STAGE, int OCC>
+template <int MODE, int FMT, bool BULK, int STAGE, int OCC, bool ROOM = false>
 __global__ void __launch_bounds__(kThreadsPerCta, OCC)
 frame_kernel(const __grid_constant__ FrameParams p) {
-    frame_body<MODE, FMT, BULK, STAGE>(p, nullptr);
+    frame_body<MODE, FMT, BULK, STAGE, ROOM>(p, nullptr);
 }
 
 // the step (fused, or the front stage alone: RCW_OBS_COLUMNS) with host-supplied actions packed into the parameters
-template <int FMT, int OCC, int STAGE = kStageFused>
+template <int FMT, int OCC, int STAGE = kStageFused, bool ROOM = false>
 __global__ void __launch_bounds__(kThreadsPerCta, OCC)
 frame_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ PackedActions a) {
-    frame_body<kModeStep, FMT, false, STAGE>(p, &a);
+    frame_body<kModeStep, FMT, false, STAGE, ROOM>(p, &a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1054,27 +1128,45 @@ frame_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ P
 // (profiles/README.md).  Here a warp owns a whole env: act! once, then its groups one after the other, the
 // ray-table row of the next group in flight while the current one is cast and painted.  No block barrier,
 // no pose exchange through shared memory, no item -> (env, group) arithmetic.
-// WORDS: the observation is the column words themselves (RCW_OBS_COLUMNS): nothing is painted.
-template <int MODE, int FMT, bool WORDS = false>
+// OUT: what a warp does with the 32 columns of a ray group.
+//   kOutPaint : render_span, as in frame_kernel (any geometry)
+//   kOutWords : the observation is the column words themselves (RCW_OBS_COLUMNS): nothing is painted
+//   kOutTable : small columns: every possible column (rows of ceiling x colour) is kept ready-made in a table of
+//               (P / 2 + 1) x 4 pitched columns (FrameParams::col_table, built on the host with the renderer's
+//               rules, L1 / L2 resident), and painting a column is copying its col_pitch bytes, whole sectors,
+//               256 bits per load and store — about 12 instead of 200 instructions per ray group.  The format
+//               only decides what is in the table, so one instantiation serves RGB8, XRGB32 and GRAY8.
+// ROOM: see MapOf — no wall layer in shared memory, no TMA, no mbarrier, no CTA barrier at all.
+enum : int { kOutPaint = 0, kOutWords = 1, kOutTable = 2 };
+
+__device__ __forceinline__ void load_nc32(const uint8_t* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+
+template <int MODE, int FMT, int OUT = kOutPaint, bool ROOM = false>
 __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActions* pa) {
     extern __shared__ __align__(128) uint32_t s_dyn[];   // wall layer(s): one shared, or one slot per warp
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ __align__(8) uint64_t s_mbar_env[kWarpsPerCta];
-    __shared__ uint2 s_col[kWarpsPerCta][32];
+    __shared__ uint2 s_col[OUT == kOutPaint ? kWarpsPerCta : 1][32];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const bool per_env_maps = p.map_env_stride != 0;
+    const bool per_env_maps = !ROOM && p.map_env_stride != 0;
     const uint32_t map_bytes = (uint32_t)p.map_words * 4u;
-    if (threadIdx.x == 0) {
-        mbar_init(&s_mbar, 1);
-        if (per_env_maps)
-            for (int k = 0; k < kWarpsPerCta; ++k) mbar_init(&s_mbar_env[k], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && !per_env_maps) {
-        mbar_arrive_expect_tx(&s_mbar, map_bytes);
-        bulk_copy_g2s(s_dyn, p.wall_map, map_bytes, &s_mbar);
+    if (!ROOM) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_mbar, 1);
+            if (per_env_maps)
+                for (int k = 0; k < kWarpsPerCta; ++k) mbar_init(&s_mbar_env[k], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && !per_env_maps) {
+            mbar_arrive_expect_tx(&s_mbar, map_bytes);
+            bulk_copy_g2s(s_dyn, p.wall_map, map_bytes, &s_mbar);
+        }
     }
     // (no block barrier below this point)  A warp without work still waits for the CTA's bulk copy, so that shared
     // memory is not released while the copy is in flight.
@@ -1082,7 +1174,7 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
     const int64_t env = p.env_first + env_rel;
     if (env_rel >= (uint32_t)p.env_count ||
         (MODE == kModeRender && p.render_mask && !__ldg(p.render_mask + env))) {       // out of range / masked render
-        if (!per_env_maps) mbar_wait(&s_mbar, 0);
+        if (!ROOM && !per_env_maps) mbar_wait(&s_mbar, 0);
         return;
     }
     const int R = p.R;
@@ -1095,6 +1187,7 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
                           &s_mbar_env[warp]);
         }
     }
+    const typename MapOf<ROOM>::type map = MapOf<ROOM>::make(p, my_map);
     const float4* const rt_lane0 = p.ray_table + min(lane, R - 1);     // group 0
     EnvPose pose;
     float4 rt;
@@ -1105,9 +1198,11 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
         const float4 rt_m = __ldg(rt_lane0 + (size_t)au_m * (size_t)R);
         const float4 rt_0 = __ldg(rt_lane0 + (size_t)in.au * (size_t)R);
         const float4 rt_p = __ldg(rt_lane0 + (size_t)au_p * (size_t)R);
-        if (per_env_maps) mbar_wait(&s_mbar_env[warp], 0);
-        else mbar_wait(&s_mbar, 0);
-        pose = act_env(p, my_map, env, in, /*writer=*/true, lane);
+        if (!ROOM) {
+            if (per_env_maps) mbar_wait(&s_mbar_env[warp], 0);
+            else mbar_wait(&s_mbar, 0);
+        }
+        pose = act_env(p, map, env, in, /*writer=*/true, lane);
         if (pose.au == in.au) rt = rt_0;
         else if (pose.au == au_m) rt = rt_m;
         else if (pose.au == au_p) rt = rt_p;
@@ -1118,8 +1213,10 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
         pose.au = __ldg(p.in.dir_au + env);
         pose.goal = __ldg(p.in.goal + env);
         rt = __ldg(rt_lane0 + (size_t)pose.au * (size_t)R);
-        if (per_env_maps) mbar_wait(&s_mbar_env[warp], 0);
-        else mbar_wait(&s_mbar, 0);
+        if (!ROOM) {
+            if (per_env_maps) mbar_wait(&s_mbar_env[warp], 0);
+            else mbar_wait(&s_mbar, 0);
+        }
     }
     uint32_t obs_slot = p.obs_slot0 + env_rel;
     if (obs_slot >= p.obs_window) obs_slot -= p.obs_window;
@@ -1129,37 +1226,65 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
     for (int g = 0; g < gpe; ++g) {
         float4 rt_next = rt;
         if (g + 1 < gpe) rt_next = __ldg(rt_row + min((g + 1) * 32 + lane, R - 1));
-        const ColumnShade cs = cast_and_shade<MODE>(p, my_map, pose, rt, g, lane, env_rel);
+        const ColumnShade cs = cast_and_shade<MODE>(p, map, pose, rt, g, lane, env_rel);
         const int r0 = g * 32;
         const int ncols = min(32, R - r0);
         const int col0 = R - r0 - ncols;               // ray r paints column R-1-r
-        if (WORDS) {
+        if (OUT == kOutWords) {
             if (lane < ncols)
                 p.col_info[(size_t)obs_slot * p.col_info_stride + (size_t)(col0 + ncols - 1 - lane)] =
                     (uint32_t)cs.pad | ((uint32_t)cs.cid << 16);
             rt = rt_next;
             continue;
         }
+        if (OUT == kOutTable) {
+            // The span's sectors are consecutive in memory: lane L copies sectors L, L + 32, ... — sector s is
+            // sector (s mod NS) of the table entry of column s / NS, whose ray sits in lane ncols - 1 - s / NS.
+            const int CP = p.col_pitch, NS = CP >> 5;
+            const uint32_t entry = (uint32_t)((cs.pad << 2) + (cs.cid - RCW_COLOR_WALL_1)) * (uint32_t)CP;
+            const int n_sec = ncols * NS;
+            int cl = (int)(((uint32_t)lane * p.sec_inv16) >> 16), sc = lane - cl * NS;
+            const int adv_cl = p.sec_adv_cl, adv_sc = p.sec_adv_u;
+            uint8_t* dst = env_obs + (size_t)col0 * CP + (lane << 5);
+#pragma unroll 2
+            for (int s = lane; s < ((n_sec + 31) & ~31); s += 32) {   // (uniform trip count: the shuffle needs all lanes)
+                const uint32_t e = __shfl_sync(0xFFFFFFFFu, entry, max(ncols - 1 - cl, 0));
+                if (s < n_sec) {
+                    uint4 lo, hi;
+                    load_nc32(p.col_table + e + (uint32_t)(sc << 5), lo, hi);
+                    store_stream32(dst, lo, hi);
+                }
+                dst += 1024;
+                cl += adv_cl;
+                sc += adv_sc;
+                if (sc >= NS) {
+                    sc -= NS;
+                    ++cl;
+                }
+            }
+            rt = rt_next;
+            continue;
+        }
         bool slow = false;
-        if (lane < ncols) s_col[warp][ncols - 1 - lane] = column_entry<FMT>(p, cs.pad, cs.cid, slow);
+        if (lane < ncols) s_col[OUT == kOutPaint ? warp : 0][ncols - 1 - lane] = column_entry<FMT>(p, cs.pad, cs.cid, slow);
         __syncwarp();
         const bool item_slow = __any_sync(0xFFFFFFFFu, slow);
-        render_span<FMT>(p, s_col[warp], env_obs, col0 * p.col_pitch, ncols, lane, item_slow);
+        render_span<FMT>(p, s_col[OUT == kOutPaint ? warp : 0], env_obs, col0 * p.col_pitch, ncols, lane, item_slow);
         __syncwarp();                                  // s_col is rewritten by the next group
         rt = rt_next;
     }
 }
 
-template <int MODE, int FMT, bool WORDS = false>
+template <int MODE, int FMT, int OUT = kOutPaint, bool ROOM = false>
 __global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSmHi)
 env_kernel(const __grid_constant__ FrameParams p) {
-    env_body<MODE, FMT, WORDS>(p, nullptr);
+    env_body<MODE, FMT, OUT, ROOM>(p, nullptr);
 }
 
-template <int FMT, bool WORDS = false>
+template <int FMT, int OUT = kOutPaint, bool ROOM = false>
 __global__ void __launch_bounds__(kThreadsPerCta, kCtasPerSmHi)
 env_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ PackedActions a) {
-    env_body<kModeStep, FMT, WORDS>(p, &a);
+    env_body<kModeStep, FMT, OUT, ROOM>(p, &a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1180,9 +1305,8 @@ __global__ void reset_kernel(const ResetParams p) {
         au = p.dir_au[env];
     } else {
         episode += 1u;
-        draw_layout(p.wall_map + (size_t)env * p.map_env_stride, p.H, p.W, p.wpr, p.N, p.seed,
-                    p.env_id_offset + (uint64_t)env,
-                    episode, gi, gj, pi, pj, au);
+        draw_layout(BitsMap{p.wall_map + (size_t)env * p.map_env_stride, p.wpr}, p.H, p.W, p.N, p.seed,
+                    p.env_id_offset + (uint64_t)env, episode, gi, gj, pi, pj, au);
     }
     p.st.pos_x[env] = __fsub_rn((float)pi, 0.5f);
     p.st.pos_y[env] = __fsub_rn((float)pj, 0.5f);
@@ -1244,89 +1368,100 @@ cudaError_t launch_build_ray_table(const float2* dirs, int N, int R, float sfov,
     return cudaGetLastError();
 }
 
-template <int MODE, int FMT, bool BULK, int STAGE, int OCC>
+template <int MODE, int FMT, bool BULK, int STAGE, int OCC, bool ROOM = false>
 static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s) {
     const bool casts = STAGE != kStagePaint, paints = STAGE != kStageFront && MODE != kModeRays;
     const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;   // per-env wall layers: one slot per env of a round
-    const size_t smem = (casts ? map_slots * (size_t)p.map_words * 4 : 0) + ((BULK && paints) ? 6 * (size_t)p.pat_stride : 0);
+    const size_t smem = ((casts && !ROOM) ? map_slots * (size_t)p.map_words * 4 : 0) + ((BULK && paints) ? 6 * (size_t)p.pat_stride : 0);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(frame_kernel<MODE, FMT, BULK, STAGE, OCC>,
+        cudaError_t e = cudaFuncSetAttribute(frame_kernel<MODE, FMT, BULK, STAGE, OCC, ROOM>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    frame_kernel<MODE, FMT, BULK, STAGE, OCC><<<ctas, kThreadsPerCta, smem, s>>>(p);
+    frame_kernel<MODE, FMT, BULK, STAGE, OCC, ROOM><<<ctas, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
-
 }
 
-template <int MODE, int FMT, bool WORDS = false>
+static size_t env_smem(const FrameParams& p, bool room) {
+    return room ? 0 : (p.map_env_stride ? kWarpsPerCta : 1) * (size_t)p.map_words * 4;
+}
+
+template <int MODE, int FMT, int OUT, bool ROOM>
 static cudaError_t launch_env_t(const FrameParams& p, cudaStream_t s) {
-    const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
-    const size_t smem = map_slots * (size_t)p.map_words * 4;
+    const size_t smem = env_smem(p, ROOM);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(env_kernel<MODE, FMT, WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(env_kernel<MODE, FMT, OUT, ROOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const unsigned ctas = (unsigned)((p.env_count + kWarpsPerCta - 1) / kWarpsPerCta);
-    env_kernel<MODE, FMT, WORDS><<<ctas, kThreadsPerCta, smem, s>>>(p);
+    env_kernel<MODE, FMT, OUT, ROOM><<<ctas, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-template <int FMT, bool WORDS = false>
+template <int FMT, int OUT, bool ROOM>
 static cudaError_t launch_env_pa_t(const FrameParams& p, const PackedActions& pa, cudaStream_t s) {
-    const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
-    const size_t smem = map_slots * (size_t)p.map_words * 4;
+    const size_t smem = env_smem(p, ROOM);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(env_kernel_pa<FMT, WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(env_kernel_pa<FMT, OUT, ROOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const unsigned ctas = (unsigned)((p.env_count + kWarpsPerCta - 1) / kWarpsPerCta);
-    env_kernel_pa<FMT, WORDS><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
+    env_kernel_pa<FMT, OUT, ROOM><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
     return cudaGetLastError();
 }
 
-template <int FMT, int OCC, int STAGE = kStageFused>
+template <int FMT, int OCC, int STAGE, bool ROOM>
 static cudaError_t launch_frame_pa_t(const FrameParams& p, const PackedActions& pa, int ctas, cudaStream_t s) {
-    const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;
-    const size_t smem = map_slots * (size_t)p.map_words * 4;
+    const size_t smem = env_smem(p, ROOM);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(frame_kernel_pa<FMT, OCC, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(frame_kernel_pa<FMT, OCC, STAGE, ROOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    frame_kernel_pa<FMT, OCC, STAGE><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
+    frame_kernel_pa<FMT, OCC, STAGE, ROOM><<<ctas, kThreadsPerCta, smem, s>>>(p, pa);
     return cudaGetLastError();
-}
-
-template <int FMT>
-static cudaError_t launch_packed(const FrameParams& p, const PackedActions& pa, const LaunchShape& sh, cudaStream_t s) {
-    if (sh.env_per_warp) return launch_env_pa_t<FMT>(p, pa, s);
-    return sh.occ4 ? launch_frame_pa_t<FMT, kCtasPerSmHi>(p, pa, sh.ctas, s)
-                   : launch_frame_pa_t<FMT, kCtasPerSmLo>(p, pa, sh.ctas, s);
-}
-
-template <int MODE>
-static cudaError_t launch_env_m(const FrameParams& p, int obs_format, cudaStream_t s) {
-    if (obs_format == RCW_OBS_GRAY8) return launch_env_t<MODE, RCW_OBS_GRAY8>(p, s);
-    if (obs_format == RCW_OBS_RGB8) return launch_env_t<MODE, RCW_OBS_RGB8>(p, s);
-    return launch_env_t<MODE, RCW_OBS_XRGB32>(p, s);
 }
 
 constexpr int kOcc = kCtasPerSmLo;
 
-// the shipped path (fused stage, lane-written sectors) exists for both register budgets
-template <int MODE, int FMT>
-static cudaError_t launch_fused(const FrameParams& p, const LaunchShape& sh, cudaStream_t s) {
-    return sh.occ4 ? launch_frame_t<MODE, FMT, false, kStageFused, kCtasPerSmHi>(p, sh.ctas, s)
-                   : launch_frame_t<MODE, FMT, false, kStageFused, kOcc>(p, sh.ctas, s);
+// env_kernel: MODE in {step, render}; OUT / FMT from the handle's format and whether it has a column table
+template <int MODE, bool ROOM>
+static cudaError_t launch_env_m(const FrameParams& p, int obs_format, const LaunchShape& sh, cudaStream_t s,
+                                const PackedActions* packed) {
+    // (a packed launch is always a step: `packed` is only passed with MODE == kModeStep)
+#define RCW_ENV_LAUNCH(FMT, OUT)                                                        \
+    return packed ? launch_env_pa_t<FMT, OUT, ROOM>(p, *packed, s) : launch_env_t<MODE, FMT, OUT, ROOM>(p, s)
+    if (obs_format == RCW_OBS_COLUMNS) { RCW_ENV_LAUNCH(RCW_OBS_RGB8, kOutWords); }
+    if (sh.table) { RCW_ENV_LAUNCH(RCW_OBS_GRAY8, kOutTable); }
+    if (obs_format == RCW_OBS_GRAY8) { RCW_ENV_LAUNCH(RCW_OBS_GRAY8, kOutPaint); }
+    if (obs_format == RCW_OBS_RGB8) { RCW_ENV_LAUNCH(RCW_OBS_RGB8, kOutPaint); }
+    RCW_ENV_LAUNCH(RCW_OBS_XRGB32, kOutPaint);
+#undef RCW_ENV_LAUNCH
 }
 
+// frame_kernel, the shipped path (fused stage or the front stage alone, lane-written sectors): both register budgets
+template <int MODE, int FMT, int STAGE, bool ROOM>
+static cudaError_t launch_item(const FrameParams& p, const LaunchShape& sh, cudaStream_t s, const PackedActions* packed) {
+    const bool hi = sh.occ4 || STAGE == kStageFront;   // the front stage alone is bound by act! + DDA
+    if (packed)
+        return hi ? launch_frame_pa_t<FMT, kCtasPerSmHi, STAGE, ROOM>(p, *packed, sh.ctas, s)
+                  : launch_frame_pa_t<FMT, kOcc, STAGE, ROOM>(p, *packed, sh.ctas, s);
+    return hi ? launch_frame_t<MODE, FMT, false, STAGE, kCtasPerSmHi, ROOM>(p, sh.ctas, s)
+              : launch_frame_t<MODE, FMT, false, STAGE, kOcc, ROOM>(p, sh.ctas, s);
+}
+
+template <int MODE, bool ROOM>
+static cudaError_t launch_shipped(const FrameParams& p, int obs_format, const LaunchShape& sh, cudaStream_t s,
+                                  const PackedActions* packed) {
+    if (sh.env_per_warp) return launch_env_m<MODE, ROOM>(p, obs_format, sh, s, packed);
+    if (obs_format == RCW_OBS_COLUMNS) return launch_item<MODE, RCW_OBS_RGB8, kStageFront, ROOM>(p, sh, s, packed);
+    if (obs_format == RCW_OBS_GRAY8) return launch_item<MODE, RCW_OBS_GRAY8, kStageFused, ROOM>(p, sh, s, packed);
+    if (obs_format == RCW_OBS_RGB8) return launch_item<MODE, RCW_OBS_RGB8, kStageFused, ROOM>(p, sh, s, packed);
+    return launch_item<MODE, RCW_OBS_XRGB32, kStageFused, ROOM>(p, sh, s, packed);
+}
+
+// measured alternatives (RCW_RENDER_PATH=bulk, RCW_SPLIT=1) and the paint stage of rcw_expand_columns: bit-packed maps only
 template <int MODE, int STAGE>
-static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, const LaunchShape& sh, cudaStream_t s) {
-    if (STAGE == kStageFused && !sh.bulk) {
-        if (obs_format == RCW_OBS_GRAY8) return launch_fused<MODE, RCW_OBS_GRAY8>(p, sh, s);
-        if (obs_format == RCW_OBS_RGB8) return launch_fused<MODE, RCW_OBS_RGB8>(p, sh, s);
-        return launch_fused<MODE, RCW_OBS_XRGB32>(p, sh, s);
-    }
+static cudaError_t launch_frame_alt(const FrameParams& p, int obs_format, const LaunchShape& sh, cudaStream_t s) {
     if (obs_format == RCW_OBS_GRAY8) return launch_frame_t<MODE, RCW_OBS_GRAY8, false, STAGE, kOcc>(p, sh.ctas, s);
     if (obs_format == RCW_OBS_RGB8)
         return sh.bulk ? launch_frame_t<MODE, RCW_OBS_RGB8, true, STAGE, kOcc>(p, sh.ctas, s)
@@ -1338,46 +1473,35 @@ static cudaError_t launch_frame_m(const FrameParams& p, int obs_format, const La
 // split = false: one fused launch.  split = true: two launches (front, then paint) through p.col_info.
 cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const LaunchShape& sh, cudaStream_t s,
                          const PackedActions* packed) {
-    if (obs_format == RCW_OBS_COLUMNS) {
-        // the observation is the front stage's output: {rows of ceiling, palette index} per column, no pixels;
-        // act! + DDA bound it, so it runs at the front-bound register budget
-        if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc>(p, sh.ctas, s);
-        if (packed) {
-            if (mode != kModeStep || p.env_count > kPackedActionEnvs) return cudaErrorInvalidValue;
-            if (sh.env_per_warp) return launch_env_pa_t<RCW_OBS_RGB8, true>(p, *packed, s);
-            return launch_frame_pa_t<RCW_OBS_RGB8, kCtasPerSmHi, kStageFront>(p, *packed, sh.ctas, s);
-        }
-        if (sh.env_per_warp && mode == kModeStep) return launch_env_t<kModeStep, RCW_OBS_RGB8, true>(p, s);
-        if (sh.env_per_warp && mode == kModeRender) return launch_env_t<kModeRender, RCW_OBS_RGB8, true>(p, s);
-        if (mode == kModeStep) return launch_frame_t<kModeStep, RCW_OBS_RGB8, false, kStageFront, kCtasPerSmHi>(p, sh.ctas, s);
-        if (mode == kModeRender) return launch_frame_t<kModeRender, RCW_OBS_RGB8, false, kStageFront, kCtasPerSmHi>(p, sh.ctas, s);
-        return cudaErrorInvalidValue;
-    }
-    if (packed) {
-        if (mode != kModeStep || sh.split || sh.bulk || p.env_count > kPackedActionEnvs) return cudaErrorInvalidValue;
-        if (obs_format == RCW_OBS_GRAY8) return launch_packed<RCW_OBS_GRAY8>(p, *packed, sh, s);
-        if (obs_format == RCW_OBS_RGB8) return launch_packed<RCW_OBS_RGB8>(p, *packed, sh, s);
-        return launch_packed<RCW_OBS_XRGB32>(p, *packed, sh, s);
-    }
-    if (mode == kModeRays) return launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc>(p, sh.ctas, s);
+    if (packed && (mode != kModeStep || p.env_count > kPackedActionEnvs)) return cudaErrorInvalidValue;
+    if (mode == kModeRays)
+        return sh.room ? launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc, true>(p, sh.ctas, s)
+                       : launch_frame_t<kModeRays, RCW_OBS_RGB8, false, kStageFused, kOcc, false>(p, sh.ctas, s);
     if (mode != kModeStep && mode != kModeRender) return cudaErrorInvalidValue;
-    if (sh.env_per_warp && !sh.split && !sh.bulk)
-        return mode == kModeStep ? launch_env_m<kModeStep>(p, obs_format, s) : launch_env_m<kModeRender>(p, obs_format, s);
+    const bool alt = obs_format != RCW_OBS_COLUMNS && (sh.split || sh.bulk);
+    if (!alt) {
+        if (mode == kModeStep)
+            return sh.room ? launch_shipped<kModeStep, true>(p, obs_format, sh, s, packed)
+                           : launch_shipped<kModeStep, false>(p, obs_format, sh, s, packed);
+        return sh.room ? launch_shipped<kModeRender, true>(p, obs_format, sh, s, nullptr)
+                       : launch_shipped<kModeRender, false>(p, obs_format, sh, s, nullptr);
+    }
+    if (packed) return cudaErrorInvalidValue;
     if (!sh.split)
-        return mode == kModeStep ? launch_frame_m<kModeStep, kStageFused>(p, obs_format, sh, s)
-                                 : launch_frame_m<kModeRender, kStageFused>(p, obs_format, sh, s);
+        return mode == kModeStep ? launch_frame_alt<kModeStep, kStageFused>(p, obs_format, sh, s)
+                                 : launch_frame_alt<kModeRender, kStageFused>(p, obs_format, sh, s);
     cudaError_t e = mode == kModeStep
                         ? launch_frame_t<kModeStep, RCW_OBS_RGB8, false, kStageFront, kOcc>(p, sh.ctas, s)
                         : launch_frame_t<kModeRender, RCW_OBS_RGB8, false, kStageFront, kOcc>(p, sh.ctas, s);
     if (e != cudaSuccess) return e;
-    return launch_frame_m<kModeRender, kStagePaint>(p, obs_format, sh, s);
+    return launch_frame_alt<kModeRender, kStagePaint>(p, obs_format, sh, s);
 }
 
 cudaError_t launch_expand_columns(const FrameParams& p, int pixel_format, int ctas, cudaStream_t s) {
     LaunchShape sh{false, true, false, ctas};
     if (pixel_format != RCW_OBS_RGB8 && pixel_format != RCW_OBS_XRGB32 && pixel_format != RCW_OBS_GRAY8)
         return cudaErrorInvalidValue;
-    return launch_frame_m<kModeRender, kStagePaint>(p, pixel_format, sh, s);
+    return launch_frame_alt<kModeRender, kStagePaint>(p, pixel_format, sh, s);
 }
 
 cudaError_t launch_reset(const ResetParams& p, cudaStream_t s) {

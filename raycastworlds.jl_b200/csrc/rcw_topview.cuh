@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
         const int j0 = t / H, i0 = t - j0 * H;
         int code = RCW_TOP_COLOR_BORDER;                      // pseudo tile column W: what a border column of the image shows
         if (j0 < W)
-            code = wall_bit(s_map, p.wpr, i0, j0) ? RCW_TOP_COLOR_WALL
+            code = BitsMap{s_map, p.wpr}.wall(i0, j0) ? RCW_TOP_COLOR_WALL
                                                   : ((i0 == gi0 && j0 == gj0) ? RCW_TOP_COLOR_GOAL : RCW_TOP_COLOR_EMPTY);
         s_tilec[t] = p.palette[code];
     }
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     for (int g = warp; g < groups; g += kTopThreads / 32) {
         const int ray = g * 32 + lane;
         const float4 rt = __ldg(p.ray_table + (size_t)au * (size_t)R + (size_t)min(ray, R - 1));
-        const RayHit hit = dda_cast(s_map, H, W, p.wpr, p.dda_flags, p.closed_border != 0, x, y, gi0, gj0, rt, lane);
+        const RayHit hit = dda_cast(BitsMap{s_map, p.wpr}, H, W, p.dda_flags, p.closed_border != 0, x, y, gi0, gj0, rt, lane);
         // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
         const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
         const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);

@@ -53,6 +53,8 @@ def test_random_configuration_matches_oracle(rcw, oracle, monkeypatch, seed):
     monkeypatch.setenv("RCW_ENV_PER_WARP", "1" if c["env_kernel"] else "0")
     monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
     monkeypatch.setenv("RCW_PACKED_ACTIONS", str(seed % 2))      # host actions: kernel parameters / staged copy
+    monkeypatch.setenv("RCW_ROOM", str((seed >> 1) & 1))         # border-only maps: counting walk / bit-packed wall layer
+    monkeypatch.setenv("RCW_COL_TABLE_KB", "0" if (seed >> 2) & 1 else "64")   # env kernel: painted / ready-made columns
     n, H, W = c["n"], c["H"], c["W"]
     kw = dict(height_tile_map_tu=H, width_tile_map_tu=W, num_directions=c["N"], num_rays=c["R"],
               height_camera_view_pu=c["P"], player_radius_wu=c["radius"], position_increment_wu=c["incr"],
@@ -146,14 +148,16 @@ def test_random_configuration_matches_oracle(rcw, oracle, monkeypatch, seed):
     env.close()
 
 
+@pytest.mark.parametrize("room", [0, 1])
 @pytest.mark.parametrize("env_kernel", [0, 1])
-def test_player_carried_outside_the_map_is_defined(rcw, oracle, monkeypatch, env_kernel):
+def test_player_carried_outside_the_map_is_defined(rcw, oracle, monkeypatch, env_kernel, room):
     """An increment larger than a tile carries the player over the border wall (the collision test only looks at
     the candidate position, collision_detection.jl:21-42), and a state injected onto a border tile can step
     outwards.  Outside the map everything counts as wall: rays stop at once, the column is full height.  The
     unchecked closed-border DDA must not be taken from there (found by the seeded fuzz test above)."""
     monkeypatch.setenv("RCW_ENV_PER_WARP", str(env_kernel))
     monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    monkeypatch.setenv("RCW_ROOM", str(room))
     n = 6
     kw = dict(num_rays=64, height_camera_view_pu=32, position_increment_wu=2.5, player_radius_wu=0.1, pu_per_tu=4)
     env = rcw.BatchedSingleRoom(n, auto_reset=False, **kw)
@@ -198,6 +202,8 @@ def test_random_operation_sequences_with_windows(rcw, oracle, monkeypatch, seed)
     whole state and every observation slot must equal the oracle's for the env rendered into it last."""
     rng = np.random.default_rng(9000 + seed)
     monkeypatch.setenv("RCW_ENV_PER_WARP", str(int(rng.integers(0, 2))))
+    monkeypatch.setenv("RCW_ROOM", str(seed & 1))
+    monkeypatch.setenv("RCW_COL_TABLE_KB", "0" if seed & 2 else "64")
     monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
     monkeypatch.setenv("RCW_PACKED_ACTIONS", str(int(rng.integers(0, 2))))
     n = int(rng.integers(2, 60))
