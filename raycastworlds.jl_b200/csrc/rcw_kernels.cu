@@ -270,6 +270,9 @@ __device__ __forceinline__ uint32_t column_byte(const ColumnBands& cb, int ob) {
 #ifndef RCW_STORE_POLICY
 #define RCW_STORE_POLICY 0
 #endif
+#ifndef RCW_TABLE_COPY
+#define RCW_TABLE_COPY 0   // env_kernel's table renderer: 0 = lane <-> column, 1 = lane <-> consecutive sectors of the span
+#endif
 __device__ __forceinline__ void store_stream16(uint8_t* p, uint4 v) {
 #if RCW_EXP == 2
     if (v.x == 0x12345u) __stcs(reinterpret_cast<uint4*>(p), v);   // experiment: compute only
@@ -562,28 +565,57 @@ __device__ __forceinline__ void dda_walk_room(const RoomMap& map, int gi0, int g
     // steps left until the border tile in the direction of travel (H, W <= 32767: FrameParams::room)
     const int ci0 = si > 0 ? map.H1 - ti : ti, cj0 = sj > 0 ? map.W1 - tj : tj;
     const int gci = si > 0 ? map.H1 - gi0 : gi0, gcj = sj > 0 ? map.W1 - gj0 : gj0;
-    uint32_t cnt = ((uint32_t)ci0 << 16) | (uint32_t)cj0;
     // a goal outside 0..32767 in either dimension can never be met: give it a pair no count reaches
     const bool goal_in = ((unsigned)gci < 0x8000u) & ((unsigned)gcj < 0x8000u);
     const uint32_t gcnt = goal_in ? (((uint32_t)gci << 16) | (uint32_t)gcj) : 0xFFFFFFFFu;
-    bool stop = map.wall(ti, tj) | (cnt == gcnt);     // the start tile itself: any border tile is a wall
-#pragma unroll 1
-    while (__any_sync(0xFFFFFFFFu, !stop)) {
-#pragma unroll
-        for (int u = 0; u < kDdaStepsPerVote; ++u) {
-            const bool cmp = TIE_LE ? (tx <= ty) : (tx < ty);
-            const bool mx = !stop & cmp, my = !stop & !cmp;
-            dist = mx ? tx : (my ? ty : dist);
-            tx = mx ? __fadd_rn(tx, dx) : tx;
-            ty = my ? __fadd_rn(ty, dy) : ty;
-            cnt -= mx ? 0x10000u : (my ? 1u : 0u);
-            dim = mx ? 1 : (my ? 2 : dim);
-            stop |= (((cnt - 0x00010001u) & 0x80008000u) != 0u) | (cnt == gcnt);   // (sticky: a lane that stopped on its start tile)
-        }
+    // A start tile on the border is a wall whichever way the ray points; such a lane never walks.  Its count is
+    // zeroed so that the stop test below holds for it in every step (the tile is restored after the loop).
+    const bool start_wall = map.wall(ti, tj);
+    uint32_t cnt = start_wall ? 0u : (((uint32_t)ci0 << 16) | (uint32_t)cj0);
+    const uint32_t stop0 = (start_wall | (cnt == gcnt)) ? 1u : 0u;
+    uint32_t last_x = 0u;
+    // The loop in PTX, so that a step stays the twelve predicated instructions it is (the compiler turns the C++
+    // form into branches and register moves, 17-19 per step).  Per step, for a lane that has not stopped:
+    //   px = tx < ty (<= with D1), py = !px;  dist = px ? tx : ty;  @px { tx += dx; count -= 0x10000 }
+    //   @py { ty += dy; count -= 1 };  stop = a half of the count reached zero (it borrows) | count == goal's.
+    // A stopped lane keeps its count, so its stop test keeps holding; the warp votes every kDdaStepsPerVote steps.
+#define RCW_ROOM_STEP(CMP)                                  \
+    "setp." CMP ".and.f32 px|py, %0, %1, !ps;\n\t"          \
+    "@!ps selp.f32 %3, %0, %1, px;\n\t"                     \
+    "@!ps selp.u32 %4, 1, 0, px;\n\t"                       \
+    "@px add.rn.f32 %0, %0, %5;\n\t"                        \
+    "@py add.rn.f32 %1, %1, %6;\n\t"                        \
+    "@px sub.u32 %2, %2, 0x10000;\n\t"                      \
+    "@py sub.u32 %2, %2, 1;\n\t"                            \
+    "sub.u32 t, %2, 0x00010001;\n\t"                        \
+    "and.b32 t, t, 0x80008000;\n\t"                         \
+    "setp.ne.u32 ps, t, 0;\n\t"                             \
+    "setp.eq.or.u32 ps, %2, %7, ps;\n\t"
+#define RCW_ROOM_LOOP(CMP)                                                                              \
+    asm volatile("{\n\t"                                                                                \
+                 ".reg .pred ps, px, py, pgo;\n\t"                                                       \
+                 ".reg .u32 t;\n\t"                                                                      \
+                 "setp.ne.u32 ps, %8, 0;\n"                                                              \
+                 "RCW_ROOM_LOOP_TOP:\n\t"                                                                \
+                 "vote.sync.any.pred pgo, !ps, 0xffffffff;\n\t"                                          \
+                 "@!pgo bra RCW_ROOM_LOOP_END;\n\t"                                                      \
+                 RCW_ROOM_STEP(CMP) RCW_ROOM_STEP(CMP)                                                  \
+                 "bra RCW_ROOM_LOOP_TOP;\n"                                                              \
+                 "RCW_ROOM_LOOP_END:\n\t"                                                                \
+                 "}"                                                                                    \
+                 : "+f"(tx), "+f"(ty), "+r"(cnt), "+f"(dist), "+r"(last_x)                              \
+                 : "f"(dx), "f"(dy), "r"(gcnt), "r"(stop0))
+    static_assert(kDdaStepsPerVote == 2, "RCW_ROOM_LOOP unrolls two steps per vote");
+    if (TIE_LE) RCW_ROOM_LOOP("le");
+    else RCW_ROOM_LOOP("lt");
+#undef RCW_ROOM_LOOP
+#undef RCW_ROOM_STEP
+    if (!start_wall) {
+        const int ci = (int)(cnt >> 16), cj = (int)(cnt & 0xFFFFu);
+        if (ci != ci0 || cj != cj0) dim = last_x ? 1 : 2;
+        ti = si > 0 ? map.H1 - ci : ci;
+        tj = sj > 0 ? map.W1 - cj : cj;
     }
-    const int ci = (int)(cnt >> 16), cj = (int)(cnt & 0xFFFFu);
-    ti = si > 0 ? map.H1 - ci : ci;
-    tj = sj > 0 ? map.W1 - cj : cj;
 }
 
 // RayCaster.cast_ray contract for the ray rt = {ray_x, ray_y, |1/ray_x|, |1/ray_y|} from (x, y).
@@ -1224,8 +1256,8 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
     const float4* const rt_row = p.ray_table + (size_t)pose.au * (size_t)R;
     const int gpe = p.gpe;
     for (int g = 0; g < gpe; ++g) {
-        float4 rt_next = rt;
-        if (g + 1 < gpe) rt_next = __ldg(rt_row + min((g + 1) * 32 + lane, R - 1));
+        // the next group's row (behind the last group: the last ray's entry once more, unused)
+        const float4 rt_next = __ldg(rt_row + min((g + 1) * 32 + lane, R - 1));
         const ColumnShade cs = cast_and_shade<MODE>(p, map, pose, rt, g, lane, env_rel);
         const int r0 = g * 32;
         const int ncols = min(32, R - r0);
@@ -1238,6 +1270,20 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
             continue;
         }
         if (OUT == kOutTable) {
+#if RCW_TABLE_COPY == 0
+            // lane <-> column: copy the column's col_pitch bytes from its table entry, sector by sector
+            const int CP = p.col_pitch;
+            if (lane < ncols) {
+                const uint8_t* src = p.col_table + (uint32_t)((cs.pad << 2) + (cs.cid - RCW_COLOR_WALL_1)) * (uint32_t)CP;
+                uint8_t* dst = env_obs + (size_t)(col0 + ncols - 1 - lane) * CP;
+#pragma unroll 3
+                for (int o = 0; o < CP; o += 32) {
+                    uint4 lo, hi;
+                    load_nc32(src + o, lo, hi);
+                    store_stream32(dst + o, lo, hi);
+                }
+            }
+#else
             // The span's sectors are consecutive in memory: lane L copies sectors L, L + 32, ... — sector s is
             // sector (s mod NS) of the table entry of column s / NS, whose ray sits in lane ncols - 1 - s / NS.
             const int CP = p.col_pitch, NS = CP >> 5;
@@ -1262,6 +1308,7 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
                     ++cl;
                 }
             }
+#endif
             rt = rt_next;
             continue;
         }

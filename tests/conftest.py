@@ -47,4 +47,8 @@ GOLDEN_CONFIGS = {
     "C": dict(H=5, W=7, N=36, R=45, P=51, radius=np.float32(0.2), incr=np.float32(0.3),
               sfov=np.float32(0.5), cam_h=np.float32(0.8), pu_per_tu=7),
     "D": dict(tie_le=1, dist_post=1),
+    # exact ties between the side distances (tile centres / corners, 8 directions, odd ray count): T with the
+    # default tie rule, U with RCW_DDA_TIE_LE — the states that let a Julia dump resolve decision D1
+    "T": dict(H=7, W=7, N=8, R=33, P=40, pu_per_tu=4),
+    "U": dict(H=7, W=7, N=8, R=33, P=40, pu_per_tu=4, tie_le=1),
 }

@@ -378,6 +378,18 @@ def main():
     for k, v in cast_case(w, st).items():
         out["D_" + k] = v
 
+    # T / U: exact ties between the two side distances — tile centres and tile corners, 8 directions (so the diagonal
+    # directions have two equal components) and an odd ray count (so the central ray IS the player's direction):
+    # the states that separate decision D1 (T: advance along dimension 1 only when side_x < side_y; U: when <=).
+    # No random numbers are drawn here, so cases A-D above stay byte-identical.
+    st = [(F(3.5), F(3.5), 0, 5, 5), (F(3.5), F(3.5), 1, 2, 2), (F(3.5), F(3.5), 2, 4, 6), (F(3.5), F(3.5), 3, 6, 2),
+          (F(3.0), F(3.0), 1, 5, 5), (F(2.0), F(4.0), 5, 4, 2), (F(3.5), F(3.0), 7, 2, 6), (F(1.0), F(1.0), 1, 3, 3),
+          (F(2.5), F(4.5), 5, 6, 6), (F(4.5), F(2.5), 3, 2, 5), (F(3.5), F(3.5), 1, 5, 5), (F(3.5), F(3.5), 5, 2, 2)]
+    for name, tie in (("T", False), ("U", True)):
+        w = PyWorld(H=7, W=7, N=8, R=33, P=40, tie_le=tie)
+        for k, v in cast_case(w, st, full_images=len(st), pu=4).items():
+            out[name + "_" + k] = v
+
     path = os.path.join(HERE, "singleroom_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

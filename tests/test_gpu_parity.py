@@ -23,6 +23,9 @@ RCW_KW = {
               position_increment_wu=np.float32(0.3), semi_field_of_view_wu=np.float32(0.5),
               camera_height_tile_wu=np.float32(0.8), pu_per_tu=7),
     "D": dict(dda_tie_le=True, dda_dist_post=True),
+    "T": dict(height_tile_map_tu=7, width_tile_map_tu=7, num_directions=8, num_rays=33, height_camera_view_pu=40, pu_per_tu=4),
+    "U": dict(height_tile_map_tu=7, width_tile_map_tu=7, num_directions=8, num_rays=33, height_camera_view_pu=40, pu_per_tu=4,
+              dda_tie_le=True),
 }
 
 
@@ -44,7 +47,7 @@ def rgb8_of(img_u32):
 # golden fixtures
 # ------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("case", ["A", "B", "C", "D"])
+@pytest.mark.parametrize("case", ["A", "B", "C", "D", "T", "U"])
 @pytest.mark.parametrize("fmt", ["rgb8", "xrgb32"])
 def test_cast_and_render_match_golden(rcw, oracle, golden, case, fmt):
     states, au, goal = golden[f"{case}_states"], golden[f"{case}_au"], golden[f"{case}_goal"]

@@ -27,7 +27,7 @@ def oracle_top_views(ref, n):
     return np.stack(out)
 
 
-@pytest.mark.parametrize("case", ["A", "B", "C", "D"])
+@pytest.mark.parametrize("case", ["A", "B", "C", "D", "T", "U"])
 def test_top_view_matches_golden_and_oracle(rcw, oracle, golden, case):
     states, au, goal = golden[f"{case}_states"], golden[f"{case}_au"], golden[f"{case}_goal"]
     n = len(states)

@@ -8,7 +8,7 @@ import pytest
 from conftest import GOLDEN_CONFIGS
 
 
-@pytest.mark.parametrize("case", ["A", "B", "C", "D"])
+@pytest.mark.parametrize("case", ["A", "B", "C", "D", "T", "U"])
 def test_cast_and_render_match_golden(oracle, golden, case):
     cfg = oracle.default_config(**GOLDEN_CONFIGS[case])
     w = oracle.World(cfg)

@@ -3,7 +3,9 @@
 # repo can be pinned against Julia.  CANNOT RUN IN THIS IMAGE (no julia); run it on any machine with
 #   julia --project -e 'import Pkg; Pkg.add(["RayCastWorlds", "NPZ"])'
 #   julia --project tools/dump_reference.jl tests/golden/singleroom_golden.npz tests/golden/julia_reference.npz
-# then `pytest tests/test_julia_pin.py` compares the oracle (and, with -m gpu, the CUDA path) with it.
+# then `python tools/resolve_julia_pin.py` (or `pytest tests/test_julia_pin.py`) evaluates the oracle under all four
+# settings of the two unpinned cast_ray decisions (D1 tie rule, D2 distance form), says which one reproduces this
+# dump and — if it is not the engine's default — exactly which default to change.
 # Until someone does, DESIGN.md and the oracle header say "parity unpinned".
 
 import NPZ
@@ -20,6 +22,8 @@ function world_for(case)
                                         num_rays = 45, height_camera_view_pu = 51, player_radius_wu = 0.2f0,
                                         position_increment_wu = 0.3f0, semi_field_of_view_wu = 0.5f0,
                                         camera_height_tile_wu = 0.8f0, pu_per_tu = 7)
+    case == "T" && return SR.SingleRoom(height_tile_map_tu = 7, width_tile_map_tu = 7, num_directions = 8, num_rays = 33,
+                                        height_camera_view_pu = 40, pu_per_tu = 4)   # exact ties: resolves D1
     error("unknown case")
 end
 
@@ -37,7 +41,7 @@ end
 function main(in_path, out_path)
     g = NPZ.npzread(in_path)
     out = Dict{String, Any}()
-    for case in ("A", "B", "C")
+    for case in ("A", "B", "C", "T")
         env = world_for(case)
         states, au, goal = g["$(case)_states"], g["$(case)_au"], g["$(case)_goal"]
         n, R = size(states, 1), length(env.world.ray_directions_wu)
@@ -62,6 +66,7 @@ function main(in_path, out_path)
         out["$(case)_hit"] = hit; out["$(case)_dim"] = dim; out["$(case)_dist"] = dist
         out["$(case)_ray_dir"] = rdir; out["$(case)_image"] = img; out["$(case)_top"] = top
         # act! trajectories
+        haskey(g, "$(case)_act_init") || continue
         init, actions = g["$(case)_act_init"], g["$(case)_act_actions"]
         ne, T = size(actions)
         pos = zeros(Float32, ne, T, 2); dir = zeros(Int32, ne, T); rew = zeros(Float32, ne, T); done = zeros(UInt8, ne, T)
