@@ -271,7 +271,9 @@ __device__ __forceinline__ uint32_t column_byte(const ColumnBands& cb, int ob) {
 #define RCW_STORE_POLICY 0
 #endif
 #ifndef RCW_TABLE_COPY
-#define RCW_TABLE_COPY 0   // env_kernel's table renderer: 0 = lane <-> column, 1 = lane <-> consecutive sectors of the span
+#define RCW_TABLE_COPY 1   // env_kernel's table renderer: 1 = lane <-> consecutive sectors of the span (coalesced stores,
+                           // shipped), 0 = lane <-> column (fewer instructions, but every warp store scatters 32 sectors
+                           // col_pitch apart: 5-25 % slower, profiles/README.md)
 #endif
 __device__ __forceinline__ void store_stream16(uint8_t* p, uint4 v) {
 #if RCW_EXP == 2
