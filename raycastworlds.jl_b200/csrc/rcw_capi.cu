@@ -392,6 +392,7 @@ static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, 
     t.slot0 = slot0;
     t.env_first = env0;
     t.env_count = n;
+    t.sm_count = (uint32_t)b->sm_count;
     RCW_CUDA(launch_top_view(t, b->stream));
     b->launches += 1;
     return RCW_OK;

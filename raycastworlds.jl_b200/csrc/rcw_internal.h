@@ -187,6 +187,7 @@ struct TopViewParams {
     size_t env_stride;       // bytes, multiple of 128
     uint32_t window, slot0;  // env_first + k lives in slot (slot0 + k) mod window
     int64_t env_first, env_count;
+    uint32_t sm_count;       // SMs of the device
 };
 
 // kernel launchers (rcw_kernels.cu)

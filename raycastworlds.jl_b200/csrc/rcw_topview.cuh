@@ -13,7 +13,14 @@
 // circle > ray > tile border > tile colour — the draw order of the reference (:472, :474-478, :480).
 // 512 KB per env at the defaults: HBM-write bound.
 
+#ifndef RCW_TOP_WALK
+#define RCW_TOP_WALK 0      // 0: whole segments in lock step (shipped); 1: chunks of 32 pixels with a closed-form start
+#endif
+#ifndef RCW_TOP_STAGGER_NS
+#define RCW_TOP_STAGGER_NS 0
+#endif
 constexpr int kTopThreads = 256;
+constexpr int kTopChunkLog = 5;          // a ray segment is drawn in chunks of 32 pixels, one lane each
 
 // utils.jl:6 — wu_to_pu(x_wu, pu_per_wu) = floor(Int, x_wu * pu_per_wu) + 1 (Float32 product)
 __device__ __forceinline__ int wu_to_pu(float x_wu, float pu) { return __float2int_rd(__fmul_rn(x_wu, pu)) + 1; }
@@ -38,11 +45,11 @@ __host__ __device__ __forceinline__ uint32_t circle_words(int rp) {
 }
 
 __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_constant__ TopViewParams p) {
-    // [wall layer][ray plane][palette 8 x u32][line list R x int2][tile colour (W + 1) x H u32][circle bitmap]
-    // [row info u16][column info u16][row-sector info u16][column offset u16]
+    // [wall layer][ray plane][palette 8 x u32][line list R x int2][chunk starts R x u32][tile colour (W + 1) x H u32]
+    // [circle bitmap][row info u16][column info u16][row-sector info u16][column offset u16]
     extern __shared__ __align__(128) uint32_t s_top[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_nlines;
+    __shared__ unsigned long long s_counts;                    // distinct segments | chunks << 32
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, Hp = p.Hp, Wp = p.Wp, pu = p.pu, R = p.R;
     const float fpu = (float)pu;
@@ -53,7 +60,8 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     uint32_t* const s_ray = s_map + p.map_words;
     uint32_t* const s_pal = s_ray + plane_words;
     int2* const s_line = reinterpret_cast<int2*>(s_pal + 8);                       // [R] end pixels of the distinct segments
-    uint32_t* const s_tilec = reinterpret_cast<uint32_t*>(s_line + R);             // [W + 1][H] tile colour; column W = border colour
+    uint32_t* const s_cstart = reinterpret_cast<uint32_t*>(s_line + R);            // [R] first chunk of every distinct segment
+    uint32_t* const s_tilec = s_cstart + R;                                        // [W + 1][H] tile colour; column W = border colour
     uint32_t* const s_circ = s_tilec + (size_t)(W + 1) * H;                        // [2 rp + 1][CW] the circle's bounding box
     uint16_t* const s_row = reinterpret_cast<uint16_t*>(s_circ + circle_words(rp));   // [Hp] tile row | border << 15
     uint16_t* const s_colinfo = s_row + ((Hp + 1) & ~1);                           // [Wp] tile column | border << 15
@@ -63,10 +71,14 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     const uint32_t env_rel = blockIdx.x;
     const int64_t env = p.env_first + env_rel;
     if (p.mask && !__ldg(p.mask + env)) return;               // masked redraw: the whole CTA leaves
+#if RCW_TOP_STAGGER_NS > 0
+    // experiment: the CTAs that start together on an SM (first wave) begin a sixth of a CTA lifetime apart
+    if (blockIdx.x < 6u * p.sm_count) __nanosleep(((blockIdx.x / p.sm_count) % 6u) * RCW_TOP_STAGGER_NS);
+#endif
 
     // ---- this env's wall layer: one TMA bulk copy; planes cleared and tables built meanwhile
     if (tid == 0) {
-        s_nlines = 0u;
+        s_counts = 0ULL;
         mbar_init(&s_bar, 1);
         mbar_arrive_expect_tx(&s_bar, (uint32_t)p.map_words * 4u);
         bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.map_words * 4u, &s_bar);
@@ -139,6 +151,96 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
         // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
         const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
         const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
+#if RCW_TOP_WALK == 1   // chunked walk (measured alternative, profiles/README.md)
+        // All segments start at the player's pixel, and neighbouring rays stop a fraction of a pixel apart (0.2 - 0.6
+        // px at the usual distances): a ray whose stop pixel equals its lower neighbour's draws exactly the same
+        // pixels and is dropped here.  The distinct segments (about 4 in 10 at the defaults) are appended to one
+        // list per env — their order only decides which lane sets a shared bit, not the picture — together with the
+        // index of their first chunk: a segment of n steps (n + 1 pixels) is drawn as n / 32 + 1 chunks of up to 32
+        // pixels, and the chunks of all segments are numbered consecutively in list order.
+        const int i2_below = __shfl_up_sync(0xFFFFFFFFu, i2, 1), j2_below = __shfl_up_sync(0xFFFFFFFFu, j2, 1);
+        const bool distinct = (ray < R) & ((lane == 0) | (i2 != i2_below) | (j2 != j2_below));
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, distinct);
+        const uint32_t nch = distinct ? ((uint32_t)max(abs(i2 - ip), abs(j2 - jp)) >> kTopChunkLog) + 1u : 0u;
+        uint32_t incl = nch;                                    // inclusive prefix sum of the chunk counts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        unsigned long long base = 0ULL;
+        if (lane == 0) base = atomicAdd(&s_counts, (unsigned long long)__popc(ballot) | ((unsigned long long)total << 32));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (distinct) {
+            const uint32_t slot = (uint32_t)base + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+            s_line[slot] = make_int2(i2, j2);
+            s_cstart[slot] = (uint32_t)(base >> 32) + incl - nch;
+        }
+    }
+    __syncthreads();          // the list is complete (and every tile colour written)
+
+    // ---- second half: lane <-> chunk.  [EXT SimpleDraw] Line(point1, point2): Bresenham, all octants, both end
+    //      points drawn; the walk reaches the end after exactly n = max(|di|, |dj|) steps, the major axis advancing in
+    //      every one of them (the all-octant form `e2 = 2 err; if e2 >= dj ...; if e2 <= di ...` reduces to that), so
+    //      one decision variable suffices: with M / m the larger / smaller of |di|, |dj| and F = 2 err' - M (err' = err
+    //      for |di| >= |dj|, -err otherwise; F starts at M - 2 m), the minor axis steps iff F <= 0, and
+    //      F += step ? 2 (M - m) : -2 m — the same pixels, ties included, in both octant families.  That recurrence
+    //      has a closed form: after k steps the minor axis has advanced s_k = floor((2 m k + M) / (2 M)) times and
+    //      F_k = M - 2 m (k + 1) + 2 M s_k (induction on k: s_{k+1} = s_k + [F_k <= 0]).  So a segment need not be
+    //      walked by one lane from its start: chunk c of a segment begins at step 32 c with one integer division, and
+    //      every lane walks at most 32 pixels — no warp waits for its longest line (the lock-step walk of whole
+    //      segments spent 1480 warp-iterations per env on 780 iterations' worth of pixels), and the CTA reaches the
+    //      barrier in front of the stream-out together.  Chunks are dealt to the lanes with a stride of 8, so the lanes
+    //      of a warp draw in different segments or far apart in the same one and rarely meet in a plane word.
+    const int n_lines = (int)(uint32_t)s_counts;
+    const uint32_t n_chunks = (uint32_t)(s_counts >> 32);
+    int search0 = 1;
+    while (search0 < n_lines) search0 <<= 1;                    // first probe distance of the segment search
+    for (uint32_t g0 = 0; g0 < n_chunks; g0 += kTopThreads) {
+        const uint32_t g = g0 + (uint32_t)(lane * (kTopThreads / 32) + warp);
+        const bool have = g < n_chunks;
+        // the segment this chunk belongs to: the last one whose first chunk is <= g
+        int seg = 0;
+        for (int d = search0 >> 1; d > 0; d >>= 1)
+            if (seg + d < n_lines && s_cstart[seg + d] <= g) seg += d;
+        const int2 end = s_line[seg];
+        const int i2 = end.x, j2 = end.y;
+        const int di = abs(i2 - ip), dj = abs(j2 - jp);
+        const int si = ip < i2 ? 1 : -1, sj = jp < j2 ? 1 : -1;
+        const bool i_major = di >= dj;
+        const int M = max(di, dj), m = min(di, dj);
+        const int k0 = have ? (int)((g - s_cstart[seg]) << kTopChunkLog) : 0;
+        const int n_px = have ? min(1 << kTopChunkLog, M - k0 + 1) : 0;       // pixels of this chunk
+        const int s0 = M > 0 ? (int)((2u * (uint32_t)m * (uint32_t)k0 + (uint32_t)M) / (2u * (uint32_t)M)) : 0;
+        int F = M - 2 * m * (k0 + 1) + 2 * M * s0;
+        // both end points inside the image => every pixel of the line is (it stays in their bounding box)
+        const bool clip = (ip < 1) | (ip > Hp) | (jp < 1) | (jp > Wp) | (i2 < 1) | (i2 > Hp) | (j2 < 1) | (j2 > Wp);
+        const int f_stay = -2 * m, f_step = 2 * (M - m);
+        if (!__any_sync(0xFFFFFFFFu, clip && have)) {
+            const int bit_si = si, bit_sj = sj * (int)SB;       // bit index steps of the two axes
+            const int adv_major = i_major ? bit_si : bit_sj, adv_both = bit_si + bit_sj;
+            uint32_t idx = (uint32_t)(jp - 1) * SB + (uint32_t)(ip - 1) + (uint32_t)(k0 * adv_major + s0 * (adv_both - adv_major));
+#pragma unroll 4
+            for (int k = 0; k < (1 << kTopChunkLog); ++k) {
+                if (k < n_px) atomicOr(s_ray + (idx >> 5), 1u << (idx & 31u));
+                const bool step = F <= 0;
+                F += step ? f_step : f_stay;
+                idx += (uint32_t)(step ? adv_both : adv_major);
+            }
+        } else {
+            int i = ip + si * (i_major ? k0 : s0), j = jp + sj * (i_major ? s0 : k0);
+            for (int k = 0; k < n_px; ++k) {
+                plane_set(s_ray, i, j, Hp, Wp, SB);
+                const bool step = F <= 0;
+                F += step ? f_step : f_stay;
+                i += (i_major | step) ? si : 0;
+                j += (!i_major | step) ? sj : 0;
+            }
+        }
+    }
+
+#else
         // All segments start at the player's pixel, and neighbouring rays stop a fraction of a pixel apart (0.2 - 0.6
         // px at the usual distances): a ray whose stop pixel equals its lower neighbour's draws exactly the same
         // pixels and is dropped here.  The distinct segments (about 4 in 10 at the defaults) are appended to one
@@ -147,7 +249,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
         const bool distinct = (ray < R) & ((lane == 0) | (i2 != i2_below) | (j2 != j2_below));
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, distinct);
         uint32_t base = 0u;
-        if (lane == 0) base = atomicAdd(&s_nlines, (uint32_t)__popc(ballot));
+        if (lane == 0) base = (uint32_t)atomicAdd(&s_counts, (unsigned long long)__popc(ballot));
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (distinct) s_line[base + (uint32_t)__popc(ballot & ((1u << lane) - 1u))] = make_int2(i2, j2);
     }
@@ -161,7 +263,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     //      iff F <= 0, and F += step ? 2 (M - m) : -2 m — the same pixels, ties included, in both octant families.
     //      The warp walks its 32 segments in lock step up to the longest one; a lane whose pixel equals its lower
     //      neighbour's (neighbouring segments share their first pixels) leaves the shared-memory atomic to it.
-    const int n_lines = (int)s_nlines;
+    const int n_lines = (int)(uint32_t)s_counts;
     for (int l0 = warp * 32; l0 < n_lines; l0 += kTopThreads) {
         const bool have = l0 + lane < n_lines;
         const int2 end = s_line[min(l0 + lane, n_lines - 1)];
@@ -209,6 +311,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
         }
     }
 
+#endif
     __syncthreads();
 
     // ---- stream the image out: one 32-byte sector (8 consecutive pixels of the column-major image) per
@@ -331,7 +434,7 @@ size_t top_view_smem_bytes(int H, int W, int R, int pu, float radius, int map_wo
     const size_t Hp = (size_t)H * pu, Wp = (size_t)W * pu;
     const size_t plane_words = (Wp * (plane_col_bits((int)Hp) >> 5) + 3) & ~(size_t)3;
     const int rp = (int)floorf(radius * (float)pu) + 1;          // wu_to_pu(radius, pu)
-    return (size_t)map_words * 4 + plane_words * 4 + 8 * 4 + (size_t)R * 8 + (size_t)(W + 1) * H * 4 +
+    return (size_t)map_words * 4 + plane_words * 4 + 8 * 4 + (size_t)R * 12 + (size_t)(W + 1) * H * 4 +
            (size_t)circle_words(rp) * 4 + 2 * ((Hp + 1) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1) +
            2 * (((Hp >> 3) + 2) & ~(size_t)1) + 2 * ((Wp + 1) & ~(size_t)1);
 }
