@@ -14,6 +14,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "librcw_oracle.so")
+# RCW_ORACLE_LIB: load another build of the same source instead (tests/test_sanitizers.py: -fsanitize=address,undefined)
+_LIB_OVERRIDE = os.environ.get("RCW_ORACLE_LIB")
 
 
 class OrcConfig(C.Structure):
@@ -46,7 +48,7 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     build()
-    L = C.CDLL(_LIB_PATH)
+    L = C.CDLL(_LIB_OVERRIDE or _LIB_PATH)
     vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
     P = C.POINTER
     sig = {
