@@ -322,6 +322,34 @@ int32_t rcw_stream(rcw_batch* b, void** stream);
 int32_t rcw_sync(rcw_batch* b);
 const char* rcw_last_error(void);
 
+/* ---- one process, several GPUs (envs are independent, single_room.jl:241-256) ----------------
+ * The batch is cut into contiguous blocks of global env ids, one handle (device, stream, observation buffer) per
+ * block.  Global env ids key the Philox streams, so every trajectory is bit-identical whatever the number of shards
+ * (and to the one-process-per-GPU layout, which is the same handles in different processes).  rcw_step* only
+ * enqueue, so one host thread keeps every GPU busy through these calls; alternatively each handle may be driven
+ * from its own host thread.  There is no collective on the step path; the only cross-shard quantity is the
+ * episode totals, three scalars summed on the host. */
+
+/* Block of shard `shard` of `n_shards`: the first total_envs % n_shards shards own one env more. */
+int32_t rcw_shard_envs(int64_t total_envs, int32_t n_shards, int32_t shard, int64_t* offset, int64_t* count);
+
+/* rcw_create for every shard: cfg->num_envs is the TOTAL, cfg->env_id_offset the global id of its first env;
+ * shard k runs on devices[k] (devices NULL: device k).  handles: [n_shards], filled on success; on failure
+ * nothing is left allocated and every entry is NULL. */
+int32_t rcw_create_sharded(const rcw_config* cfg, const float* directions_wu, const int32_t* devices, int32_t n_shards,
+                           rcw_batch** handles);
+int32_t rcw_destroy_sharded(rcw_batch* const* handles, int32_t n_shards);
+
+/* rcw_step on every shard; actions: HOST array of the whole batch, [total envs] in global env order.  A value
+ * outside 1..4 anywhere => RCW_EACTION and nothing is enqueued on any shard (the reference's @assert). */
+int32_t rcw_step_sharded(rcw_batch* const* handles, int32_t n_shards, const uint8_t* actions);
+int32_t rcw_step_random_sharded(rcw_batch* const* handles, int32_t n_shards, int32_t n_steps);
+int32_t rcw_sync_sharded(rcw_batch* const* handles, int32_t n_shards);
+
+/* rcw_episode_stats summed over the shards (in handle order, so the double sum is reproducible). */
+int32_t rcw_reduce_episode_stats(rcw_batch* const* handles, int32_t n_shards, int64_t* episodes, double* sum_return,
+                                 int64_t* sum_length, int32_t reset_counters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,4 +12,4 @@ from .single_room import (  # noqa: F401
     RLBaseEnv, SingleRoom, act, action_space, get_action_keys, get_action_names, is_terminated, play, reset, reward,
     state, state_space,
 )
-from .sharding import max_over_ranks, reduce_episode_stats, shard_envs  # noqa: F401
+from .sharding import ShardedSingleRoom, max_over_ranks, reduce_episode_stats, shard_envs  # noqa: F401

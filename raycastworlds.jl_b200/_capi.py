@@ -26,6 +26,8 @@ SYMBOLS = (
     "rcw_checkpoint_size", "rcw_save_checkpoint", "rcw_load_checkpoint",
     "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_obs_frames", "rcw_copy_obs_frame", "rcw_copy_obs", "rcw_expand_columns", "rcw_expanded_layout", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
     "rcw_sync", "rcw_last_error",
+    "rcw_shard_envs", "rcw_create_sharded", "rcw_destroy_sharded", "rcw_step_sharded", "rcw_step_random_sharded",
+    "rcw_sync_sharded", "rcw_reduce_episode_stats",
 )
 
 
@@ -120,6 +122,13 @@ def load() -> C.CDLL:
         "rcw_stream": (i32, [vp, P(vp)]),
         "rcw_sync": (i32, [vp]),
         "rcw_last_error": (C.c_char_p, []),
+        "rcw_shard_envs": (i32, [i64, i32, i32, P(i64), P(i64)]),
+        "rcw_create_sharded": (i32, [P(RcwConfig), vp, P(i32), i32, P(vp)]),
+        "rcw_destroy_sharded": (i32, [P(vp), i32]),
+        "rcw_step_sharded": (i32, [P(vp), i32, vp]),
+        "rcw_step_random_sharded": (i32, [P(vp), i32, i32]),
+        "rcw_sync_sharded": (i32, [P(vp), i32]),
+        "rcw_reduce_episode_stats": (i32, [P(vp), i32, P(i64), P(C.c_double), P(i64), i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

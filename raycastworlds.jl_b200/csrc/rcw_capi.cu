@@ -1570,4 +1570,126 @@ int32_t rcw_sync(rcw_batch* b) {
     return sync_and_check(b);
 }
 
+// ---- one process, several GPUs: independent env shards, one handle per device ----------
+// Every enqueueing entry point returns as soon as its kernels are queued, so ONE host thread keeps all the
+// GPUs busy: the sharded calls below just walk the handles.  No collective anywhere: the only cross-shard
+// quantity, the episode totals, is three scalars summed on the host.
+
+int32_t rcw_shard_envs(int64_t total_envs, int32_t n_shards, int32_t shard, int64_t* offset, int64_t* count) {
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(RCW_EINVAL, "bad shard %d of %d", shard, n_shards);
+    if (total_envs < 0) return fail(RCW_EINVAL, "total_envs must be non-negative");
+    const int64_t base = total_envs / n_shards, extra = total_envs % n_shards;
+    if (count) *count = base + (shard < extra ? 1 : 0);
+    if (offset) *offset = (int64_t)shard * base + (shard < extra ? shard : extra);
+    return RCW_OK;
+}
+
+int32_t rcw_create_sharded(const rcw_config* cfg, const float* directions_wu, const int32_t* devices, int32_t n_shards,
+                           rcw_batch** handles) {
+    if (!cfg || !handles) return fail(RCW_EINVAL, "cfg/handles is null");
+    if (n_shards < 1 || n_shards > 64) return fail(RCW_EINVAL, "n_shards must be 1..64 (got %d)", n_shards);
+    for (int32_t k = 0; k < n_shards; ++k) handles[k] = nullptr;
+    if (cfg->struct_size != sizeof(rcw_config))
+        return fail(RCW_ESIZE, "rcw_config.struct_size is %u, this library expects %zu", cfg->struct_size, sizeof(rcw_config));
+    if (cfg->num_envs < n_shards) return fail(RCW_EINVAL, "fewer envs (%lld) than shards (%d)", (long long)cfg->num_envs, n_shards);
+    for (int32_t k = 0; k < n_shards; ++k) {
+        rcw_config c = *cfg;
+        int64_t off = 0, cnt = 0;
+        rcw_shard_envs(cfg->num_envs, n_shards, k, &off, &cnt);
+        c.num_envs = cnt;
+        c.env_id_offset = cfg->env_id_offset + off;   // global env ids key the Philox streams: results do not depend on n_shards
+        c.device = devices ? devices[k] : k;
+        if (c.obs_window_envs > cnt) c.obs_window_envs = 0;
+        const int32_t rc = rcw_create(&c, directions_wu, &handles[k]);
+        if (rc != RCW_OK) {
+            std::string keep = t_last_error;
+            for (int32_t j = 0; j < k; ++j) {
+                rcw_destroy(handles[j]);
+                handles[j] = nullptr;
+            }
+            t_last_error = "shard " + std::to_string(k) + " (device " + std::to_string(c.device) + "): " + keep;
+            return rc;
+        }
+    }
+    return RCW_OK;
+}
+
+int32_t rcw_destroy_sharded(rcw_batch* const* handles, int32_t n_shards) {
+    if (!handles) return RCW_OK;
+    int32_t first = RCW_OK;
+    for (int32_t k = 0; k < n_shards; ++k) {
+        const int32_t rc = rcw_destroy(handles[k]);
+        if (first == RCW_OK) first = rc;
+    }
+    return first;
+}
+
+static int32_t check_shards(rcw_batch* const* handles, int32_t n_shards) {
+    if (!handles || n_shards < 1) return fail(RCW_EINVAL, "no handles");
+    for (int32_t k = 0; k < n_shards; ++k)
+        if (!handles[k]) return fail(RCW_EINVAL, "handle %d is null", k);
+    return RCW_OK;
+}
+
+int32_t rcw_step_sharded(rcw_batch* const* handles, int32_t n_shards, const uint8_t* actions) {
+    if (int32_t rc = check_shards(handles, n_shards)) return rc;
+    if (!actions) return fail(RCW_EINVAL, "actions is null (use rcw_step_random_sharded for the random policy)");
+    if (is_device_pointer(actions)) return fail(RCW_EINVAL, "rcw_step_sharded takes a HOST array of the whole batch");
+    // like the reference's @assert, an invalid action anywhere means nothing is enqueued anywhere
+    int64_t off = 0;
+    for (int32_t k = 0; k < n_shards; ++k) {
+        if (int32_t rc = validate_host_actions(actions + off, 0, handles[k]->cfg.num_envs)) return rc;
+        off += handles[k]->cfg.num_envs;
+    }
+    off = 0;
+    for (int32_t k = 0; k < n_shards; ++k) {
+        if (int32_t rc = rcw_step(handles[k], actions + off)) return rc;
+        off += handles[k]->cfg.num_envs;
+    }
+    return RCW_OK;
+}
+
+int32_t rcw_step_random_sharded(rcw_batch* const* handles, int32_t n_shards, int32_t n_steps) {
+    if (int32_t rc = check_shards(handles, n_shards)) return rc;
+    if (n_steps < 0) return fail(RCW_EINVAL, "n_steps must be non-negative");
+    for (int32_t s = 0; s < n_steps; ++s)            // step-major: every GPU always has work queued
+        for (int32_t k = 0; k < n_shards; ++k)
+            if (int32_t rc = rcw_step_random(handles[k], 1)) return rc;
+    return RCW_OK;
+}
+
+int32_t rcw_sync_sharded(rcw_batch* const* handles, int32_t n_shards) {
+    if (int32_t rc = check_shards(handles, n_shards)) return rc;
+    int32_t first = RCW_OK;
+    std::string msg;
+    for (int32_t k = 0; k < n_shards; ++k) {
+        const int32_t rc = rcw_sync(handles[k]);
+        if (rc != RCW_OK && first == RCW_OK) {
+            first = rc;
+            msg = t_last_error;
+        }
+    }
+    if (first != RCW_OK) t_last_error = msg;
+    return first;
+}
+
+int32_t rcw_reduce_episode_stats(rcw_batch* const* handles, int32_t n_shards, int64_t* episodes, double* sum_return,
+                                 int64_t* sum_length, int32_t reset_counters) {
+    if (int32_t rc = check_shards(handles, n_shards)) return rc;
+    int64_t ep = 0, sl = 0;
+    double sr = 0.0;
+    for (int32_t k = 0; k < n_shards; ++k) {          // fixed order: the double sum is reproducible
+        int64_t e = 0, l = 0;
+        double r = 0.0;
+        if (int32_t rc = rcw_episode_stats(handles[k], &e, &r, &l, reset_counters)) return rc;
+        ep += e;
+        sr += r;
+        sl += l;
+    }
+    if (episodes) *episodes = ep;
+    if (sum_return) *sum_return = sr;
+    if (sum_length) *sum_length = sl;
+    return RCW_OK;
+}
+
 }  // extern "C"

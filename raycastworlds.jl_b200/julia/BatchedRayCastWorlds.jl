@@ -83,7 +83,8 @@ mutable struct BatchedSingleRoom <: RCW.AbstractGame
     done::Vector{UInt8}
 end
 
-function BatchedSingleRoom(;
+# rcw_config + the reference's own direction table from the keyword arguments of SingleRoom(...) (single_room.jl:258-272)
+function build_config(;
         num_envs = 1,
         device = 0,
         T = Float32,
@@ -129,16 +130,88 @@ function BatchedSingleRoom(;
                         Int32(auto_reset), UInt64(seed), palette, UInt32(0), Int32(obs_window_envs),
                         Int32(top_view), Int32(pu_per_tu), top_palette, Int32(frame_stack),
                         Int32(result_ring), ntuple(_ -> UInt32(0), 2)))
+    return cfg, directions
+end
+
+# wrap a handle made by rcw_create / rcw_create_sharded (the wrapper owns it and destroys it when collected)
+function wrap_handle(handle::Ptr{Cvoid}, cfg::RcwConfig, num_envs::Integer)
+    env = BatchedSingleRoom(handle, Int(num_envs), Int(cfg.height_tile_map_tu), Int(cfg.width_tile_map_tu), Int(cfg.num_rays),
+                            Int(cfg.height_camera_view_pu), cfg.obs_format,
+                            cfg.goal_reward, zeros(Float32, num_envs), zeros(UInt8, num_envs))
+    finalizer(e -> (e.handle != C_NULL && ccall((:rcw_destroy, LIB), Int32, (Ptr{Cvoid},), e.handle); e.handle = C_NULL), env)
+    return env
+end
+
+function BatchedSingleRoom(; kw...)
+    cfg, directions = build_config(; kw...)
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve directions begin
         check(ccall((:rcw_create, LIB), Int32, (Ref{RcwConfig}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
                     cfg, directions, handle))
     end
-    env = BatchedSingleRoom(handle[], num_envs, height_tile_map_tu, width_tile_map_tu, num_rays,
-                            height_camera_view_pu, Int32(obs_format),
-                            Float32(goal_reward), zeros(Float32, num_envs), zeros(UInt8, num_envs))
-    finalizer(e -> (e.handle != C_NULL && ccall((:rcw_destroy, LIB), Int32, (Ptr{Cvoid},), e.handle); e.handle = C_NULL), env)
-    return env
+    return wrap_handle(handle[], cfg[], cfg[].num_envs)
+end
+
+# ---- one process, several GPUs (rcw_b200.h: independent env shards, one handle per device, no collective) -------
+# shard is 0-based like the C ABI; returns (offset, count) of the shard's block of global env ids
+function shard_envs(total_envs::Integer, n_shards::Integer, shard::Integer)
+    off = Ref{Int64}(0); cnt = Ref{Int64}(0)
+    check(ccall((:rcw_shard_envs, LIB), Int32, (Int64, Int32, Int32, Ref{Int64}, Ref{Int64}),
+                Int64(total_envs), Int32(n_shards), Int32(shard), off, cnt))
+    return off[], cnt[]
+end
+
+struct ShardedSingleRoom <: RCW.AbstractGame
+    shards::Vector{BatchedSingleRoom}
+    handles::Vector{Ptr{Cvoid}}
+    num_envs::Int
+end
+
+# num_envs is the TOTAL; shard k runs on devices[k]; every other keyword as for BatchedSingleRoom
+function ShardedSingleRoom(; devices = [0], kw...)
+    cfg, directions = build_config(; kw...)
+    n = length(devices)
+    dev = convert(Vector{Int32}, devices)
+    handles = fill(C_NULL, n)
+    GC.@preserve directions dev handles begin
+        check(ccall((:rcw_create_sharded, LIB), Int32, (Ref{RcwConfig}, Ptr{Float32}, Ptr{Int32}, Int32, Ptr{Ptr{Cvoid}}),
+                    cfg, directions, dev, Int32(n), handles))
+    end
+    shards = [wrap_handle(handles[k + 1], cfg[], shard_envs(cfg[].num_envs, n, k)[2]) for k in 0:(n - 1)]
+    return ShardedSingleRoom(shards, handles, Int(cfg[].num_envs))
+end
+
+# act!(env, actions): actions of the whole batch in global env order (host vector)
+function RCW.act!(env::ShardedSingleRoom, actions::AbstractVector{<:Integer})
+    length(actions) == env.num_envs || throw(DimensionMismatch("one action per env"))
+    a = convert(Vector{UInt8}, actions)
+    GC.@preserve a begin
+        check(ccall((:rcw_step_sharded, LIB), Int32, (Ptr{Ptr{Cvoid}}, Int32, Ptr{UInt8}), env.handles, Int32(length(env.handles)), a))
+    end
+    return nothing
+end
+
+step_random!(env::ShardedSingleRoom, n_steps::Integer = 1) =
+    check(ccall((:rcw_step_random_sharded, LIB), Int32, (Ptr{Ptr{Cvoid}}, Int32, Int32), env.handles, Int32(length(env.handles)), Int32(n_steps)))
+
+sync(env::ShardedSingleRoom) =
+    check(ccall((:rcw_sync_sharded, LIB), Int32, (Ptr{Ptr{Cvoid}}, Int32), env.handles, Int32(length(env.handles))))
+
+function episode_stats(env::ShardedSingleRoom; reset_counters = false)
+    ep = Ref{Int64}(0); sr = Ref{Float64}(0); sl = Ref{Int64}(0)
+    check(ccall((:rcw_reduce_episode_stats, LIB), Int32, (Ptr{Ptr{Cvoid}}, Int32, Ref{Int64}, Ref{Float64}, Ref{Int64}, Int32),
+                env.handles, Int32(length(env.handles)), ep, sr, sl, Int32(reset_counters)))
+    return ep[], sr[], sl[]
+end
+
+# destroys every shard now instead of at collection (the wrappers' finalizers then find C_NULL)
+function close!(env::ShardedSingleRoom)
+    check(ccall((:rcw_destroy_sharded, LIB), Int32, (Ptr{Ptr{Cvoid}}, Int32), env.handles, Int32(length(env.handles))))
+    for s in env.shards
+        s.handle = C_NULL
+    end
+    fill!(env.handles, C_NULL)
+    return nothing
 end
 
 # reset!(env) — src/single_room.jl:326-331 (layouts drawn on the device)

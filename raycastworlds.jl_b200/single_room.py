@@ -44,6 +44,60 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data
 
 
+def make_config(num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int = 8,
+                width_tile_map_tu: int = 16, num_directions: int = 128,
+                player_radius_wu: float = 1 / 8, position_increment_wu: float = 1 / 8,
+                semi_field_of_view_wu: float = 2 / 3, num_rays: int = 512,
+                camera_height_tile_wu: float = 1.0, height_camera_view_pu: int = 256,
+                goal_reward: float = 1.0, obs_format: str = "rgb8", auto_reset: bool = True,
+                seed: int = 0, env_id_offset: int = 0,
+                directions_wu: Optional[np.ndarray] = None, palette: Optional[Sequence[int]] = None,
+                dda_tie_le: bool = False, dda_dist_post: bool = False, obs_window_envs: int = 0,
+                top_view: bool = False, pu_per_tu: int = 32, top_palette: Optional[Sequence[int]] = None,
+                frame_stack: int = 1, result_ring: int = 0):
+    """rcw_config from the keyword arguments of SingleRoom(...) (single_room.jl:258-272) plus the batch fields.
+    Returns (cfg, directions or None, obs_format name)."""
+    cfg = _capi.default_config()
+    cfg.device = int(device)
+    cfg.num_envs = int(num_envs)
+    cfg.env_id_offset = int(env_id_offset)
+    cfg.height_tile_map_tu = int(height_tile_map_tu)
+    cfg.width_tile_map_tu = int(width_tile_map_tu)
+    cfg.num_directions = int(num_directions)
+    cfg.num_rays = int(num_rays)
+    cfg.height_camera_view_pu = int(height_camera_view_pu)
+    cfg.player_radius_wu = float(np.float32(player_radius_wu))
+    cfg.position_increment_wu = float(np.float32(position_increment_wu))
+    cfg.semi_field_of_view_wu = float(np.float32(semi_field_of_view_wu))
+    cfg.camera_height_tile_wu = float(np.float32(camera_height_tile_wu))
+    cfg.goal_reward = float(np.float32(goal_reward))
+    fmt = dict(_FORMATS)
+    if obs_format not in fmt:
+        raise ValueError(f"obs_format must be one of {sorted(fmt)}")
+    cfg.obs_format = fmt[obs_format]
+    cfg.auto_reset = int(bool(auto_reset))
+    cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    if palette is not None:
+        for i, c in enumerate(palette):
+            cfg.palette[i] = int(c)
+    cfg.dda_flags = (_capi.RCW_DDA_TIE_LE if dda_tie_le else 0) | (
+        _capi.RCW_DDA_DIST_POST if dda_dist_post else 0)
+    cfg.obs_window_envs = int(obs_window_envs)
+    cfg.frame_stack = int(frame_stack)
+    cfg.result_ring = int(result_ring)
+    cfg.top_view = int(bool(top_view))
+    cfg.pu_per_tu = int(pu_per_tu)
+    if top_palette is not None:
+        for i, c in enumerate(top_palette):
+            cfg.top_palette[i] = int(c)
+    dirs = None
+    if directions_wu is not None:
+        dirs = np.ascontiguousarray(directions_wu, np.float32)
+        if dirs.shape != (cfg.num_directions, 2):
+            raise ValueError("directions_wu must have shape [num_directions, 2]")
+    return cfg, dirs, obs_format
+
+
 class BatchedSingleRoom(AbstractGame):
     """`num_envs` independent SingleRoom games advanced by one kernel launch per step.
 
@@ -61,63 +115,28 @@ class BatchedSingleRoom(AbstractGame):
     ring, and with D >= 2 the host can enqueue step k + 1 before it reads the results of step k).
     """
 
-    def __init__(self, num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int = 8,
-                 width_tile_map_tu: int = 16, num_directions: int = 128,
-                 player_radius_wu: float = 1 / 8, position_increment_wu: float = 1 / 8,
-                 semi_field_of_view_wu: float = 2 / 3, num_rays: int = 512,
-                 camera_height_tile_wu: float = 1.0, height_camera_view_pu: int = 256,
-                 goal_reward: float = 1.0, obs_format: str = "rgb8", auto_reset: bool = True,
-                 seed: int = 0, env_id_offset: int = 0,
-                 directions_wu: Optional[np.ndarray] = None, palette: Optional[Sequence[int]] = None,
-                 dda_tie_le: bool = False, dda_dist_post: bool = False, obs_window_envs: int = 0,
-                 top_view: bool = False, pu_per_tu: int = 32, top_palette: Optional[Sequence[int]] = None,
-                 frame_stack: int = 1, result_ring: int = 0):
+    def __init__(self, num_envs: int = 1, **kw):
         self._lib = _capi.load()
         self._h = C.c_void_p()
-        cfg = _capi.default_config()
-        cfg.device = int(device)
-        cfg.num_envs = int(num_envs)
-        cfg.env_id_offset = int(env_id_offset)
-        cfg.height_tile_map_tu = int(height_tile_map_tu)
-        cfg.width_tile_map_tu = int(width_tile_map_tu)
-        cfg.num_directions = int(num_directions)
-        cfg.num_rays = int(num_rays)
-        cfg.height_camera_view_pu = int(height_camera_view_pu)
-        cfg.player_radius_wu = float(np.float32(player_radius_wu))
-        cfg.position_increment_wu = float(np.float32(position_increment_wu))
-        cfg.semi_field_of_view_wu = float(np.float32(semi_field_of_view_wu))
-        cfg.camera_height_tile_wu = float(np.float32(camera_height_tile_wu))
-        cfg.goal_reward = float(np.float32(goal_reward))
-        fmt = dict(_FORMATS)
-        if obs_format not in fmt:
-            raise ValueError(f"obs_format must be one of {sorted(fmt)}")
-        cfg.obs_format = fmt[obs_format]
-        cfg.auto_reset = int(bool(auto_reset))
-        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-        if palette is not None:
-            for i, c in enumerate(palette):
-                cfg.palette[i] = int(c)
-        cfg.dda_flags = (_capi.RCW_DDA_TIE_LE if dda_tie_le else 0) | (
-            _capi.RCW_DDA_DIST_POST if dda_dist_post else 0)
-        cfg.obs_window_envs = int(obs_window_envs)
-        cfg.frame_stack = int(frame_stack)
-        cfg.result_ring = int(result_ring)
-        cfg.top_view = int(bool(top_view))
-        cfg.pu_per_tu = int(pu_per_tu)
-        if top_palette is not None:
-            for i, c in enumerate(top_palette):
-                cfg.top_palette[i] = int(c)
-        dirs = None
-        if directions_wu is not None:
-            dirs = np.ascontiguousarray(directions_wu, np.float32)
-            if dirs.shape != (cfg.num_directions, 2):
-                raise ValueError("directions_wu must have shape [num_directions, 2]")
+        cfg, dirs, obs_format = make_config(num_envs, **kw)
         _capi.check(self._lib.rcw_create(C.byref(cfg), _ptr(dirs), C.byref(self._h)))
+        self._finish_init(cfg, obs_format)
+
+    @classmethod
+    def _from_handle(cls, handle, cfg, obs_format):
+        """Wrap a handle that rcw_create_sharded made (the wrapper owns it from here on)."""
+        self = cls.__new__(cls)
+        self._lib = _capi.load()
+        self._h = C.c_void_p(handle)
+        self._finish_init(cfg, obs_format)
+        return self
+
+    def _finish_init(self, cfg, obs_format):
         self.cfg = cfg
-        self.num_envs = int(num_envs)
-        self.obs_window = int(obs_window_envs) if 0 < int(obs_window_envs) < int(num_envs) else int(num_envs)
-        self.frame_stack = max(1, int(frame_stack))
-        self.result_ring = int(result_ring)
+        self.num_envs = int(cfg.num_envs)
+        self.obs_window = int(cfg.obs_window_envs) if 0 < int(cfg.obs_window_envs) < self.num_envs else self.num_envs
+        self.frame_stack = max(1, int(cfg.frame_stack))
+        self.result_ring = int(cfg.result_ring)
         self._result_views = {}
         self._ticket = C.c_int64()
         self._wait_r, self._wait_d = C.c_void_p(), C.c_void_p()
@@ -616,19 +635,21 @@ def play(game: "SingleRoom", keys, on_frame=None):
     of key names instead of keyboard events.  W / S / A / D act, R resets (and zeroes the step
     count), V switches between camera view and top view (clearing the frame buffer, :533-534), Q closes; any
     other key is reported and ignored (:540).  After every key the current view is copied into the frame buffer
-    like copy_image_to_frame_buffer! does (utils.jl:64-73: the window shows image[i, j] at row i, column j) and
-    `on_frame(frame_buffer, info)` is called, info = what the reference prints with @show (:549-551).
+    exactly as copy_image_to_frame_buffer! does — transposed, frame_buffer[j, i] = image[i, j] (utils.jl:64-73) —
+    and `on_frame(frame_buffer, info)` is called, info = what the reference prints with @show (:549-551).
     Returns (frame_buffer, info) as they stand when the keys run out or Q is pressed.
-    frame_buffer: uint32 [max(view heights), max(view widths)] (:503-506)."""
+    frame_buffer: uint32 [max(view widths), max(view heights)] like the reference's zeros(UInt32, width_image,
+    height_image) (:503-506), in Fortran order like the Julia array, so its memory is the row-major width x height
+    pixel buffer MiniFB is handed (mfb_update, :559)."""
     if not isinstance(game, SingleRoom):
         raise TypeError("play drives one SingleRoom, like the reference")
     camera, top = game.camera_view, game.top_view
-    frame_buffer = np.zeros((max(top.shape[0], camera.shape[0]), max(top.shape[1], camera.shape[1])), np.uint32)
+    frame_buffer = np.zeros((max(top.shape[1], camera.shape[1]), max(top.shape[0], camera.shape[0])), np.uint32, order="F")
     current_view, steps_taken = CAMERA_VIEW, 0
 
     def blit():
         image = game.camera_view if current_view == CAMERA_VIEW else game.top_view
-        frame_buffer[:image.shape[0], :image.shape[1]] = image
+        frame_buffer[:image.shape[1], :image.shape[0]] = image.T      # frame_buffer[j, i] = image[i, j]
 
     blit()                                                        # :512-517
     info = dict(key=None, steps_taken=0, reward=game.world.reward, done=game.world.done, view=current_view, warning=None)

@@ -204,24 +204,25 @@ def test_play_drives_the_key_bindings_without_a_window(rcw, oracle):
     ref = oracle.Batch(1, cfg=oracle.default_config(R=96, P=40, pu_per_tu=8), seed=5, auto_reset=False)
     frames = []
     fb, info = rcw.play(game, "wwdxsaVwwa", on_frame=lambda f, i: frames.append((f.copy(), i)))
-    assert fb.shape == (64, 128) and fb.dtype == np.uint32                            # max of the two views, :503-506
+    assert fb.shape == (128, 64) and fb.dtype == np.uint32                            # (width, height): max of the two views, :503-506
+    assert fb.flags.f_contiguous                                                      # the Julia array's memory: row-major pixels
     assert [i["key"] for _, i in frames] == list("WWDXSAVWWA")
     assert frames[3][1]["warning"] == "No keybinding exists for X" and frames[3][1]["steps_taken"] == 3
     assert info["steps_taken"] == 8 and info["view"] == rcw.TOP_VIEW
     for a in [1, 1, 4, 2, 3]:                                                        # W W D (X) S A
         ref.step(np.array([a], np.uint8))
     w = ref.world(0)
-    np.testing.assert_array_equal(frames[5][0][:40, :96], w.camera_view.T)           # camera view after six keys
-    assert not frames[5][0][40:].any() and not frames[5][0][:, 96:].any()            # the rest of the buffer stays zero
+    np.testing.assert_array_equal(frames[5][0][:96, :40], w.camera_view)             # fb[j, i] = image[i, j] (utils.jl:69)
+    assert not frames[5][0][96:].any() and not frames[5][0][:, 40:].any()            # the rest of the buffer stays zero
     for a in [1, 1, 3]:
         ref.step(np.array([a], np.uint8))
     w = ref.world(0)
     w.update_top_view()
-    np.testing.assert_array_equal(fb, w.top_view.T)                                   # V: top view fills the buffer
+    np.testing.assert_array_equal(fb, w.top_view)                                     # V: top view fills the buffer
     assert info["reward"] == w.state()["reward"] and bool(info["done"]) == bool(w.state()["done"])
     fb2, info2 = rcw.play(game, ["r", "q", "w"])                                      # R resets the count, Q stops before W
     assert info2["key"] == "R" and info2["steps_taken"] == 0 and info2["view"] == rcw.CAMERA_VIEW
-    np.testing.assert_array_equal(fb2[:40, :96], game.camera_view)
+    np.testing.assert_array_equal(fb2[:96, :40], game.camera_view.T)
     with pytest.raises(TypeError):
         rcw.play(rcw.BatchedSingleRoom, "w")
     game.close()

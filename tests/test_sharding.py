@@ -61,3 +61,24 @@ def test_two_rank_gloo_reduction(tmp_path):
     offs = [rcw.shard_envs(1001, 2, k) for k in range(2)]
     assert r["total"] == (1001, float(sum(o for o, _ in offs)), 10010)
     assert r["slowest"] == 2.0
+
+
+def test_library_shard_blocks_equal_the_python_helper():
+    """rcw_shard_envs (the C ABI's block partition) == sharding.shard_envs, no GPU needed."""
+    import ctypes as C
+
+    from raycastworlds_jl_b200 import _capi
+
+    lib = _capi.load()
+    for total in (0, 1, 7, 64, 1000003, 1 << 20):
+        for n in (1, 2, 3, 8, 64):
+            covered = 0
+            for k in range(n):
+                off, cnt = C.c_int64(), C.c_int64()
+                assert lib.rcw_shard_envs(total, n, k, C.byref(off), C.byref(cnt)) == _capi.RCW_OK
+                assert (off.value, cnt.value) == rcw.shard_envs(total, n, k)
+                assert off.value == covered
+                covered += cnt.value
+            assert covered == total
+    assert lib.rcw_shard_envs(10, 0, 0, None, None) == _capi.RCW_EINVAL
+    assert lib.rcw_shard_envs(10, 2, 2, None, None) == _capi.RCW_EINVAL
