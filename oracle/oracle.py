@@ -26,6 +26,8 @@ class OrcConfig(C.Structure):
         ("palette", C.c_uint32 * 6),
         ("tie_le", C.c_int32), ("dist_post", C.c_int32),
         ("pu_per_tu", C.c_int32), ("top_palette", C.c_uint32 * 6),
+        ("num_layers", C.c_int32), ("layer_kind", C.c_int32 * 4), ("layer_reward", C.c_float * 4),
+        ("layer_palette", C.c_uint32 * 8), ("layer_top_color", C.c_uint32 * 4),
     ]
 
 
@@ -57,6 +59,7 @@ def lib() -> C.CDLL:
         "orc_destroy": (None, [vp]),
         "orc_directions": (None, [i32, vp]),
         "orc_set_wall_map": (None, [vp, vp]),
+        "orc_set_layer": (i32, [vp, i32, vp]),
         "orc_set_state": (None, [vp, f32, f32, i32, i32, i32, f32, i32]),
         "orc_get_state": (None, [vp, vp, vp, vp, vp, vp]),
         "orc_reset_to": (None, [vp, i32, i32, i32, i32, i32]),
@@ -103,9 +106,9 @@ def default_config(**kw) -> OrcConfig:
     cfg = OrcConfig()
     lib().orc_config_default(C.byref(cfg))
     for k, v in kw.items():
-        if k in ("palette", "top_palette"):
+        if k in ("palette", "top_palette", "layer_kind", "layer_reward", "layer_palette", "layer_top_color"):
             for i, c in enumerate(v):
-                getattr(cfg, k)[i] = int(c)
+                getattr(cfg, k)[i] = float(c) if k == "layer_reward" else int(c)
         else:
             setattr(cfg, k, v)
     return cfg
@@ -162,6 +165,13 @@ class World:
         a = np.asfortranarray(np.asarray(wall_hw, np.uint8))
         flat = np.ascontiguousarray(a.T.reshape(-1))  # [W][H], i fastest
         self.L.orc_set_wall_map(self.p, flat.ctypes.data)
+
+    def set_layer(self, layer: int, tiles_hw: np.ndarray):
+        """tile_map[layer, :, :] = tiles (bool [H, W]); layer 1 = WALL, 3.. = the extra object layers."""
+        a = np.asfortranarray(np.asarray(tiles_hw, np.uint8))
+        flat = np.ascontiguousarray(a.T.reshape(-1))
+        if self.L.orc_set_layer(self.p, int(layer), flat.ctypes.data) != 0:
+            raise ValueError(f"no settable object layer {layer} (num_layers = {self.cfg.num_layers})")
 
     def set_state(self, x, y, au, gi, gj, reward=0.0, done=0):
         self.L.orc_set_state(self.p, np.float32(x), np.float32(y), int(au), int(gi), int(gj),

@@ -18,6 +18,8 @@
 struct orc_world {
     orc_config cfg;
     uint8_t* wall;       /* tile_map[WALL, :, :]  idx = (i-1) + H*(j-1)   (single_room.jl:55-60) */
+    uint8_t* extra[ORC_MAX_EXTRA_LAYERS]; /* tile_map[3 + k, :, :]: object layers beyond the reference's NUM_OBJECTS = 2
+                                             (single_room.jl:16-18), same indexing; NULL above cfg.num_layers */
     float* directions;   /* directions_wu [N][2]                        (single_room.jl:65-69) */
     float pos[2];        /* player_position_wu */
     int32_t au;          /* player_direction_au */
@@ -63,6 +65,7 @@ void orc_config_default(orc_config* c) {
     c->top_palette[3] = 0x00ccccccu; /* tile border            :365-368 */
     c->top_palette[4] = 0x00808080u; /* ray_color              :289 */
     c->top_palette[5] = 0x00c0c0c0u; /* player_color           :290 */
+    c->num_layers = 2;               /* NUM_OBJECTS = 2: WALL, GOAL (:16-18) */
 }
 
 /* single_room.jl:65-69 — theta in Float64, cos/sin in Float64, convert to T */
@@ -81,6 +84,9 @@ orc_world* orc_create(const orc_config* c, const float* directions) {
     w->cfg = *c;
     const int H = c->H, W = c->W, N = c->N, R = c->R, P = c->P;
     w->wall = (uint8_t*)calloc((size_t)H * W, 1);
+    if (w->cfg.num_layers < 2) w->cfg.num_layers = 2;
+    if (w->cfg.num_layers > 2 + ORC_MAX_EXTRA_LAYERS) w->cfg.num_layers = 2 + ORC_MAX_EXTRA_LAYERS;
+    for (int k = 0; k < w->cfg.num_layers - 2; ++k) w->extra[k] = (uint8_t*)calloc((size_t)H * W, 1);
     w->directions = (float*)malloc(sizeof(float) * 2 * (size_t)N);
     w->ray_stop = (int32_t*)calloc((size_t)R * 2, sizeof(int32_t));
     w->ray_dim = (int32_t*)calloc((size_t)R, sizeof(int32_t));
@@ -112,6 +118,7 @@ orc_world* orc_create(const orc_config* c, const float* directions) {
 void orc_destroy(orc_world* w) {
     if (!w) return;
     free(w->wall);
+    for (int k = 0; k < ORC_MAX_EXTRA_LAYERS; ++k) free(w->extra[k]);
     free(w->directions);
     free(w->ray_stop);
     free(w->ray_dim);
@@ -125,6 +132,18 @@ void orc_destroy(orc_world* w) {
 
 void orc_set_wall_map(orc_world* w, const uint8_t* wall) {
     for (int k = 0; k < w->cfg.H * w->cfg.W; ++k) w->wall[k] = wall[k] ? 1 : 0;
+}
+
+/* tile_map[layer, :, :] = tiles for layer 1 (WALL) or an extra object layer 3..num_layers; the GOAL layer (2) holds
+ * exactly one tile, the goal position, and is moved with orc_set_state / orc_reset_to. */
+int32_t orc_set_layer(orc_world* w, int32_t layer, const uint8_t* tiles) {
+    if (layer == 1) {
+        orc_set_wall_map(w, tiles);
+        return 0;
+    }
+    if (layer < 3 || layer > w->cfg.num_layers) return -1;
+    for (int k = 0; k < w->cfg.H * w->cfg.W; ++k) w->extra[layer - 3][k] = tiles[k] ? 1 : 0;
+    return 0;
 }
 
 void orc_set_state(orc_world* w, float x, float y, int32_t au, int32_t gi, int32_t gj,
@@ -169,7 +188,26 @@ void orc_reset_to(orc_world* w, int32_t gi, int32_t gj, int32_t pi, int32_t pj, 
 static int layer_at(const orc_world* w, int layer, int i, int j) {
     if (i < 1 || i > w->cfg.H || j < 1 || j > w->cfg.W) return 0;
     if (layer == 1) return w->wall[(i - 1) + w->cfg.H * (j - 1)];
-    return (i == w->goal[0] && j == w->goal[1]);
+    if (layer == 2) return (i == w->goal[0] && j == w->goal[1]);
+    if (layer > w->cfg.num_layers) return 0;
+    return w->extra[layer - 3][(i - 1) + w->cfg.H * (j - 1)];
+}
+
+/* findfirst(@view tile_map[:, i, j]) (single_room.jl:355): the lowest object index on the tile, 0 = none.  The camera
+ * view asks `tile_map[WALL, i, j] ? wall colours : goal colours` (:417-429), which is the same question for
+ * NUM_OBJECTS = 2; outside the map (open host map) counts as WALL. */
+static int first_object_at(const orc_world* w, int i, int j) {
+    if (i < 1 || i > w->cfg.H || j < 1 || j > w->cfg.W) return 1;
+    for (int layer = 1; layer <= w->cfg.num_layers; ++layer)
+        if (layer_at(w, layer, i, j)) return layer;
+    return 0;
+}
+
+/* camera-view colour of object `layer` hit across dimension `dim` (:417-429, palette :293-296) */
+static uint32_t object_color(const orc_world* w, int layer, int dim) {
+    if (layer <= 1) return dim == 1 ? w->cfg.palette[2] : w->cfg.palette[3];
+    if (layer == 2) return dim == 1 ? w->cfg.palette[4] : w->cfg.palette[5];
+    return w->cfg.layer_palette[2 * (layer - 3) + (dim == 1 ? 0 : 1)];
 }
 
 /* utils.jl:5 — wu_to_tu(x) = floor(Int, x) + 1 */
@@ -220,9 +258,23 @@ int32_t orc_act(orc_world* w, int32_t action) {
         }
         int hit_goal = orc_is_player_colliding(w, 2, nx, ny); /* :162 */
         int hit_wall = orc_is_player_colliding(w, 1, nx, ny); /* :163 */
+        float goal_reward = w->cfg.goal_reward;
+        /* object layers beyond WALL and GOAL behave like one of the two: a terminal layer like GOAL (its own reward,
+         * done, no move — checked in object order after GOAL), a blocking layer like WALL */
+        for (int layer = 3; layer <= w->cfg.num_layers; ++layer) {
+            if (!orc_is_player_colliding(w, layer, nx, ny)) continue;
+            if (w->cfg.layer_kind[layer - 3] == 1) {
+                if (!hit_goal) {
+                    hit_goal = 1;
+                    goal_reward = w->cfg.layer_reward[layer - 3];
+                }
+            } else {
+                hit_wall = 1;
+            }
+        }
         if (hit_goal || hit_wall) {
             if (hit_goal) { /* :166-168 */
-                w->reward = w->cfg.goal_reward;
+                w->reward = goal_reward;
                 w->done = 1;
             } else { /* :170-171 */
                 w->reward = 0.0f;
@@ -250,7 +302,7 @@ int32_t orc_act(orc_world* w, int32_t action) {
  * (the reference would throw a BoundsError there). */
 static int obstacle_at(const orc_world* w, int i, int j) {
     if (i < 1 || i > w->cfg.H || j < 1 || j > w->cfg.W) return 1;
-    return w->wall[(i - 1) + w->cfg.H * (j - 1)] || (i == w->goal[0] && j == w->goal[1]);
+    return first_object_at(w, i, j) != 0;
 }
 
 /* [EXT] RayCaster.cast_ray, contract reconstructed in SURVEY.md §8(a) a10 (call site
@@ -366,13 +418,10 @@ void orc_update_camera_view(orc_world* w) {
         int h = height_line_pu(w, i - 1);
         int dim = w->ray_dim[i - 1];
         int ih = w->ray_stop[2 * (i - 1) + 0], jh = w->ray_stop[2 * (i - 1) + 1];
-        int is_wall = 1; /* outside the map (open host map) is painted as wall */
-        if (ih >= 1 && ih <= H && jh >= 1 && jh <= w->cfg.W) is_wall = w->wall[(ih - 1) + H * (jh - 1)];
-        uint32_t color;
-        if (is_wall) /* :417-422 */
-            color = (dim == 1) ? w->cfg.palette[2] : w->cfg.palette[3];
-        else /* :424-428 */
-            color = (dim == 1) ? w->cfg.palette[4] : w->cfg.palette[5];
+        /* :417-428: wall colours if tile_map[WALL, i, j], else the goal's — the first object on the hit tile (outside the
+         * map, for an open host map, is painted as wall) */
+        const uint32_t color = object_color(w, first_object_at(w, ih, jh), dim);
+        (void)H;
         int k = R - i + 1; /* :431 */
         uint32_t* col = w->camera + (size_t)(k - 1) * P;
         if (h >= P - 1) { /* :433-434 */
@@ -397,9 +446,10 @@ void orc_camera_columns(const orc_world* w, uint32_t* out) {
         const int h = height_line_pu(w, i - 1);
         const int dim = w->ray_dim[i - 1];
         const int ih = w->ray_stop[2 * (i - 1) + 0], jh = w->ray_stop[2 * (i - 1) + 1];
-        int is_wall = 1;
-        if (ih >= 1 && ih <= H && jh >= 1 && jh <= w->cfg.W) is_wall = w->wall[(ih - 1) + H * (jh - 1)];
-        const uint32_t cid = is_wall ? (dim == 1 ? 2u : 3u) : (dim == 1 ? 4u : 5u);
+        int layer = first_object_at(w, ih, jh);
+        if (layer < 1) layer = 1;
+        (void)H;
+        const uint32_t cid = 2u * (uint32_t)layer + (dim == 1 ? 0u : 1u);   /* 2/3 wall, 4/5 goal, 6/7 object 3, ... */
         const uint32_t pad = h >= P - 1 ? 0u : (uint32_t)((P - h) / 2);
         out[R - i] = pad | (cid << 16);
     }
@@ -470,8 +520,10 @@ static void draw_tile_map(orc_world* w) {
             const int it = (i - 1) * pu + 1, jt = (j - 1) * pu + 1; /* :350-351 */
             /* findfirst over the layers WALL = 1, GOAL = 2 (:355-360) */
             uint32_t color = w->cfg.top_palette[2];
-            if (w->wall[(i - 1) + H * (j - 1)]) color = w->cfg.top_palette[0];
-            else if (i == w->goal[0] && j == w->goal[1]) color = w->cfg.top_palette[1];
+            const int object = first_object_at(w, i, j);
+            if (object == 1) color = w->cfg.top_palette[0];
+            else if (object == 2) color = w->cfg.top_palette[1];
+            else if (object >= 3) color = w->cfg.layer_top_color[object - 3];   /* tile_map_colors[object] */
             for (int b = 0; b < pu; ++b)
                 for (int a = 0; a < pu; ++a) put_pixel(w, it + a, jt + b, color); /* :353,362 */
             for (int b = 0; b < pu; ++b) {
@@ -562,10 +614,8 @@ void orc_update_camera_view_bytes(orc_world* w, int32_t fmt) {
         const int h = height_line_pu(w, i - 1);
         const int dim = w->ray_dim[i - 1];
         const int ih = w->ray_stop[2 * (i - 1) + 0], jh = w->ray_stop[2 * (i - 1) + 1];
-        int is_wall = 1;
-        if (ih >= 1 && ih <= H && jh >= 1 && jh <= w->cfg.W) is_wall = w->wall[(ih - 1) + H * (jh - 1)];
-        const uint32_t color = is_wall ? (dim == 1 ? w->cfg.palette[2] : w->cfg.palette[3])
-                                       : (dim == 1 ? w->cfg.palette[4] : w->cfg.palette[5]);
+        const uint32_t color = object_color(w, first_object_at(w, ih, jh), dim);
+        (void)H;
         uint8_t* col = w->frame8 + (size_t)(R - i) * P * bpp; /* k = R - i + 1 (:431) */
         if (h >= P - 1) {
             fill_pixels(col, P, color, fmt);
@@ -629,7 +679,9 @@ void orc_draw_layout(const orc_world* w, uint64_t seed, uint64_t env_id, uint32_
         uint32_t lin = uniform_below(draw, (uint32_t)(H * W)); /* CartesianIndices((1:H, 1:W)), i fastest */
         pi = (int)(lin % (uint32_t)H) + 1;
         pj = (int)(lin / (uint32_t)H) + 1;
-        int occupied = w->wall[(pi - 1) + H * (pj - 1)] || (pi == gi && pj == gj);
+        int occupied = (pi == gi && pj == gj);      /* any(tile_map[:, pos]) with the new goal already placed (utils.jl:27) */
+        for (int layer = 1; layer <= w->cfg.num_layers && !occupied; ++layer)
+            if (layer != 2) occupied = layer_at(w, layer, pi, pj);
         if (!occupied || t == max_tries) break;
         /* next draw: try t+1 uses word (t % 4) of Philox call 1 + t/4 */
         if ((t & 3) == 0) {

@@ -21,6 +21,8 @@
 extern "C" {
 #endif
 
+#define ORC_MAX_EXTRA_LAYERS 4
+
 typedef struct orc_config {
     int32_t H, W;          /* height_tile_map_tu, width_tile_map_tu  (single_room.jl:44-45) */
     int32_t N;             /* num_directions                         (single_room.jl:46)    */
@@ -37,6 +39,16 @@ typedef struct orc_config {
     int32_t pu_per_tu;     /* pu_per_tu of the top view                (single_room.jl:269)  */
     uint32_t top_palette[6]; /* tile_map_colors (wall, goal, empty :288), tile border (:364-367), ray_color (:289),
                                 player_color (:290) */
+    /* NUM_OBJECTS > 2 (single_room.jl:16-18).  Object k = 3 + index lives in its own layer of
+     * tile_map; it stops rays like every object (:209 any over the layers), is painted with its own colour pair
+     * (:417-429 generalised to the first object on the hit tile), shown in the top view by findfirst (:355-360),
+     * keeps the player from being placed on it (utils.jl:27), and either blocks a move like WALL or ends the
+     * episode with a reward like GOAL (:162-176). */
+    int32_t num_layers;                          /* NUM_OBJECTS, 2..6 (default 2) */
+    int32_t layer_kind[ORC_MAX_EXTRA_LAYERS];    /* 0: blocking like WALL, 1: terminal like GOAL */
+    float layer_reward[ORC_MAX_EXTRA_LAYERS];    /* reward of a terminal layer */
+    uint32_t layer_palette[2 * ORC_MAX_EXTRA_LAYERS]; /* camera colours [k][hit across dimension 1, 2] */
+    uint32_t layer_top_color[ORC_MAX_EXTRA_LAYERS];   /* tile_map_colors[3 + k] */
 } orc_config;
 
 typedef struct orc_world orc_world;
@@ -50,6 +62,7 @@ void orc_directions(int32_t N, float* out /* [N][2] */);
 
 /* direct field access, like mutating the Julia struct */
 void orc_set_wall_map(orc_world* w, const uint8_t* wall /* [W][H], i fastest */);
+int32_t orc_set_layer(orc_world* w, int32_t layer /* 1 = WALL, 3.. = extra objects */, const uint8_t* tiles /* [W][H] */);
 void orc_set_state(orc_world* w, float x, float y, int32_t au, int32_t gi, int32_t gj,
                    float reward, int32_t done);
 void orc_get_state(const orc_world* w, float* xy, int32_t* au, int32_t* goal_ij, float* reward,

@@ -52,3 +52,20 @@ GOLDEN_CONFIGS = {
     "T": dict(H=7, W=7, N=8, R=33, P=40, pu_per_tu=4),
     "U": dict(H=7, W=7, N=8, R=33, P=40, pu_per_tu=4, tie_le=1),
 }
+
+
+# Case L of the golden fixture: NUM_OBJECTS = 5 — an interior wall, blocking pillars (object 3), a
+# terminal layer with reward -1 (object 4) and one with reward 0.5 (object 5) on a 9 x 12 map.
+LAYERED_CONFIG = dict(H=9, W=12, N=32, R=64, P=48, radius=np.float32(0.15), incr=np.float32(0.2), pu_per_tu=4,
+                      num_layers=5, layer_kind=[0, 1, 1, 0], layer_reward=[0.0, -1.0, 0.5, 0.0],
+                      layer_palette=[0x00205080, 0x003070A0, 0x00A04000, 0x00C06000, 0x0000A040, 0x0000C060, 0, 0],
+                      layer_top_color=[0x000000FF, 0x00FF8000, 0x0000FF00, 0])
+
+
+def layered_oracle_world(oracle, golden):
+    """An oracle World configured and furnished like case L."""
+    w = oracle.World(oracle.default_config(**LAYERED_CONFIG))
+    w.set_layer(1, golden["L_wall"])
+    for k in range(3):
+        w.set_layer(3 + k, golden["L_extra"][k])
+    return w

@@ -29,11 +29,14 @@ class PyWorld:
     """SingleRoomWorld + camera view, src/single_room.jl:21-108,258-324."""
 
     def __init__(self, H=8, W=16, N=128, R=512, P=256, radius=1 / 8, incr=1 / 8, sfov=2 / 3, cam_h=1.0,
-                 goal_reward=1.0, tie_le=False, dist_post=False):
+                 goal_reward=1.0, tie_le=False, dist_post=False, extras=()):
         self.H, self.W, self.N, self.R, self.P = H, W, N, R, P
         self.radius, self.incr, self.sfov, self.cam_h = F(radius), F(incr), F(sfov), F(cam_h)
         self.goal_reward = F(goal_reward)
         self.tie_le, self.dist_post = tie_le, dist_post
+        # object layers 3.. (NUM_OBJECTS > 2, SURVEY.md 8(f) N2): dicts {tiles: bool [H+1, W+1] 1-based, terminal: bool,
+        # reward, colors: (dim 1, dim 2), top: top-view colour}
+        self.extras = list(extras)
         self.wall = np.zeros((H + 1, W + 1), bool)  # 1-based
         self.wall[1:, 1] = True   # :57
         self.wall[1:, W] = True   # :58
@@ -60,7 +63,22 @@ class PyWorld:
             return False  # new-engine rule for F6 (the reference throws)
         if which == "wall":
             return bool(self.wall[i, j])
-        return (i, j) == self.goal
+        if which == "goal":
+            return (i, j) == self.goal
+        return bool(self.extras[which]["tiles"][i, j])      # which = index of an extra object layer
+
+    def first_object(self, i, j):
+        """findfirst(tile_map[:, i, j]) (:355): 1 wall, 2 goal, 3 + k extra object k, 0 none; outside the map = wall."""
+        if i < 1 or i > self.H or j < 1 or j > self.W:
+            return 1
+        if self.wall[i, j]:
+            return 1
+        if (i, j) == self.goal:
+            return 2
+        for k, ex in enumerate(self.extras):
+            if ex["tiles"][i, j]:
+                return 3 + k
+        return 0
 
     # ---- collision_detection.jl:9-42
     def is_player_colliding(self, which, x, y):
@@ -91,8 +109,16 @@ class PyWorld:
                 nx, ny = F(self.pos[0] - sx), F(self.pos[1] - sy)
             hit_goal = self.is_player_colliding("goal", nx, ny)
             hit_wall = self.is_player_colliding("wall", nx, ny)
+            goal_reward = self.goal_reward
+            for k, ex in enumerate(self.extras):       # terminal layers act like GOAL (in object order), the others like WALL
+                if self.is_player_colliding(k, nx, ny):
+                    if ex["terminal"]:
+                        if not hit_goal:
+                            hit_goal, goal_reward = True, F(ex["reward"])
+                    else:
+                        hit_wall = True
             if hit_goal:
-                self.reward, self.done = self.goal_reward, True
+                self.reward, self.done = goal_reward, True
             elif hit_wall:
                 self.reward, self.done = F(0), False
             else:
@@ -121,7 +147,7 @@ class PyWorld:
         def obstacle(i, j):
             if i < 1 or i > self.H or j < 1 or j > self.W:
                 return True
-            return bool(self.wall[i, j]) or (i, j) == self.goal  # any(tile_map, dims=1) :209
+            return self.first_object(i, j) != 0  # any(tile_map, dims=1) :209
 
         while not obstacle(i, j):
             take_x = (tx <= ty) if self.tie_le else (tx < ty)
@@ -178,12 +204,13 @@ class PyWorld:
         for i in range(1, R + 1):
             h = self.height_line(i - 1)
             ih, jh = self.hit[i - 1]
-            inside = 1 <= ih <= self.H and 1 <= jh <= self.W
-            is_wall = bool(self.wall[ih, jh]) if inside else True
-            if is_wall:
+            obj = self.first_object(ih, jh)
+            if obj <= 1:
                 color = PALETTE["wall1"] if self.dim[i - 1] == 1 else PALETTE["wall2"]
-            else:
+            elif obj == 2:
                 color = PALETTE["goal1"] if self.dim[i - 1] == 1 else PALETTE["goal2"]
+            else:
+                color = self.extras[obj - 3]["colors"][0 if self.dim[i - 1] == 1 else 1]
             k = R - i + 1
             col = img[k - 1]
             if h >= P - 1:
@@ -209,10 +236,13 @@ class PyWorld:
         for j in range(1, W + 1):
             for i in range(1, H + 1):
                 it, jt = (i - 1) * pu + 1, (j - 1) * pu + 1                      # :350-351
-                if self.wall[i, j]:                                              # findfirst, :355-360
+                obj = self.first_object(i, j)                                    # findfirst, :355-360
+                if obj == 1:
                     color = 0x00FFFFFF
-                elif (i, j) == self.goal:
+                elif obj == 2:
                     color = 0x00FF0000
+                elif obj >= 3:
+                    color = self.extras[obj - 3]["top"]
                 else:
                     color = 0x00000000
                 img[it:it + pu, jt:jt + pu] = color                              # :353,362
@@ -389,6 +419,61 @@ def main():
         w = PyWorld(H=7, W=7, N=8, R=33, P=40, tie_le=tie)
         for k, v in cast_case(w, st, full_images=len(st), pu=4).items():
             out[name + "_" + k] = v
+
+    # L: NUM_OBJECTS = 5: an interior wall, blocking pillars (object 3), a terminal layer with a
+    # negative reward (object 4) and a terminal layer with reward 0.5 (object 5) on a 9 x 12 map.  A fresh generator,
+    # so the cases above stay byte-identical.
+    rng_l = np.random.default_rng(20261019)
+    H, W = 9, 12
+    tiles = [np.zeros((H + 1, W + 1), bool) for _ in range(3)]
+    for (i, j) in [(3, 4), (6, 8), (4, 9), (7, 3)]:
+        tiles[0][i, j] = True
+    for (i, j) in [(5, 5), (2, 10), (8, 6)]:
+        tiles[1][i, j] = True
+    for (i, j) in [(6, 2), (3, 7), (5, 5)]:          # (5, 5) carries objects 4 and 5: findfirst shows 4
+        tiles[2][i, j] = True
+    w = PyWorld(H=H, W=W, N=32, R=64, P=48, radius=0.15, incr=0.2,
+                extras=[dict(tiles=tiles[0], terminal=False, reward=0.0, colors=(0x00205080, 0x003070A0), top=0x000000FF),
+                        dict(tiles=tiles[1], terminal=True, reward=-1.0, colors=(0x00A04000, 0x00C06000), top=0x00FF8000),
+                        dict(tiles=tiles[2], terminal=True, reward=0.5, colors=(0x0000A040, 0x0000C060), top=0x0000FF00)])
+    w.wall[4, 5:8] = True                             # an interior wall segment
+    out["L_wall"] = w.wall[1:, 1:].copy()
+    out["L_extra"] = np.stack([t[1:, 1:] for t in tiles])
+    free = [(i, j) for i in range(2, H) for j in range(2, W) if w.first_object(i, j) == 0 or (i, j) == w.goal]
+    st = []
+    while len(st) < 16:
+        gi, gj = int(rng_l.integers(2, H)), int(rng_l.integers(2, W))
+        w.goal = (gi, gj)
+        pi, pj = free[int(rng_l.integers(0, len(free)))]
+        if w.first_object(pi, pj) != 0:
+            continue
+        w.pos, w.au = (F(pi - 0.5), F(pj - 0.5)), int(rng_l.integers(0, w.N))
+        for _ in range(int(rng_l.integers(0, 60))):
+            w.act(int(rng_l.choice([1, 1, 2, 3, 4])))
+            if w.done:
+                break
+        st.append((w.pos[0], w.pos[1], w.au, gi, gj))
+    for k, v in cast_case(w, st, full_images=len(st), pu=4).items():
+        out["L_" + k] = v
+    # act! trajectories that run into every kind of object
+    init, actions, pos, au, rew, done = [], [], [], [], [], []
+    while len(init) < 24:
+        gi, gj = int(rng_l.integers(2, H)), int(rng_l.integers(2, W))
+        pi, pj = free[int(rng_l.integers(0, len(free)))]
+        w.goal = (gi, gj)
+        if w.first_object(pi, pj) != 0:
+            continue
+        a0 = int(rng_l.integers(0, w.N))
+        w.pos, w.au = (F(pi - 0.5), F(pj - 0.5)), a0
+        acts = rng_l.choice([1, 1, 1, 1, 2, 3, 4], size=150)
+        tp, ta, tr, td = [], [], [], []
+        for a in acts:
+            w.act(int(a))
+            tp.append((w.pos[0], w.pos[1])), ta.append(w.au), tr.append(w.reward), td.append(w.done)
+        init.append((gi, gj, pi, pj, a0)), actions.append(acts), pos.append(tp), au.append(ta), rew.append(tr), done.append(td)
+    out["L_act_init"], out["L_act_actions"] = np.array(init, np.int32), np.array(actions, np.uint8)
+    out["L_act_pos"], out["L_act_au"] = np.array(pos, np.float32), np.array(au, np.int32)
+    out["L_act_reward"], out["L_act_done"] = np.array(rew, np.float32), np.array(done, np.uint8)
 
     path = os.path.join(HERE, "singleroom_golden.npz")
     np.savez_compressed(path, **out)

@@ -5,7 +5,7 @@ import zlib
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CONFIGS
+from conftest import GOLDEN_CONFIGS, layered_oracle_world
 
 
 @pytest.mark.parametrize("case", ["A", "B", "C", "D", "T", "U"])
@@ -73,3 +73,36 @@ def test_byte_formats_written_directly_equal_the_converted_uint32_view(oracle, g
         c = w.camera_view
         luma = ((77 * ((c >> 16) & 255) + 150 * ((c >> 8) & 255) + 29 * (c & 255) + 128) >> 8).astype(np.uint8)
         np.testing.assert_array_equal(w.frame_bytes("gray8"), luma)
+
+
+def test_object_layers_match_golden(oracle, golden):
+    """NUM_OBJECTS = 5 (case L): rays stop at any object, columns take the first object's colours, the top view shows
+    findfirst, terminal layers end the episode with their own reward, blocking layers refuse the move."""
+    w = layered_oracle_world(oracle, golden)
+    states, au, goal = golden["L_states"], golden["L_au"], golden["L_goal"]
+    for k in range(len(states)):
+        w.set_state(states[k, 0], states[k, 1], au[k], goal[k, 0], goal[k, 1])
+        w.cast_rays()
+        w.update_camera_view()
+        np.testing.assert_array_equal(w.ray_stop, golden["L_hit"][k])
+        np.testing.assert_array_equal(w.ray_dim, golden["L_dim"][k])
+        np.testing.assert_array_equal(w.ray_dist.view(np.uint32), golden["L_dist"][k].view(np.uint32))
+        np.testing.assert_array_equal(w.camera_view, golden["L_image"][k])
+        w.update_top_view()
+        np.testing.assert_array_equal(w.top_view, golden["L_top_image"][k])
+        cols = w.camera_columns()                       # column words carry the object's colour id 2 * object + (dim != 1)
+        assert set(np.unique(cols >> 16)) <= set(range(2, 12))
+    colours = set(np.unique(golden["L_image"]))
+    assert {0x00205080, 0x003070A0} & colours and {0x00A04000, 0x00C06000} & colours, "the fixture should show the extra objects"
+    init, actions = golden["L_act_init"], golden["L_act_actions"]
+    for ep in range(len(init)):
+        gi, gj, pi, pj, a0 = (int(v) for v in init[ep])
+        w.reset_to(gi, gj, pi, pj, a0)
+        for t, a in enumerate(actions[ep]):
+            assert w.act(int(a)) == 0
+            s = w.state()
+            assert s["pos"].view(np.uint32).tolist() == golden["L_act_pos"][ep, t].view(np.uint32).tolist()
+            assert s["au"] == golden["L_act_au"][ep, t]
+            assert s["reward"] == golden["L_act_reward"][ep, t]
+            assert s["done"] == bool(golden["L_act_done"][ep, t])
+    assert set(np.unique(golden["L_act_reward"])) == {-1.0, 0.0, 0.5, 1.0}
