@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RCW_ABI_VERSION 3
+#define RCW_ABI_VERSION 4
 
 typedef enum rcw_status {
     RCW_OK      = 0,
@@ -70,6 +70,19 @@ enum {
     RCW_COLOR_WALL_2  = 3, /* 0x00c0c0c0 */
     RCW_COLOR_GOAL_1  = 4, /* 0x00800000 */
     RCW_COLOR_GOAL_2  = 5  /* 0x00c00000 */
+};
+
+/* Object layers beyond the reference's NUM_OBJECTS = 2 (WALL = 1, GOAL = 2; single_room.jl:16-18): object 3 + k is
+ * "extra layer k" (SURVEY.md 8(f) N2).  Every object stops rays (:209, any over the layers); a column is painted with
+ * the colours of the first object on the hit tile (:417-429 generalised); the top view shows findfirst over the
+ * layers (:355-360); the player is never placed on an object (utils.jl:27); and a layer either refuses the move like
+ * WALL or ends the episode with its own reward like GOAL (:162-176; terminal layers are checked in object order
+ * after GOAL).  In RCW_OBS_COLUMNS words extra layer k has the colour ids 6 + 2 k (hit across dimension 1) and
+ * 7 + 2 k. */
+#define RCW_MAX_EXTRA_LAYERS 4
+enum {
+    RCW_LAYER_BLOCKING = 0, /* like WALL: the move is refused, reward 0                  */
+    RCW_LAYER_TERMINAL = 1  /* like GOAL: reward = layer_reward[k], done, no move        */
 };
 
 /* Indices into rcw_config.top_palette: the colours of the top view (single_room.jl:288-290, 364-367). */
@@ -135,7 +148,13 @@ typedef struct rcw_config {
                                         rcw_wait(ticket) hands out the slot once that step has finished.  With D >= 2 a
                                         host loop can enqueue step k + 1 before it reads the results of step k, so the
                                         device never idles while the host wakes up.                               */
-    uint32_t reserved[2];            /* must be zero                                           */
+    int32_t  num_object_layers;      /* NUM_OBJECTS (single_room.jl:16): 2 = WALL, GOAL (default; 0 means 2) ... 6.  Objects
+                                        3 .. num_object_layers are extra static layers, empty until rcw_set_layer    */
+    int32_t  layer_kind[RCW_MAX_EXTRA_LAYERS];       /* RCW_LAYER_BLOCKING / RCW_LAYER_TERMINAL per extra layer      */
+    float    layer_reward[RCW_MAX_EXTRA_LAYERS];     /* reward of a terminal extra layer (goal_reward's counterpart) */
+    uint32_t layer_palette[RCW_MAX_EXTRA_LAYERS][2]; /* camera-view colours 0x00RRGGBB when hit across dimension 1 / 2 */
+    uint32_t layer_top_color[RCW_MAX_EXTRA_LAYERS];  /* top-view tile colour, tile_map_colors[3 + k]                 */
+    uint32_t reserved[3];            /* must be zero                                           */
 } rcw_config;
 
 typedef struct rcw_batch rcw_batch; /* opaque */
@@ -159,6 +178,13 @@ int32_t rcw_destroy(rcw_batch* b);
  * batch.  wall: [width_tu][height_tu] bytes, Julia column-major (i fastest), nonzero = wall.
  * Does not re-render; follow with rcw_reset or rcw_render. */
 int32_t rcw_set_wall_map(rcw_batch* b, const uint8_t* wall);
+
+/* tile_map[layer, :, :] = tiles for object `layer` (1-based like the reference's constants): 1 = WALL — the same as
+ * rcw_set_wall_map — or 3 .. num_object_layers, an extra object layer shared by the batch.  Layer 2 (GOAL) is not a
+ * map: it holds one tile per env, the goal position (rcw_reset / rcw_set_state).  tiles: [width_tu][height_tu] bytes,
+ * Julia column-major (i fastest), nonzero = object present.  Not combinable with per-env wall layers.  Does not
+ * re-render; follow with rcw_reset or rcw_render. */
+int32_t rcw_set_layer(rcw_batch* b, int32_t layer, const uint8_t* tiles);
 
 /* One wall layer per env: walls is [num_envs][width_tu][height_tu] bytes (each env as above).
  * Each env's layer is staged into shared memory by its own TMA bulk copy.  rcw_set_wall_map

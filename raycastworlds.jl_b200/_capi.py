@@ -16,11 +16,13 @@ LIB_PATH = os.environ.get("RCW_LIB") or os.path.join(_PKG, "lib", "librcw_b200.s
 RCW_OK, RCW_EINVAL, RCW_EACTION, RCW_ECUDA, RCW_ENOMEM, RCW_ESIZE = 0, -1, -2, -3, -4, -5
 RCW_OBS_RGB8, RCW_OBS_XRGB32, RCW_OBS_GRAY8, RCW_OBS_COLUMNS = 0, 1, 2, 3
 RCW_DDA_TIE_LE, RCW_DDA_DIST_POST = 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
+RCW_MAX_EXTRA_LAYERS = 4
+RCW_LAYER_BLOCKING, RCW_LAYER_TERMINAL = 0, 1
 
 # every symbol include/rcw_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
-    "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_set_wall_maps", "rcw_reset",
+    "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_set_layer", "rcw_set_wall_maps", "rcw_reset",
     "rcw_step", "rcw_step_async", "rcw_wait", "rcw_step_range", "rcw_step_random", "rcw_render",
     "rcw_render_top_view", "rcw_top_view_device_ptr", "rcw_copy_top_view", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
     "rcw_checkpoint_size", "rcw_save_checkpoint", "rcw_load_checkpoint",
@@ -58,7 +60,12 @@ class RcwConfig(C.Structure):
         ("top_palette", C.c_uint32 * 6),
         ("frame_stack", C.c_int32),
         ("result_ring", C.c_int32),
-        ("reserved", C.c_uint32 * 2),
+        ("num_object_layers", C.c_int32),
+        ("layer_kind", C.c_int32 * 4),
+        ("layer_reward", C.c_float * 4),
+        ("layer_palette", (C.c_uint32 * 2) * 4),
+        ("layer_top_color", C.c_uint32 * 4),
+        ("reserved", C.c_uint32 * 3),
     ]
 
 
@@ -94,6 +101,7 @@ def load() -> C.CDLL:
         "rcw_destroy": (i32, [vp]),
         "rcw_set_wall_map": (i32, [vp, vp]),
         "rcw_set_wall_maps": (i32, [vp, vp]),
+        "rcw_set_layer": (i32, [vp, i32, vp]),
         "rcw_reset": (i32, [vp, vp, vp, vp, vp]),
         "rcw_step": (i32, [vp, vp]),
         "rcw_step_async": (i32, [vp, vp, P(i64)]),

@@ -144,7 +144,10 @@ struct rcw_batch {
     // device memory
     float2* d_dirs = nullptr;
     float4* d_ray_table = nullptr;
-    uint32_t* d_wall_map = nullptr;      // wall layer shared by the batch
+    uint32_t* d_wall_map = nullptr;      // layers shared by the batch: [wall][extra 0..3][any], map_words each (see BitsMap);
+                                         // the `any` layer sits right behind the last extra layer in use
+    int n_extra = 0;                     // extra object layers (rcw_config.num_object_layers - 2)
+    std::vector<uint32_t> h_layers;      // host copy of [wall][extra 0 .. n_extra-1], to rebuild `any` when one changes
     uint32_t* d_wall_maps_env = nullptr; // [num_envs][map_words], allocated by rcw_set_wall_maps
     bool per_env_maps = false;
     bool closed_border = true;           // every border tile of the active wall layer(s) is a wall
@@ -230,6 +233,13 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
     p.W = c.width_tile_map_tu;
     p.wpr = b->wpr;
     p.map_words = b->map_words;
+    p.n_extra = b->per_env_maps ? 0 : b->n_extra;
+    p.stage_words = p.n_extra ? (p.n_extra + 2) * b->map_words : b->map_words;
+    p.n_colors = 4 + 2 * b->n_extra;
+    for (int k = 0; k < b->n_extra; ++k) {
+        if (c.layer_kind[k] == RCW_LAYER_TERMINAL) p.layer_terminal_mask |= 1u << k;
+        p.layer_reward[k] = c.layer_reward[k];
+    }
     p.N = c.num_directions;
     p.R = c.num_rays;
     p.P = c.height_camera_view_pu;
@@ -249,8 +259,9 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
     volatile float two_s = 2.0f * c.semi_field_of_view_wu;
     p.hl_num = hl_num;
     p.two_s = two_s;
-    for (int i = 0; i < 6; ++i) {
-        const uint32_t col = c.palette[i] & 0x00FFFFFFu;
+    const int n_pal = 6 + 2 * b->n_extra;
+    for (int i = 0; i < n_pal; ++i) {
+        const uint32_t col = (i < 6 ? c.palette[i] : c.layer_palette[(i - 6) >> 1][(i - 6) & 1]) & 0x00FFFFFFu;
         if (pixel_fmt == RCW_OBS_GRAY8) {
             // BT.601 luma of the reference pixel, replicated so the colour is "flat" for the renderer
             const uint32_t y = (77u * ((col >> 16) & 255u) + 150u * ((col >> 8) & 255u) + 29u * (col & 255u) + 128u) >> 8;
@@ -262,7 +273,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
     {   // what the renderer stores per column for each palette entry (see FrameParams::col_entry)
         auto flat = [&](uint32_t col) { return pixel_fmt != RCW_OBS_RGB8 || ((col ^ (col >> 8)) & 0xFFFFu) == 0; };
         const bool cf = flat(p.palette[RCW_COLOR_CEILING]) && flat(p.palette[RCW_COLOR_FLOOR]);
-        for (int i = 0; i < 6; ++i) {
+        for (int i = 0; i < n_pal; ++i) {
             const bool slow = !(cf && flat(p.palette[i]));
             const uint32_t col = p.palette[i];
             const uint32_t word = pixel_fmt == RCW_OBS_XRGB32 ? col : (col & 0xFFu) * 0x01010101u;
@@ -370,6 +381,9 @@ static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, 
     t.W = c.width_tile_map_tu;
     t.wpr = b->wpr;
     t.map_words = b->map_words;
+    t.n_extra = b->per_env_maps ? 0 : b->n_extra;
+    t.stage_words = t.n_extra ? (t.n_extra + 2) * b->map_words : b->map_words;
+    for (int k = 0; k < b->n_extra; ++k) t.extra_color[k] = c.layer_top_color[k] & 0x00FFFFFFu;
     t.N = c.num_directions;
     t.R = c.num_rays;
     t.pu = c.pu_per_tu;
@@ -507,6 +521,39 @@ static int32_t sync_and_check(rcw_batch* b, bool need_stats = false) {
     return RCW_OK;
 }
 
+// Host layers -> device [wall][extra ...][any], and what the kernels may assume about them: `closed` (every border
+// tile carries an object: rays cannot leave the map) and `room` (the wall layer is exactly the border and there are
+// no extra layers: RoomMap kernels).  Blocks until the previous work on the stream has finished.
+static int32_t upload_layers(rcw_batch* b) {
+    const int H = b->cfg.height_tile_map_tu, W = b->cfg.width_tile_map_tu, mw = b->map_words, L = 1 + b->n_extra;
+    std::vector<uint32_t> dev((size_t)(L + 1) * mw, 0u);
+    std::copy(b->h_layers.begin(), b->h_layers.end(), dev.begin());
+    uint32_t* any = dev.data() + (size_t)L * mw;
+    for (int l = 0; l < L; ++l)
+        for (int k = 0; k < mw; ++k) any[k] |= b->h_layers[(size_t)l * mw + k];
+    bool closed = true, interior = false;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const bool obj = (any[(size_t)i * b->wpr + (j >> 5)] >> (j & 31)) & 1u;
+            const bool border = i == 0 || i == H - 1 || j == 0 || j == W - 1;
+            if (obj && !border) interior = true;
+            if (!obj && border) closed = false;
+        }
+    RCW_CUDA(cudaStreamSynchronize(b->stream));
+    // without extra layers only the wall layer is staged (the kernels read it as `any`)
+    RCW_CUDA(cudaMemcpy(b->d_wall_map, dev.data(), sizeof(uint32_t) * (b->n_extra ? dev.size() : (size_t)mw), cudaMemcpyHostToDevice));
+    b->per_env_maps = false;
+    b->closed_border = closed;
+    b->room = closed && !interior && b->n_extra == 0;
+    return RCW_OK;
+}
+
+static void pack_tiles(const uint8_t* tiles, int H, int W, int wpr, uint32_t* words) {
+    for (int j = 0; j < W; ++j)
+        for (int i = 0; i < H; ++i)
+            if (tiles[(size_t)j * H + i]) words[(size_t)i * wpr + (j >> 5)] |= 1u << (j & 31);
+}
+
 static void pack_border_walls(int H, int W, int wpr, std::vector<uint32_t>& words) {
     // tile_map[WALL, :, 1] = tile_map[WALL, :, W] = tile_map[WALL, 1, :] = tile_map[WALL, H, :] = true
     // (single_room.jl:57-60)
@@ -518,7 +565,8 @@ static void pack_border_walls(int H, int W, int wpr, std::vector<uint32_t>& word
 // the top view of one env is composed in shared memory (two bit planes + tile tables): bounded by the SM
 static int32_t check_top_view_fits(const rcw_config& c) {
     const int64_t Hp = (int64_t)c.height_tile_map_tu * c.pu_per_tu, Wp = (int64_t)c.width_tile_map_tu * c.pu_per_tu;
-    const int map_words = ((c.height_tile_map_tu * ((c.width_tile_map_tu + 31) / 32) + 3) / 4) * 4;
+    const int layers = c.num_object_layers > 2 ? c.num_object_layers : 1;     // staged: [wall][extras][any], or the wall layer alone
+    const int map_words = layers * (((c.height_tile_map_tu * ((c.width_tile_map_tu + 31) / 32) + 3) / 4) * 4);
     if (Hp > 32767 || Wp > 32767 || Hp * Wp >= (1LL << 28) ||
         top_view_smem_bytes(c.height_tile_map_tu, c.width_tile_map_tu, c.num_rays, c.pu_per_tu, c.player_radius_wu, map_words) > 200 * 1024)
         return fail(RCW_ESIZE, "a top view of %lldx%lld pixels does not fit the renderer's shared memory; "
@@ -572,6 +620,7 @@ int32_t rcw_config_init(rcw_config* cfg) {
     cfg->top_palette[RCW_TOP_COLOR_BORDER] = 0x00ccccccu;  // :364-367
     cfg->top_palette[RCW_TOP_COLOR_RAY] = 0x00808080u;     // ray_color :289
     cfg->top_palette[RCW_TOP_COLOR_PLAYER] = 0x00c0c0c0u;  // player_color :290
+    cfg->num_object_layers = 2;                            // NUM_OBJECTS :16
     return RCW_OK;
 }
 
@@ -637,12 +686,10 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // ---- wall layer ---------------------------------------------------------------------------
     b->wpr = (W + 31) / 32;
     b->map_words = ((H * b->wpr + 3) / 4) * 4;
-    std::vector<uint32_t> words((size_t)b->map_words, 0u);
-    pack_border_walls(H, W, b->wpr, words);
-    RCW_CUDA(dev_alloc(b, &b->d_wall_map, (size_t)b->map_words, false));
-    RCW_CUDA(cudaMemcpyAsync(b->d_wall_map, words.data(), sizeof(uint32_t) * words.size(),
-                             cudaMemcpyHostToDevice, b->stream));
-    RCW_CUDA(cudaStreamSynchronize(b->stream));
+    b->h_layers.assign((size_t)(1 + b->n_extra) * b->map_words, 0u);   // [wall][extra layers, empty until rcw_set_layer]
+    pack_border_walls(H, W, b->wpr, b->h_layers);
+    RCW_CUDA(dev_alloc(b, &b->d_wall_map, (size_t)(b->n_extra + 2) * b->map_words, true));
+    if (int32_t rc = upload_layers(b)) return rc;
 
     // ---- single-colour pattern buffers for the bulk renderer: palette entry k repeated as the
     //      observation's byte stream (RGB8: R,G,B,R,...; XRGB32: little-endian 0x00RRGGBB words) ----
@@ -655,6 +702,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0 && c.obs_format != RCW_OBS_GRAY8;
     if (const char* s = getenv("RCW_SPLIT")) b->split = atoi(s) != 0;
     if (c.obs_format == RCW_OBS_COLUMNS) b->bulk = b->split = false;   // nothing is painted
+    if (b->n_extra) b->bulk = b->split = false;                        // the measured alternatives know the reference's two objects only
     if (b->split) RCW_CUDA(dev_alloc(b, &b->d_col_info, (size_t)E * (size_t)R));   // 4 B per column, two-launch path only
     {
         std::vector<uint8_t> pat((size_t)6 * b->pat_stride);
@@ -741,13 +789,14 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // fit the L1 / L2 caches, and painting a column is copying it.  Built here with the renderer's own rules
     // (pixel bytes per format, the pitch padding behind the last row continues the floor).
     {
-        const size_t table_bytes = (size_t)(P / 2 + 1) * 4 * (size_t)b->col_pitch;
+        const int n_colors = 4 + 2 * b->n_extra;    // wall, goal and extra-layer colours x hit dimension
+        const size_t table_bytes = (size_t)(P / 2 + 1) * n_colors * (size_t)b->col_pitch;
         size_t limit = 64 * 1024;
         if (const char* s = getenv("RCW_COL_TABLE_KB")) limit = (size_t)atoll(s) * 1024;   // 0 disables the table
         if (b->env_per_warp && c.obs_format != RCW_OBS_COLUMNS && table_bytes <= limit) {
-            uint32_t pal[6];
-            for (int i = 0; i < 6; ++i) {
-                const uint32_t col = c.palette[i] & 0x00FFFFFFu;
+            uint32_t pal[6 + 2 * RCW_MAX_EXTRA_LAYERS];
+            for (int i = 0; i < 2 + n_colors; ++i) {
+                const uint32_t col = (i < 6 ? c.palette[i] : c.layer_palette[(i - 6) >> 1][(i - 6) & 1]) & 0x00FFFFFFu;
                 pal[i] = c.obs_format == RCW_OBS_GRAY8
                              ? ((77u * ((col >> 16) & 255u) + 150u * ((col >> 8) & 255u) + 29u * (col & 255u) + 128u) >> 8) * 0x00010101u
                              : col;
@@ -759,8 +808,8 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
             };
             std::vector<uint8_t> tab(table_bytes);
             for (int pad = 0; pad <= P / 2; ++pad)
-                for (int k = 0; k < 4; ++k) {
-                    uint8_t* colp = tab.data() + ((size_t)pad * 4 + k) * b->col_pitch;
+                for (int k = 0; k < n_colors; ++k) {
+                    uint8_t* colp = tab.data() + ((size_t)pad * n_colors + k) * b->col_pitch;
                     for (int ob = 0; ob < b->col_pitch; ++ob) {
                         const int row = ob / b->bpp;
                         const uint32_t col = row < pad ? pal[RCW_COLOR_CEILING]
@@ -817,8 +866,14 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
         return fail(RCW_ESIZE, "num_directions * num_rays must be below 2^31 (the ray table is indexed with 32 bits)");
     if (cfg->num_envs * gpe >= (1LL << 31))
         return fail(RCW_ESIZE, "num_envs * ceil(num_rays/32) must be below 2^31 per handle");
-    if ((int64_t)((H * ((W + 31) / 32) + 3) / 4) * 16 > 200 * 1024)
-        return fail(RCW_ESIZE, "bit-packed tile map does not fit in shared memory");
+    if (cfg->num_object_layers != 0 && (cfg->num_object_layers < 2 || cfg->num_object_layers > 2 + RCW_MAX_EXTRA_LAYERS))
+        return fail(RCW_EINVAL, "num_object_layers must be 2..%d (got %d)", 2 + RCW_MAX_EXTRA_LAYERS, cfg->num_object_layers);
+    const int n_extra = cfg->num_object_layers > 2 ? cfg->num_object_layers - 2 : 0;
+    for (int k = 0; k < n_extra; ++k)
+        if (cfg->layer_kind[k] != RCW_LAYER_BLOCKING && cfg->layer_kind[k] != RCW_LAYER_TERMINAL)
+            return fail(RCW_EINVAL, "layer_kind[%d] must be RCW_LAYER_BLOCKING or RCW_LAYER_TERMINAL", k);
+    if ((int64_t)((H * ((W + 31) / 32) + 3) / 4) * 16 * (n_extra ? n_extra + 2 : 1) > 200 * 1024)
+        return fail(RCW_ESIZE, "bit-packed tile map (%d layers) does not fit in shared memory", n_extra ? n_extra + 2 : 1);
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -837,6 +892,7 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
     b->device = cfg->device;
     b->bpp = bpp;
     b->gpe = gpe;
+    b->n_extra = n_extra;
     DeviceGuard g(b->device);
     if (!g.ok) {
         delete b;
@@ -859,24 +915,23 @@ int32_t rcw_set_wall_map(rcw_batch* b, const uint8_t* wall) {
     if (int32_t rc = check_handle(b)) return rc;
     if (!wall) return fail(RCW_EINVAL, "wall is null");
     DeviceGuard g(b->device);
-    const int H = b->cfg.height_tile_map_tu, W = b->cfg.width_tile_map_tu;
-    std::vector<uint32_t> words((size_t)b->map_words, 0u);
-    bool closed = true, interior_walls = false;
-    for (int j = 0; j < W; ++j)
-        for (int i = 0; i < H; ++i) {
-            const bool is_wall = wall[(size_t)j * H + i] != 0;
-            const bool border = i == 0 || i == H - 1 || j == 0 || j == W - 1;
-            if (is_wall) words[(size_t)i * b->wpr + (j >> 5)] |= 1u << (j & 31);
-            if (is_wall && !border) interior_walls = true;
-            if (!is_wall && border) closed = false;
-        }
-    RCW_CUDA(cudaStreamSynchronize(b->stream));
-    RCW_CUDA(cudaMemcpy(b->d_wall_map, words.data(), sizeof(uint32_t) * words.size(),
-                        cudaMemcpyHostToDevice));
-    b->per_env_maps = false;
-    b->closed_border = closed;
-    b->room = closed && !interior_walls;
-    return RCW_OK;
+    std::fill(b->h_layers.begin(), b->h_layers.begin() + b->map_words, 0u);
+    pack_tiles(wall, b->cfg.height_tile_map_tu, b->cfg.width_tile_map_tu, b->wpr, b->h_layers.data());
+    return upload_layers(b);
+}
+
+int32_t rcw_set_layer(rcw_batch* b, int32_t layer, const uint8_t* tiles) {
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!tiles) return fail(RCW_EINVAL, "tiles is null");
+    if (layer == 1) return rcw_set_wall_map(b, tiles);
+    if (layer == 2) return fail(RCW_EINVAL, "layer 2 (GOAL) holds one tile per env: move it with rcw_reset / rcw_set_state");
+    if (layer < 3 || layer > 2 + b->n_extra)
+        return fail(RCW_EINVAL, "no object layer %d (rcw_config.num_object_layers = %d)", layer, 2 + b->n_extra);
+    DeviceGuard g(b->device);
+    uint32_t* words = b->h_layers.data() + (size_t)(layer - 2) * b->map_words;
+    std::fill(words, words + b->map_words, 0u);
+    pack_tiles(tiles, b->cfg.height_tile_map_tu, b->cfg.width_tile_map_tu, b->wpr, words);
+    return upload_layers(b);
 }
 
 int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls) {
@@ -887,6 +942,7 @@ int32_t rcw_set_wall_maps(rcw_batch* b, const uint8_t* walls) {
     const size_t E = (size_t)b->cfg.num_envs, mw = (size_t)b->map_words, tiles = (size_t)H * W;
     if ((size_t)kWarpsPerCta * mw * 4 > 200 * 1024)
         return fail(RCW_ESIZE, "per-env tile maps of %dx%d do not fit in shared memory", H, W);
+    if (b->n_extra) return fail(RCW_EINVAL, "per-env wall layers cannot be combined with extra object layers");
     bool closed = true;
     std::vector<uint32_t> words;
     try {
@@ -1029,6 +1085,8 @@ int32_t rcw_reset(rcw_batch* b, const int32_t* goal_ij, const int32_t* player_ij
     rp.N = c.num_directions;
     rp.wall_map = b->per_env_maps ? b->d_wall_maps_env : b->d_wall_map;
     rp.map_env_stride = b->per_env_maps ? (uint32_t)b->map_words : 0u;
+    rp.n_extra = b->per_env_maps ? 0 : b->n_extra;
+    rp.map_words = b->map_words;
     rp.st = b->st[b->cur];
     rp.reward = b->d_reward;
     rp.done = b->d_done;

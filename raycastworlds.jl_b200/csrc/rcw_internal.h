@@ -69,7 +69,13 @@ struct FrameParams {
     // geometry
     int32_t H, W;            // tiles
     int32_t wpr;             // 32-bit words per bit-packed map row (bit j-1 of row i-1)
-    int32_t map_words;       // H * wpr rounded up to a multiple of 4 (16-byte TMA granule)
+    int32_t map_words;       // H * wpr rounded up to a multiple of 4 (16-byte TMA granule): one layer
+    int32_t stage_words;     // words staged in shared memory per map: map_words, or (n_extra + 2) * map_words with extra
+                             // object layers ([wall][extra ...][any], see BitsMap)
+    int32_t n_extra;         // object layers beyond WALL and GOAL (rcw_config.num_object_layers - 2)
+    uint32_t layer_terminal_mask;   // bit k: extra layer k ends the episode like GOAL (else it blocks like WALL)
+    float layer_reward[RCW_MAX_EXTRA_LAYERS];
+    int32_t n_colors;        // wall / goal / extra-layer colours a column can have: 4 + 2 * n_extra (col_table rows per pad)
     int32_t N;               // num_directions
     int32_t R;               // num_rays == observation width
     int32_t P;               // height_camera_view_pu
@@ -82,8 +88,8 @@ struct FrameParams {
     float radius, incr, goal_reward;
     float hl_num;            // camera_height_tile_wu * Float32(num_rays)   (single_room.jl:406)
     float two_s;             // 2 * semi_field_of_view_wu
-    uint32_t palette[6];
-    uint2 col_entry[6];      // renderer's {slow << 31, colour word} of a column painted with palette entry k: the
+    uint32_t palette[6 + 2 * RCW_MAX_EXTRA_LAYERS];   // RCW_COLOR_*, then extra layer k at 6 + 2 k (dim 1), 7 + 2 k (dim 2)
+    uint2 col_entry[6 + 2 * RCW_MAX_EXTRA_LAYERS];    // renderer's {slow << 31, colour word} of a column painted with palette entry k: the
                              // word is the byte-replicated colour when entry k, ceiling and floor all have R == G == B
                              // (or the format has whole-word pixels); otherwise the column takes the phase-rotated path
     uint32_t gpe_magic;      // item / gpe for any 32-bit item (gpe >= 2), branch-free round-up method (libdivide):
@@ -150,6 +156,7 @@ struct PackedActions {
 
 struct ResetParams {
     int32_t H, W, wpr, N;
+    int32_t n_extra, map_words;   // extra object layers behind the wall layer (see BitsMap)
     const uint32_t* wall_map;
     uint32_t map_env_stride;   // 0 = shared wall layer
     StateRef st;
@@ -176,6 +183,9 @@ struct TopViewParams {
     uint32_t closed_border;
     float radius;            // player_radius_wu
     uint32_t palette[6];     // RCW_TOP_COLOR_*
+    int32_t n_extra;         // extra object layers, staged behind the wall layer
+    int32_t stage_words;     // (n_extra ? n_extra + 2 : 1) * map_words
+    uint32_t extra_color[RCW_MAX_EXTRA_LAYERS];   // tile_map_colors[3 + k]
     int32_t dir_slot;
     const float2* dirs;
     const float4* ray_table;

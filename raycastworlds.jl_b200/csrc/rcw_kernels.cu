@@ -113,16 +113,31 @@ __device__ __forceinline__ uint32_t uniform_below(uint32_t u, uint32_t n) { retu
 // by the reset kernel).  RoomMap: the border tiles are walls and nothing else is — the map every SingleRoom of
 // the reference has (single_room.jl:57-60); it needs no memory at all, and its DDA counts down to the border
 // instead of probing (dda_walk_room).  The host picks the view per launch (FrameParams::room).
+// Object layers beyond WALL and GOAL (NUM_OBJECTS > 2, single_room.jl:16-18) are further bit-packed
+// layers behind the wall layer, `stride` words apart: [wall][extra 0] ... [extra n-1][any = OR of all of them], staged
+// together.  Rays stop at any object (:209), so the DDA probes the `any` layer — which IS the wall layer when there
+// are no extra objects — and only the tile a ray stopped on is looked up layer by layer.
 struct BitsMap {
-    const uint32_t* w;
+    const uint32_t* w;      // the wall layer
+    const uint32_t* any;    // wall | every extra layer (== w without extra layers)
     int wpr;
-    __device__ __forceinline__ bool wall(int i0, int j0) const { return (w[i0 * wpr + (j0 >> 5)] >> (j0 & 31)) & 1u; }
+    int n_extra;
+    int stride;             // words between consecutive layers
+    __device__ __forceinline__ static bool bit(const uint32_t* m, int wpr, int i0, int j0) {
+        return (m[i0 * wpr + (j0 >> 5)] >> (j0 & 31)) & 1u;
+    }
+    __device__ __forceinline__ bool wall(int i0, int j0) const { return bit(w, wpr, i0, j0); }
+    __device__ __forceinline__ bool obstacle(int i0, int j0) const { return bit(any, wpr, i0, j0); }
+    __device__ __forceinline__ bool extra(int k, int i0, int j0) const { return bit(w + (k + 1) * stride, wpr, i0, j0); }
 };
 struct RoomMap {
     int H1, W1;   // H - 1, W - 1
+    static constexpr int n_extra = 0;
     __device__ __forceinline__ bool wall(int i0, int j0) const {
         return ((unsigned)(i0 - 1) >= (unsigned)(H1 - 1)) | ((unsigned)(j0 - 1) >= (unsigned)(W1 - 1));
     }
+    __device__ __forceinline__ bool obstacle(int i0, int j0) const { return wall(i0, j0); }
+    __device__ __forceinline__ bool extra(int, int, int) const { return false; }
 };
 
 // Uniform random policy: action in 1..4 for (global env id, global step index).
@@ -154,7 +169,7 @@ __device__ inline void draw_layout(const Map& map, int H, int W, int N, uint64_t
         const uint32_t lin = uniform_below(draw, (uint32_t)(H * W));  // CartesianIndices, i fastest
         pi = (int)(lin % (uint32_t)H) + 1;
         pj = (int)(lin / (uint32_t)H) + 1;
-        const bool occupied = map.wall(pi - 1, pj - 1) || (pi == gi && pj == gj);
+        const bool occupied = map.obstacle(pi - 1, pj - 1) || (pi == gi && pj == gj);   // any(tile_map[:, pos]) (utils.jl:27)
         if (!occupied || t == max_tries) break;
         const int word = (int)(t & 3);
         if (word == 0) {
@@ -420,19 +435,37 @@ __device__ __forceinline__ EnvPose act_env(const FrameParams& p, const Map& map,
             const int ti = __float2int_rd(nx) + (lane % 3);        // = ip - 1 + di, 1-based
             const int tj = __float2int_rd(ny) + ((lane / 3) % 3);
             bool hit_goal = false, hit_wall = false;
+            uint32_t hit_extra = 0u;          // bit k: the circle touches a tile of extra object layer k
             if (lane < 9 && ti >= 1 && ti <= H && tj >= 1 && tj <= W) {
                 const bool is_goal = (ti == gi) && (tj == gj);
-                const bool is_wall = map.wall(ti - 1, tj - 1);
-                if (is_goal || is_wall) {
+                const bool is_obstacle = map.obstacle(ti - 1, tj - 1);
+                if (is_goal || is_obstacle) {
                     const bool c = circle_hits_tile(nx, ny, ti, tj, p.radius);
                     hit_goal = is_goal && c;
-                    hit_wall = is_wall && c;
+                    if (map.n_extra == 0) {
+                        hit_wall = is_obstacle && c;
+                    } else if (is_obstacle && c) {
+                        hit_wall = map.wall(ti - 1, tj - 1);
+                        for (int k = 0; k < map.n_extra; ++k) hit_extra |= map.extra(k, ti - 1, tj - 1) ? (1u << k) : 0u;
+                    }
                 }
             }
-            const bool any_goal = __any_sync(0xFFFFFFFFu, hit_goal);
-            const bool any_wall = __any_sync(0xFFFFFFFFu, hit_wall);
+            bool any_goal = __any_sync(0xFFFFFFFFu, hit_goal);
+            bool any_wall = __any_sync(0xFFFFFFFFu, hit_wall);
+            float goal_reward = p.goal_reward;
+            if (map.n_extra != 0) {
+                // extra objects act like one of the reference's two: a terminal layer like GOAL (its own reward, done,
+                // no move; checked in object order after GOAL), a blocking layer like WALL
+                const uint32_t touched = __reduce_or_sync(0xFFFFFFFFu, hit_extra);
+                const uint32_t terminal = touched & p.layer_terminal_mask;
+                if (!any_goal && terminal) {
+                    any_goal = true;
+                    goal_reward = p.layer_reward[__ffs(terminal) - 1];
+                }
+                any_wall |= (touched & ~p.layer_terminal_mask) != 0u;
+            }
             if (any_goal) {           // single_room.jl:166-168 — reward, done, no move
-                reward = p.goal_reward;
+                reward = goal_reward;
                 done = true;
             } else if (!any_wall) {   // :174-176
                 x = nx;
@@ -513,7 +546,8 @@ struct RayHit {
     int ti, tj;      // hit tile
     int dim;         // 1: crossed along dimension 1 (i), 2: along dimension 2 (j), 0: started inside an obstacle
     float dist;      // Euclidean distance along the unit ray
-    bool is_wall;    // the hit tile is a wall (outside the map counts as wall); otherwise it is the goal
+    int object;      // first object on the hit tile, findfirst(tile_map[:, i, j]) - 1: 0 wall (outside the map counts
+                     // as wall), 1 goal, 2 + k extra object layer k
 };
 
 // The DDA walk itself, branch-free per step.  TIE_LE: decision D1 (advance along dimension 1 on a tie).
@@ -528,10 +562,10 @@ __device__ __forceinline__ void dda_walk(const Map& map, int H, int W, int gi0, 
     auto probe = [&]() {
         bool wall;
         if (CLOSED) {
-            wall = map.wall(ti, tj);
+            wall = map.obstacle(ti, tj);
         } else {
             const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
-            wall = !inside | map.wall(inside ? ti : 0, inside ? tj : 0);
+            wall = !inside | map.obstacle(inside ? ti : 0, inside ? tj : 0);
         }
         return wall | ((ti == gi0) & (tj == gj0));
     };
@@ -664,9 +698,18 @@ __device__ __forceinline__ RayHit dda_cast(const Map& map, int H, int W, uint32_
     h.tj = tj;
     h.dim = dim;
     h.dist = dist;
-    // which layer stopped the ray: a wall (outside the map counts as wall), else this env's goal
+    // which object stopped the ray (single_room.jl:417-429 asks tile_map[WALL, i, j], else GOAL; with more objects:
+    // the first one on the tile): a wall (outside the map counts as wall), this env's goal, an extra layer
     const bool inside = ((unsigned)ti < (unsigned)H) & ((unsigned)tj < (unsigned)W);
-    h.is_wall = !inside | map.wall(inside ? ti : 0, inside ? tj : 0);
+    const int i0 = inside ? ti : 0, j0 = inside ? tj : 0;
+    h.object = 0;
+    if (inside & !map.wall(i0, j0)) {
+        h.object = 1;
+        if (map.n_extra != 0 && !((ti == gi0) & (tj == gj0))) {
+            h.object = 0;                       // (a stopped ray stands on an object; none found = treated as wall)
+            for (int k = map.n_extra - 1; k >= 0; --k) h.object = map.extra(k, i0, j0) ? 2 + k : h.object;
+        }
+    }
     return h;
 }
 
@@ -684,7 +727,6 @@ __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, cons
     const RayHit hit = dda_cast(map, p.H, p.W, p.dda_flags, p.closed_border != 0, pose.x, pose.y, gi0, gj0, rt, lane);
     const int ti = hit.ti, tj = hit.tj, dim = hit.dim;
     const float dist = hit.dist;
-    const bool is_wall = hit.is_wall;
 
     if (MODE == kModeRays) {
         if (ray < R) {
@@ -705,7 +747,7 @@ __device__ __forceinline__ ColumnShade cast_and_shade(const FrameParams& p, cons
     if (isfinite(hl) && hl < (float)P) h = max(__float2int_rd(hl), 0);
     ColumnShade cs;
     cs.pad = (h >= P - 1) ? 0 : ((P - h) >> 1);
-    cs.cid = (is_wall ? RCW_COLOR_WALL_1 : RCW_COLOR_GOAL_1) + (dim == 1 ? 0 : 1);
+    cs.cid = RCW_COLOR_WALL_1 + 2 * hit.object + (dim == 1 ? 0 : 1);   // 2/3 wall, 4/5 goal, 6 + 2 k / 7 + 2 k extra layer k
     return cs;
 }
 
@@ -938,7 +980,9 @@ enum : int { kStageFused = 0, kStageFront = 1, kStagePaint = 2 };
 template <bool ROOM>
 struct MapOf {
     using type = BitsMap;
-    __device__ static __forceinline__ BitsMap make(const FrameParams& p, const uint32_t* words) { return BitsMap{words, p.wpr}; }
+    __device__ static __forceinline__ BitsMap make(const FrameParams& p, const uint32_t* words) {
+        return BitsMap{words, p.n_extra ? words + (p.n_extra + 1) * p.map_words : words, p.wpr, p.n_extra, p.map_words};
+    }
 };
 template <>
 struct MapOf<true> {
@@ -966,7 +1010,7 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
     const uint32_t pat_bytes = (BULK && kPaints) ? 6u * (uint32_t)p.pat_stride : 0u;
     uint32_t* const s_map = s_dyn + pat_bytes / 4;
     const bool per_env_maps = kStagesMap && p.map_env_stride != 0;
-    const uint32_t map_bytes = (uint32_t)p.map_words * 4u;
+    const uint32_t map_bytes = (uint32_t)p.stage_words * 4u;   // every layer of the map (one without extra objects)
     const uint32_t shared_bytes = (kStagesMap && !per_env_maps) ? map_bytes : 0u;
     if (kStagesMap || pat_bytes) {
         if (threadIdx.x == 0) {
@@ -1021,7 +1065,7 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
             const uint32_t* my_map = s_map;
             if (per_env_maps) {
                 // this env's wall layer -> its slot (one round per CTA in this mode, see grid_for)
-                my_map = s_map + slot * (uint32_t)p.map_words;
+                my_map = s_map + slot * (uint32_t)p.stage_words;
                 if (leader && lane == 0) {
                     mbar_arrive_expect_tx(&s_mbar_env[slot], map_bytes);
                     bulk_copy_g2s(const_cast<uint32_t*>(my_map), p.wall_map + (size_t)env * p.map_env_stride,
@@ -1101,9 +1145,10 @@ __device__ __forceinline__ void frame_body(const FrameParams& p, const PackedAct
                 cs.cid = (int)(info >> 16);
                 // the words may come from a caller's replay buffer: a stale or uninitialised row must not index
                 // outside the palette or paint outside its column — clamp, and leave a sticky flag for the host
-                const bool bad = (cs.cid < RCW_COLOR_WALL_1) | (cs.cid > RCW_COLOR_GOAL_2) | (cs.pad > (p.P >> 1));
+                const int max_cid = RCW_COLOR_GOAL_2 + 2 * p.n_extra;
+                const bool bad = (cs.cid < RCW_COLOR_WALL_1) | (cs.cid > max_cid) | (cs.pad > (p.P >> 1));
                 if (bad) {
-                    cs.cid = min(max(cs.cid, (int)RCW_COLOR_WALL_1), (int)RCW_COLOR_GOAL_2);
+                    cs.cid = min(max(cs.cid, (int)RCW_COLOR_WALL_1), max_cid);
                     cs.pad = min(cs.pad, p.P >> 1);
                     if (p.stats) atomicExch(&p.stats->bad_columns, 1);
                 }
@@ -1189,7 +1234,7 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const bool per_env_maps = !ROOM && p.map_env_stride != 0;
-    const uint32_t map_bytes = (uint32_t)p.map_words * 4u;
+    const uint32_t map_bytes = (uint32_t)p.stage_words * 4u;   // every layer of the map (one without extra objects)
     if (!ROOM) {
         if (threadIdx.x == 0) {
             mbar_init(&s_mbar, 1);
@@ -1214,7 +1259,7 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
     const int R = p.R;
     const uint32_t* my_map = s_dyn;
     if (per_env_maps) {
-        my_map = s_dyn + (uint32_t)warp * (uint32_t)p.map_words;
+        my_map = s_dyn + (uint32_t)warp * (uint32_t)p.stage_words;
         if (lane == 0) {
             mbar_arrive_expect_tx(&s_mbar_env[warp], map_bytes);
             bulk_copy_g2s(const_cast<uint32_t*>(my_map), p.wall_map + (size_t)env * p.map_env_stride, map_bytes,
@@ -1276,7 +1321,7 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
             // lane <-> column: copy the column's col_pitch bytes from its table entry, sector by sector
             const int CP = p.col_pitch;
             if (lane < ncols) {
-                const uint8_t* src = p.col_table + (uint32_t)((cs.pad << 2) + (cs.cid - RCW_COLOR_WALL_1)) * (uint32_t)CP;
+                const uint8_t* src = p.col_table + (uint32_t)(cs.pad * p.n_colors + (cs.cid - RCW_COLOR_WALL_1)) * (uint32_t)CP;
                 uint8_t* dst = env_obs + (size_t)(col0 + ncols - 1 - lane) * CP;
 #pragma unroll 3
                 for (int o = 0; o < CP; o += 32) {
@@ -1289,7 +1334,7 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
             // The span's sectors are consecutive in memory: lane L copies sectors L, L + 32, ... — sector s is
             // sector (s mod NS) of the table entry of column s / NS, whose ray sits in lane ncols - 1 - s / NS.
             const int CP = p.col_pitch, NS = CP >> 5;
-            const uint32_t entry = (uint32_t)((cs.pad << 2) + (cs.cid - RCW_COLOR_WALL_1)) * (uint32_t)CP;
+            const uint32_t entry = (uint32_t)(cs.pad * p.n_colors + (cs.cid - RCW_COLOR_WALL_1)) * (uint32_t)CP;
             const int n_sec = ncols * NS;
             int cl = (int)(((uint32_t)lane * p.sec_inv16) >> 16), sc = lane - cl * NS;
             const int adv_cl = p.sec_adv_cl, adv_sc = p.sec_adv_u;
@@ -1354,7 +1399,9 @@ __global__ void reset_kernel(const ResetParams p) {
         au = p.dir_au[env];
     } else {
         episode += 1u;
-        draw_layout(BitsMap{p.wall_map + (size_t)env * p.map_env_stride, p.wpr}, p.H, p.W, p.N, p.seed,
+        const uint32_t* const words = p.wall_map + (size_t)env * p.map_env_stride;
+        draw_layout(BitsMap{words, p.n_extra ? words + (p.n_extra + 1) * p.map_words : words, p.wpr, p.n_extra, p.map_words},
+                    p.H, p.W, p.N, p.seed,
                     p.env_id_offset + (uint64_t)env, episode, gi, gj, pi, pj, au);
     }
     p.st.pos_x[env] = __fsub_rn((float)pi, 0.5f);
@@ -1421,7 +1468,7 @@ template <int MODE, int FMT, bool BULK, int STAGE, int OCC, bool ROOM = false>
 static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s) {
     const bool casts = STAGE != kStagePaint, paints = STAGE != kStageFront && MODE != kModeRays;
     const size_t map_slots = p.map_env_stride ? kWarpsPerCta : 1;   // per-env wall layers: one slot per env of a round
-    const size_t smem = ((casts && !ROOM) ? map_slots * (size_t)p.map_words * 4 : 0) + ((BULK && paints) ? 6 * (size_t)p.pat_stride : 0);
+    const size_t smem = ((casts && !ROOM) ? map_slots * (size_t)p.stage_words * 4 : 0) + ((BULK && paints) ? 6 * (size_t)p.pat_stride : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(frame_kernel<MODE, FMT, BULK, STAGE, OCC, ROOM>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1432,7 +1479,7 @@ static cudaError_t launch_frame_t(const FrameParams& p, int ctas, cudaStream_t s
 }
 
 static size_t env_smem(const FrameParams& p, bool room) {
-    return room ? 0 : (p.map_env_stride ? kWarpsPerCta : 1) * (size_t)p.map_words * 4;
+    return room ? 0 : (p.map_env_stride ? kWarpsPerCta : 1) * (size_t)p.stage_words * 4;
 }
 
 template <int MODE, int FMT, int OUT, bool ROOM>

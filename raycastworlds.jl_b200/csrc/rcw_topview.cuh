@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     const uint32_t SB = plane_col_bits(Hp);                    // bits per plane column
     const uint32_t plane_words = ((uint32_t)Wp * (SB >> 5) + 3u) & ~3u;   // the plane is cleared as uint4
     uint32_t* const s_map = s_top;
-    uint32_t* const s_ray = s_map + p.map_words;
+    uint32_t* const s_ray = s_map + p.stage_words;
     uint32_t* const s_pal = s_ray + plane_words;
     int2* const s_line = reinterpret_cast<int2*>(s_pal + 8);                       // [R] end pixels of the distinct segments
     uint32_t* const s_cstart = reinterpret_cast<uint32_t*>(s_line + R);            // [R] first chunk of every distinct segment
@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     if (tid == 0) {
         s_counts = 0ULL;
         mbar_init(&s_bar, 1);
-        mbar_arrive_expect_tx(&s_bar, (uint32_t)p.map_words * 4u);
-        bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.map_words * 4u, &s_bar);
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)p.stage_words * 4u);
+        bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.stage_words * 4u, &s_bar);
     }
     {
         uint4* const z = reinterpret_cast<uint4*>(s_ray);       // 16-byte aligned: map_words is a multiple of 4
@@ -131,14 +131,18 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     __syncthreads();          // mbarrier initialised, plane cleared
     mbar_wait(&s_bar, 0);
 
-    // ---- draw_tile_map! colour of every tile: findfirst over the layers WALL, GOAL (:355-360)
+    // ---- draw_tile_map! colour of every tile: findfirst over the layers WALL, GOAL (:355-360), then the extra objects
+    const BitsMap map{s_map, p.n_extra ? s_map + (p.n_extra + 1) * p.map_words : s_map, p.wpr, p.n_extra, p.map_words};
     for (int t = tid; t < H * (W + 1); t += kTopThreads) {
         const int j0 = t / H, i0 = t - j0 * H;
         int code = RCW_TOP_COLOR_BORDER;                      // pseudo tile column W: what a border column of the image shows
         if (j0 < W)
-            code = BitsMap{s_map, p.wpr}.wall(i0, j0) ? RCW_TOP_COLOR_WALL
-                                                  : ((i0 == gi0 && j0 == gj0) ? RCW_TOP_COLOR_GOAL : RCW_TOP_COLOR_EMPTY);
-        s_tilec[t] = p.palette[code];
+            code = map.wall(i0, j0) ? RCW_TOP_COLOR_WALL
+                                    : ((i0 == gi0 && j0 == gj0) ? RCW_TOP_COLOR_GOAL : RCW_TOP_COLOR_EMPTY);
+        uint32_t colour = p.palette[code];
+        if (code == RCW_TOP_COLOR_EMPTY && j0 < W)        // tile_map_colors[findfirst(...)] over the extra objects
+            for (int k = p.n_extra - 1; k >= 0; --k) colour = map.extra(k, i0, j0) ? p.extra_color[k] : colour;
+        s_tilec[t] = colour;
     }
 
     // ---- the ray segments (:474-478), first half: lane <-> ray, where each ray stops, as a pixel
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     for (int g = warp; g < groups; g += kTopThreads / 32) {
         const int ray = g * 32 + lane;
         const float4 rt = __ldg(p.ray_table + (size_t)au * (size_t)R + (size_t)min(ray, R - 1));
-        const RayHit hit = dda_cast(BitsMap{s_map, p.wpr}, H, W, p.dda_flags, p.closed_border != 0, x, y, gi0, gj0, rt, lane);
+        const RayHit hit = dda_cast(map, H, W, p.dda_flags, p.closed_border != 0, x, y, gi0, gj0, rt, lane);
         // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
         const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
         const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
@@ -430,6 +434,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     }
 }
 
+// map_words: words staged for the map (every object layer)
 size_t top_view_smem_bytes(int H, int W, int R, int pu, float radius, int map_words) {
     const size_t Hp = (size_t)H * pu, Wp = (size_t)W * pu;
     const size_t plane_words = (Wp * (plane_col_bits((int)Hp) >> 5) + 3) & ~(size_t)3;
@@ -440,7 +445,7 @@ size_t top_view_smem_bytes(int H, int W, int R, int pu, float radius, int map_wo
 }
 
 cudaError_t launch_top_view(const TopViewParams& p, cudaStream_t s) {
-    const size_t smem = top_view_smem_bytes(p.H, p.W, p.R, p.pu, p.radius, p.map_words);
+    const size_t smem = top_view_smem_bytes(p.H, p.W, p.R, p.pu, p.radius, p.stage_words);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(top_view_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

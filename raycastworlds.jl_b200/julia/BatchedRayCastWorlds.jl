@@ -26,7 +26,10 @@ const RCW_OBS_RGB8 = Int32(0)
 const RCW_OBS_XRGB32 = Int32(1)
 const RCW_OBS_GRAY8 = Int32(2)      # BT.601 luma of the reference pixel, one byte per pixel
 const RCW_OBS_COLUMNS = Int32(3)    # one UInt32 per ray column: pad | colour id << 16 (see expand_columns)
-const RCW_ABI_VERSION = Int32(3)
+const RCW_ABI_VERSION = Int32(4)
+const RCW_MAX_EXTRA_LAYERS = 4
+const RCW_LAYER_BLOCKING = Int32(0)   # an extra object layer that refuses the move like WALL
+const RCW_LAYER_TERMINAL = Int32(1)   # ... that ends the episode with its own reward like GOAL
 
 version() = ccall((:rcw_version, LIB), Int32, ())
 
@@ -57,7 +60,12 @@ struct RcwConfig
     top_palette::NTuple{6, UInt32}
     frame_stack::Int32
     result_ring::Int32
-    reserved::NTuple{2, UInt32}
+    num_object_layers::Int32
+    layer_kind::NTuple{4, Int32}
+    layer_reward::NTuple{4, Float32}
+    layer_palette::NTuple{8, UInt32}      # [k][hit across dimension 1, 2], row-major like the C array
+    layer_top_color::NTuple{4, UInt32}
+    reserved::NTuple{3, UInt32}
 end
 
 last_error() = unsafe_string(ccall((:rcw_last_error, LIB), Cstring, ()))
@@ -107,6 +115,12 @@ function build_config(;
         pu_per_tu = 32,
         frame_stack = 1,
         result_ring = 0,
+        # object layers beyond WALL and GOAL (NUM_OBJECTS > 2, single_room.jl:16-18): one entry per extra layer
+        num_object_layers = 2,
+        layer_kind = Int32[],            # RCW_LAYER_BLOCKING / RCW_LAYER_TERMINAL
+        layer_reward = Float32[],
+        layer_palette = NTuple{2, UInt32}[],   # (colour when hit across dimension 1, dimension 2)
+        layer_top_color = UInt32[],
     )
     T === Float32 || error("librcw_b200 computes in Float32 (the reference default, single_room.jl:43)")
     version() == RCW_ABI_VERSION || error("librcw_b200 ABI $(version()), this binding was written for $(RCW_ABI_VERSION)")
@@ -129,7 +143,12 @@ function build_config(;
                         Float32(camera_height_tile_wu), Float32(goal_reward), Int32(obs_format),
                         Int32(auto_reset), UInt64(seed), palette, UInt32(0), Int32(obs_window_envs),
                         Int32(top_view), Int32(pu_per_tu), top_palette, Int32(frame_stack),
-                        Int32(result_ring), ntuple(_ -> UInt32(0), 2)))
+                        Int32(result_ring), Int32(num_object_layers),
+                        ntuple(k -> k <= length(layer_kind) ? Int32(layer_kind[k]) : Int32(0), 4),
+                        ntuple(k -> k <= length(layer_reward) ? Float32(layer_reward[k]) : 0f0, 4),
+                        ntuple(k -> (k + 1) ÷ 2 <= length(layer_palette) ? UInt32(layer_palette[(k + 1) ÷ 2][2 - k % 2]) : UInt32(0), 8),
+                        ntuple(k -> k <= length(layer_top_color) ? UInt32(layer_top_color[k]) : UInt32(0), 4),
+                        ntuple(_ -> UInt32(0), 3)))
     return cfg, directions
 end
 
@@ -452,6 +471,15 @@ function set_wall_map!(env::BatchedSingleRoom, wall::AbstractArray{<:Union{Bool,
     end
     return nothing
 end
+# tile_map[layer, :, :] = tiles for every env: layer 1 = WALL, 3 .. num_object_layers = extra object layers
+# (tiles: height_tu x width_tu Bool matrix, column-major like the reference's BitArray slices)
+function set_layer!(env::BatchedSingleRoom, layer::Integer, tiles::AbstractMatrix{Bool})
+    size(tiles) == (env.height_tile_map_tu, env.width_tile_map_tu) || throw(DimensionMismatch("tiles must be height_tu x width_tu"))
+    bytes = convert(Array{UInt8}, tiles)
+    GC.@preserve bytes check(ccall((:rcw_set_layer, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}), env.handle, Int32(layer), bytes))
+    return nothing
+end
+
 
 # reset!(env) for the envs whose mask entry is true only (the others keep state and observation)
 function reset_masked!(env::BatchedSingleRoom, mask::AbstractVector{Bool})

@@ -54,7 +54,9 @@ def make_config(num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int =
                 directions_wu: Optional[np.ndarray] = None, palette: Optional[Sequence[int]] = None,
                 dda_tie_le: bool = False, dda_dist_post: bool = False, obs_window_envs: int = 0,
                 top_view: bool = False, pu_per_tu: int = 32, top_palette: Optional[Sequence[int]] = None,
-                frame_stack: int = 1, result_ring: int = 0):
+                frame_stack: int = 1, result_ring: int = 0, num_object_layers: int = 2,
+                layer_kind: Sequence[int] = (), layer_reward: Sequence[float] = (),
+                layer_palette: Sequence[Sequence[int]] = (), layer_top_color: Sequence[int] = ()):
     """rcw_config from the keyword arguments of SingleRoom(...) (single_room.jl:258-272) plus the batch fields.
     Returns (cfg, directions or None, obs_format name)."""
     cfg = _capi.default_config()
@@ -90,6 +92,18 @@ def make_config(num_envs: int = 1, *, device: int = 0, height_tile_map_tu: int =
     if top_palette is not None:
         for i, c in enumerate(top_palette):
             cfg.top_palette[i] = int(c)
+    # object layers beyond WALL and GOAL (NUM_OBJECTS > 2, single_room.jl:16-18): per extra layer its kind ("blocking" /
+    # "terminal" or RCW_LAYER_*), reward (terminal layers), camera colours (dim 1, dim 2) and top-view colour
+    cfg.num_object_layers = int(num_object_layers)
+    kinds = {"blocking": _capi.RCW_LAYER_BLOCKING, "terminal": _capi.RCW_LAYER_TERMINAL}
+    for k, v in enumerate(layer_kind):
+        cfg.layer_kind[k] = kinds[v] if isinstance(v, str) else int(v)
+    for k, v in enumerate(layer_reward):
+        cfg.layer_reward[k] = float(np.float32(v))
+    for k, pair in enumerate(layer_palette):
+        cfg.layer_palette[k][0], cfg.layer_palette[k][1] = int(pair[0]), int(pair[1])
+    for k, v in enumerate(layer_top_color):
+        cfg.layer_top_color[k] = int(v)
     dirs = None
     if directions_wu is not None:
         dirs = np.ascontiguousarray(directions_wu, np.float32)
@@ -313,6 +327,15 @@ class BatchedSingleRoom(AbstractGame):
             raise ValueError("wall map must be [height_tile_map_tu, width_tile_map_tu]")
         flat = np.ascontiguousarray(w.T.reshape(-1))  # [W][H], i fastest (Julia column-major)
         _capi.check(self._lib.rcw_set_wall_map(self._h, _ptr(flat)))
+
+    def set_layer(self, layer: int, tiles_hw):
+        """tile_map[layer, :, :] = tiles_hw (bool [H, W]) for every env: layer 1 = WALL, 3 .. num_object_layers = the
+        extra object layers (single_room.jl:16-18 with NUM_OBJECTS > 2)."""
+        t = np.asarray(tiles_hw).astype(np.uint8)
+        if t.shape != (self.cfg.height_tile_map_tu, self.cfg.width_tile_map_tu):
+            raise ValueError("tiles must be [height_tile_map_tu, width_tile_map_tu]")
+        flat = np.ascontiguousarray(t.T.reshape(-1))
+        _capi.check(self._lib.rcw_set_layer(self._h, int(layer), _ptr(flat)))
 
     def set_wall_maps(self, walls_ehw):
         """walls_ehw: bool [num_envs, H, W] — one wall layer per env (tile_map[WALL, :, :] of env e)."""

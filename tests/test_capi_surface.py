@@ -47,7 +47,7 @@ def test_library_has_sm100a_code_and_no_oracle():
 
 def test_config_struct_layout_and_defaults():
     cfg = _capi.default_config()
-    assert cfg.struct_size == C.sizeof(_capi.RcwConfig) == 160
+    assert cfg.struct_size == C.sizeof(_capi.RcwConfig) == 248
     assert (cfg.height_tile_map_tu, cfg.width_tile_map_tu) == (8, 16)        # single_room.jl:44-45
     assert (cfg.num_directions, cfg.num_rays, cfg.height_camera_view_pu) == (128, 512, 256)
     assert cfg.player_radius_wu == 0.125 and cfg.position_increment_wu == 0.125
@@ -55,6 +55,7 @@ def test_config_struct_layout_and_defaults():
     assert list(cfg.palette) == [0xFFFFFF, 0x404040, 0x808080, 0xC0C0C0, 0x800000, 0xC00000]
     assert (cfg.obs_window_envs, cfg.top_view, cfg.pu_per_tu, cfg.frame_stack, cfg.result_ring) == (0, 0, 32, 0, 0)  # :269; the top view is opt-in for a batch
     assert list(cfg.top_palette) == [0xFFFFFF, 0xFF0000, 0x000000, 0xCCCCCC, 0x808080, 0xC0C0C0]  # :288-290, 364-367
+    assert cfg.num_object_layers == 2 and not any(cfg.layer_kind) and not any(cfg.layer_top_color)      # NUM_OBJECTS = 2, :16
     assert _capi.load().rcw_version() == _capi.ABI_VERSION
 
 
@@ -67,7 +68,8 @@ def test_validation_errors_without_gpu():
     assert b"struct_size" in lib.rcw_last_error()
     for field, value in [("num_envs", 0), ("height_tile_map_tu", 2), ("player_radius_wu", 0.6),
                          ("obs_format", 7), ("num_rays", 0), ("dda_flags", 8), ("obs_window_envs", -1), ("pu_per_tu", 0),
-                         ("top_view", 2), ("frame_stack", 65), ("result_ring", 65), ("result_ring", -1)]:
+                         ("top_view", 2), ("frame_stack", 65), ("result_ring", 65), ("result_ring", -1),
+                         ("num_object_layers", 1), ("num_object_layers", 7)]:
         cfg = _capi.default_config()
         setattr(cfg, field, value)
         assert lib.rcw_create(C.byref(cfg), None, C.byref(h)) == _capi.RCW_EINVAL, field
