@@ -519,8 +519,11 @@ def run_b200(args):
         sampler.stop()
 
     if rank == 0:
-        launch_ms = region_ms / K / (-(-n // env_window))
-        achieved = min(n, env_window) * bytes_per_step_env / (launch_ms * 1e-3) / 1e9
+        # launches of the step kernel per step, counted by the library: the observation windows of a step, times two when
+        # the multi-step call runs the batch as two half-batches on two streams (their ramps and tails overlap)
+        step_launches = max(1, launches_per_region // K // (2 if args.top_view else 1))
+        launch_ms = region_ms / K / step_launches
+        achieved = n * bytes_per_step_env / step_launches / (launch_ms * 1e-3) / 1e9
         traffic, traffic_src = (None, None) if args.top_view else measured_traffic(n, kw, fmt)
         cfg = config_block(n, world, kw, fmt, args.map, args.top_view)
         line = {
@@ -529,7 +532,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
             "timing": dict(summarize(times), obs_window_envs=env_window,
-                           launches_per_step=-(-n // env_window) * (2 if args.top_view else 1),
+                           launches_per_step=launches_per_region // K,
                            l2=(f"each step writes {n * bytes_per_step_env / 1e9:.2f} GB of observations, larger than the 126 MB L2; no flush needed"
                                if n * bytes_per_step_env > 126e6 else
                                f"each step writes {n * bytes_per_step_env / 1e6:.1f} MB of observations: L2-resident, the step is bound by act! + DDA (issue), not by HBM"),
@@ -538,8 +541,13 @@ def run_b200(args):
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "rcw::frame_kernel<kModeStep, fused>" + (" + rcw::top_view_kernel" if args.top_view else ""),
-                "algorithmic_bytes_per_launch": min(n, env_window) * bytes_per_step_env,
+                "algorithmic_bytes_per_launch": n * bytes_per_step_env // step_launches,
                 "launch_ms": launch_ms, "peak_source": peak_src,
+                "launch_note": (f"a step is {step_launches} launches of the step kernel"
+                                + (" — two half-batches on two streams inside rcw_step_random(K), running concurrently so that one's "
+                                   "launch ramp / tail is filled by the other; launch_ms = step time / launches is therefore the "
+                                   "EFFECTIVE time per launch (a half-batch launch timed alone, as ncu serialises it, lasts longer: "
+                                   "profiles/README.md)" if step_launches == 2 * (-(-n // env_window)) else "")),
             },
             "e2e": e2e, "e2e_lockstep": e2e_lockstep, "e2e_obs_to_host": e2e_obs,
             "gpu_launches": launches_per_region,

@@ -124,6 +124,10 @@ struct rcw_batch {
     rcw_config cfg{};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // second half-batch of the steps of a multi-step call (never visible to the caller)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool two_streams = true;             // RCW_TWO_STREAMS=0: every step is one launch on `stream`
+    int64_t two_streams_min = 512;       // smallest batch that is split (below it a step is launch-latency bound anyway)
     int sm_count = 0;
     int bpp = 3;
     int gpe = 0;
@@ -154,6 +158,7 @@ struct rcw_batch {
     bool room = true;                    // the shared wall layer is exactly the border of the map (SingleRoom's own map,
                                          // single_room.jl:57-60): kernels without a wall layer in shared memory (RoomMap)
     bool room_allowed = true;            // RCW_ROOM=0 keeps every launch on the bit-packed wall layer (tests, A/B)
+    bool room_forced = false;            // RCW_ROOM=2: RoomMap kernels also where the store stream bounds the step
     uint8_t* d_col_table = nullptr;      // ready-made columns for env_kernel's table renderer (small columns only)
     StateRef st[2]{};
     int cur = 0;
@@ -361,14 +366,19 @@ static int grid_for(const rcw_batch* b, int64_t env_count) {
 static LaunchShape shape_for(const rcw_batch* b, int64_t n) {
     LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, n)};
     sh.env_per_warp = b->env_per_warp && n >= b->env_per_warp_min;
-    sh.room = b->room && b->room_allowed && !b->per_env_maps;
+    // RoomMap kernels where act! + DDA bound the step (front-bound register budget, env kernel, column words).  Where the
+    // store stream bounds it (default camera) the bit-packed kernel is 1.2 % faster (0.2270 vs 0.2296 ms per 4096 envs,
+    // A/B on one box: its TMA-staged prologue paces the first stores), so it stays there; RCW_ROOM=2 forces RoomMap.
+    sh.room = b->room && b->room_allowed && !b->per_env_maps &&
+              (b->occ4 || sh.env_per_warp || b->cfg.obs_format == RCW_OBS_COLUMNS || b->room_forced);
     sh.table = sh.env_per_warp && b->d_col_table != nullptr;
     return sh;
 }
 
 // update_top_view! for envs [env0, env0 + n) from state `st`, into the slots that start at slot0.
 static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, int64_t n, uint32_t slot0,
-                                const uint8_t* d_mask = nullptr) {
+                                const uint8_t* d_mask = nullptr, cudaStream_t stream = nullptr) {
+    if (!stream) stream = b->stream;
     const rcw_config& c = b->cfg;
     if (!b->d_top) {
         const size_t px = (size_t)c.height_tile_map_tu * c.pu_per_tu * (size_t)c.width_tile_map_tu * c.pu_per_tu;
@@ -407,7 +417,7 @@ static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, 
     t.env_first = env0;
     t.env_count = n;
     t.sm_count = (uint32_t)b->sm_count;
-    RCW_CUDA(launch_top_view(t, b->stream));
+    RCW_CUDA(launch_top_view(t, stream));
     b->launches += 1;
     return RCW_OK;
 }
@@ -638,6 +648,9 @@ int32_t rcw_destroy(rcw_batch* b) {
     if (b->h_results) cudaFreeHost(b->h_results);
     for (cudaEvent_t ev : b->result_ready)
         if (ev) cudaEventDestroy(ev);
+    if (b->stream2) cudaStreamDestroy(b->stream2);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->stream) cudaStreamDestroy(b->stream);
     release_dir_slot(b->device, b->dir_slot);
     cudaGetLastError();
@@ -655,6 +668,13 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     RCW_CUDA(cudaGetDeviceProperties(&prop, b->device));
     b->sm_count = prop.multiProcessorCount;
     RCW_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    // a second stream for the multi-step calls, whose steps run as two half-batches that overlap each other's
+    // launch ramp and tail (enqueue_random_steps_two_streams)
+    RCW_CUDA(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking));
+    RCW_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    RCW_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    if (const char* s = getenv("RCW_TWO_STREAMS")) b->two_streams = atoi(s) != 0;
+    if (const char* s = getenv("RCW_TWO_STREAMS_MIN")) b->two_streams_min = atoll(s);
     if (const char* s = getenv("RCW_CTAS_PER_SM")) b->ctas_per_sm = atoi(s);
     else b->ctas_per_sm = -1;   // decided below, once the observation geometry is known
 
@@ -782,7 +802,10 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     b->obs_window = (c.obs_window_envs > 0 && c.obs_window_envs < E) ? c.obs_window_envs : E;
     b->obs_bytes = b->obs_env_stride * (size_t)b->obs_window;
     RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, /*zero=*/b->frame_stack > 1));   // older ring positions start black
-    if (const char* s = getenv("RCW_ROOM")) b->room_allowed = atoi(s) != 0;
+    if (const char* s = getenv("RCW_ROOM")) {
+        b->room_allowed = atoi(s) != 0;
+        b->room_forced = atoi(s) == 2;
+    }
     // ---- ready-made columns (env_kernel's table renderer) ------------------------------------------
     // update_camera_view! paints one of (P / 2 + 1) x 4 possible columns (rows of ceiling = rows of floor x
     // wall / goal colour per hit dimension, single_room.jl:417-439).  When they are small, all of them together
@@ -1232,11 +1255,54 @@ int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64
     return enqueue_range_step(b, d_actions, env0, n);
 }
 
+// n steps of the random policy as two half-batches, one per stream.  Envs are independent, the state is
+// struct-of-arrays and every launch touches only its own envs' entries, so the two halves never meet: each stream
+// simply runs its half's steps back to back, and the end of one half's launch (a few half-empty waves and ~3 us
+// of launch gap) is filled by the other half's kernel.  Measured (tools/two_stream_probe.py, default camera): 0.0643
+// -> 0.0541 ms per step at 1024 envs (+19 %), 0.2270 -> 0.2178 at 4096 (+4.2 %), +1 % at 16,384.  Only inside a
+// multi-step call: between single rcw_step calls the caller may enqueue consumers of the observations on the
+// handle's stream, and those must stay ordered with the next step.  fork: the side stream waits for everything
+// enqueued on the handle's stream so far; join: the handle's stream waits for the side stream's last step.
+static int32_t enqueue_random_steps_two_streams(rcw_batch* b, int32_t n_steps) {
+    const int64_t E = b->cfg.num_envs;
+    const int64_t half = (E / 2) & ~(int64_t)(kWarpsPerCta - 1);
+    RCW_CUDA(cudaEventRecord(b->ev_fork, b->stream));
+    RCW_CUDA(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
+    for (int32_t s = 0; s < n_steps; ++s) {
+        b->frame_newest = (b->frame_newest + 1) % b->frame_stack;
+        FrameParams p;
+        fill_frame_params(b, p);
+        for (int part = 0; part < 2; ++part) {
+            cudaStream_t stream = part ? b->stream : b->stream2;
+            p.env_first = part ? half : 0;
+            p.env_count = part ? E - half : half;
+            p.obs_slot0 = (uint32_t)p.env_first;
+            RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, shape_for(b, p.env_count), stream));
+            b->launches += 1;
+            if (b->cfg.top_view)
+                if (int32_t rc = enqueue_top_view(b, p.out, p.env_first, p.env_count, p.obs_slot0, nullptr, stream)) return rc;
+        }
+        b->cur ^= 1;
+        b->step_index += 1;
+    }
+    RCW_CUDA(cudaEventRecord(b->ev_join, b->stream2));
+    RCW_CUDA(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
+    return RCW_OK;
+}
+
 int32_t rcw_step_random(rcw_batch* b, int32_t n_steps) {
     NvtxRange nvtx("rcw_step_random");
     if (int32_t rc = check_handle(b)) return rc;
     if (n_steps < 0) return fail(RCW_EINVAL, "n_steps must be non-negative");
     DeviceGuard g(b->device);
+    if (n_steps >= 2 && b->two_streams && !b->split && !b->bulk && b->obs_window == b->cfg.num_envs &&
+        b->cfg.num_envs >= b->two_streams_min && b->cfg.num_envs >= 2 * kWarpsPerCta) {
+        if (b->cfg.top_view && !b->d_top) {    // (the top views are allocated by their first draw)
+            if (int32_t rc = enqueue_frame(b, kModeStep, nullptr)) return rc;
+            --n_steps;
+        }
+        return enqueue_random_steps_two_streams(b, n_steps);
+    }
     for (int32_t s = 0; s < n_steps; ++s)
         if (int32_t rc = enqueue_frame(b, kModeStep, nullptr)) return rc;
     return RCW_OK;

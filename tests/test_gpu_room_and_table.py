@@ -75,8 +75,9 @@ def test_env_kernel_variants_match_oracle(rcw, oracle, monkeypatch, room, table_
 @pytest.mark.parametrize("room", [0, 1])
 @pytest.mark.parametrize("flags", [dict(), dict(dda_tie_le=True), dict(dda_dist_post=True), dict(dda_tie_le=True, dda_dist_post=True)])
 def test_item_kernel_room_and_bits_walks_agree(rcw, oracle, monkeypatch, room, flags):
-    """Default camera (item kernel), all four settings of the unpinned DDA decisions D1 / D2."""
-    monkeypatch.setenv("RCW_ROOM", str(room))
+    """Default camera (item kernel), all four settings of the unpinned DDA decisions D1 / D2.  (RCW_ROOM=2 forces the
+    RoomMap kernel where the handle would keep the bit-packed one because the stores bound the step.)"""
+    monkeypatch.setenv("RCW_ROOM", str(2 * room))
     n, seed, steps = 9, 77, 60
     env = rcw.BatchedSingleRoom(n, seed=seed, **flags)
     cfg = oracle.default_config(tie_le=flags.get("dda_tie_le", False), dist_post=flags.get("dda_dist_post", False))

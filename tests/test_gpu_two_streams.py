@@ -1,0 +1,84 @@
+"""rcw_step_random(n >= 2) runs its steps as two half-batches on two streams (VERDICT r01 #4a): the halves overlap each
+other's launch ramp and tail.  Nothing about the results may change: states, observations (every ring position),
+top views and episode totals equal the oracle's, whatever the split, and equal the single-stream run's."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rcw():
+    import raycastworlds_jl_b200 as m
+    return m
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+CASES = [
+    dict(n=9, kw=dict(), okw=dict()),                                                              # default camera, odd batch
+    dict(n=64, kw=dict(num_rays=84, height_camera_view_pu=84, obs_format="gray8"), okw=dict(R=84, P=84)),   # env kernel + table
+    dict(n=37, kw=dict(num_rays=96, height_camera_view_pu=40, top_view=True, pu_per_tu=4), okw=dict(R=96, P=40, pu_per_tu=4)),
+    dict(n=21, kw=dict(num_rays=128, height_camera_view_pu=64, obs_format="xrgb32", height_tile_map_tu=5, width_tile_map_tu=6,
+                       num_directions=16), okw=dict(R=128, P=64, H=5, W=6, N=16)),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("two", [0, 1])
+def test_multi_step_calls_match_oracle(rcw, oracle, monkeypatch, case, two):
+    c = CASES[case]
+    monkeypatch.setenv("RCW_TWO_STREAMS", str(two))
+    monkeypatch.setenv("RCW_TWO_STREAMS_MIN", "8")
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    n, seed = c["n"], 40 + case
+    env = rcw.BatchedSingleRoom(n, seed=seed, **c["kw"])
+    ref = oracle.Batch(n, cfg=oracle.default_config(**c["okw"]), seed=seed)
+    launches0 = env.launch_count()
+    total = 0
+    for steps in (2, 1, 7, 150, 3):                      # multi-step calls of several lengths, a single step in between
+        env.step_random(steps)
+        ref.rollout(steps)
+        total += steps
+        st = env.get_state()
+        pos, au, goal = ref.states()
+        np.testing.assert_array_equal(bits(st["pos"]), bits(pos))
+        np.testing.assert_array_equal(st["dir_au"], au)
+        np.testing.assert_array_equal(st["goal"], goal)
+        r, d = ref.reward_done()
+        np.testing.assert_array_equal(st["reward"], r)
+        np.testing.assert_array_equal(st["done"], d)
+        fmt = c["kw"].get("obs_format", "rgb8")
+        want = {"rgb8": ref.obs_rgb8, "xrgb32": ref.obs_u32, "gray8": ref.obs_gray8}[fmt]()
+        np.testing.assert_array_equal(env.copy_obs(), want)
+        if c["kw"].get("top_view"):
+            top = env.copy_top_view()
+            for e in (0, n - 1):
+                w = ref.world(e)
+                w.update_top_view()
+                np.testing.assert_array_equal(top[e], w.top_view)
+        assert env.episode_stats() == ref.episode_stats()
+    per_step = 2 if c["kw"].get("top_view") else 1
+    launched = env.launch_count() - launches0
+    if two:
+        assert launched > total * per_step, "the multi-step calls should have been split into two launches per step"
+    else:
+        assert launched == total * per_step
+    env.close()
+
+
+def test_frame_ring_with_two_streams(rcw, oracle, monkeypatch):
+    monkeypatch.setenv("RCW_TWO_STREAMS_MIN", "8")
+    n, K, seed = 24, 4, 3
+    env = rcw.BatchedSingleRoom(n, seed=seed, num_rays=64, height_camera_view_pu=32, frame_stack=K)
+    ref = oracle.Batch(n, cfg=oracle.default_config(R=64, P=32), seed=seed)
+    frames = []
+    for _ in range(3):
+        ref.rollout(1)
+        frames.append(ref.obs_rgb8())
+    env.step_random(3)
+    for age in range(3):
+        np.testing.assert_array_equal(env.copy_obs(age=age), frames[2 - age])
+    env.close()
