@@ -14,18 +14,24 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=2000)
 ap.add_argument("--parts", type=int, default=2)
+ap.add_argument("--op", choices=["step", "top"], default="step", help="what to time: env steps or rcw_render_top_view")
 args = ap.parse_args()
 
 
 def run(handles, steps):
     for h in handles:
-        h.step_random(20)
+        h.step_random(200 if args.op == "top" else 20)
+        if args.op == "top":
+            h.render_top_view()
     for h in handles:
         h.sync()
     t0 = time.perf_counter()
     for _ in range(steps):
         for h in handles:
-            h.step_random(1)
+            if args.op == "top":
+                h.render_top_view()
+            else:
+                h.step_random(1)
     for h in handles:
         h.sync()
     return (time.perf_counter() - t0) / steps * 1e3
