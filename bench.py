@@ -524,7 +524,7 @@ def run_b200(args):
         step_launches = max(1, launches_per_region // K // (2 if args.top_view else 1))
         launch_ms = region_ms / K / step_launches
         achieved = n * bytes_per_step_env / step_launches / (launch_ms * 1e-3) / 1e9
-        traffic, traffic_src = (None, None) if args.top_view else measured_traffic(n, kw, fmt)
+        traffic, traffic_src = (None, None) if args.top_view else measured_traffic(n // step_launches, kw, fmt)   # per launch, like achieved
         cfg = config_block(n, world, kw, fmt, args.map, args.top_view)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
