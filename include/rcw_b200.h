@@ -51,7 +51,7 @@ typedef enum rcw_obs_format {
     RCW_OBS_XRGB32 = 1, /* uint32 [num_envs][num_rays columns][height_px]     (bit-identical to the reference's UInt32 pixels) */
     RCW_OBS_GRAY8  = 2, /* uint8  [num_envs][num_rays columns][height_px]     learner-facing: BT.601 luma of the reference
                            pixel, (77 R + 150 G + 29 B + 128) >> 8; a third of the RGB8 write */
-    RCW_OBS_COLUMNS = 3 /* uint32 [num_envs][num_rays columns]: the camera view BEFORE it is expanded into pixels —
+    RCW_OBS_COLUMNS = 3, /* uint32 [num_envs][num_rays columns]: the camera view BEFORE it is expanded into pixels —
                            what update_camera_view! decides per ray (single_room.jl:404-439): word = pad | cid << 16,
                            pad = rows of ceiling = rows of floor (0: the whole column has the wall colour; the wall
                            band has height_px - 2 pad rows), cid = RCW_COLOR_WALL_1 .. RCW_COLOR_GOAL_2.  Lossless
@@ -59,6 +59,9 @@ typedef enum rcw_obs_format {
                            of height_px * 3: 2 KB instead of 393 KB per default frame, for replay buffers that
                            rasterise only the frames they sample.  NOT rendered pixels: steps in
                            this format are bound by act! and the DDA, not by HBM writes. */
+    RCW_OBS_GRAY16F = 4 /* float16 [num_envs][num_rays columns][height_px]: the GRAY8 luma divided by 255 and rounded to IEEE
+                           binary16 — the normalised frame a convolutional learner takes, without a conversion kernel
+                           behind the renderer (single_room.jl:576 is the consumer hand-off) */
     /* dense on the host (rcw_copy_obs); on the device columns may be pitched, see rcw_obs_layout */
 } rcw_obs_format;
 

@@ -354,6 +354,10 @@ class Batch:
         r, g, b = (c >> 16) & 255, (c >> 8) & 255, c & 255
         return ((77 * r + 150 * g + 29 * b + 128) >> 8).astype(np.uint8)
 
+    def obs_gray16f(self):
+        """The GRAY8 luma / 255 in IEEE binary16: one binary32 division, one rounding to half (RCW_OBS_GRAY16F)."""
+        return (self.obs_gray8().astype(np.float32) / np.float32(255)).astype(np.float16)
+
     def obs_u32(self):
         out = np.empty((self.num_envs, self.cfg.R, self.cfg.P), np.uint32)
         for e in range(self.num_envs):

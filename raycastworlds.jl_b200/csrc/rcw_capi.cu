@@ -14,6 +14,8 @@
 
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost a pointer test unless a profiler is attached
 
+#include <cuda_fp16.h>
+
 #include "rcw_internal.h"
 
 using namespace rcw;
@@ -218,7 +220,18 @@ static cudaError_t dev_alloc(rcw_batch* b, T** out, size_t count, bool zero = tr
     return e;
 }
 
-static int bytes_per_pixel(int fmt) { return fmt == RCW_OBS_RGB8 ? 3 : (fmt == RCW_OBS_GRAY8 ? 1 : 4); }
+static int bytes_per_pixel(int fmt) {
+    return fmt == RCW_OBS_RGB8 ? 3 : (fmt == RCW_OBS_GRAY8 ? 1 : (fmt == RCW_OBS_GRAY16F ? 2 : 4));
+}
+
+// BT.601 luma of a 0x00RRGGBB pixel (RCW_OBS_GRAY8), and the same luma / 255 as IEEE binary16 bits (RCW_OBS_GRAY16F)
+static uint32_t luma_of(uint32_t col) {
+    return (77u * ((col >> 16) & 255u) + 150u * ((col >> 8) & 255u) + 29u * (col & 255u) + 128u) >> 8;
+}
+static uint32_t luma_half_bits(uint32_t col) {
+    volatile float v = (float)luma_of(col) / 255.0f;     // one binary32 division, then one rounding to binary16
+    return (uint32_t)__half_as_ushort(__float2half_rn(v));
+}
 
 // bytes of one column of an observation: the pixels of the column, or its one RCW_OBS_COLUMNS word
 static int column_bytes(const rcw_batch* b) {
@@ -249,6 +262,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
     p.R = c.num_rays;
     p.P = c.height_camera_view_pu;
     p.gpe = b->gpe;
+    p.px_bytes = px_bpp;
     p.col_bytes = px_col_bytes;
     p.col_pitch = px_col_pitch;
     p.dda_flags = c.dda_flags;
@@ -269,8 +283,9 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
         const uint32_t col = (i < 6 ? c.palette[i] : c.layer_palette[(i - 6) >> 1][(i - 6) & 1]) & 0x00FFFFFFu;
         if (pixel_fmt == RCW_OBS_GRAY8) {
             // BT.601 luma of the reference pixel, replicated so the colour is "flat" for the renderer
-            const uint32_t y = (77u * ((col >> 16) & 255u) + 150u * ((col >> 8) & 255u) + 29u * (col & 255u) + 128u) >> 8;
-            p.palette[i] = y * 0x00010101u;
+            p.palette[i] = luma_of(col) * 0x00010101u;
+        } else if (pixel_fmt == RCW_OBS_GRAY16F) {
+            p.palette[i] = luma_half_bits(col) * 0x00010001u;   // two pixels per word
         } else {
             p.palette[i] = col;
         }
@@ -281,7 +296,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
         for (int i = 0; i < n_pal; ++i) {
             const bool slow = !(cf && flat(p.palette[i]));
             const uint32_t col = p.palette[i];
-            const uint32_t word = pixel_fmt == RCW_OBS_XRGB32 ? col : (col & 0xFFu) * 0x01010101u;
+            const uint32_t word = (pixel_fmt == RCW_OBS_XRGB32 || pixel_fmt == RCW_OBS_GRAY16F) ? col : (col & 0xFFu) * 0x01010101u;
             p.col_entry[i] = make_uint2(slow ? 0x80000000u : 0u, slow ? col : word);
         }
     }
@@ -719,7 +734,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // is kept as a measured alternative (profiles/): its per-lane UBLKCP issue serialises and its
     // 16-byte band edges leave partial sectors, so it is slower than the sector writer.
     b->bulk = false;
-    if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0 && c.obs_format != RCW_OBS_GRAY8;
+    if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0 && c.obs_format != RCW_OBS_GRAY8 && c.obs_format != RCW_OBS_GRAY16F;
     if (const char* s = getenv("RCW_SPLIT")) b->split = atoi(s) != 0;
     if (c.obs_format == RCW_OBS_COLUMNS) b->bulk = b->split = false;   // nothing is painted
     if (b->n_extra) b->bulk = b->split = false;                        // the measured alternatives know the reference's two objects only
@@ -820,13 +835,12 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
             uint32_t pal[6 + 2 * RCW_MAX_EXTRA_LAYERS];
             for (int i = 0; i < 2 + n_colors; ++i) {
                 const uint32_t col = (i < 6 ? c.palette[i] : c.layer_palette[(i - 6) >> 1][(i - 6) & 1]) & 0x00FFFFFFu;
-                pal[i] = c.obs_format == RCW_OBS_GRAY8
-                             ? ((77u * ((col >> 16) & 255u) + 150u * ((col >> 8) & 255u) + 29u * (col & 255u) + 128u) >> 8) * 0x00010101u
-                             : col;
+                pal[i] = c.obs_format == RCW_OBS_GRAY8 ? luma_of(col) * 0x00010101u
+                                                       : (c.obs_format == RCW_OBS_GRAY16F ? luma_half_bits(col) * 0x00010001u : col);
             }
             auto pixel_byte = [&](uint32_t col, int k) -> uint8_t {   // byte k of a pixel of colour 0x00RRGGBB
                 if (c.obs_format == RCW_OBS_RGB8) return (uint8_t)(col >> (16 - 8 * k));
-                if (c.obs_format == RCW_OBS_XRGB32) return (uint8_t)(col >> (8 * k));
+                if (c.obs_format == RCW_OBS_XRGB32 || c.obs_format == RCW_OBS_GRAY16F) return (uint8_t)(col >> (8 * k));
                 return (uint8_t)col;
             };
             std::vector<uint8_t> tab(table_bytes);
@@ -866,6 +880,7 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
     if (cfg->height_camera_view_pu > 32767)
         return fail(RCW_EINVAL, "height_camera_view_pu must be below 32768");
     if (cfg->obs_format != RCW_OBS_RGB8 && cfg->obs_format != RCW_OBS_XRGB32 && cfg->obs_format != RCW_OBS_GRAY8 &&
+        cfg->obs_format != RCW_OBS_GRAY16F &&
         cfg->obs_format != RCW_OBS_COLUMNS)
         return fail(RCW_EINVAL, "unknown obs_format %d", cfg->obs_format);
     if (cfg->num_envs < 1) return fail(RCW_EINVAL, "num_envs must be positive");
@@ -1617,8 +1632,9 @@ int32_t rcw_copy_obs_frame(rcw_batch* b, int64_t env0, int64_t n, int32_t age, v
 int32_t rcw_expanded_layout(rcw_batch* b, int32_t pixel_format, size_t* env_stride_bytes,
                             size_t* column_stride_bytes, size_t* column_bytes) {
     if (int32_t rc = check_handle(b)) return rc;
-    if (pixel_format != RCW_OBS_RGB8 && pixel_format != RCW_OBS_XRGB32 && pixel_format != RCW_OBS_GRAY8)
-        return fail(RCW_EINVAL, "pixel_format must be RCW_OBS_RGB8, RCW_OBS_XRGB32 or RCW_OBS_GRAY8");
+    if (pixel_format != RCW_OBS_RGB8 && pixel_format != RCW_OBS_XRGB32 && pixel_format != RCW_OBS_GRAY8 &&
+        pixel_format != RCW_OBS_GRAY16F)
+        return fail(RCW_EINVAL, "pixel_format must be RCW_OBS_RGB8, RCW_OBS_XRGB32, RCW_OBS_GRAY8 or RCW_OBS_GRAY16F");
     const size_t cb = (size_t)b->cfg.height_camera_view_pu * bytes_per_pixel(pixel_format);
     const size_t pitch = (cb + 31) & ~(size_t)31;
     if (column_bytes) *column_bytes = cb;

@@ -80,6 +80,7 @@ struct FrameParams {
     int32_t R;               // num_rays == observation width
     int32_t P;               // height_camera_view_pu
     int32_t gpe;             // 32-ray groups per env = ceil(R / 32)
+    int32_t px_bytes;        // bytes per pixel of the format being painted (1, 2, 3 or 4)
     int32_t col_bytes;       // P * bytes per pixel
     int32_t col_pitch;       // bytes between consecutive columns: col_bytes rounded up to a multiple of 32
     uint32_t dda_flags;

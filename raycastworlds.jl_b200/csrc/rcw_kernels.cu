@@ -860,7 +860,7 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
             const uint2 info = colinfo[lane];
             cb.b1 = (int)(info.x & 0x7FFFFFFFu);
             cb.b2 = CB - cb.b1;
-            cb.wall = info.y & 0x00FFFFFFu;
+            cb.wall = FMT == RCW_OBS_RGB8 ? (info.y & 0x00FFFFFFu) : info.y;   // (whole-word formats keep all four bytes: GRAY16F)
             uint8_t* const col = span + lane * CB;
             if (cb.b1 & 31) {
                 const int sa = cb.b1 & ~31, sb = cb.b2 & ~31;
@@ -932,7 +932,7 @@ __device__ __forceinline__ void render_span(const FrameParams& p, const uint2* c
         const uint2 info = colinfo[lane];
         cb.b1 = (int)(info.x & 0x7FFFFFFFu);
         cb.b2 = CB - cb.b1;
-        cb.wall = info.y & 0x00FFFFFFu;
+        cb.wall = FMT == RCW_OBS_RGB8 ? (info.y & 0x00FFFFFFu) : info.y;   // (whole-word formats keep all four bytes: GRAY16F)
         uint8_t* const col = span + lane * CP;
         const int sa = cb.b1 & ~31, sb = cb.b2 & ~31;
         if (!item_slow && sa != sb) {
@@ -953,7 +953,9 @@ template <int FMT>
 __device__ __forceinline__ uint2 column_entry(const FrameParams& p, int pad, int cid, bool& slow) {
     const uint2 e = p.col_entry[cid];
     slow = FMT == RCW_OBS_RGB8 && (e.x != 0u);
-    return make_uint2((uint32_t)(pad * PixelFormat<FMT>::kBpp) | e.x, e.y);
+    // bytes per pixel from the launch, not from FMT: RCW_OBS_GRAY16F (two-byte pixels, one 16-bit pattern repeated)
+    // runs on the XRGB32 instantiations — to the renderer both are whole 32-bit words of one value
+    return make_uint2((uint32_t)(pad * p.px_bytes) | e.x, e.y);
 }
 
 // item / gpe for the 32-bit work-item index (exact for every n: FrameParams::gpe_magic / gpe_shift)
@@ -1530,7 +1532,7 @@ static cudaError_t launch_env_m(const FrameParams& p, int obs_format, const Laun
     if (sh.table) { RCW_ENV_LAUNCH(RCW_OBS_GRAY8, kOutTable); }
     if (obs_format == RCW_OBS_GRAY8) { RCW_ENV_LAUNCH(RCW_OBS_GRAY8, kOutPaint); }
     if (obs_format == RCW_OBS_RGB8) { RCW_ENV_LAUNCH(RCW_OBS_RGB8, kOutPaint); }
-    RCW_ENV_LAUNCH(RCW_OBS_XRGB32, kOutPaint);
+    RCW_ENV_LAUNCH(RCW_OBS_XRGB32, kOutPaint);   // XRGB32 and GRAY16F (see column_entry)
 #undef RCW_ENV_LAUNCH
 }
 
@@ -1595,7 +1597,8 @@ cudaError_t launch_frame(const FrameParams& p, int mode, int obs_format, const L
 
 cudaError_t launch_expand_columns(const FrameParams& p, int pixel_format, int ctas, cudaStream_t s) {
     LaunchShape sh{false, true, false, ctas};
-    if (pixel_format != RCW_OBS_RGB8 && pixel_format != RCW_OBS_XRGB32 && pixel_format != RCW_OBS_GRAY8)
+    if (pixel_format != RCW_OBS_RGB8 && pixel_format != RCW_OBS_XRGB32 && pixel_format != RCW_OBS_GRAY8 &&
+        pixel_format != RCW_OBS_GRAY16F)
         return cudaErrorInvalidValue;
     return launch_frame_alt<kModeRender, kStagePaint>(p, pixel_format, sh, s);
 }

@@ -26,6 +26,7 @@ const RCW_OBS_RGB8 = Int32(0)
 const RCW_OBS_XRGB32 = Int32(1)
 const RCW_OBS_GRAY8 = Int32(2)      # BT.601 luma of the reference pixel, one byte per pixel
 const RCW_OBS_COLUMNS = Int32(3)    # one UInt32 per ray column: pad | colour id << 16 (see expand_columns)
+const RCW_OBS_GRAY16F = Int32(4)   # Float16 [num_envs][num_rays][height_px]: GRAY8 luma / 255 (normalised learner frames)
 const RCW_ABI_VERSION = Int32(4)
 const RCW_MAX_EXTRA_LAYERS = 4
 const RCW_LAYER_BLOCKING = Int32(0)   # an extra object layer that refuses the move like WALL
@@ -328,12 +329,13 @@ function obs_device_ptr(env::BatchedSingleRoom)
 end
 
 # dense host array for n envs in the handle's observation format:
-# RGB8 UInt8[3, P, R, n] | XRGB32 UInt32[P, R, n] (the reference's camera_view, :300) | GRAY8 UInt8[P, R, n] | COLUMNS UInt32[R, n]
+# RGB8 UInt8[3, P, R, n] | XRGB32 UInt32[P, R, n] (the reference's camera_view, :300) | GRAY8 UInt8[P, R, n] | GRAY16F Float16[P, R, n] | COLUMNS UInt32[R, n]
 function _host_obs(env::BatchedSingleRoom, n, fmt = env.obs_format)
     P, R = env.height_camera_view_pu, env.num_rays
     fmt == RCW_OBS_RGB8 && return Array{UInt8}(undef, 3, P, R, n)
     fmt == RCW_OBS_XRGB32 && return Array{UInt32}(undef, P, R, n)
     fmt == RCW_OBS_GRAY8 && return Array{UInt8}(undef, P, R, n)
+    fmt == RCW_OBS_GRAY16F && return Array{Float16}(undef, P, R, n)
     return Array{UInt32}(undef, R, n)
 end
 

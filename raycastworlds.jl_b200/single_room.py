@@ -33,7 +33,7 @@ NUM_VIEWS, CAMERA_VIEW, TOP_VIEW = 2, 1, 2  # single_room.jl:237-239
 
 
 _FORMATS = (("rgb8", _capi.RCW_OBS_RGB8), ("xrgb32", _capi.RCW_OBS_XRGB32), ("gray8", _capi.RCW_OBS_GRAY8),
-            ("columns", _capi.RCW_OBS_COLUMNS))
+            ("columns", _capi.RCW_OBS_COLUMNS), ("gray16f", _capi.RCW_OBS_GRAY16F))
 
 
 class AbstractGame:
@@ -116,7 +116,7 @@ class BatchedSingleRoom(AbstractGame):
     """`num_envs` independent SingleRoom games advanced by one kernel launch per step.
 
     Keyword arguments are those of the reference constructor (single_room.jl:258-272); the
-    additional ones are `num_envs`, `device`, `obs_format` ("rgb8" | "xrgb32" | "gray8"), `auto_reset`,
+    additional ones are `num_envs`, `device`, `obs_format` ("rgb8" | "xrgb32" | "gray8" | "gray16f" | "columns"), `auto_reset`,
     `seed`, `env_id_offset` (global id of env 0 when a batch is sharded over GPUs),
     `directions_wu` (the host's own [N, 2] float32 direction table), the two switches for the
     unpinned RayCaster.cast_ray decisions (`dda_tie_le`, `dda_dist_post`) and `obs_window_envs`
@@ -155,7 +155,7 @@ class BatchedSingleRoom(AbstractGame):
         self._ticket = C.c_int64()
         self._wait_r, self._wait_d = C.c_void_p(), C.c_void_p()
         self.obs_format = obs_format
-        self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1, "columns": 4}[obs_format]
+        self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1, "columns": 4, "gray16f": 2}[obs_format]
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -408,11 +408,15 @@ class BatchedSingleRoom(AbstractGame):
                 return torch.as_strided(flat, (slots, k, R, P, 3), (env_stride, fs, col_stride, 3, 1))
             if self.obs_format == "gray8":
                 return torch.as_strided(flat, (slots, k, R, P), (env_stride, fs, col_stride, 1))
+            if self.obs_format == "gray16f":
+                return torch.as_strided(flat.view(torch.float16), (slots, k, R, P), (env_stride // 2, fs // 2, col_stride // 2, 1))
             return torch.as_strided(flat.view(torch.int32), (slots, k, R, P), (env_stride // 4, fs // 4, col_stride // 4, 1))
         if self.obs_format == "rgb8":
             return torch.as_strided(flat, (slots, R, P, 3), (env_stride, col_stride, 3, 1))
         if self.obs_format == "gray8":
             return torch.as_strided(flat, (slots, R, P), (env_stride, col_stride, 1))
+        if self.obs_format == "gray16f":
+            return torch.as_strided(flat.view(torch.float16), (slots, R, P), (env_stride // 2, col_stride // 2, 1))
         words = flat.view(torch.int32)
         return torch.as_strided(words, (slots, R, P), (env_stride // 4, col_stride // 4, 1))
 
@@ -433,8 +437,8 @@ class BatchedSingleRoom(AbstractGame):
         the handle's stream."""
         import torch
 
-        if pixel_format not in ("rgb8", "xrgb32", "gray8"):
-            raise ValueError("pixel_format must be rgb8, xrgb32 or gray8")
+        if pixel_format not in ("rgb8", "xrgb32", "gray8", "gray16f"):
+            raise ValueError("pixel_format must be rgb8, xrgb32, gray8 or gray16f")
         dev = torch.device("cuda", self.cfg.device)
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
         if columns is None:
@@ -459,6 +463,8 @@ class BatchedSingleRoom(AbstractGame):
             return torch.as_strided(buf, (n, R, P, 3), (es, cs, 3, 1))
         if pixel_format == "gray8":
             return torch.as_strided(buf, (n, R, P), (es, cs, 1))
+        if pixel_format == "gray16f":
+            return torch.as_strided(buf.view(torch.float16), (n, R, P), (es // 2, cs // 2, 1))
         return torch.as_strided(buf.view(torch.int32), (n, R, P), (es // 4, cs // 4, 1))
 
     def copy_obs(self, env0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None, age: int = 0):
@@ -467,7 +473,7 @@ class BatchedSingleRoom(AbstractGame):
         n = min(self.num_envs - env0, self.obs_window) if n is None else n
         R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
         shape = (n, R, P, 3) if self.obs_format == "rgb8" else ((n, R) if self.obs_format == "columns" else (n, R, P))
-        dtype = np.uint32 if self.obs_format in ("xrgb32", "columns") else np.uint8
+        dtype = np.uint32 if self.obs_format in ("xrgb32", "columns") else (np.float16 if self.obs_format == "gray16f" else np.uint8)
         if out is None:
             out = np.empty(shape, dtype)
         _capi.check(self._lib.rcw_copy_obs_frame(self._h, env0, n, int(age), _ptr(out)))
