@@ -46,7 +46,7 @@ if ROOT not in sys.path:
 METRIC = "rendered env-steps/sec"
 UNIT = "env-steps/s"
 SEED = 0x5EED
-BPP = {"rgb8": 3, "xrgb32": 4, "gray8": 1, "columns": 4, "gray16f": 2}
+BPP = {"rgb8": 3, "xrgb32": 4, "gray8": 1, "columns": 4, "gray16f": 2, "gray8_half": 1}
 
 
 def parse_args():
@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
-    ap.add_argument("--obs-format", choices=["rgb8", "xrgb32", "gray8", "columns", "gray16f"], default="rgb8")
+    ap.add_argument("--obs-format", choices=["rgb8", "xrgb32", "gray8", "columns", "gray16f", "gray8_half"], default="rgb8")
     ap.add_argument("--map", choices=["default", "large"], default="default",
                     help="default: 8x16 tiles / 128 directions; large: 64x64 / 256 (BASELINE config 5)")
     ap.add_argument("--rays", type=int, default=512, help="num_rays = observation width (default 512)")
@@ -89,6 +89,8 @@ def geometry(map_name="default", rays=512, height=256):
 def frame_bytes(kw, fmt):
     if fmt == "columns":   # 4 bytes per column: not rendered pixels, the step is bound by act! + DDA
         return kw["num_rays"] * 4
+    if fmt == "gray8_half":   # the 2 x 2 box-filtered frame: a quarter of the GRAY8 bytes
+        return (kw["num_rays"] // 2) * (kw["height_camera_view_pu"] // 2)
     return kw["num_rays"] * kw["height_camera_view_pu"] * BPP[fmt]
 
 
@@ -195,7 +197,7 @@ def measured_traffic(n_envs, kw, fmt):
 # CPU arm
 # --------------------------------------------------------------------------------------------
 
-ORACLE_RENDER = {"rgb8": "rgb8", "xrgb32": "xrgb32", "gray8": "gray8", "columns": "none", "gray16f": "gray8"}
+ORACLE_RENDER = {"rgb8": "rgb8", "xrgb32": "xrgb32", "gray8": "gray8", "columns": "none", "gray16f": "gray8", "gray8_half": "gray8"}
 
 
 def oracle_cfg(orc, kw):

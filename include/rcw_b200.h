@@ -59,9 +59,14 @@ typedef enum rcw_obs_format {
                            of height_px * 3: 2 KB instead of 393 KB per default frame, for replay buffers that
                            rasterise only the frames they sample.  NOT rendered pixels: steps in
                            this format are bound by act! and the DDA, not by HBM writes. */
-    RCW_OBS_GRAY16F = 4 /* float16 [num_envs][num_rays columns][height_px]: the GRAY8 luma divided by 255 and rounded to IEEE
+    RCW_OBS_GRAY16F = 4, /* float16 [num_envs][num_rays columns][height_px]: the GRAY8 luma divided by 255 and rounded to IEEE
                            binary16 — the normalised frame a convolutional learner takes, without a conversion kernel
                            behind the renderer (single_room.jl:576 is the consumer hand-off) */
+    RCW_OBS_GRAY8_HALF = 5 /* uint8 [num_envs][num_rays / 2 columns][height_px / 2]: the GRAY8 frame under a 2 x 2 box filter,
+                           (a + b + c + d + 2) >> 2 over two adjacent columns x two adjacent rows, computed from the two
+                           rays' column decisions without ever writing the full-resolution frame: a quarter of the GRAY8
+                           bytes with every ray still contributing (anti-aliased, unlike a camera of half the rays).
+                           num_rays and height_px must be even.   */
     /* dense on the host (rcw_copy_obs); on the device columns may be pitched, see rcw_obs_layout */
 } rcw_obs_format;
 

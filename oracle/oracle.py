@@ -354,6 +354,11 @@ class Batch:
         r, g, b = (c >> 16) & 255, (c >> 8) & 255, c & 255
         return ((77 * r + 150 * g + 29 * b + 128) >> 8).astype(np.uint8)
 
+    def obs_gray8_half(self):
+        """The GRAY8 frame under a 2 x 2 box filter, (a + b + c + d + 2) >> 2 (RCW_OBS_GRAY8_HALF): [n, R / 2, P / 2]."""
+        g = self.obs_gray8().astype(np.uint32)
+        return ((g[:, 0::2, 0::2] + g[:, 0::2, 1::2] + g[:, 1::2, 0::2] + g[:, 1::2, 1::2] + 2) >> 2).astype(np.uint8)
+
     def obs_gray16f(self):
         """The GRAY8 luma / 255 in IEEE binary16: one binary32 division, one rounding to half (RCW_OBS_GRAY16F)."""
         return (self.obs_gray8().astype(np.float32) / np.float32(255)).astype(np.float16)

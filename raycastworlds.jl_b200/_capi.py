@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RCW_LIB") or os.path.join(_PKG, "lib", "librcw_b200.so")
 
 RCW_OK, RCW_EINVAL, RCW_EACTION, RCW_ECUDA, RCW_ENOMEM, RCW_ESIZE = 0, -1, -2, -3, -4, -5
-RCW_OBS_RGB8, RCW_OBS_XRGB32, RCW_OBS_GRAY8, RCW_OBS_COLUMNS, RCW_OBS_GRAY16F = 0, 1, 2, 3, 4
+RCW_OBS_RGB8, RCW_OBS_XRGB32, RCW_OBS_GRAY8, RCW_OBS_COLUMNS, RCW_OBS_GRAY16F, RCW_OBS_GRAY8_HALF = 0, 1, 2, 3, 4, 5
 RCW_DDA_TIE_LE, RCW_DDA_DIST_POST = 1, 2
 ABI_VERSION = 4
 RCW_MAX_EXTRA_LAYERS = 4

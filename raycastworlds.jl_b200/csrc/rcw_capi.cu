@@ -221,7 +221,13 @@ static cudaError_t dev_alloc(rcw_batch* b, T** out, size_t count, bool zero = tr
 }
 
 static int bytes_per_pixel(int fmt) {
-    return fmt == RCW_OBS_RGB8 ? 3 : (fmt == RCW_OBS_GRAY8 ? 1 : (fmt == RCW_OBS_GRAY16F ? 2 : 4));
+    return fmt == RCW_OBS_RGB8 ? 3 : ((fmt == RCW_OBS_GRAY8 || fmt == RCW_OBS_GRAY8_HALF) ? 1 : (fmt == RCW_OBS_GRAY16F ? 2 : 4));
+}
+
+// columns / rows of one observation of a handle: the camera's, or half of each under the 2 x 2 box filter
+static int obs_columns(const rcw_config& c) { return c.obs_format == RCW_OBS_GRAY8_HALF ? c.num_rays / 2 : c.num_rays; }
+static int obs_rows(const rcw_config& c) {
+    return c.obs_format == RCW_OBS_GRAY8_HALF ? c.height_camera_view_pu / 2 : c.height_camera_view_pu;
 }
 
 // BT.601 luma of a 0x00RRGGBB pixel (RCW_OBS_GRAY8), and the same luma / 255 as IEEE binary16 bits (RCW_OBS_GRAY16F)
@@ -235,7 +241,7 @@ static uint32_t luma_half_bits(uint32_t col) {
 
 // bytes of one column of an observation: the pixels of the column, or its one RCW_OBS_COLUMNS word
 static int column_bytes(const rcw_batch* b) {
-    return b->cfg.obs_format == RCW_OBS_COLUMNS ? 4 : b->cfg.height_camera_view_pu * b->bpp;
+    return b->cfg.obs_format == RCW_OBS_COLUMNS ? 4 : obs_rows(b->cfg) * b->bpp;
 }
 
 // pixel_fmt: the format the renderer fields are prepared for (-1: the handle's own; rcw_expand_columns paints
@@ -244,7 +250,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
     const rcw_config& c = b->cfg;
     if (pixel_fmt < 0) pixel_fmt = c.obs_format == RCW_OBS_COLUMNS ? (int)RCW_OBS_RGB8 : c.obs_format;
     const int px_bpp = bytes_per_pixel(pixel_fmt);
-    const int px_col_bytes = c.height_camera_view_pu * px_bpp;
+    const int px_col_bytes = (pixel_fmt == RCW_OBS_GRAY8_HALF ? c.height_camera_view_pu / 2 : c.height_camera_view_pu) * px_bpp;
     const int px_col_pitch = (px_col_bytes + 31) & ~31;
     memset(&p, 0, sizeof(p));
     p.H = c.height_tile_map_tu;
@@ -281,7 +287,7 @@ static void fill_frame_params(const rcw_batch* b, FrameParams& p, int pixel_fmt 
     const int n_pal = 6 + 2 * b->n_extra;
     for (int i = 0; i < n_pal; ++i) {
         const uint32_t col = (i < 6 ? c.palette[i] : c.layer_palette[(i - 6) >> 1][(i - 6) & 1]) & 0x00FFFFFFu;
-        if (pixel_fmt == RCW_OBS_GRAY8) {
+        if (pixel_fmt == RCW_OBS_GRAY8 || pixel_fmt == RCW_OBS_GRAY8_HALF) {
             // BT.601 luma of the reference pixel, replicated so the colour is "flat" for the renderer
             p.palette[i] = luma_of(col) * 0x00010101u;
         } else if (pixel_fmt == RCW_OBS_GRAY16F) {
@@ -736,7 +742,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     b->bulk = false;
     if (const char* s = getenv("RCW_RENDER_PATH")) b->bulk = strcmp(s, "bulk") == 0 && c.obs_format != RCW_OBS_GRAY8 && c.obs_format != RCW_OBS_GRAY16F;
     if (const char* s = getenv("RCW_SPLIT")) b->split = atoi(s) != 0;
-    if (c.obs_format == RCW_OBS_COLUMNS) b->bulk = b->split = false;   // nothing is painted
+    if (c.obs_format == RCW_OBS_COLUMNS || c.obs_format == RCW_OBS_GRAY8_HALF) b->bulk = b->split = false;   // nothing / no full frame is painted
     if (b->n_extra) b->bulk = b->split = false;                        // the measured alternatives know the reference's two objects only
     if (b->split) RCW_CUDA(dev_alloc(b, &b->d_col_info, (size_t)E * (size_t)R));   // 4 B per column, two-launch path only
     {
@@ -789,9 +795,9 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
 
     // ---- observations ---------------------------------------------------------------------------
     // every column starts on a 32-byte sector, every env on a 128-byte line (see rcw_obs_layout)
-    b->col_pitch = c.obs_format == RCW_OBS_COLUMNS ? 4 : (P * b->bpp + 31) & ~31;
+    b->col_pitch = c.obs_format == RCW_OBS_COLUMNS ? 4 : (obs_rows(c) * b->bpp + 31) & ~31;
     b->frame_stack = c.frame_stack > 1 ? c.frame_stack : 1;
-    b->frame_stride = (((size_t)R * b->col_pitch) + 127) & ~(size_t)127;
+    b->frame_stride = (((size_t)obs_columns(c) * b->col_pitch) + 127) & ~(size_t)127;
     b->obs_env_stride = b->frame_stride * (size_t)b->frame_stack;
     // Grid shape: one CTA per 8 items and the hardware scheduler balances the tail (measured best once
     // the register budget below is chosen per geometry; RCW_CTAS_PER_SM > 0 caps the grid and loops).
@@ -810,10 +816,15 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
     // 160x120 6701 -> 6113, 256x192 7366 -> 6305.
     b->env_per_warp = b->gpe <= 8 && 32 * b->col_pitch <= 10240;
     if (c.obs_format == RCW_OBS_COLUMNS) b->env_per_warp = true;   // nothing is painted: act! + DDA only, any width
+    if (c.obs_format == RCW_OBS_GRAY8_HALF) b->env_per_warp = true;   // the box filter is composed by env_kernel only
     if (const char* s = getenv("RCW_ENV_PER_WARP")) b->env_per_warp = atoi(s) != 0;   // 1 forces it for any width
     if (const char* s = getenv("RCW_PACKED_ACTIONS")) b->no_packed_actions = atoi(s) == 0;
     b->env_per_warp_min = kEnvPerWarpMinEnvs;
     if (const char* s = getenv("RCW_ENV_PER_WARP_MIN")) b->env_per_warp_min = atoll(s);   // tests force the kernel on small batches
+    if (c.obs_format == RCW_OBS_GRAY8_HALF) {   // whatever the switches say: only env_kernel composes the box filter
+        b->env_per_warp = true;
+        b->env_per_warp_min = 0;
+    }
     b->obs_window = (c.obs_window_envs > 0 && c.obs_window_envs < E) ? c.obs_window_envs : E;
     b->obs_bytes = b->obs_env_stride * (size_t)b->obs_window;
     RCW_CUDA(dev_alloc(b, &b->d_obs, b->obs_bytes, /*zero=*/b->frame_stack > 1));   // older ring positions start black
@@ -831,7 +842,7 @@ static int32_t create_impl(rcw_batch* b, const float* directions_wu) {
         const size_t table_bytes = (size_t)(P / 2 + 1) * n_colors * (size_t)b->col_pitch;
         size_t limit = 64 * 1024;
         if (const char* s = getenv("RCW_COL_TABLE_KB")) limit = (size_t)atoll(s) * 1024;   // 0 disables the table
-        if (b->env_per_warp && c.obs_format != RCW_OBS_COLUMNS && table_bytes <= limit) {
+        if (b->env_per_warp && c.obs_format != RCW_OBS_COLUMNS && c.obs_format != RCW_OBS_GRAY8_HALF && table_bytes <= limit) {
             uint32_t pal[6 + 2 * RCW_MAX_EXTRA_LAYERS];
             for (int i = 0; i < 2 + n_colors; ++i) {
                 const uint32_t col = (i < 6 ? c.palette[i] : c.layer_palette[(i - 6) >> 1][(i - 6) & 1]) & 0x00FFFFFFu;
@@ -879,8 +890,10 @@ int32_t rcw_create(const rcw_config* cfg, const float* directions_wu, rcw_batch*
         return fail(RCW_EINVAL, "num_rays and height_camera_view_pu must be positive");
     if (cfg->height_camera_view_pu > 32767)
         return fail(RCW_EINVAL, "height_camera_view_pu must be below 32768");
+    if (cfg->obs_format == RCW_OBS_GRAY8_HALF && ((cfg->num_rays | cfg->height_camera_view_pu) & 1))
+        return fail(RCW_EINVAL, "RCW_OBS_GRAY8_HALF needs an even num_rays and height_camera_view_pu (2 x 2 blocks)");
     if (cfg->obs_format != RCW_OBS_RGB8 && cfg->obs_format != RCW_OBS_XRGB32 && cfg->obs_format != RCW_OBS_GRAY8 &&
-        cfg->obs_format != RCW_OBS_GRAY16F &&
+        cfg->obs_format != RCW_OBS_GRAY16F && cfg->obs_format != RCW_OBS_GRAY8_HALF &&
         cfg->obs_format != RCW_OBS_COLUMNS)
         return fail(RCW_EINVAL, "unknown obs_format %d", cfg->obs_format);
     if (cfg->num_envs < 1) return fail(RCW_EINVAL, "num_envs must be positive");
@@ -1600,7 +1613,7 @@ int32_t rcw_copy_obs_frame(rcw_batch* b, int64_t env0, int64_t n, int32_t age, v
     if (age < 0 || age >= b->frame_stack)
         return fail(RCW_ESIZE, "frame age %d outside 0..%d", age, b->frame_stack - 1);
     DeviceGuard g(b->device);
-    const size_t R = (size_t)b->cfg.num_rays, col_bytes = (size_t)column_bytes(b);
+    const size_t R = (size_t)obs_columns(b->cfg), col_bytes = (size_t)column_bytes(b);   // columns of one observation
     const int64_t slot0 = env0 % b->obs_window;
     if (slot0 + n > b->obs_window) {   // the range wraps around the window: two pieces
         const int64_t n1 = b->obs_window - slot0;

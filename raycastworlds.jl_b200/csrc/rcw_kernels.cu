@@ -1218,7 +1218,9 @@ frame_kernel_pa(const __grid_constant__ FrameParams p, const __grid_constant__ P
 //               256 bits per load and store — about 12 instead of 200 instructions per ray group.  The format
 //               only decides what is in the table, so one instantiation serves RGB8, XRGB32 and GRAY8.
 // ROOM: see MapOf — no wall layer in shared memory, no TMA, no mbarrier, no CTA barrier at all.
-enum : int { kOutPaint = 0, kOutWords = 1, kOutTable = 2 };
+//   kOutHalf  : RCW_OBS_GRAY8_HALF — the GRAY8 frame under a 2 x 2 box filter, composed from the column decisions of
+//               the two rays of every output column; the full-resolution frame is never written
+enum : int { kOutPaint = 0, kOutWords = 1, kOutTable = 2, kOutHalf = 3 };
 
 __device__ __forceinline__ void load_nc32(const uint8_t* p, uint4& lo, uint4& hi) {
     asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -1358,6 +1360,73 @@ __device__ __forceinline__ void env_body(const FrameParams& p, const PackedActio
                 }
             }
 #endif
+            rt = rt_next;
+            continue;
+        }
+        if (OUT == kOutHalf) {
+            // Output column c covers image columns 2 c and 2 c + 1, i.e. (ray i paints column R - i, :431, and R is even)
+            // the rays of one even / odd lane pair; output row r covers rows 2 r and 2 r + 1.  A column of the full frame
+            // is ceiling for rows < pad, the hit object's luma for pad <= row < P - pad, floor below (:433-439), so a
+            // 2 x 2 block is uniform almost everywhere: lane L takes the 32-byte sectors L, L + 32, ... of the span's
+            // consecutive output columns, fetches the two rays' {pad, luma} with two shuffles, and only where a block
+            // row straddles a band boundary of either ray is the box filter evaluated pixel by pixel.
+            const int P = p.P, CP = p.col_pitch, NS = CP >> 5;        // pitch / sectors of an OUTPUT column (P / 2 rows)
+            const uint32_t mine = (uint32_t)cs.pad | ((p.palette[cs.cid] & 0xFFu) << 16);
+            const uint32_t C = p.palette[RCW_COLOR_CEILING] & 0xFFu, F = p.palette[RCW_COLOR_FLOOR] & 0xFFu;
+            const int n_sec = (ncols >> 1) * NS;
+            int cl = (int)(((uint32_t)lane * p.sec_inv16) >> 16), sc = lane - cl * NS;
+            const int adv_cl = p.sec_adv_cl, adv_sc = p.sec_adv_u;
+            uint8_t* dst = env_obs + (size_t)(col0 >> 1) * CP + (lane << 5);
+#pragma unroll 1
+            for (int s = lane; s < ((n_sec + 31) & ~31); s += 32) {   // (uniform trip count: the shuffles need all lanes)
+                const int la = max(ncols - 2 - 2 * cl, 0);            // output column cl of the span <- rays of lanes la, la + 1
+                const uint32_t ia = __shfl_sync(0xFFFFFFFFu, mine, la), ib = __shfl_sync(0xFFFFFFFFu, mine, la + 1);
+                if (s < n_sec) {
+                    const int pa = (int)(ia & 0xFFFFu), pb = (int)(ib & 0xFFFFu);
+                    const uint32_t Wa = ia >> 16, Wb = ib >> 16;
+                    // Output rows, P2 = P / 2 of them.  Ray a's two columns of a block row are both ceiling above row
+                    // pa >> 1 and both object from row (pa + 1) >> 1 on (a block row in between, for an odd pad, mixes
+                    // them), mirrored at the bottom.  So the output column is ceiling above T0, the two objects' mean
+                    // between T1 and M0, floor from M1 on, and only the few rows of [T0, T1) and [M0, M1) — as many as
+                    // the two rays' pads differ, about one — need the filter evaluated: the sector is written as the
+                    // three flat bands and those rows are then stored over it, byte by byte (same lane, program order).
+                    const int P2 = P >> 1;
+                    const int T0 = min(pa, pb) >> 1, T1 = (max(pa, pb) + 1) >> 1, M0 = P2 - T1, M1 = P2 - T0;
+                    const uint32_t mid = ((2u * Wa + 2u * Wb + 2u) >> 2) * 0x01010101u;
+                    const uint32_t Cw = C * 0x01010101u, Fw = F * 0x01010101u;
+                    const int q0 = sc << 5;                           // first output row of this sector
+                    uint32_t w[8];
+                    if (q0 + 32 <= T0 || q0 >= M1 || (q0 >= T0 && q0 + 32 <= M1)) {
+                        const uint32_t v = q0 + 32 <= T0 ? Cw : (q0 >= M1 ? Fw : mid);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) w[k] = v;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t m1 = low_bytes_mask(T0 - q0 - 4 * k), m2 = low_bytes_mask(M1 - q0 - 4 * k);
+                            w[k] = (Cw & m1) | (((mid & m2) | (Fw & ~m2)) & ~m1);
+                        }
+                    }
+                    store_stream32(dst, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+                    auto pixel = [&](int pad, uint32_t W, int row) { return row < pad ? C : (row < P - pad ? W : F); };
+                    auto patch = [&](int lo, int hi) {                // output rows [lo, hi) of this sector, filtered
+                        for (int r = max(lo, q0); r < min(hi, q0 + 32); ++r) {
+                            const uint32_t sum = pixel(pa, Wa, 2 * r) + pixel(pa, Wa, 2 * r + 1) + pixel(pb, Wb, 2 * r) +
+                                                 pixel(pb, Wb, 2 * r + 1);
+                            dst[r - q0] = (uint8_t)((sum + 2u) >> 2);
+                        }
+                    };
+                    patch(T0, T1);
+                    patch(M0, M1);
+                }
+                dst += 1024;
+                cl += adv_cl;
+                sc += adv_sc;
+                if (sc >= NS) {
+                    sc -= NS;
+                    ++cl;
+                }
+            }
             rt = rt_next;
             continue;
         }
@@ -1529,6 +1598,7 @@ static cudaError_t launch_env_m(const FrameParams& p, int obs_format, const Laun
 #define RCW_ENV_LAUNCH(FMT, OUT)                                                        \
     return packed ? launch_env_pa_t<FMT, OUT, ROOM>(p, *packed, s) : launch_env_t<MODE, FMT, OUT, ROOM>(p, s)
     if (obs_format == RCW_OBS_COLUMNS) { RCW_ENV_LAUNCH(RCW_OBS_RGB8, kOutWords); }
+    if (obs_format == RCW_OBS_GRAY8_HALF) { RCW_ENV_LAUNCH(RCW_OBS_GRAY8, kOutHalf); }
     if (sh.table) { RCW_ENV_LAUNCH(RCW_OBS_GRAY8, kOutTable); }
     if (obs_format == RCW_OBS_GRAY8) { RCW_ENV_LAUNCH(RCW_OBS_GRAY8, kOutPaint); }
     if (obs_format == RCW_OBS_RGB8) { RCW_ENV_LAUNCH(RCW_OBS_RGB8, kOutPaint); }
@@ -1551,6 +1621,7 @@ template <int MODE, bool ROOM>
 static cudaError_t launch_shipped(const FrameParams& p, int obs_format, const LaunchShape& sh, cudaStream_t s,
                                   const PackedActions* packed) {
     if (sh.env_per_warp) return launch_env_m<MODE, ROOM>(p, obs_format, sh, s, packed);
+    if (obs_format == RCW_OBS_GRAY8_HALF) return cudaErrorInvalidValue;   // (only env_kernel composes the box filter)
     if (obs_format == RCW_OBS_COLUMNS) return launch_item<MODE, RCW_OBS_RGB8, kStageFront, ROOM>(p, sh, s, packed);
     if (obs_format == RCW_OBS_GRAY8) return launch_item<MODE, RCW_OBS_GRAY8, kStageFused, ROOM>(p, sh, s, packed);
     if (obs_format == RCW_OBS_RGB8) return launch_item<MODE, RCW_OBS_RGB8, kStageFused, ROOM>(p, sh, s, packed);

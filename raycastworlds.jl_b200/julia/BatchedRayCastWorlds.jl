@@ -26,6 +26,7 @@ const RCW_OBS_RGB8 = Int32(0)
 const RCW_OBS_XRGB32 = Int32(1)
 const RCW_OBS_GRAY8 = Int32(2)      # BT.601 luma of the reference pixel, one byte per pixel
 const RCW_OBS_COLUMNS = Int32(3)    # one UInt32 per ray column: pad | colour id << 16 (see expand_columns)
+const RCW_OBS_GRAY8_HALF = Int32(5) # UInt8 [num_envs][num_rays / 2][height_px / 2]: the GRAY8 frame under a 2 x 2 box filter
 const RCW_OBS_GRAY16F = Int32(4)   # Float16 [num_envs][num_rays][height_px]: GRAY8 luma / 255 (normalised learner frames)
 const RCW_ABI_VERSION = Int32(4)
 const RCW_MAX_EXTRA_LAYERS = 4
@@ -336,6 +337,7 @@ function _host_obs(env::BatchedSingleRoom, n, fmt = env.obs_format)
     fmt == RCW_OBS_XRGB32 && return Array{UInt32}(undef, P, R, n)
     fmt == RCW_OBS_GRAY8 && return Array{UInt8}(undef, P, R, n)
     fmt == RCW_OBS_GRAY16F && return Array{Float16}(undef, P, R, n)
+    fmt == RCW_OBS_GRAY8_HALF && return Array{UInt8}(undef, P ÷ 2, R ÷ 2, n)
     return Array{UInt32}(undef, R, n)
 end
 

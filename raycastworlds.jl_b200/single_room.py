@@ -33,7 +33,7 @@ NUM_VIEWS, CAMERA_VIEW, TOP_VIEW = 2, 1, 2  # single_room.jl:237-239
 
 
 _FORMATS = (("rgb8", _capi.RCW_OBS_RGB8), ("xrgb32", _capi.RCW_OBS_XRGB32), ("gray8", _capi.RCW_OBS_GRAY8),
-            ("columns", _capi.RCW_OBS_COLUMNS), ("gray16f", _capi.RCW_OBS_GRAY16F))
+            ("columns", _capi.RCW_OBS_COLUMNS), ("gray16f", _capi.RCW_OBS_GRAY16F), ("gray8_half", _capi.RCW_OBS_GRAY8_HALF))
 
 
 class AbstractGame:
@@ -155,7 +155,11 @@ class BatchedSingleRoom(AbstractGame):
         self._ticket = C.c_int64()
         self._wait_r, self._wait_d = C.c_void_p(), C.c_void_p()
         self.obs_format = obs_format
-        self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1, "columns": 4, "gray16f": 2}[obs_format]
+        self.bytes_per_pixel = {"rgb8": 3, "xrgb32": 4, "gray8": 1, "columns": 4, "gray16f": 2, "gray8_half": 1}[obs_format]
+        # columns x rows of one observation: the camera's, or half of each under the 2 x 2 box filter ("gray8_half")
+        half = obs_format == "gray8_half"
+        self.obs_cols = int(cfg.num_rays) // 2 if half else int(cfg.num_rays)
+        self.obs_rows = int(cfg.height_camera_view_pu) // 2 if half else int(cfg.height_camera_view_pu)
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -360,7 +364,7 @@ class BatchedSingleRoom(AbstractGame):
         """[env slots, width (= num_rays columns), height_camera_view_pu, (3)]; the pixel row is the
         fastest index, as in the reference's Array{UInt32}(P, R).  env slots = num_envs unless an
         observation window was configured."""
-        R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
+        R, P = self.obs_cols, self.obs_rows
         if self.obs_format == "columns":
             return (self.obs_window, R)      # one uint32 word per column: pad | palette index << 16
         return (self.obs_window, R, P, 3) if self.obs_format == "rgb8" else (self.obs_window, R, P)
@@ -391,7 +395,7 @@ class BatchedSingleRoom(AbstractGame):
 
         ptr, total, _ = self.obs_device_ptr()
         env_stride, col_stride, _, _ = self.obs_layout()
-        R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
+        R, P = self.obs_cols, self.obs_rows
         holder = _CudaBuffer(ptr, total, self)
         flat = torch.as_tensor(holder, device=torch.device("cuda", self.cfg.device))
         slots = self.obs_window
@@ -406,14 +410,14 @@ class BatchedSingleRoom(AbstractGame):
             k, _, fs = self.obs_frames()
             if self.obs_format == "rgb8":
                 return torch.as_strided(flat, (slots, k, R, P, 3), (env_stride, fs, col_stride, 3, 1))
-            if self.obs_format == "gray8":
+            if self.obs_format in ("gray8", "gray8_half"):
                 return torch.as_strided(flat, (slots, k, R, P), (env_stride, fs, col_stride, 1))
             if self.obs_format == "gray16f":
                 return torch.as_strided(flat.view(torch.float16), (slots, k, R, P), (env_stride // 2, fs // 2, col_stride // 2, 1))
             return torch.as_strided(flat.view(torch.int32), (slots, k, R, P), (env_stride // 4, fs // 4, col_stride // 4, 1))
         if self.obs_format == "rgb8":
             return torch.as_strided(flat, (slots, R, P, 3), (env_stride, col_stride, 3, 1))
-        if self.obs_format == "gray8":
+        if self.obs_format in ("gray8", "gray8_half"):
             return torch.as_strided(flat, (slots, R, P), (env_stride, col_stride, 1))
         if self.obs_format == "gray16f":
             return torch.as_strided(flat.view(torch.float16), (slots, R, P), (env_stride // 2, col_stride // 2, 1))
@@ -471,7 +475,7 @@ class BatchedSingleRoom(AbstractGame):
         """Blocking device->host copy of the observations of envs [env0, env0+n); with a frame ring, `age`
         selects the frame (0 = newest)."""
         n = min(self.num_envs - env0, self.obs_window) if n is None else n
-        R, P = self.cfg.num_rays, self.cfg.height_camera_view_pu
+        R, P = self.obs_cols, self.obs_rows
         shape = (n, R, P, 3) if self.obs_format == "rgb8" else ((n, R) if self.obs_format == "columns" else (n, R, P))
         dtype = np.uint32 if self.obs_format in ("xrgb32", "columns") else (np.float16 if self.obs_format == "gray16f" else np.uint8)
         if out is None:
