@@ -669,7 +669,10 @@ int32_t rcw_destroy(rcw_batch* b) {
     if (b->h_results) cudaFreeHost(b->h_results);
     for (cudaEvent_t ev : b->result_ready)
         if (ev) cudaEventDestroy(ev);
-    if (b->stream2) cudaStreamDestroy(b->stream2);
+    if (b->stream2) {
+        cudaStreamSynchronize(b->stream2);
+        cudaStreamDestroy(b->stream2);
+    }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -1296,25 +1299,32 @@ static int32_t enqueue_random_steps_two_streams(rcw_batch* b, int32_t n_steps) {
     const int64_t half = (E / 2) & ~(int64_t)(kWarpsPerCta - 1);
     RCW_CUDA(cudaEventRecord(b->ev_fork, b->stream));
     RCW_CUDA(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
-    for (int32_t s = 0; s < n_steps; ++s) {
-        b->frame_newest = (b->frame_newest + 1) % b->frame_stack;
-        FrameParams p;
-        fill_frame_params(b, p);
-        for (int part = 0; part < 2; ++part) {
-            cudaStream_t stream = part ? b->stream : b->stream2;
-            p.env_first = part ? half : 0;
-            p.env_count = part ? E - half : half;
-            p.obs_slot0 = (uint32_t)p.env_first;
-            RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, shape_for(b, p.env_count), stream));
-            b->launches += 1;
-            if (b->cfg.top_view)
-                if (int32_t rc = enqueue_top_view(b, p.out, p.env_first, p.env_count, p.obs_slot0, nullptr, stream)) return rc;
+    auto steps = [&]() -> int32_t {
+        for (int32_t s = 0; s < n_steps; ++s) {
+            b->frame_newest = (b->frame_newest + 1) % b->frame_stack;
+            FrameParams p;
+            fill_frame_params(b, p);
+            for (int part = 0; part < 2; ++part) {
+                cudaStream_t stream = part ? b->stream : b->stream2;
+                p.env_first = part ? half : 0;
+                p.env_count = part ? E - half : half;
+                p.obs_slot0 = (uint32_t)p.env_first;
+                RCW_CUDA(launch_frame(p, kModeStep, b->cfg.obs_format, shape_for(b, p.env_count), stream));
+                b->launches += 1;
+                if (b->cfg.top_view)
+                    if (int32_t rc = enqueue_top_view(b, p.out, p.env_first, p.env_count, p.obs_slot0, nullptr, stream)) return rc;
+            }
+            b->cur ^= 1;
+            b->step_index += 1;
         }
-        b->cur ^= 1;
-        b->step_index += 1;
-    }
-    RCW_CUDA(cudaEventRecord(b->ev_join, b->stream2));
-    RCW_CUDA(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
+        return RCW_OK;
+    };
+    const int32_t rc = steps();
+    // join whatever happened: the handle's stream must cover everything that was enqueued on the side stream
+    cudaError_t e = cudaEventRecord(b->ev_join, b->stream2);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_join, 0);
+    if (rc != RCW_OK) return rc;
+    RCW_CUDA(e);
     return RCW_OK;
 }
 
