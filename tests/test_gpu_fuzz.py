@@ -332,3 +332,130 @@ def test_huge_tile_map_needs_opt_in_shared_memory(rcw, oracle, monkeypatch, env_
     with pytest.raises(rcw.RcwError) as ei:                       # 3000 x 3000 tiles: 1.1 MB, does not fit an SM
         rcw.BatchedSingleRoom(1, height_tile_map_tu=3000, width_tile_map_tu=3000)
     assert ei.value.code == rcw._capi.RCW_ESIZE
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_layered_configuration_matches_oracle(rcw, oracle, monkeypatch, seed):
+    """Seeded random maps with 1-4 extra object layers (NUM_OBJECTS 3-6; blocking / terminal kinds, rewards, colours
+    drawn at random, objects allowed to overlap each other, walls and goals), every observation format, both step
+    kernels: injected states driven by explicit actions, or Philox episodes with auto-reset."""
+    rng = np.random.default_rng(BASE + 70000 + seed)
+    monkeypatch.setenv("RCW_ENV_PER_WARP", str(seed & 1))
+    monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
+    monkeypatch.setenv("RCW_COL_TABLE_KB", "0" if seed & 2 else "64")
+    monkeypatch.setenv("RCW_TWO_STREAMS_MIN", "8")
+    H, W = int(rng.integers(4, 20)), int(rng.integers(4, 40))
+    N = int(rng.choice([8, 32, 128]))
+    R = int(rng.choice([2, 32, 34, 64, 84, 130]))
+    P = int(rng.choice([2, 16, 32, 50, 84, 96]))
+    fmt = str(rng.choice(["rgb8", "xrgb32", "gray8", "gray16f", "gray8_half", "columns"]))
+    n_extra = int(rng.integers(1, 5))
+    n = int(rng.integers(2, 30))
+    kinds = [int(v) for v in rng.integers(0, 2, n_extra)]
+    rewards = [float(np.float32(v)) for v in rng.uniform(-2, 2, n_extra)]
+    pal2 = [(int(a), int(b)) for a, b in rng.integers(0, 1 << 24, (n_extra, 2))]
+    tops = [int(v) for v in rng.integers(0, 1 << 24, n_extra)]
+    radius, incr = float(np.float32(rng.uniform(0.05, 0.4))), float(np.float32(rng.uniform(0.05, 0.5)))
+    walls = np.zeros((H, W), bool)
+    walls[0, :] = walls[-1, :] = walls[:, 0] = walls[:, -1] = True
+    walls[1:-1, 1:-1] |= rng.random((H - 2, W - 2)) < 0.08
+    if rng.random() < 0.25:                              # an open border: rays may leave the map (painted as wall)
+        walls[0, 1:-1] &= rng.random(W - 2) < 0.5
+    extra = rng.random((n_extra, H, W)) < 0.08
+    kw = dict(height_tile_map_tu=H, width_tile_map_tu=W, num_directions=N, num_rays=R, height_camera_view_pu=P,
+              player_radius_wu=radius, position_increment_wu=incr, obs_format=fmt, pu_per_tu=int(rng.choice([1, 3, 4, 8])),
+              num_object_layers=2 + n_extra, layer_kind=kinds, layer_reward=rewards, layer_palette=pal2, layer_top_color=tops)
+    flat_pal = [c for pair in pal2 for c in pair] + [0] * (8 - 2 * n_extra)
+    cfg = oracle.default_config(H=H, W=W, N=N, R=R, P=P, radius=np.float32(radius), incr=np.float32(incr), pu_per_tu=kw["pu_per_tu"],
+                                num_layers=2 + n_extra, layer_kind=kinds + [0] * (4 - n_extra),
+                                layer_reward=rewards + [0.0] * (4 - n_extra), layer_palette=flat_pal,
+                                layer_top_color=tops + [0] * (4 - n_extra))
+
+    def furnish_world(w):
+        w.set_layer(1, walls)
+        for k in range(n_extra):
+            w.set_layer(3 + k, extra[k])
+
+    philox = bool(rng.integers(0, 2)) and (~(walls | extra.any(0)))[1:-1, 1:-1].sum() >= 2
+    if philox:
+        env = rcw.BatchedSingleRoom(n, seed=seed, env_id_offset=5, **kw)
+        env.set_layer(1, walls)
+        for k in range(n_extra):
+            env.set_layer(3 + k, extra[k])
+        env.reset()
+        ref = oracle.Batch(n, cfg=cfg, seed=seed, env_id_offset=5)
+        for e in range(n):
+            furnish_world(ref.world(e))
+        ref.reset()
+        steps = int(rng.integers(2, 250))
+        env.step_random(steps)
+        ref.rollout(steps)
+        worlds = [ref.world(e) for e in range(n)]
+        assert env.episode_stats() == ref.episode_stats()
+    else:
+        pos = np.stack([rng.uniform(0.05, H - 0.05, n), rng.uniform(0.05, W - 0.05, n)], 1).astype(np.float32)
+        au = rng.integers(0, N, n).astype(np.int32)
+        goal = np.stack([rng.integers(1, H + 1, n), rng.integers(1, W + 1, n)], 1).astype(np.int32)
+        env = rcw.BatchedSingleRoom(n, seed=seed, auto_reset=False, **kw)
+        env.set_layer(1, walls)
+        for k in range(n_extra):
+            env.set_layer(3 + k, extra[k])
+        env.set_state(pos=pos, dir_au=au, goal=goal)
+        env.render()
+        worlds = []
+        for e in range(n):
+            w = oracle.World(cfg)
+            furnish_world(w)
+            w.set_state(pos[e, 0], pos[e, 1], au[e], goal[e, 0], goal[e, 1])
+            w.cast_rays()
+            w.update_camera_view()
+            worlds.append(w)
+        for _ in range(int(rng.integers(0, 30))):
+            a = rng.choice([1, 1, 2, 3, 4], size=n).astype(np.uint8)
+            env.act(a)
+            for e in range(n):
+                assert worlds[e].step(int(a[e])) == 0
+    st = env.get_state()
+    case = f"seed {seed}: {H}x{W} N={N} R={R} P={P} {fmt} extra={n_extra} kinds={kinds} philox={philox}"
+    np.testing.assert_array_equal(bits(st["pos"]), bits(np.stack([w.state()["pos"] for w in worlds])), err_msg=case)
+    np.testing.assert_array_equal(st["dir_au"], np.array([w.state()["au"] for w in worlds], np.int32), err_msg=case)
+    np.testing.assert_array_equal(st["goal"], np.stack([w.state()["goal"] for w in worlds]), err_msg=case)
+    if philox:      # the step's reward / done survive the same-step auto-reset: the batch keeps them, not the re-drawn world
+        want_r, want_d = ref.reward_done()
+    else:
+        want_r = np.array([w.state()["reward"] for w in worlds], np.float32)
+        want_d = np.array([w.state()["done"] for w in worlds], np.uint8)
+    np.testing.assert_array_equal(st["reward"], want_r, err_msg=case)
+    np.testing.assert_array_equal(st["done"], want_d, err_msg=case)
+
+    def gray(u32):
+        r, g, b = (u32 >> 16) & 255, (u32 >> 8) & 255, u32 & 255
+        return ((77 * r + 150 * g + 29 * b + 128) >> 8).astype(np.uint32)
+
+    def want(w):
+        if fmt == "rgb8":
+            return w.obs_rgb8()
+        if fmt == "xrgb32":
+            return w.camera_view
+        if fmt == "columns":
+            return w.camera_columns()
+        g = gray(w.camera_view)
+        if fmt == "gray8":
+            return g.astype(np.uint8)
+        if fmt == "gray16f":
+            return (g.astype(np.float32) / np.float32(255)).astype(np.float16)
+        return ((g[0::2, 0::2] + g[0::2, 1::2] + g[1::2, 0::2] + g[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+
+    obs = env.copy_obs()
+    rays = env.get_rays()
+    for e in range(n):
+        np.testing.assert_array_equal(obs[e], want(worlds[e]), err_msg=f"env {e}, {case}")
+        np.testing.assert_array_equal(rays["hit"][e], worlds[e].ray_stop, err_msg=f"env {e}, {case}")
+        np.testing.assert_array_equal(rays["dim"][e], worlds[e].ray_dim, err_msg=case)
+        np.testing.assert_array_equal(bits(rays["dist"][e]), bits(worlds[e].ray_dist), err_msg=case)
+    env.render_top_view()
+    top = env.copy_top_view()
+    for e in range(n):
+        worlds[e].update_top_view()
+        np.testing.assert_array_equal(top[e], worlds[e].top_view, err_msg=f"top view, env {e}, {case}")
+    env.close()
