@@ -387,11 +387,14 @@ static int grid_for(const rcw_batch* b, int64_t env_count) {
 static LaunchShape shape_for(const rcw_batch* b, int64_t n) {
     LaunchShape sh{b->bulk, b->split, b->occ4, grid_for(b, n)};
     sh.env_per_warp = b->env_per_warp && n >= b->env_per_warp_min;
-    // RoomMap kernels where act! + DDA bound the step (front-bound register budget, env kernel, column words).  Where the
-    // store stream bounds it (default camera) the bit-packed kernel is 1.2 % faster (0.2270 vs 0.2296 ms per 4096 envs,
-    // A/B on one box: its TMA-staged prologue paces the first stores), so it stays there; RCW_ROOM=2 forces RoomMap.
+    // RoomMap kernels where act! + DDA bound the step: a warp owns a whole env (env_kernel), nothing is painted (column
+    // words), or the item kernel's items are small (32 columns under 16 KB: 512x256 GRAY8 1.064 -> 1.133 of the copy peak,
+    // 160x120 RGB8 1.026 -> 1.041).  Where the store stream bounds the item kernel the bit-packed variant is faster even
+    // though it executes more instructions — default camera 0.2270 vs 0.2296 ms per 4096 envs, 256x192 RGB8 1.135 vs 1.123,
+    // 64x64 maps at the default camera (config 5, 20 DDA iterations per item) 3.527 vs 3.611 ms per 65,536 envs, all A/B on
+    // one box — so it stays there; RCW_ROOM=2 forces RoomMap.
     sh.room = b->room && b->room_allowed && !b->per_env_maps &&
-              (b->occ4 || sh.env_per_warp || b->cfg.obs_format == RCW_OBS_COLUMNS || b->room_forced);
+              (sh.env_per_warp || b->cfg.obs_format == RCW_OBS_COLUMNS || 32 * b->col_pitch < 16384 || b->room_forced);
     sh.table = sh.env_per_warp && b->d_col_table != nullptr;
     return sh;
 }
