@@ -441,6 +441,7 @@ static int32_t enqueue_top_view(rcw_batch* b, const StateRef& st, int64_t env0, 
     t.env_first = env0;
     t.env_count = n;
     t.sm_count = (uint32_t)b->sm_count;
+    t.room = (b->room && b->room_allowed && !b->per_env_maps) ? 1u : 0u;
     RCW_CUDA(launch_top_view(t, stream));
     b->launches += 1;
     return RCW_OK;

@@ -199,6 +199,7 @@ struct TopViewParams {
     uint32_t window, slot0;  // env_first + k lives in slot (slot0 + k) mod window
     int64_t env_first, env_count;
     uint32_t sm_count;       // SMs of the device
+    uint32_t room;           // the wall layer is exactly the border of the map: RoomMap kernel, nothing staged
 };
 
 // kernel launchers (rcw_kernels.cu)

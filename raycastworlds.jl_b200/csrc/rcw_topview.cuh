@@ -44,6 +44,8 @@ __host__ __device__ __forceinline__ uint32_t circle_words(int rp) {
     return D * ((D + 31u) >> 5);
 }
 
+// ROOM: the wall layer is exactly the border of the map (RoomMap): no layer is staged, the DDA counts down to the border.
+template <bool ROOM>
 __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_constant__ TopViewParams p) {
     // [wall layer][ray plane][palette 8 x u32][line list R x int2][chunk starts R x u32][tile colour (W + 1) x H u32]
     // [circle bitmap][row info u16][column info u16][row-sector info u16][column offset u16]
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     const uint32_t SB = plane_col_bits(Hp);                    // bits per plane column
     const uint32_t plane_words = ((uint32_t)Wp * (SB >> 5) + 3u) & ~3u;   // the plane is cleared as uint4
     uint32_t* const s_map = s_top;
-    uint32_t* const s_ray = s_map + p.stage_words;
+    uint32_t* const s_ray = s_map + (ROOM ? 0 : p.stage_words);
     uint32_t* const s_pal = s_ray + plane_words;
     int2* const s_line = reinterpret_cast<int2*>(s_pal + 8);                       // [R] end pixels of the distinct segments
     uint32_t* const s_cstart = reinterpret_cast<uint32_t*>(s_line + R);            // [R] first chunk of every distinct segment
@@ -79,9 +81,11 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     // ---- this env's wall layer: one TMA bulk copy; planes cleared and tables built meanwhile
     if (tid == 0) {
         s_counts = 0ULL;
-        mbar_init(&s_bar, 1);
-        mbar_arrive_expect_tx(&s_bar, (uint32_t)p.stage_words * 4u);
-        bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.stage_words * 4u, &s_bar);
+        if (!ROOM) {
+            mbar_init(&s_bar, 1);
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)p.stage_words * 4u);
+            bulk_copy_g2s(s_map, p.wall_map + (size_t)env * p.map_env_stride, (uint32_t)p.stage_words * 4u, &s_bar);
+        }
     }
     {
         uint4* const z = reinterpret_cast<uint4*>(s_ray);       // 16-byte aligned: map_words is a multiple of 4
@@ -129,10 +133,12 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
         }
     }
     __syncthreads();          // mbarrier initialised, plane cleared
-    mbar_wait(&s_bar, 0);
+    if (!ROOM) mbar_wait(&s_bar, 0);
 
     // ---- draw_tile_map! colour of every tile: findfirst over the layers WALL, GOAL (:355-360), then the extra objects
-    const BitsMap map{s_map, p.n_extra ? s_map + (p.n_extra + 1) * p.map_words : s_map, p.wpr, p.n_extra, p.map_words};
+    typename std::conditional<ROOM, RoomMap, BitsMap>::type map;
+    if constexpr (ROOM) map = RoomMap{H - 1, W - 1};
+    else map = BitsMap{s_map, p.n_extra ? s_map + (p.n_extra + 1) * p.map_words : s_map, p.wpr, p.n_extra, p.map_words};
     for (int t = tid; t < H * (W + 1); t += kTopThreads) {
         const int j0 = t / H, i0 = t - j0 * H;
         int code = RCW_TOP_COLOR_BORDER;                      // pseudo tile column W: what a border column of the image shows
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
                                     : ((i0 == gi0 && j0 == gj0) ? RCW_TOP_COLOR_GOAL : RCW_TOP_COLOR_EMPTY);
         uint32_t colour = p.palette[code];
         if (code == RCW_TOP_COLOR_EMPTY && j0 < W)        // tile_map_colors[findfirst(...)] over the extra objects
-            for (int k = p.n_extra - 1; k >= 0; --k) colour = map.extra(k, i0, j0) ? p.extra_color[k] : colour;
+            for (int k = map.n_extra - 1; k >= 0; --k) colour = map.extra(k, i0, j0) ? p.extra_color[k] : colour;
         s_tilec[t] = colour;
     }
 
@@ -445,11 +451,13 @@ size_t top_view_smem_bytes(int H, int W, int R, int pu, float radius, int map_wo
 }
 
 cudaError_t launch_top_view(const TopViewParams& p, cudaStream_t s) {
-    const size_t smem = top_view_smem_bytes(p.H, p.W, p.R, p.pu, p.radius, p.stage_words);
+    const size_t smem = top_view_smem_bytes(p.H, p.W, p.R, p.pu, p.radius, p.room ? 0 : p.stage_words);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(top_view_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = p.room ? cudaFuncSetAttribute(top_view_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(top_view_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    top_view_kernel<<<(unsigned)p.env_count, kTopThreads, smem, s>>>(p);
+    if (p.room) top_view_kernel<true><<<(unsigned)p.env_count, kTopThreads, smem, s>>>(p);
+    else top_view_kernel<false><<<(unsigned)p.env_count, kTopThreads, smem, s>>>(p);
     return cudaGetLastError();
 }
