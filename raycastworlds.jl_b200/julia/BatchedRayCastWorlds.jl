@@ -202,6 +202,12 @@ function ShardedSingleRoom(; devices = [0], kw...)
     return ShardedSingleRoom(shards, handles, Int(cfg[].num_envs))
 end
 
+# reset!(env): every shard draws new layouts on its device (keyed by global env id)
+function RCW.reset!(env::ShardedSingleRoom)
+    foreach(RCW.reset!, env.shards)
+    return nothing
+end
+
 # act!(env, actions): actions of the whole batch in global env order (host vector)
 function RCW.act!(env::ShardedSingleRoom, actions::AbstractVector{<:Integer})
     length(actions) == env.num_envs || throw(DimensionMismatch("one action per env"))

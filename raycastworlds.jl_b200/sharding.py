@@ -110,6 +110,23 @@ class ShardedSingleRoom:
                                                        C.byref(sl), int(reset_counters)))
         return ep.value, sr.value, sl.value
 
+    def reset(self):
+        """reset!(env) on every shard (layouts drawn on the devices, keyed by global env id)."""
+        for sh in self.shards:
+            sh.reset()
+
+    def copy_obs(self):
+        """The shards' observations concatenated in global env order (blocking device -> host copies)."""
+        import numpy as np
+
+        return np.concatenate([sh.copy_obs() for sh in self.shards])
+
+    def reward_done(self):
+        import numpy as np
+
+        parts = [sh.reward_done() for sh in self.shards]
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
     def get_state(self):
         """The shards' states concatenated in global env order."""
         import numpy as np

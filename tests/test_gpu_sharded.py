@@ -63,6 +63,10 @@ def test_sharded_batch_matches_oracle(rcw, oracle, n_shards, total):
         assert ref.step(a) == 0
     env.sync()
     check_against_oracle(env, ref, total)
+    np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    r, d = env.reward_done()
+    np.testing.assert_array_equal(r, ref.reward_done()[0])
+    np.testing.assert_array_equal(d, ref.reward_done()[1])
     assert ref.episode_stats()[0] > 0
     # an invalid action anywhere: nothing is enqueued on any shard (the reference's @assert, single_room.jl:140)
     before = [s.launch_count() for s in env.shards]
