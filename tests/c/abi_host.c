@@ -110,6 +110,48 @@ int main(int argc, char** argv) {
     int64_t launches;
     CHECK(rcw_launch_count(b, &launches));
     if (launches < steps) return 5;
+
+    /* One process, several handles (one per GPU in production; here the three shards share device 0): the same batch
+     * cut into contiguous blocks of global env ids, stepped with the same action stream, must end in the same state,
+     * with the same episode totals summed over the shards.  Shard 1's first env is compared pixel for pixel too. */
+    {
+        enum { SHARDS = 3 };
+        int32_t devices[SHARDS] = {0, 0, 0};
+        rcw_batch* shard[SHARDS];
+        rcw_config scfg = cfg;
+        scfg.result_ring = 0;
+        CHECK(rcw_create_sharded(&scfg, NULL, devices, SHARDS, shard));
+        for (int s = 1; s <= steps; ++s) {
+            for (int64_t e = 0; e < n; ++e) actions[e] = (uint8_t)(1 + ((e + s) % 7 == 0 ? 2 : 0) + ((e * 31 + s) % 11 == 0 ? 1 : 0));
+            CHECK(rcw_step_sharded(shard, SHARDS, actions));
+        }
+        CHECK(rcw_sync_sharded(shard, SHARDS));
+        int64_t ep1, len1, ep2, len2;
+        double ret1, ret2;
+        CHECK(rcw_episode_stats(b, &ep1, &ret1, &len1, 0));
+        CHECK(rcw_reduce_episode_stats(shard, SHARDS, &ep2, &ret2, &len2, 0));
+        if (ep1 != ep2 || len1 != len2 || ret1 != ret2) return 8;
+        float* spos = (float*)malloc(sizeof(float) * 2 * (size_t)n);
+        CHECK(rcw_get_state(b, pos, NULL, NULL, NULL, NULL));
+        int64_t off = 0, cnt = 0, off1 = 0;
+        for (int k = 0; k < SHARDS; ++k) {
+            CHECK(rcw_shard_envs(n, SHARDS, k, &off, &cnt));
+            if (k == 1) off1 = off;
+            CHECK(rcw_get_state(shard[k], spos + 2 * off, NULL, NULL, NULL, NULL));
+        }
+        if (memcmp(pos, spos, sizeof(float) * 2 * (size_t)n) != 0) return 9;
+        uint8_t* obs1 = (uint8_t*)malloc(dense);
+        CHECK(rcw_copy_obs(b, off1, 1, obs));
+        CHECK(rcw_copy_obs(shard[1], 0, 1, obs1));
+        if (memcmp(obs, obs1, dense) != 0) return 10;
+        /* an invalid action anywhere: nothing is enqueued on any shard */
+        actions[n - 1] = 9;
+        if (rcw_step_sharded(shard, SHARDS, actions) != RCW_EACTION) return 11;
+        CHECK(rcw_destroy_sharded(shard, SHARDS));
+        free(spos);
+        free(obs1);
+        printf("sharded %lld %.6f %lld\n", (long long)ep2, ret2, (long long)len2);
+    }
     CHECK(rcw_destroy(b));
     free(obs);
     free(actions);

@@ -49,6 +49,7 @@ def test_c_host_matches_oracle(host_binary, oracle):
     r = subprocess.run([host_binary, str(n), str(steps), str(seed)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lines = [ln.split() for ln in r.stdout.strip().splitlines()]
+    sharded = lines.pop()
     ring = lines.pop()
     assert [int(ln[0]) for ln in lines] == [10, 20, 30, 40, 50, 60]
     ref = oracle.Batch(n, cfg=oracle.default_config(R=96, P=64), seed=seed)
@@ -70,3 +71,7 @@ def test_c_host_matches_oracle(host_binary, oracle):
             k += 1
     # every step's rewards / terminations as read from the pinned result ring (rcw_step_async / rcw_wait)
     assert ring[0] == "ring" and float(ring[1]) == sum_reward and int(ring[2]) == sum_done
+    # the same batch as three shards driven through rcw_*_sharded from C: the program itself compares state, pixels and
+    # episode totals with the single handle (exit codes 8-11); the totals it prints are the oracle's
+    ep, ret, length = ref.episode_stats()
+    assert sharded[0] == "sharded" and (int(sharded[1]), float(sharded[2]), int(sharded[3])) == (ep, ret, length)

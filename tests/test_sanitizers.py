@@ -74,4 +74,4 @@ def test_c_host_under_asan_and_ubsan(tmp_path):
     text = r.stdout + r.stderr
     assert findings(text) == [], "\n".join(findings(text)[:20])
     assert r.returncode == 0, text[-2000:]
-    assert r.stdout.strip().splitlines()[-1].startswith("ring")
+    assert r.stdout.strip().splitlines()[-1].startswith("sharded") and r.stdout.strip().splitlines()[-2].startswith("ring")
