@@ -82,3 +82,34 @@ def test_frame_ring_with_two_streams(rcw, oracle, monkeypatch):
     for age in range(3):
         np.testing.assert_array_equal(env.copy_obs(age=age), frames[2 - age])
     env.close()
+
+
+def test_default_split_at_bench_size_sampled_against_oracle(rcw, oracle):
+    """The bench's own shape — 4096 default-camera envs stepped by one rcw_step_random(K) call, which the handle runs as
+    two half-batches on two streams without any switch set — against oracle batches of 48 envs placed at the start, around
+    the split and at the end of the batch (the Philox streams are keyed by global env id, so a sub-range can be replayed
+    on its own)."""
+    n, steps, seed = 4096, 1500, 24301
+    env = rcw.BatchedSingleRoom(n, seed=seed)
+    launches0 = env.launch_count()
+    env.step_random(steps)
+    assert env.launch_count() - launches0 == 2 * steps
+    st = env.get_state()
+    stats = env.episode_stats()
+    assert stats[0] > 0
+    for off in (0, 2048 - 24, n - 48):
+        ref = oracle.Batch(48, seed=seed, env_id_offset=off)
+        ref.rollout(steps, threads=4, render=False)
+        pos, au, goal = ref.states()
+        np.testing.assert_array_equal(bits(st["pos"][off:off + 48]), bits(pos))
+        np.testing.assert_array_equal(st["dir_au"][off:off + 48], au)
+        np.testing.assert_array_equal(st["goal"][off:off + 48], goal)
+        r, d = ref.reward_done()
+        np.testing.assert_array_equal(st["reward"][off:off + 48], r)
+        np.testing.assert_array_equal(st["done"][off:off + 48], d)
+        for e in (0, 23, 24, 47):
+            w = ref.world(e)
+            w.cast_rays()
+            w.update_camera_view()
+            np.testing.assert_array_equal(env.copy_obs(off + e, 1)[0], w.obs_rgb8())
+    env.close()
