@@ -244,6 +244,15 @@ int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64
  * seed / global env id / step index); the benchmark path. */
 int32_t rcw_step_random(rcw_batch* b, int32_t n_steps);
 
+/* n_steps of rcw_step driven by an action tape: actions [n_steps][num_envs] (host or device pointer), step s takes row
+ * s.  For action sequences known in advance — replays, evaluation of open-loop plans, action repeat.  A host tape is
+ * validated as a whole before anything is enqueued (RCW_EACTION, the reference's @assert); a device tape like a device
+ * array of rcw_step.  Like rcw_step_random, a multi-step call lets the launches of consecutive steps overlap (the
+ * batch runs as two half-batches on two streams, joined before the call returns its stream to the caller), which
+ * single rcw_step calls cannot do because the caller may order work of its own between them.  The observation
+ * buffer holds the last step's frames (all of them with a frame ring). */
+int32_t rcw_step_tape(rcw_batch* b, const uint8_t* actions, int32_t n_steps);
+
 /* cast_rays!(world) + update_camera_view!(env) (single_room.jl:195-231,374-444) from the
  * current state, without acting. */
 int32_t rcw_render(rcw_batch* b);

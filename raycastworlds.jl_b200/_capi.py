@@ -23,7 +23,7 @@ RCW_LAYER_BLOCKING, RCW_LAYER_TERMINAL = 0, 1
 # every symbol include/rcw_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "rcw_version", "rcw_config_init", "rcw_create", "rcw_destroy", "rcw_set_wall_map", "rcw_set_layer", "rcw_set_wall_maps", "rcw_reset",
-    "rcw_step", "rcw_step_async", "rcw_wait", "rcw_step_range", "rcw_step_random", "rcw_render",
+    "rcw_step", "rcw_step_async", "rcw_wait", "rcw_step_range", "rcw_step_random", "rcw_step_tape", "rcw_render",
     "rcw_render_top_view", "rcw_top_view_device_ptr", "rcw_copy_top_view", "rcw_get_state", "rcw_set_state", "rcw_get_rays",
     "rcw_checkpoint_size", "rcw_save_checkpoint", "rcw_load_checkpoint",
     "rcw_obs_device_ptr", "rcw_obs_layout", "rcw_obs_frames", "rcw_copy_obs_frame", "rcw_copy_obs", "rcw_expand_columns", "rcw_expanded_layout", "rcw_episode_stats", "rcw_launch_count", "rcw_stream",
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
         "rcw_wait": (i32, [vp, i64, P(vp), P(vp)]),
         "rcw_step_range": (i32, [vp, vp, i64, i64]),
         "rcw_step_random": (i32, [vp, i32]),
+        "rcw_step_tape": (i32, [vp, vp, i32]),
         "rcw_render": (i32, [vp]),
         "rcw_render_top_view": (i32, [vp]),
         "rcw_top_view_device_ptr": (i32, [vp, P(vp), P(C.c_size_t), P(C.c_size_t)]),

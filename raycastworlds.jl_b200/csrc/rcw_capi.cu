@@ -170,6 +170,8 @@ struct rcw_batch {
     uint32_t* d_ep_length = nullptr;
     DeviceStats* d_stats = nullptr;
     uint8_t* d_actions = nullptr;
+    uint8_t* d_tape = nullptr;          // device copy of a host action tape (rcw_step_tape), grown on demand
+    size_t tape_capacity = 0;
     uint8_t* d_obs = nullptr;
     size_t obs_env_stride = 0;    // bytes between consecutive envs (all ring positions of an env)
     size_t frame_stride = 0;      // bytes between consecutive ring positions of one env (rcw_config.frame_stack)
@@ -1298,7 +1300,8 @@ int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64
 // multi-step call: between single rcw_step calls the caller may enqueue consumers of the observations on the
 // handle's stream, and those must stay ordered with the next step.  fork: the side stream waits for everything
 // enqueued on the handle's stream so far; join: the handle's stream waits for the side stream's last step.
-static int32_t enqueue_random_steps_two_streams(rcw_batch* b, int32_t n_steps) {
+// d_tape: nullptr = the random policy; otherwise device actions [n_steps][num_envs], step s reads row s
+static int32_t enqueue_steps_two_streams(rcw_batch* b, int32_t n_steps, const uint8_t* d_tape = nullptr) {
     const int64_t E = b->cfg.num_envs;
     const int64_t half = (E / 2) & ~(int64_t)(kWarpsPerCta - 1);
     RCW_CUDA(cudaEventRecord(b->ev_fork, b->stream));
@@ -1308,6 +1311,7 @@ static int32_t enqueue_random_steps_two_streams(rcw_batch* b, int32_t n_steps) {
             b->frame_newest = (b->frame_newest + 1) % b->frame_stack;
             FrameParams p;
             fill_frame_params(b, p);
+            p.actions = d_tape ? d_tape + (size_t)s * (size_t)E : nullptr;   // (the kernels index the actions by env)
             for (int part = 0; part < 2; ++part) {
                 cudaStream_t stream = part ? b->stream : b->stream2;
                 p.env_first = part ? half : 0;
@@ -1332,18 +1336,60 @@ static int32_t enqueue_random_steps_two_streams(rcw_batch* b, int32_t n_steps) {
     return RCW_OK;
 }
 
+// multi-step calls of at least two steps on a batch that is rendered in one launch may run as two half-batches
+static bool two_streams_apply(const rcw_batch* b, int32_t n_steps) {
+    return n_steps >= 2 && b->two_streams && !b->split && !b->bulk && b->obs_window == b->cfg.num_envs &&
+           b->cfg.num_envs >= b->two_streams_min && b->cfg.num_envs >= 2 * kWarpsPerCta;
+}
+
+int32_t rcw_step_tape(rcw_batch* b, const uint8_t* actions, int32_t n_steps) {
+    NvtxRange nvtx("rcw_step_tape");
+    if (int32_t rc = check_handle(b)) return rc;
+    if (!actions) return fail(RCW_EINVAL, "actions is null (use rcw_step_random for the random policy)");
+    if (n_steps < 0) return fail(RCW_EINVAL, "n_steps must be non-negative");
+    if (n_steps == 0) return RCW_OK;
+    DeviceGuard g(b->device);
+    const size_t E = (size_t)b->cfg.num_envs, total = E * (size_t)n_steps;
+    const uint8_t* d_tape = actions;
+    if (is_device_pointer(actions)) {
+        b->device_actions_pending = true;       // an invalid value is reported by the next blocking call
+    } else {
+        // the reference's @assert for every step of the tape, before anything is enqueued
+        if (int32_t rc = validate_host_actions(actions, 0, (int64_t)total)) return rc;
+        if (b->tape_capacity < total) {
+            uint8_t* fresh = nullptr;
+            RCW_CUDA(dev_alloc(b, &fresh, total, false));      // (an outgrown tape buffer stays allocated until rcw_destroy)
+            b->d_tape = fresh;
+            b->tape_capacity = total;
+        }
+        RCW_CUDA(cudaMemcpyAsync(b->d_tape, actions, total, cudaMemcpyHostToDevice, b->stream));
+        if (is_pinned_host(actions)) RCW_CUDA(cudaStreamSynchronize(b->stream));   // host pointers are only touched during the call
+        d_tape = b->d_tape;
+    }
+    if (two_streams_apply(b, n_steps)) {
+        int32_t first = 0;
+        if (b->cfg.top_view && !b->d_top) {    // (the top views are allocated by their first draw)
+            if (int32_t rc = enqueue_frame(b, kModeStep, d_tape)) return rc;
+            first = 1;
+        }
+        return enqueue_steps_two_streams(b, n_steps - first, d_tape + (size_t)first * E);
+    }
+    for (int32_t s = 0; s < n_steps; ++s)
+        if (int32_t rc = enqueue_frame(b, kModeStep, d_tape + (size_t)s * E)) return rc;
+    return RCW_OK;
+}
+
 int32_t rcw_step_random(rcw_batch* b, int32_t n_steps) {
     NvtxRange nvtx("rcw_step_random");
     if (int32_t rc = check_handle(b)) return rc;
     if (n_steps < 0) return fail(RCW_EINVAL, "n_steps must be non-negative");
     DeviceGuard g(b->device);
-    if (n_steps >= 2 && b->two_streams && !b->split && !b->bulk && b->obs_window == b->cfg.num_envs &&
-        b->cfg.num_envs >= b->two_streams_min && b->cfg.num_envs >= 2 * kWarpsPerCta) {
+    if (two_streams_apply(b, n_steps)) {
         if (b->cfg.top_view && !b->d_top) {    // (the top views are allocated by their first draw)
             if (int32_t rc = enqueue_frame(b, kModeStep, nullptr)) return rc;
             --n_steps;
         }
-        return enqueue_random_steps_two_streams(b, n_steps);
+        return enqueue_steps_two_streams(b, n_steps);
     }
     for (int32_t s = 0; s < n_steps; ++s)
         if (int32_t rc = enqueue_frame(b, kModeStep, nullptr)) return rc;

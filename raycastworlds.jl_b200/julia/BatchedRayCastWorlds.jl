@@ -302,6 +302,16 @@ end
 step_random!(env::BatchedSingleRoom, n_steps = 1) =
     check(ccall((:rcw_step_random, LIB), Int32, (Ptr{Cvoid}, Int32), env.handle, Int32(n_steps)))
 
+# size(actions, 2) steps driven by an action tape: actions[e, s] is the action of env e in step s (num_envs x n_steps,
+# column-major = the C ABI's [n_steps][num_envs]); a multi-step call, consecutive steps may overlap on the device
+function act_tape!(env::BatchedSingleRoom, actions::Matrix{UInt8})
+    size(actions, 1) == env.num_envs || throw(DimensionMismatch("one row per env"))
+    GC.@preserve actions begin
+        check(ccall((:rcw_step_tape, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32), env.handle, actions, Int32(size(actions, 2))))
+    end
+    return nothing
+end
+
 # cast_rays! + update_camera_view! — src/single_room.jl:195-231, 374-444
 function RCW.cast_rays!(env::BatchedSingleRoom)
     check(ccall((:rcw_render, LIB), Int32, (Ptr{Cvoid},), env.handle))

@@ -274,6 +274,19 @@ class BatchedSingleRoom(AbstractGame):
         a = np.ascontiguousarray(a)
         _capi.check(self._lib.rcw_step_range(self._h, _ptr(a), int(env0), n))
 
+    def act_tape(self, actions):
+        """rcw_step_tape: len(actions) steps driven by an action tape, uint8 [n_steps, num_envs] (numpy, or a CUDA torch
+        tensor).  A multi-step call: consecutive steps may overlap on the device (two half-batches on two streams)."""
+        if hasattr(actions, "data_ptr"):
+            if tuple(actions.shape[1:]) != (self.num_envs,) or not actions.is_contiguous() or actions.element_size() != 1:
+                raise ValueError("a device tape must be a contiguous uint8 [n_steps, num_envs] tensor")
+            _capi.check(self._lib.rcw_step_tape(self._h, C.c_void_p(actions.data_ptr()), int(actions.shape[0])))
+            return
+        a = np.ascontiguousarray(actions, np.uint8)
+        if a.ndim != 2 or a.shape[1] != self.num_envs:
+            raise ValueError(f"actions must have shape (n_steps, {self.num_envs})")
+        _capi.check(self._lib.rcw_step_tape(self._h, _ptr(a), a.shape[0]))
+
     def step_random(self, n_steps: int = 1):
         _capi.check(self._lib.rcw_step_random(self._h, int(n_steps)))
 

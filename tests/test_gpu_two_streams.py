@@ -113,3 +113,49 @@ def test_default_split_at_bench_size_sampled_against_oracle(rcw, oracle):
             w.update_camera_view()
             np.testing.assert_array_equal(env.copy_obs(off + e, 1)[0], w.obs_rgb8())
     env.close()
+
+
+@pytest.mark.parametrize("two,device_tape", [(0, False), (1, False), (1, True)])
+def test_action_tape_matches_oracle(rcw, oracle, monkeypatch, two, device_tape):
+    """rcw_step_tape: the steps of a host or device action tape, run as two half-batches on two streams (or one launch
+    per step with RCW_TWO_STREAMS=0), equal the oracle stepping the same rows one by one."""
+    monkeypatch.setenv("RCW_TWO_STREAMS", str(two))
+    monkeypatch.setenv("RCW_TWO_STREAMS_MIN", "8")
+    n, T, seed = 45, 120, 19
+    kw = dict(num_rays=96, height_camera_view_pu=40, top_view=True, pu_per_tu=4)
+    env = rcw.BatchedSingleRoom(n, seed=seed, **kw)
+    ref = oracle.Batch(n, cfg=oracle.default_config(R=96, P=40, pu_per_tu=4), seed=seed)
+    rng = np.random.default_rng(3)
+    tape = rng.choice([1, 1, 1, 2, 3, 4], size=(T, n)).astype(np.uint8)
+    if device_tape:
+        import torch
+
+        env.act_tape(torch.from_numpy(tape).cuda())
+    else:
+        env.act_tape(tape[:1])                     # a one-step tape, then the rest
+        env.act_tape(tape[1:])
+    for t in range(T):
+        assert ref.step(tape[t]) == 0
+    st = env.get_state()
+    pos, au, goal = ref.states()
+    np.testing.assert_array_equal(bits(st["pos"]), bits(pos))
+    np.testing.assert_array_equal(st["dir_au"], au)
+    np.testing.assert_array_equal(st["goal"], goal)
+    r, d = ref.reward_done()
+    np.testing.assert_array_equal(st["reward"], r)
+    np.testing.assert_array_equal(st["done"], d)
+    np.testing.assert_array_equal(env.copy_obs(), ref.obs_rgb8())
+    top = env.copy_top_view()
+    for e in (0, n - 1):
+        w = ref.world(e)
+        w.update_top_view()
+        np.testing.assert_array_equal(top[e], w.top_view)
+    assert env.episode_stats() == ref.episode_stats()
+    # an invalid action anywhere on a host tape: nothing is enqueued (the reference's @assert)
+    before = env.launch_count()
+    bad = tape[:3].copy()
+    bad[2, n - 1] = 0
+    with pytest.raises(rcw.InvalidActionError):
+        env.act_tape(bad)
+    assert env.launch_count() == before
+    env.close()
