@@ -27,9 +27,15 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
-@pytest.mark.parametrize("two", [0, 1])
+@pytest.mark.parametrize("two", [0, 1, 2])
 def test_multi_step_calls_match_oracle(rcw, oracle, monkeypatch, case, two):
     c = CASES[case]
+    if two == 2:                                         # top views as two half-batches like the steps, not as a pipeline
+        if not c["kw"].get("top_view"):
+            pytest.skip("only differs with top views")
+        monkeypatch.setenv("RCW_TOP_PIPELINE", "0")
+        two = 1
+    pipelined = two == 1 and bool(c["kw"].get("top_view")) and __import__("os").environ.get("RCW_TOP_PIPELINE") != "0"
     monkeypatch.setenv("RCW_TWO_STREAMS", str(two))
     monkeypatch.setenv("RCW_TWO_STREAMS_MIN", "8")
     monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
@@ -62,9 +68,9 @@ def test_multi_step_calls_match_oracle(rcw, oracle, monkeypatch, case, two):
         assert env.episode_stats() == ref.episode_stats()
     per_step = 2 if c["kw"].get("top_view") else 1
     launched = env.launch_count() - launches0
-    if two:
+    if two and not pipelined:
         assert launched > total * per_step, "the multi-step calls should have been split into two launches per step"
-    else:
+    else:       # one stream — or, with top views, the two-stage pipeline: step kernels on one stream, top view kernels on the other
         assert launched == total * per_step
     env.close()
 
