@@ -75,6 +75,16 @@ def test_validation_errors_without_gpu():
         assert lib.rcw_create(C.byref(cfg), None, C.byref(h)) == _capi.RCW_EINVAL, field
         assert not h.value
     assert lib.rcw_step(None, None) == _capi.RCW_EINVAL
+    assert lib.rcw_step_tape(None, None, 3) == _capi.RCW_EINVAL and lib.rcw_set_layer(None, 3, None) == _capi.RCW_EINVAL
+    assert lib.rcw_step_sharded(None, 2, None) == _capi.RCW_EINVAL and lib.rcw_sync_sharded(None, 0) == _capi.RCW_EINVAL
+    for field, value in [("layer_kind", 2)]:                 # per-layer settings are validated for the layers in use
+        cfg = _capi.default_config()
+        cfg.num_object_layers = 3
+        cfg.layer_kind[0] = value
+        assert lib.rcw_create(C.byref(cfg), None, C.byref(h)) == _capi.RCW_EINVAL, field
+    cfg = _capi.default_config()
+    cfg.obs_format, cfg.num_rays = _capi.RCW_OBS_GRAY8_HALF, 33       # the 2 x 2 box filter needs even sizes
+    assert lib.rcw_create(C.byref(cfg), None, C.byref(h)) == _capi.RCW_EINVAL
     assert lib.rcw_sync(None) == _capi.RCW_EINVAL
     assert lib.rcw_destroy(None) == _capi.RCW_OK
 
