@@ -241,7 +241,10 @@ int32_t rcw_wait(rcw_batch* b, int64_t ticket, const float** reward, const uint8
 int32_t rcw_step_range(rcw_batch* b, const uint8_t* actions, int64_t env0, int64_t n);
 
 /* n_steps of rcw_step with a uniform random policy drawn on the device (Philox keyed by
- * seed / global env id / step index); the benchmark path. */
+ * seed / global env id / step index); the benchmark path.  A call of two or more steps may overlap the launches of
+ * consecutive steps on a second, internal stream (two half-batches, or — with rcw_config.top_view — step kernels and
+ * top view kernels as a two-stage pipeline); the internal stream is joined before the call returns, so everything
+ * the caller enqueues on rcw_stream afterwards is ordered behind all n_steps. */
 int32_t rcw_step_random(rcw_batch* b, int32_t n_steps);
 
 /* n_steps of rcw_step driven by an action tape: actions [n_steps][num_envs] (host or device pointer), step s takes row
