@@ -200,10 +200,11 @@ def test_random_operation_sequences_with_windows(rcw, oracle, monkeypatch, seed)
     """Random sequences of whole-batch steps, range steps (unaligned, wrapping the observation window), masked
     resets to host layouts, partial set_state, and a checkpoint round trip through a fresh handle; afterwards the
     whole state and every observation slot must equal the oracle's for the env rendered into it last."""
-    rng = np.random.default_rng(9000 + seed)
+    rng = np.random.default_rng(BASE + 9000 + seed)
     monkeypatch.setenv("RCW_ENV_PER_WARP", str(int(rng.integers(0, 2))))
     monkeypatch.setenv("RCW_ROOM", str(seed & 1))
     monkeypatch.setenv("RCW_COL_TABLE_KB", "0" if seed & 2 else "64")
+    monkeypatch.setenv("RCW_TWO_STREAMS_MIN", "8")
     monkeypatch.setenv("RCW_ENV_PER_WARP_MIN", "1")
     monkeypatch.setenv("RCW_PACKED_ACTIONS", str(int(rng.integers(0, 2))))
     n = int(rng.integers(2, 60))
@@ -238,8 +239,16 @@ def test_random_operation_sequences_with_windows(rcw, oracle, monkeypatch, seed)
             owner[e % win] = e
     rendered(range(n))
     for _ in range(int(rng.integers(3, 14))):
-        op = rng.choice(["act", "range", "range", "reset", "state", "checkpoint"])
-        if op == "act":
+        op = rng.choice(["act", "range", "range", "reset", "state", "checkpoint", "tape"])
+        if op == "tape":      # a multi-step call (two streams / the step + top-view pipeline when the batch is not windowed)
+            T = int(rng.integers(2, 6))
+            tape = rng.choice([1, 1, 2, 3, 4], size=(T, n)).astype(np.uint8)
+            env.act_tape(tape)
+            for t in range(T):
+                for e in range(n):
+                    assert worlds[e].step(int(tape[t, e])) == 0
+            rendered(range(n))
+        elif op == "act":
             acts = rng.choice([1, 1, 2, 3, 4], size=n).astype(np.uint8)
             env.act(acts)
             for e in range(n):
