@@ -90,11 +90,13 @@ def test_frame_ring_with_two_streams(rcw, oracle, monkeypatch):
     env.close()
 
 
-def test_default_split_at_bench_size_sampled_against_oracle(rcw, oracle):
+def test_default_split_at_bench_size_sampled_against_oracle(rcw, oracle, monkeypatch):
     """The bench's own shape — 4096 default-camera envs stepped by one rcw_step_random(K) call, which the handle runs as
     two half-batches on two streams without any switch set — against oracle batches of 48 envs placed at the start, around
     the split and at the end of the batch (the Philox streams are keyed by global env id, so a sub-range can be replayed
     on its own)."""
+    for var in ("RCW_TWO_STREAMS", "RCW_TWO_STREAMS_MIN"):        # the handle's own defaults, whatever the caller exported
+        monkeypatch.delenv(var, raising=False)
     n, steps, seed = 4096, 1500, 24301
     env = rcw.BatchedSingleRoom(n, seed=seed)
     launches0 = env.launch_count()
