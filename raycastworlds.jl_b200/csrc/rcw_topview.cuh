@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
         // player_position_wu + ray_distance_wu[i] * ray_direction_wu (:476), one rounding per operation
         const int i2 = wu_to_pu(__fadd_rn(x, __fmul_rn(hit.dist, rt.x)), fpu);
         const int j2 = wu_to_pu(__fadd_rn(y, __fmul_rn(hit.dist, rt.y)), fpu);
-#if RCW_TOP_WALK == 1   // chunked walk (measured alternative, profiles/README.md)
+#if RCW_TOP_WALK >= 1   // chunked walk (1) / lock-step first ring + chunked remainder (2): measured alternatives, profiles/README.md
         // All segments start at the player's pixel, and neighbouring rays stop a fraction of a pixel apart (0.2 - 0.6
         // px at the usual distances): a ray whose stop pixel equals its lower neighbour's draws exactly the same
         // pixels and is dropped here.  The distinct segments (about 4 in 10 at the defaults) are appended to one
@@ -171,7 +171,13 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
         const int i2_below = __shfl_up_sync(0xFFFFFFFFu, i2, 1), j2_below = __shfl_up_sync(0xFFFFFFFFu, j2, 1);
         const bool distinct = (ray < R) & ((lane == 0) | (i2 != i2_below) | (j2 != j2_below));
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, distinct);
+#if RCW_TOP_WALK == 2
+        // hybrid: the first 32 steps of every segment are walked in lock step (below); chunks cover steps 32 ..
+        const int n_steps = max(abs(i2 - ip), abs(j2 - jp));
+        const uint32_t nch = (distinct && n_steps >= 32) ? ((uint32_t)(n_steps - 32) >> kTopChunkLog) + 1u : 0u;
+#else
         const uint32_t nch = distinct ? ((uint32_t)max(abs(i2 - ip), abs(j2 - jp)) >> kTopChunkLog) + 1u : 0u;
+#endif
         uint32_t incl = nch;                                    // inclusive prefix sum of the chunk counts
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -205,11 +211,68 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
     //      of a warp draw in different segments or far apart in the same one and rarely meet in a plane word.
     const int n_lines = (int)(uint32_t)s_counts;
     const uint32_t n_chunks = (uint32_t)(s_counts >> 32);
+#if RCW_TOP_WALK == 2
+    // ---- the first ring: steps 0 .. 31 of every segment, lane <-> segment in lock step.  Next to the player the 225
+    //      segments of a default env draw 7.2 K pixels onto 600: neighbouring lanes (neighbouring rays) are on the same
+    //      pixel most of the time, and a lane whose pixel equals its lower neighbour's leaves the atomic to it.
+    for (int l0 = warp * 32; l0 < n_lines; l0 += kTopThreads) {
+        const bool have1 = l0 + lane < n_lines;
+        const int2 end = s_line[min(l0 + lane, n_lines - 1)];
+        const int i2 = end.x, j2 = end.y;
+        const int di = abs(i2 - ip), dj = abs(j2 - jp);
+        const int si = ip < i2 ? 1 : -1, sj = jp < j2 ? 1 : -1;
+        const int M = max(di, dj), m = min(di, dj);
+        const int n = have1 ? min(M, 31) : -1;
+        const int n_max = __reduce_max_sync(0xFFFFFFFFu, n);
+        const int n_below = __shfl_up_sync(0xFFFFFFFFu, n, 1);
+        const bool clip = (ip < 1) | (ip > Hp) | (jp < 1) | (jp > Wp) | (i2 < 1) | (i2 > Hp) | (j2 < 1) | (j2 > Wp);
+        const bool i_major = di >= dj;
+        const int f_stay = -2 * m, f_step = 2 * (M - m);
+        int F = M - 2 * m;
+        if (!__any_sync(0xFFFFFFFFu, clip && have1)) {
+            const int bit_si = si, bit_sj = sj * (int)SB;
+            const int adv_major = i_major ? bit_si : bit_sj, adv_both = bit_si + bit_sj;
+            const int n_dup = lane > 0 ? n_below : -1;
+            uint32_t idx = (uint32_t)(jp - 1) * SB + (uint32_t)(ip - 1);
+#pragma unroll 2
+            for (int k = 0; k <= n_max; ++k) {
+                const uint32_t below = __shfl_up_sync(0xFFFFFFFFu, idx, 1);
+                const bool dup = (k <= n_dup) & (below == idx);
+                if ((k <= n) & !dup) atomicOr(s_ray + (idx >> 5), 1u << (idx & 31u));
+                const bool step = F <= 0;
+                F += step ? f_step : f_stay;
+                idx += (uint32_t)(step ? adv_both : adv_major);
+            }
+        } else if (have1) {
+            int i = ip, j = jp;
+            for (int k = 0; k <= n; ++k) {
+                plane_set(s_ray, i, j, Hp, Wp, SB);
+                const bool step = F <= 0;
+                F += step ? f_step : f_stay;
+                i += (i_major | step) ? si : 0;
+                j += (!i_major | step) ? sj : 0;
+            }
+        }
+    }
+    constexpr int kFirstChunkStep = 32;
+    // chunks: thread t takes chunks t T .. t T + T - 1 (T = rounds): the lanes of a warp are T chunks apart, mostly in
+    // different segments, and only the CTA's last few threads ever idle
+    const uint32_t n_rounds = (n_chunks + kTopThreads - 1) / kTopThreads;
+#else
+    constexpr int kFirstChunkStep = 0;
+#endif
     int search0 = 1;
     while (search0 < n_lines) search0 <<= 1;                    // first probe distance of the segment search
+#if RCW_TOP_WALK == 2
+    for (uint32_t t = 0; t < n_rounds; ++t) {
+        const uint32_t g = (uint32_t)tid * n_rounds + t;
+        if (!__any_sync(0xFFFFFFFFu, g < n_chunks)) break;
+        const bool have = g < n_chunks;
+#else
     for (uint32_t g0 = 0; g0 < n_chunks; g0 += kTopThreads) {
         const uint32_t g = g0 + (uint32_t)(lane * (kTopThreads / 32) + warp);
         const bool have = g < n_chunks;
+#endif
         // the segment this chunk belongs to: the last one whose first chunk is <= g
         int seg = 0;
         for (int d = search0 >> 1; d > 0; d >>= 1)
@@ -220,7 +283,7 @@ __global__ void __launch_bounds__(kTopThreads, 6) top_view_kernel(const __grid_c
         const int si = ip < i2 ? 1 : -1, sj = jp < j2 ? 1 : -1;
         const bool i_major = di >= dj;
         const int M = max(di, dj), m = min(di, dj);
-        const int k0 = have ? (int)((g - s_cstart[seg]) << kTopChunkLog) : 0;
+        const int k0 = have ? kFirstChunkStep + (int)((g - s_cstart[seg]) << kTopChunkLog) : 0;
         const int n_px = have ? min(1 << kTopChunkLog, M - k0 + 1) : 0;       // pixels of this chunk
         const int s0 = M > 0 ? (int)((2u * (uint32_t)m * (uint32_t)k0 + (uint32_t)M) / (2u * (uint32_t)M)) : 0;
         int F = M - 2 * m * (k0 + 1) + 2 * M * s0;
